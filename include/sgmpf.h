@@ -1,0 +1,146 @@
+/*
+ * sgmpf.h -- C-ABI of the B200 (sm_100a) buffered particle-filter gradient library.
+ *
+ * This is the drop-in boundary for ONE hot path of the reference `sgmcmc_ssm` package: the batched
+ * time loop of the buffered particle filter / smoother behind
+ *     sampler.noisy_gradient(kind='pf', ...) -> Helper.pf_gradient_estimate(...)
+ *     -> particle_filters.buffered_smoother.buffered_pf_wrapper(...)
+ * (reference files, relative to sgmcmc_ssm/:
+ *     particle_filters/buffered_smoother.py:12-199   time loop, dispatch on `pf`, average_statistic
+ *     particle_filters/pf.py:7-377                   pf step, nemeth / poyiadjis / paris / filter
+ *     particle_filters/kernels.py:82-138             LatentGaussianKernel
+ *     models/{svm,lgssm,garch}/kernels.py            proposal + reweight
+ *     models/{svm,lgssm,garch}/helper.py             complete-data score functions)
+ *
+ * The reference is pure Python/numpy and has no FFI of its own; the binding a maintainer adds is the
+ * ctypes stub shown in INTEGRATION.md.  One call to sgm_pf_run() executes the whole t-loop for a
+ * batch of independent work items (chain x sequence x subsequence) on the given CUDA stream.
+ *
+ * Conventions
+ *   - plain C, no torch / C++ types; all pointers are DEVICE pointers unless marked HOST
+ *   - the library allocates nothing and keeps no global mutable state except a thread-local error
+ *     string; every buffer (incl. workspace) is caller-owned
+ *   - calls are asynchronous on `stream`; there is no hidden synchronisation; the per-item `status`
+ *     flags are read by the caller after its own sync
+ *   - return value: 0 on success, negative SGM_ERR_* otherwise (never throws, never aborts)
+ */
+#ifndef SGMPF_H_
+#define SGMPF_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SGM_VERSION 100 /* 0.1.0 */
+
+/* model: models/{lgssm,svm,garch} */
+enum { SGM_MODEL_LGSSM = 0, SGM_MODEL_SVM = 1, SGM_MODEL_GARCH = 2 };
+/* proposal kernel: Helper._get_kernel (svm/helper.py:56-65, garch/helper.py:48-57, lgssm/helper.py:1200-1214) */
+enum { SGM_KERNEL_PRIOR = 0, SGM_KERNEL_OPTIMAL = 1 };
+/* smoother: buffered_pf_wrapper `pf` string (buffered_smoother.py:156-199).
+ * "poyiadjis_N" is SGM_PF_NEMETH with lambduh = 1.0 (buffered_smoother.py:175-180). */
+enum { SGM_PF_NEMETH = 0, SGM_PF_POY_N2 = 1, SGM_PF_PARIS = 2, SGM_PF_FILTER = 3 };
+/* arithmetic / storage type of the particle arrays */
+enum { SGM_F32 = 0, SGM_F64 = 1 };
+/* random numbers: device Philox4x32-10, or arrays recorded from the reference's numpy stream */
+enum { SGM_RNG_PHILOX = 0, SGM_RNG_INJECTED = 1 };
+/* resampling scheme.  MULTINOMIAL = reference semantics (pf.py:27-29; iid uniforms, child i gets
+ * searchsorted(cdf, u_i, 'right')).  MULTINOMIAL_SORTED draws the *order statistics* of N iid
+ * uniforms directly (same law up to a permutation of the children, which every estimator here is
+ * invariant to) so ancestor indices are non-decreasing and the gather streams.  SYSTEMATIC and
+ * STRATIFIED are extensions (not in the reference).  In INJECTED mode the uniforms are used as given;
+ * pass SORTED only if they are ascending. */
+enum { SGM_RESAMPLE_MULTINOMIAL = 0, SGM_RESAMPLE_MULTINOMIAL_SORTED = 1,
+       SGM_RESAMPLE_SYSTEMATIC = 2, SGM_RESAMPLE_STRATIFIED = 3 };
+/* additive statistic carried by the smoother */
+enum { SGM_STAT_SCORE = 0,     /* complete-data log-likelihood gradient (pf_gradient_estimate)   */
+       SGM_STAT_SUFF = 1,      /* [x', x'^2, x x'] (lgssm/svm) or [x', x'^2, x'^4] (garch)        */
+       SGM_STAT_NONE = 2 };    /* log-likelihood only (pf_loglikelihood_estimate)                 */
+
+/* error codes */
+enum { SGM_OK = 0, SGM_ERR_INVALID = -1, SGM_ERR_UNSUPPORTED = -2, SGM_ERR_WORKSPACE = -3,
+       SGM_ERR_CUDA = -4, SGM_ERR_DEVICE = -5 };
+
+/* per-item status bits (device int32) */
+enum { SGM_STATUS_NAN_WEIGHT = 1,   /* NaN / +inf log-weight: np.random.choice would raise ValueError */
+       SGM_STATUS_ZERO_WEIGHT = 2,  /* all weights underflowed                                         */
+       SGM_STATUS_AR_OVERFLOW = 4 };/* PaRIS accept-reject hit max_accept_reject (exact fallback used) */
+
+#define SGM_THETA_STRIDE 12
+/* theta layout (doubles, values exactly as the reference Parameters object computes them):
+ *   SVM   : A, LQinv, Qinv, LRinv, Rinv
+ *   LGSSM : A, LQinv, Qinv, C, LRinv, Rinv
+ *   GARCH : alpha, beta, gamma, mu, phi, lambduh, LRinv, Rinv, R                                    */
+
+typedef struct sgm_pf_desc {
+    int32_t struct_bytes;          /* sizeof(sgm_pf_desc), checked */
+    int32_t model, kernel, pf, dtype, rng_mode, resample, stat_kind;
+    int32_t n_items;               /* B: work items in this batch                                   */
+    int32_t n_particles;           /* N                                                             */
+    int32_t max_T;                 /* max over items of T_buf                                       */
+    int32_t Ntilde;                /* PaRIS backward samples per particle (pf.py:185)               */
+    int32_t accept_reject;         /* PaRIS: 1 = accept-reject (default), 0 = naive O(N^2)          */
+    int32_t max_accept_reject;     /* <0: int(100*log10(N/10)) (pf.py:284-285)                      */
+    int32_t manual_sample_threshold; /* <0: int(10*log10(N/10)) (pf.py:286-287); INJECTED mode only */
+    int32_t item_id_base;          /* global index of item 0 (keeps Philox streams rank-invariant)  */
+    double lambduh;                /* Nemeth shrinkage (pf.py:140); 1.0 = Poyiadjis O(N)            */
+    uint64_t seed, offset;         /* Philox key / call counter                                     */
+
+    /* per-item inputs */
+    const double* obs;             /* flat observations                                             */
+    const int64_t* obs_off;        /* [B] start of the item's buffered window in obs                */
+    const int32_t* T_buf;          /* [B] window length (left buffer + subsequence + right buffer)  */
+    const int32_t* t1;             /* [B] relative subsequence start  (buffered_smoother.py:96)     */
+    const int32_t* tL;             /* [B] relative subsequence end (exclusive)                      */
+    const double* step_weights;    /* flat per-step weights, or NULL                                */
+    const int64_t* wts_off;        /* [B] offset into step_weights, -1 = all ones; may be NULL      */
+    const double* theta;           /* [B][SGM_THETA_STRIDE]                                         */
+    const double* prior_mean;      /* [B]                                                           */
+    const double* prior_var;       /* [B]                                                           */
+
+    /* INJECTED randoms (float64, reference consumption order) */
+    const double* inj_z0;          /* [B][N]          sample_x0 normals                             */
+    const double* inj_u;           /* [B][max_T][N]   resampling uniforms                           */
+    const double* inj_z;           /* [B][max_T][N]   proposal normals                              */
+    const double* inj_extra;       /* flat PaRIS accept-reject / exact-sampling uniforms            */
+    const int64_t* inj_extra_off;  /* [B][max_T]      start of (item, step)'s slice of inj_extra    */
+
+    /* outputs */
+    double* grad;                  /* [B][8]  final weighted-average statistic (average_statistic)  */
+    double* loglik;                /* [B]     log-likelihood estimate over [t1, tL)                 */
+    int32_t* status;               /* [B]                                                           */
+    void* out_x;                   /* optional [B][N][n]  final particles (dtype)                   */
+    void* out_lw;                  /* optional [B][N]     final log-weights (dtype)                 */
+    void* out_stats;               /* optional [B][N][p]  final statistics (dtype)                  */
+    int32_t* trace_anc;            /* optional [B][max_T][N]       ancestor indices per step        */
+    void* trace_x;                 /* optional [B][max_T+1][N][n]  particles per step (dtype)       */
+    void* trace_lw;                /* optional [B][max_T+1][N]     log-weights per step (dtype)     */
+    int32_t* trace_J;              /* optional [B][max_T][N][Ntilde] PaRIS backward indices         */
+
+    void* workspace;               /* >= sgm_pf_workspace_bytes(desc), 256-byte aligned             */
+    uint64_t workspace_bytes;
+} sgm_pf_desc;
+
+/* library version (SGM_VERSION) */
+int sgm_version(void);
+/* 0 iff the current CUDA device has compute capability 10.x (B200); SGM_ERR_DEVICE otherwise */
+int sgm_device_check(void);
+/* thread-local description of the last error returned on this thread */
+const char* sgm_last_error(void);
+/* statistic width p and latent width n for (model, stat_kind); negative on error */
+int sgm_stat_dim(int32_t model, int32_t stat_kind);
+int sgm_state_dim(int32_t model);
+/* bytes of workspace sgm_pf_run needs for this descriptor (0 on invalid descriptor) */
+uint64_t sgm_pf_workspace_bytes(const sgm_pf_desc* d);
+/* run the whole buffered t-loop for the batch on `stream` (a cudaStream_t passed as void*) */
+int sgm_pf_run(const sgm_pf_desc* d, void* stream);
+/* number of kernel launches the last sgm_pf_run on this thread issued (for bench accounting) */
+int64_t sgm_last_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SGMPF_H_ */

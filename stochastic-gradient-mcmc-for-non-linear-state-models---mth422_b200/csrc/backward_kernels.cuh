@@ -1,0 +1,377 @@
+// Backward-weight smoothers that run after pf_step_kernel has produced the new particles:
+//   * Poyiadjis O(N^2)  (pf.py:84-136)   -- flash-attention-style: tiles of old particles staged in
+//     shared memory, per-child online max / sum, exp-weights times (statistics + score) accumulated
+//     in registers; the (N, N) backward-weight matrix is never materialised.
+//   * PaRIS            (pf.py:183-341)   -- accept-reject backward sampling with exact fallback.
+//       PHILOX mode : every child runs its own accept-reject loop (counter-based draws);
+//                     children that exhaust max_accept_reject go to an exact O(N) sampler.
+//       INJECTED mode: one CTA per item replays the reference's round structure (stable compaction
+//                     of the unresolved list L, uniforms consumed at a running offset) so that the
+//                     recorded numpy stream lines up draw for draw.
+#pragma once
+#include "pf_kernels.cuh"
+
+namespace sgm {
+
+constexpr int JT = 512;        // old particles per shared-memory tile in the O(N^2) kernel
+constexpr int EXACT_CTAS = 32; // CTAs per item for the PaRIS exact fallback
+
+template <class R, class Model>
+__device__ __forceinline__ void stat_of(const KArgs& a, const typename Model::template Theta<R>& th, const R* xa, const R* xn, R y, bool in_sub, R* h) {
+    h[0] = h[1] = h[2] = h[3] = (R)0;
+    if (in_sub) {
+        if (a.stat_kind == SGM_STAT_SCORE) Model::score(th, xa, xn, y, h);
+        else if (a.stat_kind == SGM_STAT_SUFF) Model::suff(xa, xn, h);
+    }
+}
+
+// ---- Poyiadjis O(N^2) ------------------------------------------------------------------------------
+template <class R, class Model>
+__global__ void __launch_bounds__(NT) poyiadjis_n2_kernel(KArgs a, int t) {
+    constexpr int NX = Model::NX, NP = Model::NP, W = NX + NP;
+    __shared__ R s_x[NX][JT];
+    __shared__ R s_S[NP][JT];
+    __shared__ R s_lw[JT];
+    __shared__ R s_k[2][JT];
+    const int b = blockIdx.y, tid = threadIdx.x;
+    if (t >= a.T_buf[b]) return;
+    const int N = a.N, par = t & 1;
+    const size_t item_off = (size_t)b * N;
+    const int i = blockIdx.x * NT + tid;
+    const bool valid = i < N;
+    const typename Model::template Theta<R> th = Model::template load<R>(a.theta + (size_t)b * SGM_THETA_STRIDE);
+    const R y = (R)a.obs[a.obs_off[b] + t];
+    const bool in_sub = (t >= a.t1[b]) && (t < a.tL[b]);
+    const R wt = in_sub ? ((a.wts_off && a.wts_off[b] >= 0) ? (R)a.step_weights[a.wts_off[b] + (t - a.t1[b])] : (R)1) : (R)0;
+    const int nws = stat_width<Model>(a.stat_kind);
+
+    R rn[W];
+#pragma unroll
+    for (int q = 0; q < W; ++q) rn[q] = (R)0;
+    if (valid) load_rec<R, W>(a.rec[par ^ 1], a.tail[par ^ 1], item_off + i, rn);
+    const R* xi = rn + NP;
+    const R* lw_old = reinterpret_cast<const R*>(a.lw[par]) + item_off;
+
+    R m = -Mth<R>::inf(), l = (R)0, acc[4] = {(R)0, (R)0, (R)0, (R)0};
+    for (int j0 = 0; j0 < N; j0 += JT) {
+        const int jn = min(JT, N - j0);
+        __syncthreads();
+        for (int j = tid; j < jn; j += NT) {
+            R rj[W];
+            load_rec<R, W>(a.rec[par], a.tail[par], item_off + j0 + j, rj);
+#pragma unroll
+            for (int q = 0; q < NP; ++q) s_S[q][j] = rj[q];
+#pragma unroll
+            for (int q = 0; q < NX; ++q) s_x[q][j] = rj[NP + q];
+            s_lw[j] = lw_old[j0 + j];
+            R k[2];
+            Model::jkey(th, rj + NP, k);
+            s_k[0][j] = k[0]; s_k[1][j] = k[1];
+        }
+        __syncthreads();
+        // pass 1: tile max of the backward log-weights  lw_j + log q(x'_i | x_j)   (pf.py:115-121)
+        R tm = -Mth<R>::inf();
+        for (int j = 0; j < jn; ++j) {
+            const R k[2] = {s_k[0][j], s_k[1][j]};
+            tm = fmax(tm, s_lw[j] + Model::log_trans_key(th, k, xi));
+        }
+        if (tm == -Mth<R>::inf()) continue;          // whole tile has zero weight (warp-divergent skip is fine)
+        if (tm > m) {
+            const R sc = (m == -Mth<R>::inf()) ? (R)0 : Mth<R>::exp(m - tm);
+            l *= sc;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) acc[q] *= sc;
+            m = tm;
+        }
+        // pass 2: accumulate exp-weights times (statistics_j + h(x_j, x'_i) * scale)   (pf.py:123-135)
+        for (int j = 0; j < jn; ++j) {
+            const R k[2] = {s_k[0][j], s_k[1][j]};
+            const R p = Mth<R>::exp(s_lw[j] + Model::log_trans_key(th, k, xi) - m);
+            R xj[NX];
+#pragma unroll
+            for (int q = 0; q < NX; ++q) xj[q] = s_x[q][j];
+            R h[4];
+            stat_of<R, Model>(a, th, xj, xi, y, in_sub, h);
+            l += p;
+#pragma unroll
+            for (int q = 0; q < NP; ++q) acc[q] += p * (s_S[q][j] + h[q] * wt);
+        }
+    }
+    if (valid) {
+        const R il = (R)1 / l;
+        for (int q = 0; q < NP; ++q) rn[q] = (q < nws) ? acc[q] * il : (R)0;
+        store_rec<R, W>(a.rec[par ^ 1], a.tail[par ^ 1], item_off + i, rn);
+    }
+}
+
+// Per-tile weighted statistic sums for the final average (only on an item's last step).
+template <class R, class Model>
+__global__ void __launch_bounds__(NT) stat_ws_kernel(KArgs a, int t) {
+    constexpr int NX = Model::NX, NP = Model::NP, W = NX + NP;
+    __shared__ double sh_d[NWARP];
+    const int b = blockIdx.y, g = blockIdx.x, tid = threadIdx.x;
+    if (t != a.T_buf[b] - 1) return;
+    const int N = a.N, par = (t & 1) ^ 1;          // buffers written by step t
+    const size_t item_off = (size_t)b * N;
+    const int nws = stat_width<Model>(a.stat_kind);
+    double* part = a.part[par] + ((size_t)b * a.G + g) * PSTRIDE;
+    const R m = (R)part[0];
+    const R* lw = reinterpret_cast<const R*>(a.lw[par]) + item_off;
+    const int i0 = g * TILE + tid * KPT;
+    double ws[4] = {0.0, 0.0, 0.0, 0.0};
+    for (int c = 0; c < KPT; ++c) {
+        const int i = i0 + c;
+        if (i < N) {
+            R r[W];
+            load_rec<R, W>(a.rec[par], a.tail[par], item_off + i, r);
+            const R w = (m == -Mth<R>::inf()) ? (R)0 : Mth<R>::exp(lw[i] - m);
+            for (int q = 0; q < nws; ++q) ws[q] += (double)(r[q] * w);
+        }
+    }
+    for (int q = 0; q < nws; ++q) ws[q] = block_sum(ws[q], sh_d);
+    if (tid == 0) for (int q = 0; q < 4; ++q) part[2 + q] = ws[q];
+}
+
+template <class R, class Model>
+int launch_poyiadjis_n2(const KArgs& a, int t, cudaStream_t stream) {
+    poyiadjis_n2_kernel<R, Model><<<dim3((a.N + NT - 1) / NT, a.B), NT, 0, stream>>>(a, t);
+    stat_ws_kernel<R, Model><<<dim3(a.G, a.B), NT, 0, stream>>>(a, t);
+    return 2;
+}
+
+// ---- PaRIS ------------------------------------------------------------------------------------------
+// Exact draw(s) from the backward kernel of child i:  J ~ Cat(softmax_j(lw_j + log q(x'_i | x_j)))
+// (pf.py:328-339 and the naive branch :226-237).  Block-cooperative, fixed summation order.
+template <class R, class Model>
+__device__ __forceinline__ void exact_backward_sample(const KArgs& a, const typename Model::template Theta<R>& th, int par,
+                                                      size_t item_off, const R* xi, int nu, const double* u, int32_t* Jout,
+                                                      int Jstride, R* sh_r, double* sh_d) {
+    constexpr int NX = Model::NX, NP = Model::NP, W = NX + NP;
+    const int N = a.N, tid = threadIdx.x;
+    const R* lw_old = reinterpret_cast<const R*>(a.lw[par]) + item_off;
+    const int per = (N + NT - 1) / NT;
+    const int j0 = tid * per, j1 = min(N, j0 + per);
+    R m = -Mth<R>::inf();
+    for (int j = j0; j < j1; ++j) {
+        R rj[W];
+        load_rec<R, W>(a.rec[par], a.tail[par], item_off + j, rj);
+        m = nan_max(m, lw_old[j] + Model::log_trans(th, rj + NP, xi));
+    }
+    m = block_max(m, sh_r);
+    double loc = 0.0;
+    for (int j = j0; j < j1; ++j) {
+        R rj[W];
+        load_rec<R, W>(a.rec[par], a.tail[par], item_off + j, rj);
+        loc += (double)Mth<R>::exp(lw_old[j] + Model::log_trans(th, rj + NP, xi) - m);
+    }
+    double total;
+    const double pre = block_excl_scan(loc, sh_d, total);
+    for (int k = 0; k < nu; ++k) {
+        double target = u[k] * total;
+        if (!(target < total)) target = total * (1.0 - 1.2e-16);
+        if (tid == 0) Jout[k * Jstride] = N - 1;
+    }
+    __syncthreads();
+    for (int k = 0; k < nu; ++k) {
+        double target = u[k] * total;
+        if (!(target < total)) target = total * (1.0 - 1.2e-16);
+        if (target >= pre && target < pre + loc) {
+            double run = pre;
+            int found = j1 - 1;
+            for (int j = j0; j < j1; ++j) {
+                R rj[W];
+                load_rec<R, W>(a.rec[par], a.tail[par], item_off + j, rj);
+                run += (double)Mth<R>::exp(lw_old[j] + Model::log_trans(th, rj + NP, xi) - m);
+                if (run > target) { found = j; break; }
+            }
+            Jout[k * Jstride] = found;
+        }
+    }
+    __syncthreads();
+}
+
+// PHILOX mode: independent accept-reject loop per (child, replicate)  (pf.py:292-325 in law).
+template <class R, class Model>
+__global__ void __launch_bounds__(NT) paris_ar_kernel(KArgs a, int t) {
+    constexpr int NX = Model::NX, NP = Model::NP, W = NX + NP;
+    __shared__ CdfHeader hdr;
+    const int b = blockIdx.y, g = blockIdx.x, tid = threadIdx.x;
+    if (t >= a.T_buf[b]) return;
+    const int N = a.N, G = a.G, par = t & 1;
+    const size_t item_off = (size_t)b * N;
+    build_cdf_header(a.part[par] + (size_t)b * G * PSTRIDE, G, 0, hdr);
+    const typename Model::template Theta<R> th = Model::template load<R>(a.theta + (size_t)b * SGM_THETA_STRIDE);
+    const R ltmax = Model::log_trans_max(th);
+    const R* fine_old = reinterpret_cast<const R*>(a.fine[par]) + item_off;
+    RngKey key = a.key; key.item += (uint32_t)b;
+    const int tries = a.accept_reject ? a.max_ar : 0;
+    for (int c = 0; c < KPT; ++c) {
+        const int i = g * TILE + c * NT + tid;      // strided: neighbouring lanes, neighbouring children
+        if (i >= N) continue;
+        R rn[W];
+        load_rec<R, W>(a.rec[par ^ 1], a.tail[par ^ 1], item_off + i, rn);
+        for (int jt = 0; jt < a.Ntilde; ++jt) {
+            int J = -1;
+            for (int r = 0; r < tries; ++r) {
+                const uint4 raw = rng_raw(key, (uint32_t)i, (uint32_t)t, STREAM_PARIS, (uint32_t)(jt * a.max_ar + r));
+                const int I = search_cdf<R>(u01d(raw.x, raw.y) * hdr.total, hdr, G, fine_old, N);
+                R ra[W];
+                load_rec<R, W>(a.rec[par], a.tail[par], item_off + I, ra);
+                const R thr = Mth<R>::exp(Model::log_trans(th, ra + NP, rn + NP) - ltmax);
+                if ((R)u01d(raw.z, raw.w) <= thr) { J = I; break; }
+            }
+            a.Jidx[(item_off + i) * a.Ntilde + jt] = J;
+            if (J < 0) {
+                const int slot = atomicAdd(a.counters + b * 16, 1);
+                a.Llist[0][item_off * a.Ntilde + slot] = i * a.Ntilde + jt;
+            }
+        }
+    }
+}
+
+template <class R, class Model>
+__global__ void __launch_bounds__(NT) paris_exact_kernel(KArgs a, int t) {
+    constexpr int NX = Model::NX, NP = Model::NP, W = NX + NP;
+    __shared__ R sh_r[NWARP];
+    __shared__ double sh_d[NWARP];
+    const int b = blockIdx.y;
+    if (t >= a.T_buf[b]) return;
+    const int N = a.N, par = t & 1;
+    const size_t item_off = (size_t)b * N;
+    const int count = a.counters[b * 16];
+    if (count > 0 && blockIdx.x == 0 && threadIdx.x == 0 && a.accept_reject) a.status[b] |= SGM_STATUS_AR_OVERFLOW;
+    const typename Model::template Theta<R> th = Model::template load<R>(a.theta + (size_t)b * SGM_THETA_STRIDE);
+    RngKey key = a.key; key.item += (uint32_t)b;
+    for (int e = blockIdx.x; e < count; e += gridDim.x) {
+        const int entry = a.Llist[0][item_off * a.Ntilde + e];
+        const int i = entry / a.Ntilde, jt = entry % a.Ntilde;
+        R rn[W];
+        load_rec<R, W>(a.rec[par ^ 1], a.tail[par ^ 1], item_off + i, rn);
+        const uint4 raw = rng_raw(key, (uint32_t)i, (uint32_t)t, STREAM_EXACT, (uint32_t)jt);
+        const double u = u01d(raw.x, raw.y);
+        exact_backward_sample<R, Model>(a, th, par, item_off, rn + NP, 1, &u, a.Jidx + (item_off + i) * a.Ntilde + jt, 1, sh_r, sh_d);
+    }
+}
+
+// INJECTED mode: replay of accept_reject_based_backward_sampling (pf.py:260-341) / the naive branch
+// (pf.py:226-237) with the recorded uniforms, one CTA per item.
+template <class R, class Model>
+__global__ void __launch_bounds__(NT) paris_injected_kernel(KArgs a, int t) {
+    constexpr int NX = Model::NX, NP = Model::NP, W = NX + NP;
+    __shared__ CdfHeader hdr;
+    __shared__ R sh_r[NWARP];
+    __shared__ double sh_d[NWARP];
+    __shared__ int sh_i[NWARP];
+    const int b = blockIdx.x, tid = threadIdx.x;
+    if (t >= a.T_buf[b]) return;
+    const int N = a.N, G = a.G, par = t & 1, Nt = a.Ntilde;
+    const size_t item_off = (size_t)b * N;
+    build_cdf_header(a.part[par] + (size_t)b * G * PSTRIDE, G, 0, hdr);
+    const typename Model::template Theta<R> th = Model::template load<R>(a.theta + (size_t)b * SGM_THETA_STRIDE);
+    const R ltmax = Model::log_trans_max(th);
+    const R* fine_old = reinterpret_cast<const R*>(a.fine[par]) + item_off;
+    const double* extra = a.inj_extra + a.inj_extra_off[(size_t)b * a.max_T + t];
+    int32_t* Jb = a.Jidx + item_off * Nt;
+    int64_t off = 0;
+    if (!a.accept_reject) {
+        for (int i = 0; i < N; ++i) {
+            R rn[W];
+            load_rec<R, W>(a.rec[par ^ 1], a.tail[par ^ 1], item_off + i, rn);
+            exact_backward_sample<R, Model>(a, th, par, item_off, rn + NP, Nt, extra + off, Jb + (size_t)i * Nt, 1, sh_r, sh_d);
+            off += Nt;
+        }
+        return;
+    }
+    int32_t* Lcur = a.Llist[0] + item_off * Nt;
+    int32_t* Lnext = a.Llist[1] + item_off;
+    for (int jt = 0; jt < Nt; ++jt) {
+        for (int k = tid; k < N; k += NT) Lcur[k] = k;
+        __syncthreads();
+        int size_L = N;
+        bool converged = false;
+        for (int round = 0; round < a.max_ar; ++round) {
+            if (size_L == 0) { converged = true; break; }
+            if (size_L <= a.manual_thresh) break;
+            int new_count = 0;
+            for (int base = 0; base < size_L; base += NT) {
+                const int k = base + tid;
+                int flag = 0, i = 0;
+                if (k < size_L) {
+                    i = Lcur[k];
+                    const int I = search_cdf<R>(extra[off + k] * hdr.total, hdr, G, fine_old, N);
+                    R ra[W], rn[W];
+                    load_rec<R, W>(a.rec[par], a.tail[par], item_off + I, ra);
+                    load_rec<R, W>(a.rec[par ^ 1], a.tail[par ^ 1], item_off + i, rn);
+                    const R thr = Mth<R>::exp(Model::log_trans(th, ra + NP, rn + NP) - ltmax);
+                    if ((R)extra[off + size_L + k] <= thr) Jb[(size_t)i * Nt + jt] = I; else flag = 1;
+                }
+                int chunk_total;
+                const int pos = block_excl_scan(flag, sh_i, chunk_total);
+                if (flag) Lnext[new_count + pos] = i;
+                new_count += chunk_total;
+            }
+            off += 2 * (int64_t)size_L;
+            size_L = new_count;
+            int32_t* tmp = Lcur; Lcur = Lnext; Lnext = tmp;
+            __syncthreads();
+        }
+        if (!converged) {
+            if (size_L > 0 && tid == 0 && size_L > a.manual_thresh) a.status[b] |= SGM_STATUS_AR_OVERFLOW;
+            for (int e = 0; e < size_L; ++e) {
+                const int i = Lcur[e];
+                R rn[W];
+                load_rec<R, W>(a.rec[par ^ 1], a.tail[par ^ 1], item_off + i, rn);
+                exact_backward_sample<R, Model>(a, th, par, item_off, rn + NP, 1, extra + off + e, Jb + (size_t)i * Nt + jt, 1, sh_r, sh_d);
+            }
+            off += size_L;
+        }
+        __syncthreads();
+    }
+}
+
+// statistics update  tau'_i = mean_k( tau[J_ik] + h(x[J_ik], x'_i) * scale )   (pf.py:239-256)
+template <class R, class Model>
+__global__ void __launch_bounds__(NT) paris_update_kernel(KArgs a, int t) {
+    constexpr int NX = Model::NX, NP = Model::NP, W = NX + NP;
+    const int b = blockIdx.y, tid = threadIdx.x;
+    if (t >= a.T_buf[b]) return;
+    const int N = a.N, par = t & 1, Nt = a.Ntilde;
+    const size_t item_off = (size_t)b * N;
+    const int i = blockIdx.x * NT + tid;
+    if (blockIdx.x == 0 && tid == 0) a.counters[b * 16] = 0;
+    if (i >= N) return;
+    const typename Model::template Theta<R> th = Model::template load<R>(a.theta + (size_t)b * SGM_THETA_STRIDE);
+    const R y = (R)a.obs[a.obs_off[b] + t];
+    const bool in_sub = (t >= a.t1[b]) && (t < a.tL[b]);
+    const R wt = in_sub ? ((a.wts_off && a.wts_off[b] >= 0) ? (R)a.step_weights[a.wts_off[b] + (t - a.t1[b])] : (R)1) : (R)0;
+    const int nws = stat_width<Model>(a.stat_kind);
+    R rn[W];
+    load_rec<R, W>(a.rec[par ^ 1], a.tail[par ^ 1], item_off + i, rn);
+    R acc[4] = {(R)0, (R)0, (R)0, (R)0};
+    for (int k = 0; k < Nt; ++k) {
+        const int J = a.Jidx[(item_off + i) * Nt + k];
+        if (a.trace_J) a.trace_J[(((size_t)b * a.max_T + t) * N + i) * Nt + k] = J;
+        R ra[W], h[4];
+        load_rec<R, W>(a.rec[par], a.tail[par], item_off + J, ra);
+        stat_of<R, Model>(a, th, ra + NP, rn + NP, y, in_sub, h);
+        for (int q = 0; q < NP; ++q) acc[q] += ra[q] + h[q] * wt;
+    }
+    for (int q = 0; q < NP; ++q) rn[q] = (q < nws) ? acc[q] / (R)Nt : (R)0;
+    store_rec<R, W>(a.rec[par ^ 1], a.tail[par ^ 1], item_off + i, rn);
+}
+
+template <class R, class Model>
+int launch_paris(const KArgs& a, int t, cudaStream_t stream) {
+    int n = 0;
+    if (a.rng_mode == SGM_RNG_INJECTED) {
+        paris_injected_kernel<R, Model><<<a.B, NT, 0, stream>>>(a, t); ++n;
+    } else {
+        paris_ar_kernel<R, Model><<<dim3(a.G, a.B), NT, 0, stream>>>(a, t); ++n;
+        paris_exact_kernel<R, Model><<<dim3(EXACT_CTAS, a.B), NT, 0, stream>>>(a, t); ++n;
+    }
+    paris_update_kernel<R, Model><<<dim3((a.N + NT - 1) / NT, a.B), NT, 0, stream>>>(a, t); ++n;
+    stat_ws_kernel<R, Model><<<dim3(a.G, a.B), NT, 0, stream>>>(a, t); ++n;
+    return n;
+}
+
+}  // namespace sgm

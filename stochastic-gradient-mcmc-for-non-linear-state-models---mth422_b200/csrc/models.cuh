@@ -1,0 +1,223 @@
+// Per-model device functors: proposal (rv), incremental log-weight (reweight), transition log-density,
+// complete-data score and sufficient statistics.  Each cites the reference lines it restates
+// (paths relative to /root/reference/sgmcmc_ssm/).  Everything is templated on the arithmetic type R.
+#pragma once
+#include <cuda_runtime.h>
+#include "../../include/sgmpf.h"
+
+namespace sgm {
+
+template <class R> struct Mth;
+template <> struct Mth<float> {
+    static __device__ __forceinline__ float exp(float x) { return __expf(x); }
+    static __device__ __forceinline__ float log(float x) { return __logf(x); }
+    static __device__ __forceinline__ float sqrt(float x) { return sqrtf(x); }
+    static __device__ __forceinline__ float rcp(float x) { return __frcp_rn(x); }
+    static __device__ __forceinline__ float inf() { return __int_as_float(0x7f800000); }
+};
+template <> struct Mth<double> {
+    static __device__ __forceinline__ double exp(double x) { return ::exp(x); }
+    static __device__ __forceinline__ double log(double x) { return ::log(x); }
+    static __device__ __forceinline__ double sqrt(double x) { return ::sqrt(x); }
+    static __device__ __forceinline__ double rcp(double x) { return 1.0 / x; }
+    static __device__ __forceinline__ double inf() { return __longlong_as_double(0x7ff0000000000000LL); }
+};
+
+constexpr double LOG_2PI_D = 1.8378770664093453;
+
+// ------------------------------------------------------------------------------------------------
+// Latent-Gaussian AR(1) state shared by LGSSM and SVM (particle_filters/kernels.py:82-138, n = 1)
+// ------------------------------------------------------------------------------------------------
+template <class R> struct GaussTheta {
+    R A, LQinv, Qinv, C, LRinv, Rinv;
+    R invLQ, invLR, logLQinv, logLRinv;     // LQinv**-1, LRinv**-1, log LQinv, log LRinv
+    R opt_sd, opt_iprec, opt_var, opt_lvar; // LGSSM optimal kernel: prec**-0.5, 1/prec, 1/Qinv+1/Rinv, log of it
+};
+
+struct SvmPrior {
+    static constexpr int NX = 1, NP = 3, MODEL = SGM_MODEL_SVM;
+    template <class R> using Theta = GaussTheta<R>;
+    template <class R> static __device__ __forceinline__ Theta<R> load(const double* th) {
+        Theta<R> t;   // theta: A, LQinv, Qinv, LRinv, Rinv
+        t.A = (R)th[0]; t.LQinv = (R)th[1]; t.Qinv = (R)th[2]; t.LRinv = (R)th[3]; t.Rinv = (R)th[4]; t.C = (R)1;
+        t.invLQ = (R)(1.0 / th[1]); t.invLR = (R)(1.0 / th[3]); t.logLQinv = (R)::log(th[1]); t.logLRinv = (R)::log(th[3]);
+        t.opt_sd = t.opt_iprec = t.opt_var = t.opt_lvar = (R)0;
+        return t;
+    }
+    // svm/kernels.py:34-37
+    template <class R> static __device__ __forceinline__ void propagate(const Theta<R>& t, const R* xa, R y, R z, R* xn) {
+        xn[0] = t.invLQ * z + xa[0] * t.A;
+    }
+    // svm/kernels.py:57-62
+    template <class R> static __device__ __forceinline__ R log_weight(const Theta<R>& t, const R* xa, const R* xn, R y) {
+        return (R)(-0.5 * LOG_2PI_D) + (R)-0.5 * (y * y) * Mth<R>::exp(-xn[0]) * t.Rinv + t.logLRinv + (R)-0.5 * xn[0];
+    }
+    // svm/helper.py:342-348 ; order [dLRinv, dLQinv, dA]
+    template <class R> static __device__ __forceinline__ void score(const Theta<R>& t, const R* xa, const R* xn, R y, R* h) {
+        const R d = xn[0] - t.A * xa[0];
+        h[2] = t.Qinv * d * xa[0];
+        h[1] = t.invLQ - (d * d) * t.LQinv;
+        const R dy2 = (y * y) * Mth<R>::exp(-xn[0]);       // y^2 / exp(x')
+        h[0] = t.invLR - dy2 * t.LRinv;
+    }
+    // particle_filters/kernels.py:121-126
+    template <class R> static __device__ __forceinline__ R log_trans(const Theta<R>& t, const R* xa, const R* xn) {
+        const R d = xn[0] - t.A * xa[0];
+        return (R)-0.5 * (d * d) * t.Qinv + (R)(-0.5 * LOG_2PI_D) + t.logLQinv;
+    }
+    // particle_filters/kernels.py:134-138
+    template <class R> static __device__ __forceinline__ R log_trans_max(const Theta<R>& t) {
+        return (R)(-0.5 * LOG_2PI_D) + t.logLQinv;
+    }
+    // per-parent part of log_trans, hoisted out of the O(N^2) pair loop
+    template <class R> static __device__ __forceinline__ void jkey(const Theta<R>& t, const R* xa, R* k) {
+        k[0] = t.A * xa[0]; k[1] = (R)(-0.5 * LOG_2PI_D) + t.logLQinv;
+    }
+    template <class R> static __device__ __forceinline__ R log_trans_key(const Theta<R>& t, const R* k, const R* xn) {
+        const R d = xn[0] - k[0];
+        return (R)-0.5 * (d * d) * t.Qinv + k[1];
+    }
+    // lgssm/helper.py:1338-1363 (n = 1): [x', x'^2, x x']
+    template <class R> static __device__ __forceinline__ void suff(const R* xa, const R* xn, R* h) {
+        h[0] = xn[0]; h[1] = xn[0] * xn[0]; h[2] = xa[0] * xn[0];
+    }
+    template <class R> static __device__ __forceinline__ void init(R mean, R sd, R z, R* x) { x[0] = mean + sd * z; }
+};
+
+struct LgssmPrior {
+    static constexpr int NX = 1, NP = 4, MODEL = SGM_MODEL_LGSSM;
+    template <class R> using Theta = GaussTheta<R>;
+    template <class R> static __device__ __forceinline__ Theta<R> load(const double* th) {
+        Theta<R> t;   // theta: A, LQinv, Qinv, C, LRinv, Rinv
+        t.A = (R)th[0]; t.LQinv = (R)th[1]; t.Qinv = (R)th[2]; t.C = (R)th[3]; t.LRinv = (R)th[4]; t.Rinv = (R)th[5];
+        t.invLQ = (R)(1.0 / th[1]); t.invLR = (R)(1.0 / th[4]); t.logLQinv = (R)::log(th[1]); t.logLRinv = (R)::log(th[4]);
+        const double prec = th[2] + th[3] * th[3] * th[5];          // lgssm/kernels.py:91-93
+        const double var = 1.0 / th[2] + 1.0 / th[5];                // lgssm/kernels.py:118
+        t.opt_sd = (R)(1.0 / ::sqrt(prec)); t.opt_iprec = (R)(1.0 / prec); t.opt_var = (R)var; t.opt_lvar = (R)::log(var);
+        return t;
+    }
+    // lgssm/kernels.py:29-33
+    template <class R> static __device__ __forceinline__ void propagate(const Theta<R>& t, const R* xa, R y, R z, R* xn) {
+        xn[0] = t.invLQ * z + xa[0] * t.A;
+    }
+    // lgssm/kernels.py:58-62
+    template <class R> static __device__ __forceinline__ R log_weight(const Theta<R>& t, const R* xa, const R* xn, R y) {
+        const R d = y - t.C * xn[0];
+        return (R)(-0.5 * LOG_2PI_D) + (R)-0.5 * (d * d) * t.Rinv + t.logLRinv;
+    }
+    // lgssm/helper.py:1270-1277 ; order [dLRinv, dLQinv, dC, dA]
+    template <class R> static __device__ __forceinline__ void score(const Theta<R>& t, const R* xa, const R* xn, R y, R* h) {
+        const R d = xn[0] - t.A * xa[0];
+        h[3] = t.Qinv * d * xa[0];
+        h[1] = t.invLQ - (d * d) * t.LQinv;
+        const R dy = y - t.C * xn[0];
+        h[2] = t.Rinv * dy * xn[0];
+        h[0] = t.invLR - (dy * dy) * t.LRinv;
+    }
+    template <class R> static __device__ __forceinline__ R log_trans(const Theta<R>& t, const R* xa, const R* xn) {
+        return SvmPrior::log_trans(t, xa, xn);
+    }
+    template <class R> static __device__ __forceinline__ R log_trans_max(const Theta<R>& t) { return SvmPrior::log_trans_max(t); }
+    template <class R> static __device__ __forceinline__ void jkey(const Theta<R>& t, const R* xa, R* k) { SvmPrior::jkey(t, xa, k); }
+    template <class R> static __device__ __forceinline__ R log_trans_key(const Theta<R>& t, const R* k, const R* xn) {
+        return SvmPrior::log_trans_key(t, k, xn);
+    }
+    template <class R> static __device__ __forceinline__ void suff(const R* xa, const R* xn, R* h) { SvmPrior::suff(xa, xn, h); }
+    template <class R> static __device__ __forceinline__ void init(R mean, R sd, R z, R* x) { x[0] = mean + sd * z; }
+};
+
+struct LgssmOptimal : LgssmPrior {
+    // lgssm/kernels.py:87-97
+    template <class R> static __device__ __forceinline__ void propagate(const Theta<R>& t, const R* xa, R y, R z, R* xn) {
+        const R mp = xa[0] * t.A * t.Qinv + y * t.C * t.Rinv;
+        xn[0] = t.opt_sd * z + mp * t.opt_iprec;
+    }
+    // lgssm/kernels.py:117-120 (ignores C, as the reference does)
+    template <class R> static __device__ __forceinline__ R log_weight(const Theta<R>& t, const R* xa, const R* xn, R y) {
+        const R d = y - t.A * xa[0];
+        return (R)-0.5 * (d * d) / t.opt_var - (R)(0.5 * LOG_2PI_D) - (R)0.5 * t.opt_lvar;
+    }
+};
+
+// ------------------------------------------------------------------------------------------------
+// GARCH(1,1) + noise; particle = (x, sigma2)  (models/garch/kernels.py)
+// ------------------------------------------------------------------------------------------------
+template <class R> struct GarchTheta {
+    R alpha, beta, gamma, mu, phi, lam, LRinv, Rinv, Rv, invLR, logLRinv, ltmax;
+};
+
+struct GarchPrior {
+    static constexpr int NX = 2, NP = 4, MODEL = SGM_MODEL_GARCH;
+    template <class R> using Theta = GarchTheta<R>;
+    template <class R> static __device__ __forceinline__ Theta<R> load(const double* th) {
+        Theta<R> t;   // theta: alpha, beta, gamma, mu, phi, lambduh, LRinv, Rinv, R
+        t.alpha = (R)th[0]; t.beta = (R)th[1]; t.gamma = (R)th[2]; t.mu = (R)th[3]; t.phi = (R)th[4]; t.lam = (R)th[5];
+        t.LRinv = (R)th[6]; t.Rinv = (R)th[7]; t.Rv = (R)th[8];
+        t.invLR = (R)(1.0 / th[6]); t.logLRinv = (R)::log(th[6]);
+        t.ltmax = (R)(-0.5 * LOG_2PI_D - 0.5 * ::log(th[0]));       // garch/kernels.py:41-43
+        return t;
+    }
+    template <class R> static __device__ __forceinline__ R sigma2_next(const Theta<R>& t, const R* xa) {
+        return t.alpha + t.beta * (xa[0] * xa[0]) + t.gamma * xa[1];
+    }
+    // garch/kernels.py:60-68
+    template <class R> static __device__ __forceinline__ void propagate(const Theta<R>& t, const R* xa, R y, R z, R* xn) {
+        const R s2 = sigma2_next(t, xa);
+        xn[0] = Mth<R>::sqrt(s2) * z;
+        xn[1] = s2;
+    }
+    // garch/kernels.py:82-89
+    template <class R> static __device__ __forceinline__ R log_weight(const Theta<R>& t, const R* xa, const R* xn, R y) {
+        const R d = y - xn[0];
+        return (R)(-0.5 * LOG_2PI_D) + (R)-0.5 * (d * d) * t.Rinv + t.logLRinv;
+    }
+    // garch/helper.py:350-372 ; order [dLRinv, dlog_mu, dlogit_phi, dlogit_lambduh]
+    template <class R> static __device__ __forceinline__ void score(const Theta<R>& t, const R* xa, const R* xn, R y, R* h) {
+        const R v = xn[1];
+        const R gv = (R)-0.5 * (v - xn[0] * xn[0]) / (v * v);
+        const R xa2 = xa[0] * xa[0];
+        h[1] = gv * ((R)1 - t.phi) * t.mu;
+        h[2] = gv * (-t.mu + t.lam * xa2 + ((R)1 - t.lam) * xa[1]) * ((R)1 - t.phi) * t.phi;
+        h[3] = gv * t.phi * (xa2 - xa[1]) * ((R)1 - t.lam) * t.lam;
+        const R dy = y - xn[0];
+        h[0] = t.invLR - (dy * dy) * t.LRinv;
+    }
+    // garch/kernels.py:28-34 : sigma2 from the candidate parent
+    template <class R> static __device__ __forceinline__ R log_trans(const Theta<R>& t, const R* xa, const R* xn) {
+        const R s2 = sigma2_next(t, xa);
+        return (R)-0.5 * (xn[0] * xn[0]) / s2 - (R)(0.5 * LOG_2PI_D) - (R)0.5 * Mth<R>::log(s2);
+    }
+    template <class R> static __device__ __forceinline__ R log_trans_max(const Theta<R>& t) { return t.ltmax; }
+    template <class R> static __device__ __forceinline__ void jkey(const Theta<R>& t, const R* xa, R* k) {
+        const R s2 = sigma2_next(t, xa);
+        k[0] = (R)1 / s2; k[1] = -(R)(0.5 * LOG_2PI_D) - (R)0.5 * Mth<R>::log(s2);
+    }
+    template <class R> static __device__ __forceinline__ R log_trans_key(const Theta<R>& t, const R* k, const R* xn) {
+        return (R)-0.5 * (xn[0] * xn[0]) * k[0] + k[1];
+    }
+    // garch/helper.py:414-434: [x', x'^2, x'^4]
+    template <class R> static __device__ __forceinline__ void suff(const R* xa, const R* xn, R* h) {
+        const R x2 = xn[0] * xn[0];
+        h[0] = xn[0]; h[1] = x2; h[2] = x2 * x2;
+    }
+    // garch/kernels.py:99-104 : sigma2_0 = 0
+    template <class R> static __device__ __forceinline__ void init(R mean, R sd, R z, R* x) { x[0] = mean + sd * z; x[1] = (R)0; }
+};
+
+struct GarchOptimal : GarchPrior {
+    // garch/kernels.py:147-158
+    template <class R> static __device__ __forceinline__ void propagate(const Theta<R>& t, const R* xa, R y, R z, R* xn) {
+        const R s2 = sigma2_next(t, xa);
+        const R var = (R)1 / (t.Rinv + (R)1 / s2);
+        const R mean = var * (y * t.Rinv);
+        xn[0] = mean + Mth<R>::sqrt(var) * z;
+        xn[1] = s2;
+    }
+    // garch/kernels.py:172-180
+    template <class R> static __device__ __forceinline__ R log_weight(const Theta<R>& t, const R* xa, const R* xn, R y) {
+        const R var = xn[1] + t.Rv;
+        return (R)(-0.5 * LOG_2PI_D) + (R)-0.5 * (y * y) / var + (R)-0.5 * Mth<R>::log(var);
+    }
+};
+
+}  // namespace sgm

@@ -1,0 +1,80 @@
+// Counter-based RNG: Philox4x32-10 (Salmon et al. 2011), uniform / normal / exponential transforms.
+// Counter layout (rank- and launch-geometry-invariant, so sharding items over GPUs reproduces the
+// single-GPU stream):  c0 = index (particle quad, particle, or tile), c1 = step | stream<<16 | sub<<20,
+// c2 = global item id, c3 = call offset;  key = 64-bit seed.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace sgm {
+
+enum : uint32_t { STREAM_NORMAL = 0, STREAM_UNIFORM = 1, STREAM_GAMMA = 2, STREAM_PARIS = 3, STREAM_EXACT = 4 };
+
+struct RngKey { uint32_t k0, k1, item, offset; };
+
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint32_t k0, uint32_t k1) {
+    constexpr uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t hi0 = __umulhi(M0, c.x), lo0 = M0 * c.x;
+        const uint32_t hi1 = __umulhi(M1, c.z), lo1 = M1 * c.z;
+        c = make_uint4(hi1 ^ c.y ^ k0, lo1, hi0 ^ c.w ^ k1, lo0);
+        k0 += W0; k1 += W1;
+    }
+    return c;
+}
+__device__ __forceinline__ uint4 rng_raw(const RngKey& k, uint32_t index, uint32_t step, uint32_t stream, uint32_t sub) {
+    return philox4x32_10(make_uint4(index, (step & 0xffffu) | (stream << 16) | (sub << 20), k.item, k.offset), k.k0, k.k1);
+}
+// open-interval uniforms
+__device__ __forceinline__ float u01f(uint32_t x) { return ((float)(x >> 9) + 0.5f) * (1.0f / 8388608.0f); }             // (0,1), 23 bits
+__device__ __forceinline__ double u01d(uint32_t a, uint32_t b) {                                                         // (0,1), 52 bits
+    return ((double)(((uint64_t)(a >> 6) << 26) | (uint64_t)(b >> 6)) + 0.5) * (1.0 / 4503599627370496.0);
+}
+
+// 4 uniforms in (0,1) for particle quad q
+__device__ __forceinline__ void rng_uniform4(const RngKey& k, uint32_t q, uint32_t step, uint32_t stream, float* u) {
+    const uint4 r = rng_raw(k, q, step, stream, 0);
+    u[0] = u01f(r.x); u[1] = u01f(r.y); u[2] = u01f(r.z); u[3] = u01f(r.w);
+}
+__device__ __forceinline__ void rng_uniform4(const RngKey& k, uint32_t q, uint32_t step, uint32_t stream, double* u) {
+    const uint4 r0 = rng_raw(k, q, step, stream, 0), r1 = rng_raw(k, q, step, stream, 1);
+    u[0] = u01d(r0.x, r0.y); u[1] = u01d(r0.z, r0.w); u[2] = u01d(r1.x, r1.y); u[3] = u01d(r1.z, r1.w);
+}
+// 4 standard normals for particle quad q (Box-Muller)
+__device__ __forceinline__ void rng_normal4(const RngKey& k, uint32_t q, uint32_t step, float* z) {
+    const uint4 r = rng_raw(k, q, step, STREAM_NORMAL, 0);
+    const float r0 = sqrtf(-2.0f * __logf(u01f(r.x))), r1 = sqrtf(-2.0f * __logf(u01f(r.z)));
+    float s0, c0, s1, c1;
+    __sincosf(6.28318530717958647692f * u01f(r.y), &s0, &c0);
+    __sincosf(6.28318530717958647692f * u01f(r.w), &s1, &c1);
+    z[0] = r0 * c0; z[1] = r0 * s0; z[2] = r1 * c1; z[3] = r1 * s1;
+}
+__device__ __forceinline__ void rng_normal4(const RngKey& k, uint32_t q, uint32_t step, double* z) {
+    const uint4 a = rng_raw(k, q, step, STREAM_NORMAL, 0), b = rng_raw(k, q, step, STREAM_NORMAL, 1);
+    const double r0 = sqrt(-2.0 * log(u01d(a.x, a.y))), r1 = sqrt(-2.0 * log(u01d(b.x, b.y)));
+    double s0, c0, s1, c1;
+    sincospi(2.0 * u01d(a.z, a.w), &s0, &c0);
+    sincospi(2.0 * u01d(b.z, b.w), &s1, &c1);
+    z[0] = r0 * c0; z[1] = r0 * s0; z[2] = r1 * c1; z[3] = r1 * s1;
+}
+// Gamma(shape, 1), shape >= 1 (Marsaglia & Tsang 2000), double precision, own sub-stream per attempt.
+__device__ inline double rng_gamma(const RngKey& k, uint32_t index, uint32_t step, double shape) {
+    const double d = shape - 1.0 / 3.0, c = 1.0 / sqrt(9.0 * d);
+    for (uint32_t attempt = 0; attempt < 64; ++attempt) {
+        const uint4 r = rng_raw(k, index, step, STREAM_GAMMA, attempt);
+        const double u1 = u01d(r.x, r.y), u2 = u01d(r.z, r.w);
+        double s, co;
+        sincospi(2.0 * u2, &s, &co);
+        const double x = sqrt(-2.0 * log(u1)) * co;
+        const uint4 r2 = rng_raw(k, index, step, STREAM_GAMMA, attempt + 2048u);
+        const double u = u01d(r2.x, r2.y);
+        double v = 1.0 + c * x;
+        if (v <= 0.0) continue;
+        v = v * v * v;
+        if (log(u) < 0.5 * x * x + d - d * v + d * log(v)) return d * v;
+    }
+    return d;   // unreachable in practice (acceptance > 95 % per attempt)
+}
+
+}  // namespace sgm

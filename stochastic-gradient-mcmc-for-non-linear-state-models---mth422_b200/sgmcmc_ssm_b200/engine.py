@@ -1,0 +1,315 @@
+"""Host side of the C-ABI: packs a batch of buffered-subsequence work items, launches
+`sgm_pf_run` on the current CUDA stream and reads back gradients / log-likelihoods.
+
+PyTorch is used for device memory, pinned staging buffers and streams only.  One call moves ONE
+packed host buffer to the device and ONE packed result buffer back.
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _native as nat
+
+_SEED = [None]
+_CALLS = [0]
+
+
+class Config(object):
+    """Library-wide defaults; every entry can be overridden per call through **kwargs
+    (the reference passes unknown kwargs through every layer, so the drop-in accepts them too)."""
+    dtype = "f32"                    # particle arithmetic / storage: 'f32' or 'f64'
+    rng = "philox"                   # 'philox' (device) or 'injected' (numpy legacy stream, parity mode)
+    resample = "multinomial_sorted"  # 'multinomial' | 'multinomial_sorted' | 'systematic' | 'stratified'
+    device = None                    # torch device; default = current CUDA device
+
+
+config = Config()
+
+
+def set_seed(seed):
+    """Seed of the device Philox streams (call counter restarts)."""
+    _SEED[0] = int(seed) & (2 ** 64 - 1)
+    _CALLS[0] = 0
+
+
+def _next_seed_offset():
+    if _SEED[0] is None:
+        _SEED[0] = int(np.random.randint(0, 2 ** 31 - 1))
+    _CALLS[0] += 1
+    return _SEED[0], _CALLS[0]
+
+
+def _device(device=None):
+    if device is None:
+        device = config.device
+    if device is None:
+        if not torch.cuda.is_available():
+            raise RuntimeError("sgmcmc_ssm_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+        device = torch.device("cuda", torch.cuda.current_device())
+    return torch.device(device)
+
+
+class _DeviceState(object):
+    """Grow-only buffers cached per device."""
+
+    def __init__(self, device):
+        self.device = device
+        self.workspace = None
+        self.pin_in = None
+        self.dev_in = None
+        self.pin_out = None
+        self.dev_out = None
+        self.checked = False
+
+    @staticmethod
+    def _grow(t, nbytes, **kw):
+        if t is None or t.numel() < nbytes:
+            t = torch.empty(int(nbytes * 1.25) + 256, dtype=torch.uint8, **kw)
+        return t
+
+    def buffers(self, ws_bytes, in_bytes, out_bytes):
+        self.workspace = self._grow(self.workspace, ws_bytes + 256, device=self.device)
+        self.pin_in = self._grow(self.pin_in, in_bytes, pin_memory=True)
+        self.dev_in = self._grow(self.dev_in, in_bytes + 256, device=self.device)
+        self.pin_out = self._grow(self.pin_out, out_bytes, pin_memory=True)
+        self.dev_out = self._grow(self.dev_out, out_bytes + 256, device=self.device)
+
+
+_STATES = {}
+
+
+def _state(device):
+    key = (device.type, device.index)
+    if key not in _STATES:
+        _STATES[key] = _DeviceState(device)
+    st = _STATES[key]
+    if not st.checked:
+        with torch.cuda.device(device):
+            nat.check(nat.load().sgm_device_check())
+        st.checked = True
+    return st
+
+
+def _align(x, a=256):
+    return (x + a - 1) // a * a
+
+
+def _aligned_ptr(t):
+    return _align(t.data_ptr())
+
+
+class PFItems(object):
+    """A batch of independent work items (chain x sequence x subsequence)."""
+
+    def __init__(self):
+        self.obs, self.t1, self.tL, self.weights, self.theta, self.prior_mean, self.prior_var = [], [], [], [], [], [], []
+
+    def add(self, observations, theta, t1=0, tL=None, weights=None, prior_mean=0.0, prior_var=1.0):
+        obs = np.ascontiguousarray(np.asarray(observations, dtype=np.float64).reshape(-1))
+        T = obs.shape[0]
+        tL = T if tL is None else int(tL)
+        if weights is not None:
+            weights = np.ascontiguousarray(np.asarray(weights, dtype=np.float64).reshape(-1))
+            if weights.shape[0] < tL - int(t1):
+                raise ValueError("weights shorter than the subsequence")
+        th = np.zeros(nat.THETA_STRIDE)
+        th[:len(theta)] = np.asarray(theta, dtype=np.float64)
+        self.obs.append(obs); self.t1.append(int(t1)); self.tL.append(tL); self.weights.append(weights)
+        self.theta.append(th); self.prior_mean.append(float(prior_mean)); self.prior_var.append(float(prior_var))
+        return self
+
+    def __len__(self):
+        return len(self.obs)
+
+
+class PFResult(object):
+    """Handle of an asynchronous sgm_pf_run; `.wait()` synchronises and parses the packed result."""
+
+    def __init__(self, **kw):
+        self.__dict__.update(kw)
+        self._done = False
+
+    def wait(self, check=True):
+        if self._done:
+            return self
+        self._event.synchronize()
+        B = self.B
+        out = self._pin_out.numpy()
+        self.grad = out[:B * 64].view(np.float64).reshape(B, 8)[:, :max(self.p, 0)].copy()
+        self.loglik = out[B * 64:B * 72].view(np.float64).copy()
+        self.status = out[B * 72:B * 76].view(np.int32).copy()
+        self._done = True
+        if check:
+            bad = self.status & (nat.STATUS_NAN_WEIGHT | nat.STATUS_ZERO_WEIGHT)
+            if np.any(bad):
+                raise ValueError("probabilities contain NaN (degenerate particle weights in item(s) {0})".format(
+                    np.nonzero(bad)[0].tolist()))
+        return self
+
+    def tensor(self, name):
+        """Optional device outputs (x, lw, stats, anc, trace_x, trace_lw, J) as torch tensors."""
+        self.wait()
+        return self._extra[name]
+
+
+def run_pf(model, kernel, pf, items, N, dtype=None, rng=None, resample=None, stat_kind="score",
+           lambduh=None, Ntilde=2, accept_reject=True, max_accept_reject=None,
+           manual_sample_threshold=None, seed=None, offset=None, item_id_base=0, injected=None,
+           want=(), device=None, sync=True, check=True):
+    """Run the buffered particle filter / smoother for a batch of work items on the GPU.
+
+    Mirrors particle_filters/buffered_smoother.py:156-199 (`pf` dispatch) for a whole batch.
+    Returns a PFResult with .grad (B, p), .loglik (B,), .status (B,).
+    """
+    lib = nat.load()
+    device = _device(device)
+    st = _state(device)
+    dtype = dtype or config.dtype
+    rng = rng or config.rng
+    resample = resample or config.resample
+    if pf not in nat.PF:
+        raise ValueError("Unrecognized pf = {0}".format(pf))
+    if lambduh is None:
+        lambduh = 1.0 if pf == "poyiadjis_N" else 0.95          # buffered_smoother.py:175-180, pf.py:140
+    if pf == "poyiadjis_N":
+        lambduh = 1.0
+    B = len(items)
+    if B == 0:
+        raise ValueError("empty batch")
+    N = int(N)
+    model_id, kernel_id = nat.MODEL[model], nat.KERNEL[kernel]
+    p = lib.sgm_stat_dim(model_id, nat.STAT[stat_kind])
+    n = lib.sgm_state_dim(model_id)
+    T_buf = np.array([o.shape[0] for o in items.obs], dtype=np.int32)
+    max_T = int(T_buf.max())
+    np_real = np.float64 if dtype == "f64" else np.float32
+    t_real = torch.float64 if dtype == "f64" else torch.float32
+
+    # ---- pack the host buffer ------------------------------------------------------------------
+    obs_off = np.zeros(B, dtype=np.int64)
+    obs_off[1:] = np.cumsum(T_buf[:-1])
+    n_obs = int(T_buf.sum())
+    has_w = any(w is not None for w in items.weights)
+    wts_off = np.full(B, -1, dtype=np.int64)
+    wlen = 0
+    if has_w:
+        for b, w in enumerate(items.weights):
+            if w is not None:
+                wts_off[b] = wlen
+                wlen += w.shape[0]
+    sections = [("obs", n_obs * 8), ("wts", max(wlen, 1) * 8), ("theta", B * nat.THETA_STRIDE * 8),
+                ("prior_mean", B * 8), ("prior_var", B * 8), ("obs_off", B * 8), ("wts_off", B * 8),
+                ("T_buf", B * 4), ("t1", B * 4), ("tL", B * 4)]
+    offs, tot = {}, 0
+    for name, nb in sections:
+        offs[name] = tot
+        tot = _align(tot + nb, 16)
+    in_bytes, out_bytes = tot, B * 76 + 64
+
+    desc = nat.SgmPfDesc()
+    desc.struct_bytes = ctypes.sizeof(nat.SgmPfDesc)
+    desc.model, desc.kernel, desc.pf, desc.dtype = model_id, kernel_id, nat.PF[pf], nat.DTYPE[dtype]
+    desc.rng_mode, desc.resample, desc.stat_kind = nat.RNG[rng], nat.RESAMPLE[resample], nat.STAT[stat_kind]
+    desc.n_items, desc.n_particles, desc.max_T = B, N, max_T
+    desc.Ntilde, desc.accept_reject = int(Ntilde), int(bool(accept_reject))
+    desc.max_accept_reject = -1 if max_accept_reject is None else int(max_accept_reject)
+    desc.manual_sample_threshold = -1 if manual_sample_threshold is None else int(manual_sample_threshold)
+    desc.item_id_base = int(item_id_base)
+    desc.lambduh = float(lambduh)
+    if seed is None or offset is None:
+        s, o = _next_seed_offset()
+        seed = s if seed is None else seed
+        offset = o if offset is None else offset
+    desc.seed, desc.offset = int(seed) & (2 ** 64 - 1), int(offset)
+
+    with torch.cuda.device(device):
+        extra = {}
+
+        def opt(name, shape, tdtype):
+            if name in want:
+                extra[name] = torch.empty(shape, dtype=tdtype, device=device)
+                return extra[name].data_ptr()
+            return None
+
+        desc.out_x = opt("x", (B, N, n), t_real)
+        desc.out_lw = opt("lw", (B, N), t_real)
+        desc.out_stats = opt("stats", (B, N, lib.sgm_stat_dim(model_id, 0)), t_real)   # record width
+        desc.trace_anc = opt("anc", (B, max_T, N), torch.int32)
+        desc.trace_x = opt("trace_x", (B, max_T + 1, N, n), t_real)
+        desc.trace_lw = opt("trace_lw", (B, max_T + 1, N), t_real)
+        desc.trace_J = opt("J", (B, max_T, N, int(Ntilde)), torch.int32)
+        keep = []
+        if rng == "injected":
+            if injected is None:
+                raise ValueError("rng='injected' needs the recorded randoms")
+
+            def dev64(a, shape):
+                a = np.ascontiguousarray(np.asarray(a, dtype=np.float64)).reshape(shape)
+                tns = torch.from_numpy(a).to(device)
+                keep.append(tns)
+                return tns.data_ptr()
+
+            desc.inj_z0 = dev64(injected["z0"], (B, N))
+            desc.inj_u = dev64(injected["u"], (B, max_T, N))
+            desc.inj_z = dev64(injected["z"], (B, max_T, N))
+            if "extra" in injected and injected["extra"] is not None:
+                flat = np.concatenate([np.asarray(e, dtype=np.float64).ravel() for e in injected["extra"]] + [np.zeros(1)])
+                lens = np.array([np.asarray(e).size for e in injected["extra"]], dtype=np.int64)
+                eoff = np.zeros(B * max_T, dtype=np.int64)
+                eoff[1:] = np.cumsum(lens)[:-1]
+                desc.inj_extra = dev64(flat, (-1,))
+                toff = torch.from_numpy(eoff).to(device)
+                keep.append(toff)
+                desc.inj_extra_off = toff.data_ptr()
+
+        # workspace size needs only the scalar fields (+ which optional outputs are set)
+        desc.obs = desc.obs_off = desc.T_buf = desc.t1 = desc.tL = desc.theta = desc.prior_mean = desc.prior_var = 1
+        desc.grad = desc.loglik = desc.status = 1
+        ws_bytes = lib.sgm_pf_workspace_bytes(ctypes.byref(desc))
+        if ws_bytes == 0:
+            nat.check(lib.sgm_pf_run(ctypes.byref(desc), None) or -1)
+        st.buffers(ws_bytes, in_bytes, out_bytes)
+
+        host = st.pin_in.numpy()
+
+        def view(name, dt, count):
+            return host[offs[name]:offs[name] + count * np.dtype(dt).itemsize].view(dt)
+
+        view("obs", np.float64, n_obs)[:] = np.concatenate(items.obs)
+        if has_w:
+            view("wts", np.float64, wlen)[:] = np.concatenate([w for w in items.weights if w is not None])
+        view("theta", np.float64, B * nat.THETA_STRIDE)[:] = np.concatenate(items.theta)
+        view("prior_mean", np.float64, B)[:] = items.prior_mean
+        view("prior_var", np.float64, B)[:] = items.prior_var
+        view("obs_off", np.int64, B)[:] = obs_off
+        view("wts_off", np.int64, B)[:] = wts_off
+        view("T_buf", np.int32, B)[:] = T_buf
+        view("t1", np.int32, B)[:] = items.t1
+        view("tL", np.int32, B)[:] = items.tL
+
+        base_in = _aligned_ptr(st.dev_in)
+        sh = base_in - st.dev_in.data_ptr()
+        st.dev_in[sh:sh + in_bytes].copy_(st.pin_in[:in_bytes], non_blocking=True)
+        for name in ("obs", "theta", "prior_mean", "prior_var", "obs_off", "wts_off", "T_buf", "t1", "tL"):
+            setattr(desc, name, base_in + offs[name])
+        desc.step_weights = (base_in + offs["wts"]) if has_w else None
+        base_out = _aligned_ptr(st.dev_out)
+        desc.grad, desc.loglik, desc.status = base_out, base_out + B * 64, base_out + B * 72
+        desc.workspace = _aligned_ptr(st.workspace)
+        desc.workspace_bytes = ws_bytes
+
+        stream = torch.cuda.current_stream(device)
+        nat.check(lib.sgm_pf_run(ctypes.byref(desc), ctypes.c_void_p(stream.cuda_stream)))
+        launches = int(lib.sgm_last_launch_count())
+        so = base_out - st.dev_out.data_ptr()
+        st.pin_out[:out_bytes].copy_(st.dev_out[so:so + out_bytes], non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record(stream)
+
+    res = PFResult(B=B, N=N, p=p, n=n, max_T=max_T, T_buf=T_buf, _event=ev, _pin_out=st.pin_out, _extra=extra,
+                   _keep=keep, launches=launches, h2d_bytes=in_bytes, d2h_bytes=out_bytes,
+                   particle_steps=int(N) * int(T_buf.sum()), ws_bytes=int(ws_bytes))
+    if sync:
+        res.wait(check=check)
+    return res

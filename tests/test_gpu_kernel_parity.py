@@ -1,0 +1,78 @@
+"""GPU parity, kernel level: CUDA path (through the C-ABI, INJECTED randoms, f64) vs the CPU oracle
+and vs the reference-generated golden cases, for every (model, kernel, smoother) combination.
+
+Tolerances (written here as the spec demands):
+  * ancestor indices: bit-exact (a mismatch is only tolerated at a CDF tie, none occur in these cases)
+  * particles / log-weights: rtol 1e-10 (f64; differences are libm-vs-libdevice ulps and FMA contraction)
+  * statistics / gradient / log-likelihood: rtol 1e-8, atol 1e-9
+"""
+import numpy as np
+import pytest
+
+from oracle import pf_oracle as po
+from tests import _cases as C
+
+pytestmark = pytest.mark.gpu
+
+
+def _run_case(name, dtype="f64"):
+    import sgmcmc_ssm_b200 as sg
+    c = C.case(name)
+    model, kernel, pf = C.parse_kernel_case(name)
+    theta = C.theta_dict(model, c["theta"])
+    K = po.make_kernel(model, kernel, theta)
+    N = int(c["N"])
+    opts = C.case_opts(c)
+    rec = po.LegacyStream(int(c["seed"]), record=True)
+    kw = dict(t1=int(c["t1"]), tL=int(c["tL"]), weights=c["weights"], prior_mean=float(c["prior_mean"]),
+              prior_var=float(c["prior_var"]))
+    ref = po.buffered_pf(pf, c["obs"], K, N, K.score, K.p, rec, save_all=True, **kw, **opts)
+    parts = po.split_events(rec.events, N)
+    items = sg.PFItems().add(c["obs"], c["theta"], t1=kw["t1"], tL=kw["tL"], weights=c["weights"],
+                             prior_mean=kw["prior_mean"], prior_var=kw["prior_var"])
+    want = ("x", "lw", "stats", "anc") + (("J",) if pf == "paris" else ())
+    res = sg.run_pf(model, kernel, pf, items, N, dtype=dtype, rng="injected", resample="multinomial",
+                    injected=dict(z0=parts["z0"], u=parts["u"], z=parts["z"], extra=parts["extra"]),
+                    want=want, **opts)
+    return c, ref, res, K
+
+
+@pytest.mark.parametrize("name", C.case_names("k"))
+def test_kernel_case_f64_matches_oracle_and_reference(name):
+    c, ref, res, K = _run_case(name)
+    model, kernel, pf = C.parse_kernel_case(name)
+    anc = res.tensor("anc")[0].cpu().numpy()
+    np.testing.assert_array_equal(anc, np.array(ref["trace"]["ancestors"]))
+    if pf == "paris":
+        np.testing.assert_array_equal(res.tensor("J")[0].cpu().numpy(), np.array(ref["trace"]["J"]))
+    x = res.tensor("x")[0].cpu().numpy()
+    np.testing.assert_allclose(x, ref["x_t"].reshape(x.shape), rtol=1e-10, atol=1e-12)
+    np.testing.assert_allclose(x, c["x_t"].reshape(x.shape), rtol=1e-10, atol=1e-12)
+    np.testing.assert_allclose(res.tensor("lw")[0].cpu().numpy(), c["log_weights"], rtol=1e-10, atol=1e-12)
+    np.testing.assert_allclose(res.loglik[0], c["loglik"], rtol=1e-9, atol=1e-10)
+    if pf == "filter":
+        np.testing.assert_allclose(res.grad[0], c["statistics"], rtol=1e-8, atol=1e-9)
+    else:
+        stats = res.tensor("stats")[0].cpu().numpy()[:, :K.p]
+        np.testing.assert_allclose(stats, c["statistics"], rtol=1e-8, atol=1e-9)
+        avg = po.average_statistic(dict(statistics=c["statistics"], log_weights=c["log_weights"]))
+        np.testing.assert_allclose(res.grad[0], avg, rtol=1e-8, atol=1e-9)
+
+
+@pytest.mark.parametrize("name", [n for n in C.case_names("k") if "paris" not in n])
+def test_kernel_case_f32_close_to_reference(name):
+    """f32 arithmetic with the same injected randoms.  Ancestors may flip where a uniform falls
+    within f32 round-off of a CDF boundary, so compare the weighted-average statistic:
+    |diff| <= 2e-3 * (|ref| + mean |stat|)."""
+    c, ref, res, K = _run_case(name, dtype="f32")
+    model, kernel, pf = C.parse_kernel_case(name)
+    anc = res.tensor("anc")[0].cpu().numpy()
+    ref_anc = np.array(ref["trace"]["ancestors"])
+    assert np.mean(anc != ref_anc) < 5e-3
+    np.testing.assert_allclose(res.loglik[0], c["loglik"], rtol=2e-4, atol=2e-4)
+    if pf == "filter":
+        expect = c["statistics"]
+    else:
+        expect = po.average_statistic(dict(statistics=c["statistics"], log_weights=c["log_weights"]))
+    scale = np.abs(expect) + np.mean(np.abs(c["statistics"]))
+    assert np.all(np.abs(res.grad[0] - expect) <= 2e-3 * scale), (res.grad[0], expect)
