@@ -22,7 +22,8 @@ namespace sgm {
 
 constexpr int KPT = 8;                 // consecutive particles per thread
 constexpr int TILE = NT * KPT;         // 2048 particles per CTA tile
-constexpr int MAX_TILES = 1024;        // N <= 2^21
+constexpr int MAX_TILES = 512;         // N <= 2^20
+constexpr int CAP = 4096;              // parents staged in shared memory per CTA (sorted resampling)
 constexpr int PSTRIDE = 8;             // doubles per `part` entry
 constexpr int ACC_STRIDE = 8;          // doubles per `acc` entry
 
@@ -38,6 +39,7 @@ struct KArgs {
     const double* inj_z0; const double* inj_u; const double* inj_z; const double* inj_extra; const int64_t* inj_extra_off;
     void* rec[2]; void* tail[2]; void* fine[2]; void* lw[2]; double* part[2]; double* acc;
     int32_t* Jidx; int32_t* Llist[2]; int32_t* counters;
+    const double* gam;     // [B][max_T][G + 2] exclusive prefix of per-tile Gamma draws (sorted multinomial)
     double* grad; double* loglik; int32_t* status;
     void* out_x; void* out_lw; void* out_stats; int32_t* trace_anc; void* trace_x; void* trace_lw; int32_t* trace_J;
 };
@@ -61,72 +63,88 @@ template <class R, int W> __device__ __forceinline__ void store_rec(void* rec, v
 // ---- shared-memory CDF header built by every CTA --------------------------------------------------
 struct CdfHeader {
     double coarse[MAX_TILES + 1];   // exclusive prefix of tile masses in units of exp(-M); [G] = total
+    double e[MAX_TILES];            // exp(m_g - M)
     double einv[MAX_TILES];         // exp(M - m_g)
-    double red[NWARP];
     double M, total;
     double sbar[4];
 };
 
-// Builds hdr from part[]; returns false if the weights are degenerate (status flagged by caller).
-// Also returns (through hdr.sbar) sum_g e_g * ws_g[k] / total for k < nws.
+// Built by warp 0 with shuffles only (one block barrier at the end).  hdr.sbar[k] receives
+// sum_g e_g * ws_g[k] / total for k < nws.  Fixed summation order -> deterministic.
 __device__ __forceinline__ void build_cdf_header(const double* __restrict__ part, int G, int nws, CdfHeader& hdr) {
-    const int tid = threadIdx.x;
-    double m = -Mth<double>::inf();
-    for (int g = tid; g < G; g += NT) m = nan_max(m, part[(size_t)g * PSTRIDE]);
-    const double M = block_max(m, hdr.red);
-    const int per = (G + NT - 1) / NT;
-    const int g0 = tid * per;
-    double loc = 0.0, ws[4] = {0.0, 0.0, 0.0, 0.0};
-    for (int k = 0; k < per; ++k) {
-        const int g = g0 + k;
-        if (g < G) {
-            const double* p = part + (size_t)g * PSTRIDE;
-            const double e = (p[0] == -Mth<double>::inf()) ? 0.0 : ::exp(p[0] - M);
-            loc += e * p[1];
-            for (int q = 0; q < nws; ++q) ws[q] += e * p[2 + q];
+    if (threadIdx.x < 32) {
+        const int lane = threadIdx.x;
+        double m = -Mth<double>::inf();
+        for (int g = lane; g < G; g += 32) m = nan_max(m, part[(size_t)g * PSTRIDE]);
+        const double M = warp_max(m);
+        double carry = 0.0, ws[4] = {0.0, 0.0, 0.0, 0.0};
+        for (int g0 = 0; g0 < G; g0 += 32) {
+            const int g = g0 + lane;
+            double e = 0.0, v = 0.0;
+            if (g < G) {
+                const double* p = part + (size_t)g * PSTRIDE;
+                e = (p[0] == -Mth<double>::inf()) ? 0.0 : ::exp(p[0] - M);
+                v = e * p[1];
+                for (int q = 0; q < nws; ++q) ws[q] += e * p[2 + q];
+            }
+            const double incl = warp_incl_scan(v);
+            if (g < G) { hdr.coarse[g] = carry + (incl - v); hdr.e[g] = e; hdr.einv[g] = 1.0 / e; }
+            carry += __shfl_sync(FULL, incl, 31);
         }
-    }
-    double total;
-    double run = block_excl_scan(loc, hdr.red, total);
-    for (int k = 0; k < per; ++k) {
-        const int g = g0 + k;
-        if (g < G) {
-            const double* p = part + (size_t)g * PSTRIDE;
-            const double e = (p[0] == -Mth<double>::inf()) ? 0.0 : ::exp(p[0] - M);
-            hdr.coarse[g] = run;
-            hdr.einv[g] = 1.0 / e;
-            run += e * p[1];
+        for (int q = 0; q < nws; ++q) {
+            const double sq = warp_sum(ws[q]);
+            if (lane == 0) hdr.sbar[q] = sq / carry;
         }
+        if (lane == 0) { hdr.coarse[G] = carry; hdr.M = M; hdr.total = carry; }
     }
-    for (int q = 0; q < nws; ++q) {
-        const double s = block_sum(ws[q], hdr.red);
-        if (tid == 0) hdr.sbar[q] = s / total;
-    }
-    if (tid == 0) { hdr.coarse[G] = total; hdr.M = M; hdr.total = total; }
     __syncthreads();
 }
 
+// tile g with coarse[g] <= target < coarse[g + 1]  (branch-free, CTA-uniform trip count)
+__device__ __forceinline__ int coarse_search(double target, const CdfHeader& hdr, int G, int step0) {
+    int pos = 0;
+    for (int step = step0; step > 0; step >>= 1)
+        if (pos + step <= G && hdr.coarse[pos + step] <= target) pos += step;
+    return min(pos, G - 1);
+}
+__device__ __forceinline__ int pow2_floor(int x) { return 1 << (31 - __clz(max(x, 1))); }
+
 // searchsorted(cdf, u, side='right') on the hierarchical CDF: first index whose cumulative mass
-// exceeds target = u * total.
+// exceeds target = u * total.  One thread, dependent loads (used off the hot path).
 template <class R>
 __device__ __forceinline__ int search_cdf(double target, const CdfHeader& hdr, int G, const R* __restrict__ fine, int N) {
     if (!(target < hdr.total)) target = hdr.total * (1.0 - 1.2e-16);
-    int lo = 0, hi = G;
-    while (lo < hi) {                           // tile whose [coarse[g], coarse[g+1]) contains target
-        const int mid = (lo + hi) >> 1;
-        if (hdr.coarse[mid + 1] <= target) lo = mid + 1; else hi = mid;
-    }
-    const int g = min(lo, G - 1);
+    const int g = coarse_search(target, hdr, G, pow2_floor(G));
     const R r = (R)((target - hdr.coarse[g]) * hdr.einv[g]);
     const int base = g * TILE;
     const int len = min(TILE, N - base);
     const R* f = fine + base;
-    lo = 0; hi = len;
-    while (lo < hi) {
-        const int mid = (lo + hi) >> 1;
-        if (f[mid] <= r) lo = mid + 1; else hi = mid;
-    }
-    return base + min(lo, len - 1);
+    int pos = 0;
+#pragma unroll
+    for (int step = TILE / 2; step > 0; step >>= 1)
+        if (pos + step <= len && f[pos + step - 1] <= r) pos += step;
+    return base + min(pos, len - 1);
+}
+
+// Same search executed cooperatively by a full warp (all lanes pass the same target):
+// 32-ary probing, three dependent loads instead of eleven.
+template <class R>
+__device__ __forceinline__ int warp_search_cdf(double target, const CdfHeader& hdr, int G, const R* __restrict__ fine, int N) {
+    const int lane = threadIdx.x & 31;
+    if (!(target < hdr.total)) target = hdr.total * (1.0 - 1.2e-16);
+    const int g = coarse_search(target, hdr, G, pow2_floor(G));
+    const R r = (R)((target - hdr.coarse[g]) * hdr.einv[g]);
+    const int base = g * TILE;
+    const int len = min(TILE, N - base);
+    const R* f = fine + base;
+    constexpr int SEG = TILE / 32;                                   // 64
+    bool le = (lane * SEG < len) ? (f[min(len, (lane + 1) * SEG) - 1] <= r) : false;
+    const int s1 = __popc(__ballot_sync(FULL, le)) * SEG;
+    le = (s1 + lane * 2 < len) ? (f[min(s1 + lane * 2 + 1, len - 1)] <= r) : false;
+    const int s2 = s1 + __popc(__ballot_sync(FULL, le)) * 2;
+    int res = s2;
+    if (s2 < len && f[s2] <= r) res = s2 + 1;
+    return base + min(res, len - 1);
 }
 
 // ---- per-tile epilogue: tile max, tile-local scan of exp(lw - m), per-tile partials ---------------
@@ -240,13 +258,21 @@ __device__ __forceinline__ void item_bookkeeping(const KArgs& a, int b, int t_do
 }
 
 // ---- one resample -> propagate -> reweight -> statistic-update step (pf.py:7-38, 138-181, 40-82) ---
+// Resampling search, two paths:
+//   sorted targets (order-statistics multinomial / systematic / stratified, or INJECTED uniforms the
+//   caller declares ascending): the CTA's 2048 children hit one contiguous parent range [lo, hi]; two
+//   warp-cooperative searches find it, the CDF of that range is staged in shared memory in global
+//   units, and each thread merges its 8 consecutive children against it (streaming gather).
+//   iid targets (reference semantics): per-child coarse (shared) + fine (global) branch-free binary
+//   searches, the 8 children of a thread interleaved for memory-level parallelism.
 template <class R, class Model>
 __global__ void __launch_bounds__(NT) pf_step_kernel(KArgs a, int t) {
     constexpr int NX = Model::NX, NP = Model::NP, W = NX + NP;
     __shared__ CdfHeader hdr;
+    __shared__ R s_cdf[CAP];
     __shared__ R sh_r[NWARP];
     __shared__ double sh_d[NWARP];
-    __shared__ double sh_gam[2];
+    __shared__ int s_range[2];
     const int b = blockIdx.y, g = blockIdx.x, tid = threadIdx.x;
     const int Tb = a.T_buf[b];
     if (t >= Tb) return;
@@ -260,12 +286,13 @@ __global__ void __launch_bounds__(NT) pf_step_kernel(KArgs a, int t) {
     build_cdf_header(a.part[par] + (size_t)b * G * PSTRIDE, G, hdr_ws ? nws : 0, hdr);
     if (g == 0 && tid == 0) item_bookkeeping(a, b, t - 1, hdr, nws);
 
-    const R* fine_old = reinterpret_cast<const R*>(a.fine[par]) + item_off;
+    const R* __restrict__ fine_old = reinterpret_cast<const R*>(a.fine[par]) + item_off;
     const int i0 = g * TILE + tid * KPT;
+    const int n_valid = min(TILE, N - g * TILE);             // children in this tile
     RngKey key = a.key; key.item += (uint32_t)b;
     const double total = hdr.total;
 
-    // ---- uniforms for the resampling step -------------------------------------------------------
+    // ---- resampling targets  u_i * total ------------------------------------------------------------
     double target[KPT];
     if (a.rng_mode == SGM_RNG_INJECTED) {
         const double* u = a.inj_u + ((size_t)b * a.max_T + t) * N;
@@ -278,9 +305,9 @@ __global__ void __launch_bounds__(NT) pf_step_kernel(KArgs a, int t) {
 #pragma unroll
         for (int c = 0; c < KPT; ++c) target[c] = (double)u[c] * total;
     } else if (a.resample == SGM_RESAMPLE_MULTINOMIAL_SORTED) {
-        // Order statistics of N iid uniforms via exponential spacings: within a tile the normalised
-        // partial sums of P Exp(1) draws are independent of their total, which is Gamma(P, 1); so the
-        // tile totals are drawn directly (one Gamma per tile) and no cross-tile pass is needed.
+        // Order statistics of N iid uniforms via exponential spacings.  Within a tile the normalised
+        // partial sums of P Exp(1) draws are independent of their total, which is Gamma(P, 1); the tile
+        // totals are therefore drawn directly (gamma_prefix_kernel) and no cross-tile scan is needed.
         R e[KPT], run = (R)0;
         rng_uniform4(key, (uint32_t)(i0 >> 2), (uint32_t)t, STREAM_UNIFORM, e);
         rng_uniform4(key, (uint32_t)(i0 >> 2) + 1u, (uint32_t)t, STREAM_UNIFORM, e + 4);
@@ -288,18 +315,8 @@ __global__ void __launch_bounds__(NT) pf_step_kernel(KArgs a, int t) {
         for (int c = 0; c < KPT; ++c) { e[c] = (i0 + c < N) ? -Mth<R>::log(e[c]) : (R)0; run += e[c]; }
         R tile_sum;
         R pre = block_excl_scan(run, sh_r, tile_sum);
-        // gamma prefix for this tile: sum of Gamma(P_g') for g' < g, and the grand total
-        double gl = 0.0, gt = 0.0;
-        for (int g2 = tid; g2 <= G; g2 += NT) {
-            const double shape = (g2 == G) ? 1.0 : (double)min(TILE, N - g2 * TILE);
-            const double gam = rng_gamma(key, (uint32_t)g2, (uint32_t)t, shape);
-            gt += gam;
-            if (g2 < g) gl += gam;
-            if (g2 == g) sh_gam[0] = gam;
-        }
-        gl = block_sum(gl, sh_d);
-        gt = block_sum(gt, sh_d);
-        const double scale = total / gt, gmine = sh_gam[0] / (double)tile_sum;
+        const double* gam = a.gam + ((size_t)b * a.max_T + t) * (G + 2);
+        const double gl = gam[g], gmine = (gam[g + 1] - gam[g]) / (double)tile_sum, scale = total / gam[G + 1];
 #pragma unroll
         for (int c = 0; c < KPT; ++c) { pre += e[c]; target[c] = (gl + gmine * (double)pre) * scale; }
     } else {
@@ -316,6 +333,75 @@ __global__ void __launch_bounds__(NT) pf_step_kernel(KArgs a, int t) {
         }
 #pragma unroll
         for (int c = 0; c < KPT; ++c) target[c] = ((double)(i0 + c) + (double)u[c]) / (double)N * total;
+    }
+#pragma unroll
+    for (int c = 0; c < KPT; ++c) if (!(target[c] < total)) target[c] = total * (1.0 - 1.2e-16);
+
+    // ---- ancestor search ----------------------------------------------------------------------------
+    int anc[KPT];
+    bool staged = false;
+    if (a.resample != SGM_RESAMPLE_MULTINOMIAL) {
+        const int last = n_valid - 1, w_last = (last / KPT) >> 5, l_last = (last / KPT) & 31, c_last = last % KPT;
+        const int warp = tid >> 5;
+        if (warp == 0) {
+            const int lo = warp_search_cdf<R>(__shfl_sync(FULL, target[0], 0), hdr, G, fine_old, N);
+            if (tid == 0) s_range[0] = lo;
+        }
+        if (warp == w_last) {
+            double tl = target[0];
+#pragma unroll
+            for (int c = 1; c < KPT; ++c) if (c == c_last) tl = target[c];
+            const int hi = warp_search_cdf<R>(__shfl_sync(FULL, tl, l_last), hdr, G, fine_old, N);
+            if ((tid & 31) == 0) s_range[1] = hi;
+        }
+        __syncthreads();
+        const int lo = s_range[0], range = s_range[1] - lo + 1;
+        if (range >= 1 && range <= CAP) {
+            staged = true;
+            const double cbase = hdr.coarse[lo / TILE];
+            for (int k = tid; k < range; k += NT) {
+                const int p = lo + k, gp = p / TILE;
+                s_cdf[k] = (R)((hdr.coarse[gp] - cbase) + (double)fine_old[p] * hdr.e[gp]);
+            }
+            __syncthreads();
+            // first child: branch-free binary search over the staged range; the rest merge forward
+            int pos = 0;
+            {
+                const R rt = (R)(target[0] - cbase);
+                for (int step = pow2_floor(range); step > 0; step >>= 1)
+                    if (pos + step <= range && s_cdf[pos + step - 1] <= rt) pos += step;
+                pos = min(pos, range - 1);
+            }
+            anc[0] = lo + pos;
+#pragma unroll
+            for (int c = 1; c < KPT; ++c) {
+                const R rt = (R)(target[c] - cbase);
+                if (i0 + c < N) while (pos < range - 1 && s_cdf[pos] <= rt) ++pos;
+                anc[c] = lo + pos;
+            }
+        }
+    }
+    if (!staged) {
+        int gsel[KPT], pos[KPT], len[KPT];
+        R rr[KPT];
+        const int step0 = pow2_floor(G);
+#pragma unroll
+        for (int c = 0; c < KPT; ++c) {
+            gsel[c] = coarse_search(target[c], hdr, G, step0);
+            rr[c] = (R)((target[c] - hdr.coarse[gsel[c]]) * hdr.einv[gsel[c]]);
+            len[c] = min(TILE, N - gsel[c] * TILE);
+            pos[c] = 0;
+        }
+#pragma unroll 1
+        for (int step = TILE / 2; step > 0; step >>= 1) {
+#pragma unroll
+            for (int c = 0; c < KPT; ++c) {
+                const int idx = pos[c] + step;
+                if (idx <= len[c] && fine_old[gsel[c] * TILE + idx - 1] <= rr[c]) pos[c] = idx;
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < KPT; ++c) anc[c] = gsel[c] * TILE + min(pos[c], len[c] - 1);
     }
 
     // ---- proposal normals ------------------------------------------------------------------------
@@ -337,44 +423,76 @@ __global__ void __launch_bounds__(NT) pf_step_kernel(KArgs a, int t) {
     R sbar[4] = {(R)0, (R)0, (R)0, (R)0};
     if (shrink) for (int q = 0; q < nws; ++q) sbar[q] = (R)((1.0 - a.lambduh) * hdr.sbar[q]);
 
+    const void* rec_old = a.rec[par];
+    const void* tail_old = a.tail[par];
     void* rec_new = a.rec[par ^ 1];
     void* tail_new = a.tail[par ^ 1];
     R lwn[KPT];
 #pragma unroll
-    for (int c = 0; c < KPT; ++c) {
-        const int i = i0 + c;
-        lwn[c] = (R)0;
-        if (i < N) {
-            const int anc = search_cdf<R>(target[c], hdr, G, fine_old, N);
-            R ra[W], rn[W];
-            load_rec<R, W>(a.rec[par], a.tail[par], item_off + anc, ra);
-            Model::propagate(th, ra + NP, y, z[c], rn + NP);
-            lwn[c] = Model::log_weight(th, ra + NP, rn + NP, y);
-            R h[4] = {(R)0, (R)0, (R)0, (R)0};
-            if (in_sub) {
-                if (a.stat_kind == SGM_STAT_SCORE) Model::score(th, ra + NP, rn + NP, y, h);
-                else if (a.stat_kind == SGM_STAT_SUFF) Model::suff(ra + NP, rn + NP, h);
-            }
+    for (int h0 = 0; h0 < KPT; h0 += 4) {
+        R ra[4][W];
 #pragma unroll
-            for (int q = 0; q < NP; ++q) {
-                if (carries) rn[q] = shrink ? (lam * ra[q] + sbar[q] + h[q] * wt) : (ra[q] + h[q] * wt);   // pf.py:175-179
-                else if (a.pf == SGM_PF_FILTER) rn[q] = h[q] * wt;                                         // pf.py:70-71
-                else rn[q] = (R)0;                                                                           // set by the backward kernel
+        for (int c = 0; c < 4; ++c)                       // four independent parent gathers in flight
+            if (i0 + h0 + c < N) load_rec<R, W>(rec_old, tail_old, item_off + anc[h0 + c], ra[c]);
+#pragma unroll
+        for (int c4 = 0; c4 < 4; ++c4) {
+            const int c = h0 + c4, i = i0 + c;
+            lwn[c] = (R)0;
+            if (i < N) {
+                R rn[W];
+                Model::propagate(th, ra[c4] + NP, y, z[c], rn + NP);
+                lwn[c] = Model::log_weight(th, ra[c4] + NP, rn + NP, y);
+                R h[4] = {(R)0, (R)0, (R)0, (R)0};
+                if (in_sub) {
+                    if (a.stat_kind == SGM_STAT_SCORE) Model::score(th, ra[c4] + NP, rn + NP, y, h);
+                    else if (a.stat_kind == SGM_STAT_SUFF) Model::suff(ra[c4] + NP, rn + NP, h);
+                }
+#pragma unroll
+                for (int q = 0; q < NP; ++q) {
+                    if (carries) rn[q] = shrink ? (lam * ra[c4][q] + sbar[q] + h[q] * wt) : (ra[c4][q] + h[q] * wt);   // pf.py:175-179
+                    else if (a.pf == SGM_PF_FILTER) rn[q] = h[q] * wt;                                               // pf.py:70-71
+                    else rn[q] = (R)0;                                                                                // set by the backward kernel
+                }
+                store_rec<R, W>(rec_new, tail_new, item_off + i, rn);
+                if (a.need_lw) reinterpret_cast<R*>(a.lw[par ^ 1])[item_off + i] = lwn[c];
+                if (a.trace_anc) a.trace_anc[((size_t)b * a.max_T + t) * N + i] = anc[c];
+                if (a.trace_x) {
+                    R* tx = reinterpret_cast<R*>(a.trace_x) + (((size_t)b * (a.max_T + 1) + t + 1) * N + i) * NX;
+                    for (int q = 0; q < NX; ++q) tx[q] = rn[NP + q];
+                }
+                if (a.trace_lw) reinterpret_cast<R*>(a.trace_lw)[((size_t)b * (a.max_T + 1) + t + 1) * N + i] = lwn[c];
             }
-            store_rec<R, W>(rec_new, tail_new, item_off + i, rn);
-            if (a.need_lw) reinterpret_cast<R*>(a.lw[par ^ 1])[item_off + i] = lwn[c];
-            if (a.trace_anc) a.trace_anc[((size_t)b * a.max_T + t) * N + i] = anc;
-            if (a.trace_x) {
-                R* tx = reinterpret_cast<R*>(a.trace_x) + (((size_t)b * (a.max_T + 1) + t + 1) * N + i) * NX;
-                for (int q = 0; q < NX; ++q) tx[q] = rn[NP + q];
-            }
-            if (a.trace_lw) reinterpret_cast<R*>(a.trace_lw)[((size_t)b * (a.max_T + 1) + t + 1) * N + i] = lwn[c];
         }
     }
     const bool need_ws = (nws > 0) && (a.pf == SGM_PF_FILTER || shrink || (carries && t == Tb - 1));
     tile_epilogue<R, W, NP>(lwn, i0, N, reinterpret_cast<R*>(a.fine[par ^ 1]) + item_off,
                             a.part[par ^ 1] + ((size_t)b * G + g) * PSTRIDE, rec_new, tail_new, item_off,
                             need_ws, nws, sh_r, sh_d);
+}
+
+// Per-(item, step) exclusive prefix of Gamma(P_g, 1) tile totals (+ one Exp(1) for the (N+1)-th
+// spacing) used by the order-statistics multinomial resampler.  gam[b][t][0..G+1].
+__global__ void __launch_bounds__(NT) gamma_prefix_kernel(KArgs a, double* gam_out) {
+    __shared__ double sh_d[NWARP];
+    const int t = blockIdx.x, b = blockIdx.y, tid = threadIdx.x, G = a.G, N = a.N;
+    RngKey key = a.key; key.item += (uint32_t)b;
+    const int per = (G + 1 + NT - 1) / NT, g0 = tid * per;
+    double loc = 0.0;
+    for (int k = 0; k < per; ++k) {
+        const int g2 = g0 + k;
+        if (g2 <= G) loc += rng_gamma(key, (uint32_t)g2, (uint32_t)t, (g2 == G) ? 1.0 : (double)min(TILE, N - g2 * TILE));
+    }
+    double total;
+    double run = block_excl_scan(loc, sh_d, total);
+    double* out = gam_out + ((size_t)b * a.max_T + t) * (G + 2);
+    for (int k = 0; k < per; ++k) {
+        const int g2 = g0 + k;
+        if (g2 <= G) {
+            out[g2] = run;
+            run += rng_gamma(key, (uint32_t)g2, (uint32_t)t, (g2 == G) ? 1.0 : (double)min(TILE, N - g2 * TILE));
+        }
+    }
+    if (tid == 0) out[G + 1] = total;
 }
 
 // ---- final: last log-likelihood term + average_statistic (buffered_smoother.py:151-154) -----------

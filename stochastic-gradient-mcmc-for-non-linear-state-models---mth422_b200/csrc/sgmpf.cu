@@ -25,7 +25,7 @@ int fail(int code, const char* fmt, const char* extra = "") {
 size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
 
 struct Layout {
-    size_t rec[2], tail[2], fine[2], lw[2], part[2], acc, Jidx, Llist[2], counters, total;
+    size_t rec[2], tail[2], fine[2], lw[2], part[2], acc, gam, Jidx, Llist[2], counters, total;
 };
 
 bool backward_pf(int pf) { return pf == SGM_PF_POY_N2 || pf == SGM_PF_PARIS; }
@@ -42,7 +42,7 @@ int validate(const sgm_pf_desc* d) {
     if (d->resample < 0 || d->resample > SGM_RESAMPLE_STRATIFIED) return fail(SGM_ERR_INVALID, "unknown resample");
     if (d->stat_kind < 0 || d->stat_kind > SGM_STAT_NONE) return fail(SGM_ERR_INVALID, "unknown stat_kind");
     if (d->n_items < 1 || d->n_items > 65535) return fail(SGM_ERR_INVALID, "n_items must be in [1, 65535]");
-    if (d->n_particles < 1 || d->n_particles > TILE * MAX_TILES) return fail(SGM_ERR_INVALID, "n_particles must be in [1, 2^21]");
+    if (d->n_particles < 1 || d->n_particles > TILE * MAX_TILES) return fail(SGM_ERR_INVALID, "n_particles must be in [1, 2^20]");
     if (d->max_T < 0 || d->max_T > 65000) return fail(SGM_ERR_INVALID, "max_T out of range");
     if (!d->obs || !d->obs_off || !d->T_buf || !d->t1 || !d->tL || !d->theta || !d->prior_mean || !d->prior_var)
         return fail(SGM_ERR_INVALID, "missing per-item input array");
@@ -75,6 +75,9 @@ Layout make_layout(const sgm_pf_desc* d) {
     for (int k = 0; k < 2; ++k) { L.lw[k] = off; off = align_up(off + (need_lw ? B * N * es : 0)); }
     for (int k = 0; k < 2; ++k) { L.part[k] = off; off = align_up(off + B * G * PSTRIDE * 8); }
     L.acc = off; off = align_up(off + B * ACC_STRIDE * 8);
+    if (d->rng_mode == SGM_RNG_PHILOX && d->resample == SGM_RESAMPLE_MULTINOMIAL_SORTED) {
+        L.gam = off; off = align_up(off + B * (size_t)d->max_T * (G + 2) * 8);
+    }
     if (d->pf == SGM_PF_PARIS) {
         L.Jidx = off; off = align_up(off + B * N * (size_t)d->Ntilde * 4);
         L.Llist[0] = off; off = align_up(off + B * N * (size_t)d->Ntilde * 4);
@@ -127,6 +130,11 @@ int run_impl(const sgm_pf_desc* d, cudaStream_t stream) {
 
     const dim3 grid(a.G, a.B), block(NT);
     int64_t launches = 0;
+    if (d->rng_mode == SGM_RNG_PHILOX && d->resample == SGM_RESAMPLE_MULTINOMIAL_SORTED && a.max_T > 0) {
+        double* gam = reinterpret_cast<double*>(ws + L.gam);
+        a.gam = gam;
+        gamma_prefix_kernel<<<dim3(a.max_T, a.B), block, 0, stream>>>(a, gam); ++launches;
+    }
     pf_init_kernel<R, Model><<<grid, block, 0, stream>>>(a); ++launches;
     for (int t = 0; t < a.max_T; ++t) {
         pf_step_kernel<R, Model><<<grid, block, 0, stream>>>(a, t); ++launches;

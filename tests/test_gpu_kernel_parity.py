@@ -84,3 +84,32 @@ def test_kernel_case_f32_close_to_reference(name):
     scale = np.abs(expect) + np.mean(np.abs(c["statistics"]))
     tol = 2e-3 if tight else 0.25
     assert np.all(np.abs(res.grad[0] - expect) <= tol * scale), (res.grad[0], expect, flips)
+
+
+@pytest.mark.parametrize("name", ["k/svm_prior_poyiadjis_N_1000_d", "k/garch_optimal_poyiadjis_N_1000_d",
+                                  "k/lgssm_optimal_nemeth_200_lambduh0.8", "k/lgssm_prior_poyiadjis_N_64_d"])
+@pytest.mark.parametrize("N", [None, 5000])
+def test_sorted_uniform_path_f64(name, N):
+    """The streaming (sorted-target) resampling path: feed the SAME ascending uniforms to the oracle
+    (which is still the reference algorithm: searchsorted of each uniform) and to the CUDA kernel with
+    resample='multinomial_sorted'.  Ancestors bit-exact, statistics to 1e-8.  N=5000 spans 3 tiles."""
+    import sgmcmc_ssm_b200 as sg
+    c = C.case(name)
+    model, kernel, pf = C.parse_kernel_case(name)
+    K = po.make_kernel(model, kernel, C.theta_dict(model, c["theta"]))
+    N = int(c["N"]) if N is None else N
+    T = c["obs"].shape[0]
+    rs = np.random.RandomState(int(c["seed"]))
+    z0, z = rs.normal(size=N), rs.normal(size=(T, N))
+    u = np.sort(rs.random_sample((T, N)), axis=1)
+    flat_z = np.concatenate([z0, z.ravel()])
+    kw = dict(t1=int(c["t1"]), tL=int(c["tL"]), weights=c["weights"], prior_mean=float(c["prior_mean"]),
+              prior_var=float(c["prior_var"]))
+    opts = C.case_opts(c)
+    ref = po.buffered_pf(pf, c["obs"], K, N, K.score, K.p, po.InjectedStream(u.ravel(), flat_z), save_all=True, **kw, **opts)
+    items = sg.PFItems().add(c["obs"], c["theta"], **kw)
+    res = sg.run_pf(model, kernel, pf, items, N, dtype="f64", rng="injected", resample="multinomial_sorted",
+                    injected=dict(z0=z0, u=u, z=z), want=("x", "stats", "anc"), **opts)
+    np.testing.assert_array_equal(res.tensor("anc")[0].cpu().numpy(), np.array(ref["trace"]["ancestors"]))
+    np.testing.assert_allclose(res.grad[0], po.average_statistic(ref), rtol=1e-8, atol=1e-9)
+    np.testing.assert_allclose(res.loglik[0], ref["loglikelihood_estimate"], rtol=1e-9, atol=1e-10)
