@@ -1,0 +1,121 @@
+"""Drop-in for sgmcmc_ssm/particle_filters/buffered_smoother.py: same entry points and return dict,
+with the whole time loop executed by the CUDA library (one C-ABI call per batch of work items).
+
+  buffered_pf_wrapper(pf=, observations=, parameters=, N=, kernel=, additive_statistic_func=,
+                      statistic_dim=, t1=, tL=, weights=, prior_mean=, prior_var=, **kwargs) -> dict
+      keys x_t (N, n), log_weights (N,), statistics (N, p) [(p,) for pf='filter'],
+      loglikelihood_estimate (float)                       (buffered_smoother.py:12-149, 156-199)
+  average_statistic(out) -> (p,)                           (buffered_smoother.py:151-154)
+  batched_pf(...)  -- the batched form used by the samplers (new; one launch for a whole minibatch)
+
+Unknown kwargs are ignored, as in the reference (they flow through every layer there).  The
+additive statistic must be one of the library's named statistics (the model score functions or the
+sufficient statistics); arbitrary Python callables cannot run on the device.
+"""
+import numpy as np
+
+from .. import engine
+from . import statistics as S
+
+_PF_NAMES = ("nemeth", "poyiadjis_N", "poyiadjis_N2", "paris", "filter")
+_ENGINE_KW = ("dtype", "rng", "resample", "lambduh", "Ntilde", "accept_reject", "max_accept_reject",
+              "manual_sample_threshold", "seed", "offset", "device", "item_id_base")
+
+
+def _theta(model, parameters):
+    return S.MODEL_SPECS[model]["theta"](parameters)
+
+
+def _draw_injected(N, T_list):
+    """Consume the GLOBAL numpy legacy stream exactly as the reference would for these items
+    (SURVEY Appendix B): per item: N normals (sample_x0), then per step N uniforms (np.random.choice)
+    and N normals (kernel.rv)."""
+    B, max_T = len(T_list), max(T_list)
+    z0 = np.zeros((B, N))
+    u = np.zeros((B, max_T, N))
+    z = np.zeros((B, max_T, N))
+    for b, T in enumerate(T_list):
+        z0[b] = np.random.normal(size=N)
+        for t in range(T):
+            u[b, t] = np.random.random_sample(N)
+            z[b, t] = np.random.normal(size=N)
+    return dict(z0=z0, u=u, z=z)
+
+
+def batched_pf(pf, model, kernel, items, N, stat_kind="score", want=(), sync=True, **kwargs):
+    """Run one batch of work items; returns engine.PFResult."""
+    if pf not in _PF_NAMES:
+        raise ValueError("Unrecognized pf = {0}".format(pf))       # buffered_smoother.py:198
+    kw = {k: kwargs[k] for k in _ENGINE_KW if k in kwargs and kwargs[k] is not None}
+    rng = kw.get("rng", engine.config.rng)
+    if rng == "injected" and "injected" not in kwargs:
+        if pf == "paris":
+            raise NotImplementedError("rng='injected' with pf='paris' needs a recorded stream "
+                                      "(data-dependent number of draws); pass injected=dict(...)")
+        kw["injected"] = _draw_injected(int(N), [o.shape[0] for o in items.obs])
+        kw.setdefault("resample", "multinomial")
+    elif "injected" in kwargs:
+        kw["injected"] = kwargs["injected"]
+    return engine.run_pf(model, kernel, pf, items, N, stat_kind=stat_kind, want=want, sync=sync, **kw)
+
+
+def buffered_pf_wrapper(pf, observations=None, parameters=None, N=1000, kernel=None,
+                        additive_statistic_func=None, statistic_dim=None, t1=0, tL=None, weights=None,
+                        prior_mean=0.0, prior_var=1.0, save_all=False, elementwise_statistic=False,
+                        **kwargs):
+    if pf not in _PF_NAMES:
+        raise ValueError("Unrecognized pf = {0}".format(pf))
+    if kernel is None or getattr(kernel, "model", None) is None:
+        raise ValueError("kernel must be one of the library's Kernel objects")
+    if kernel.kernel == "highdim":
+        raise NotImplementedError("n > 1 latent states are outside the CUDA path")
+    kernel.set_parameters(parameters=parameters)
+    model = kernel.model
+    stat_kind = S.stat_kind_of(additive_statistic_func)
+    observations = np.asarray(observations, dtype=float)
+    T = observations.shape[0]
+    tL = T if tL is None else tL
+    items = engine.PFItems().add(observations, _theta(model, parameters), t1=t1, tL=tL, weights=weights,
+                                 prior_mean=float(np.ravel(prior_mean)[0]), prior_var=float(np.ravel(prior_var)[0]))
+    if elementwise_statistic:
+        return S.elementwise_run(pf, model, kernel.kernel, items, N, stat_kind, t1, tL, **kwargs)
+    want = ("x", "lw") + (() if pf == "filter" else ("stats",)) + (("trace_x", "trace_lw") if save_all else ())
+    res = batched_pf(pf, model, kernel.kernel, items, N, stat_kind=stat_kind, want=want, **kwargs)
+    p = res.p
+    out = dict(x_t=res.tensor("x")[0].double().cpu().numpy(),
+               log_weights=res.tensor("lw")[0].double().cpu().numpy(),
+               loglikelihood_estimate=float(res.loglik[0]))
+    if pf == "filter":
+        out["statistics"] = res.grad[0].copy()
+    else:
+        out["statistics"] = res.tensor("stats")[0][:, :p].double().cpu().numpy()
+        out["_average_statistic"] = res.grad[0].copy()
+    if save_all:
+        out["all_x_t"] = res.tensor("trace_x")[0].double().cpu().numpy()
+        out["all_log_weights"] = res.tensor("trace_lw")[0].double().cpu().numpy()
+    return out
+
+
+def pf_wrapper(observations, parameters, N, kernel, smoother, additive_statistic_func, statistic_dim,
+               **kwargs):
+    """buffered_smoother.py:12-149 signature; `smoother` is one of the named functions of
+    particle_filters.pf (they carry the `pf` string)."""
+    pf = getattr(smoother, "pf_name", None)
+    if pf is None:
+        raise ValueError("smoother must be one of particle_filters.pf.{nemeth,poyiadjis,paris}_smoother / pf_filter")
+    if pf == "nemeth" and kwargs.get("lambduh") == 1.0:
+        pf = "poyiadjis_N"
+    return buffered_pf_wrapper(pf, observations=observations, parameters=parameters, N=N, kernel=kernel,
+                               additive_statistic_func=additive_statistic_func, statistic_dim=statistic_dim,
+                               **kwargs)
+
+
+def average_statistic(out):
+    """sum_i statistics[i, :] * softmax(log_weights)[i]   (buffered_smoother.py:151-154).
+    The device already reduced it (fused into the last step); recompute only for foreign dicts."""
+    if "_average_statistic" in out:
+        return out["_average_statistic"]
+    lw = np.asarray(out["log_weights"])
+    w = np.exp(lw - np.max(lw))
+    w /= np.sum(w)
+    return np.sum(np.asarray(out["statistics"]).T * w, axis=1)

@@ -1,0 +1,157 @@
+"""CPU tests of the host-side mirror of the reference API (no GPU): parameter containers, priors,
+subsequence sampling, synthetic-data generators, and that the C-ABI library loads and exports every
+symbol include/sgmpf.h declares."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from tests import _cases as C
+from oracle import pf_oracle as po
+
+import sgmcmc_ssm_b200  # noqa: F401
+from sgmcmc_ssm_b200.models.svm import SVMParameters, SVMPrior, SVMSampler, generate_svm_data
+from sgmcmc_ssm_b200.models.lgssm import LGSSMParameters, LGSSMPrior, LGSSMSampler, generate_lgssm_data
+from sgmcmc_ssm_b200.models.garch import GARCHParameters, GARCHPrior, GARCHSampler, generate_garch_data
+from sgmcmc_ssm_b200.sgmcmc_sampler import random_subsequence_and_weights
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def svm_params():
+    return SVMParameters(A=np.eye(1) * 0.95, LQinv=np.linalg.cholesky(np.linalg.inv(np.eye(1) * 0.5)),
+                         LRinv=np.linalg.cholesky(np.linalg.inv(np.eye(1) * 0.5)))
+
+
+def lgssm_params():
+    return LGSSMParameters(A=np.eye(1) * 0.9, C=np.eye(1), LQinv=np.linalg.cholesky(np.linalg.inv(np.eye(1) * 0.1)),
+                           LRinv=np.linalg.cholesky(np.linalg.inv(np.eye(1) * 1.0)))
+
+
+def garch_params():
+    log_mu, logit_phi, logit_lambduh = GARCHParameters.convert_alpha_beta_gamma(0.1, 0.8, 0.05)
+    return GARCHParameters(log_mu=log_mu, logit_phi=logit_phi, logit_lambduh=logit_lambduh,
+                           LRinv=np.linalg.cholesky(np.linalg.inv(np.eye(1) * 0.3 ** 2)))
+
+
+MODELS = dict(svm=(svm_params, SVMPrior, SVMSampler), lgssm=(lgssm_params, LGSSMPrior, LGSSMSampler),
+              garch=(garch_params, GARCHPrior, GARCHSampler))
+
+
+def test_cabi_library_exports_every_declared_symbol():
+    from sgmcmc_ssm_b200 import _native as nat
+    lib = nat.load()
+    header = open(os.path.join(ROOT, "include", "sgmpf.h")).read()
+    declared = set(re.findall(r"\b(sgm_[a-z_]+)\s*\(", header))
+    assert declared == set(nat.EXPORTS), declared ^ set(nat.EXPORTS)
+    for sym in declared:
+        assert getattr(lib, sym) is not None
+    assert lib.sgm_version() == 100
+    assert lib.sgm_stat_dim(nat.MODEL["svm"], 0) == 3 and lib.sgm_stat_dim(nat.MODEL["garch"], 0) == 4
+    assert lib.sgm_state_dim(nat.MODEL["garch"]) == 2
+    # descriptor validation happens before any CUDA call
+    d = nat.SgmPfDesc()
+    assert lib.sgm_pf_workspace_bytes(ctypes.byref(d)) == 0
+    assert lib.sgm_pf_run(ctypes.byref(d), None) == -1 and b"size mismatch" in lib.sgm_last_error()
+
+
+def test_no_cpu_fallback_without_cuda():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    import sgmcmc_ssm_b200 as sg
+    items = sg.PFItems().add(np.zeros(4), [0.9, 1, 1, 1, 1])
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        sg.run_pf("svm", "prior", "poyiadjis_N", items, 16)
+
+
+@pytest.mark.parametrize("model", ["svm", "lgssm", "garch"])
+def test_prior_matches_reference(model):
+    """default prior hyper-parameters, logprior and grad_logprior vs the reference (s/prior_<model>)."""
+    c = C.case("s/prior_" + model)
+    make, Prior, _ = MODELS[model]
+    params = make()
+    np.testing.assert_allclose(np.concatenate([np.ravel(params.var_dict[k]) for k in sorted(params.var_dict)]),
+                               c["param_values"], rtol=0, atol=1e-15)
+    prior = Prior.generate_default_prior(n=1, m=1)
+    for k, v in c.items():
+        if k.startswith("hyper_"):
+            np.testing.assert_allclose(prior.hyperparams[k[6:]], v, rtol=1e-14)
+    np.testing.assert_allclose(prior.logprior(params), c["logprior"], rtol=1e-12)
+    g = prior.grad_logprior(params)
+    assert sorted(g) == [str(k) for k in c["grad_keys"]]
+    np.testing.assert_allclose(np.concatenate([np.ravel(g[k]) for k in sorted(g)]), c["grad_values"], rtol=1e-12)
+
+
+@pytest.mark.parametrize("name", [n for n in C.case_names("s") if n.startswith("s/subseq_")])
+def test_random_subsequence_and_weights_matches_reference(name):
+    c = C.case(name)
+    style = name.rsplit("_", 1)[1]
+    np.random.seed(int(c["seed"]))
+    s, e, w = random_subsequence_and_weights(S=int(c["S"]), T=int(c["T"]), partition_style=style)
+    assert (s, e) == (int(c["start"]), int(c["end"]))
+    np.testing.assert_array_equal(w, c["weights"])
+    np.testing.assert_array_equal(po.subsequence_weights(int(c["S"]), int(c["T"]), s, style), c["weights"])
+
+
+def test_data_generators_reproduce_reference_streams():
+    """np.random.seed(2024) then svm, lgssm, garch T=200 -- the series stored with the sampler cases."""
+    np.random.seed(2024)
+    for model, gen in (("svm", generate_svm_data), ("lgssm", generate_lgssm_data), ("garch", generate_garch_data)):
+        data = gen(T=200, parameters=MODELS[model][0]())
+        np.testing.assert_allclose(data["observations"], C.case("s/sgld_" + model)["obs"], rtol=0, atol=1e-14)
+
+
+def test_parameter_containers():
+    p = svm_params()
+    assert list(p.var_dict) == ["A", "LQinv_vec", "LRinv_vec"] and p.dim == {"n": 1, "m": 1}
+    np.testing.assert_allclose(p.Qinv, p.LQinv ** 2 + 1e-16)
+    q = SVMParameters(**SVMParameters.from_vector_to_dict(p.as_vector(), **p.dim))
+    np.testing.assert_array_equal(q.as_vector(), p.as_vector())
+    c = p.copy()
+    c += {k: np.ones_like(v) for k, v in p.var_dict.items()}
+    assert c.A[0, 0] == p.A[0, 0] + 1
+    # projection: |A| clipped to 0.9999, negative Cholesky diagonal reflected, LGSSM C fixed to identity
+    c.A = np.array([[1.7]])
+    c.LQinv_vec = np.array([-2.0])
+    c.project_parameters()
+    assert abs(c.A[0, 0] - 0.9999) < 1e-12 and abs(c.LQinv_vec[0] - 2.0) < 1e-12
+    l = lgssm_params()
+    l.C = np.array([[3.0]])
+    l.project_parameters()
+    assert l.C[0, 0] == 1.0 and list(l.var_dict) == ["A", "C", "LQinv_vec", "LRinv_vec"]
+    g = garch_params()
+    np.testing.assert_allclose([g.alpha[0], g.beta[0], g.gamma[0]], [0.1, 0.8, 0.05], rtol=1e-12)
+    assert list(g.var_dict) == ["log_mu", "logit_phi", "logit_lambduh", "LRinv_vec"]
+    with pytest.raises(ValueError):
+        GARCHParameters.convert_alpha_beta_gamma(0.1, 0.9, 0.2)
+
+
+def test_sampler_errors_and_kwargs_contract():
+    obs = np.zeros((50, 1))
+    s = SVMSampler(n=1, m=1, observations=obs, parameters=svm_params())
+    with pytest.raises(ValueError, match="Use SGRLD"):
+        s.sample_sgld(epsilon=0.1, preconditioner=object(), kind="pf", N=10)
+    with pytest.raises(NotImplementedError):
+        s.noisy_gradient(kind="marginal")
+    with pytest.raises(ValueError, match="Unrecognized kind"):
+        s.noisy_gradient(kind="bogus")
+    with pytest.raises(NotImplementedError, match="No Default Preconditioner"):
+        s.get_iter_step("SGRLD", epsilon=0.1, subsequence_length=10, buffer_length=2)
+    with pytest.raises(NotImplementedError, match="not analytic"):
+        s.message_helper._get_kernel("optimal")
+    with pytest.raises(ValueError, match="Unrecoginized kernel"):
+        s.message_helper._get_kernel("nope")
+    with pytest.raises(ValueError, match="Unrecognized pf"):
+        s.message_helper.pf_gradient_estimate(obs[:10], s.parameters, pf="nope", N=10)
+    bad = svm_params()
+    bad.A = np.array([[1.5]])
+    with pytest.raises(ValueError, match="AR parameter"):
+        s.message_helper.pf_gradient_estimate(obs[:10], bad, N=10)
+    names, kws = s.get_iter_step("SGLD", epsilon=0.1, subsequence_length=10, buffer_length=2, kind="pf",
+                                 pf_kwargs=dict(pf="paris", N=100, Ntilde=3), steps_per_iteration=2)
+    assert names == ["sample_sgld", "project_parameters"] * 2 and kws[0]["Ntilde"] == 3 and kws[0]["N"] == 100
+    bd = s._random_subsequence_and_buffers(buffer_length=4, subsequence_length=-1)
+    assert (bd["subsequence_start"], bd["subsequence_end"], bd["weights"]) == (0, 50, None)
