@@ -57,6 +57,16 @@ def _window(observations, bd):
                 weights=bd["weights"])
 
 
+def _merge_injected(drawn):
+    """Concatenate per-item recorded randoms along the batch axis (time axis padded)."""
+    max_T = max(d["u"].shape[1] for d in drawn)
+
+    def pad(a):
+        return np.pad(a, ((0, 0), (0, max_T - a.shape[1]), (0, 0)))
+    return dict(z0=np.concatenate([d["z0"] for d in drawn]), u=np.concatenate([pad(d["u"]) for d in drawn]),
+                z=np.concatenate([pad(d["z"]) for d in drawn]))
+
+
 _NOT_PF = "kind='{0}' (analytic message passing) is outside the particle-filter hot path; use kind='pf'"
 
 
@@ -82,12 +92,22 @@ class SGMCMCSampler(object):
             raise ValueError("Unrecognized kind = {0}".format(kind))
         if kwargs.get("N", None) is None:
             kwargs["N"] = num_samples
-        buffer_dicts = [self._random_subsequence_and_buffers(buffer_length=buffer_length,
-                                                             subsequence_length=subsequence_length, T=T)
-                        for _ in range(minibatch_size)]
+        from . import engine
+        from .particle_filters.buffered_smoother import _draw_injected
         kwargs.pop("parameters", None)
-        ll = self.message_helper.pf_loglikelihood_estimate_batch(
-            [_window(observations, bd) for bd in buffer_dicts], self.parameters, **kwargs)
+        replay = kwargs.get("rng", engine.config.rng) == "injected" and "injected" not in kwargs
+        windows, drawn = [], []
+        for _ in range(minibatch_size):
+            # the reference draws a subsequence and runs its filter before drawing the next one (:214-237)
+            bd = self._random_subsequence_and_buffers(buffer_length=buffer_length,
+                                                      subsequence_length=subsequence_length, T=T)
+            windows.append(_window(observations, bd))
+            if replay:
+                drawn.append(_draw_injected(int(kwargs["N"]), [windows[-1]["observations"].shape[0]]))
+        if replay:
+            kwargs["injected"] = _merge_injected(drawn)
+            kwargs.setdefault("resample", "multinomial")
+        ll = self.message_helper.pf_loglikelihood_estimate_batch(windows, self.parameters, **kwargs)
         noisy_loglikelihood = float(np.sum(ll)) * 1.0 / minibatch_size
         if np.isnan(noisy_loglikelihood):
             raise ValueError("NaNs in loglikelihood")
@@ -450,11 +470,7 @@ class SeqSGMCMCSampler(object):
             windows += w
             S += seqs[k].shape[0]
         if replay:
-            max_T = max(d["u"].shape[1] for d in drawn)
-            pad = lambda a: np.pad(a, ((0, 0), (0, max_T - a.shape[1]), (0, 0)))
-            kwargs["injected"] = dict(z0=np.concatenate([d["z0"] for d in drawn]),
-                                      u=np.concatenate([pad(d["u"]) for d in drawn]),
-                                      z=np.concatenate([pad(d["z"]) for d in drawn]))
+            kwargs["injected"] = _merge_injected(drawn)
             kwargs.setdefault("resample", "multinomial")
         grads, _ = self.message_helper.pf_gradient_estimate_batch(windows, self.parameters, **kwargs)
         noisy_grad = {var: np.zeros_like(value) for var, value in self.parameters.as_dict().items()}
