@@ -1,0 +1,357 @@
+#!/usr/bin/env python3
+"""bench.py -- buffered particle-filter gradient throughput (BASELINE.json metric: particle-steps/sec).
+
+  python bench.py --gpus N --steps K --warmup W            # this repo (CUDA, sm_100a)
+  python bench.py --impl reference --gpus N --steps K ...   # the reference algorithm on the host CPU cores
+
+Workload (BASELINE.json configs[1]): SVM synthetic T=10000 (A, Q, R) = (0.95, 0.5, 0.5), Poyiadjis O(N)
+smoother, N = 2^16 particles per subsequence, subsequence 40 + buffers 10 (T_buf = 60 steps), a minibatch
+of M subsequences per GPU (weak scaling), f32 particle arithmetic with f64 CDF offsets, device Philox
+randoms, order-statistics multinomial resampling (same law as the reference's multinomial).
+
+A "step" = one noisy-gradient evaluation of the minibatch = one pass of the hot path over one batch.
+  value : device-timed (CUDA events, max over ranks), inputs resident in HBM; includes the per-step
+          NCCL all-reduce of the gradient sums when N > 1.
+  e2e   : the same metric through the public API `sampler.noisy_gradient(kind='pf', ...)` with HOST
+          observation buffers: packing, H2D, all kernels, D2H and the all-reduce inside the timed region.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG_DIR = os.path.join(ROOT, "stochastic-gradient-mcmc-for-non-linear-state-models---mth422_b200")
+for _p in (ROOT, PKG_DIR):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+import numpy as np  # noqa: E402
+
+METRIC = "particle-steps/sec (buffered PF grad, SVM N=2^16)"
+UNIT = "particle-steps/s"
+N_PARTICLES = 1 << 16
+SUBSEQ, BUFFER, T_SERIES = 40, 10, 10000
+ALG_BYTES = 40            # e * (2 (n + p) + 2), SVM f32: 4 * (2 * 4 + 2)
+
+
+def svm_series(T=T_SERIES, seed=12345):
+    """Synthetic SVM series under the reference's generator semantics (svm/parameters.py:75-135),
+    vectorised-free re-statement: x_t = A x_{t-1} + N(0, Q), y_t ~ N(0, R exp(x_t))."""
+    rs = np.random.RandomState(seed)
+    A, Q, R = 0.95, 0.5, 0.5
+    x = np.sqrt(Q / (1 - A * A)) * rs.normal()
+    y = np.zeros((T, 1))
+    for t in range(T):
+        x = A * x + np.sqrt(Q) * rs.normal()
+        y[t, 0] = np.sqrt(R) * np.exp(0.5 * x) * rs.normal()
+    return y
+
+
+def svm_theta():
+    LQinv, LRinv = np.sqrt(1 / 0.5), np.sqrt(1 / 0.5)
+    return dict(A=0.95, LQinv=LQinv, Qinv=LQinv * LQinv + 1e-16, LRinv=LRinv, Rinv=LRinv * LRinv + 1e-16)
+
+
+def draw_windows(n, T=T_SERIES, seed=777):
+    """n subsequence starts + 'uniform' partition weights (sgmcmc_sampler.py:1969-2017)."""
+    from oracle import pf_oracle as po
+    rs = np.random.RandomState(seed)
+    out = []
+    for _ in range(n):
+        start = int(rs.randint(0, T - SUBSEQ + 1))
+        lo, hi = max(0, start - BUFFER), min(T, start + SUBSEQ + BUFFER)
+        out.append(dict(start=start, lo=lo, hi=hi, weights=po.subsequence_weights(SUBSEQ, T, start)))
+    return out
+
+
+# ------------------------------------------------------------------------------------------------------
+# reference arm: the reference's algorithm (oracle port, numpy) on all host cores
+# ------------------------------------------------------------------------------------------------------
+def _cpu_one_gradient(args):
+    y, w, seed = args
+    from oracle import pf_oracle as po
+    rng = po.LegacyStream(seed, native_choice=True)       # np.random.choice(range(N), p=...) like pf.py:28-29
+    obs = y[w["lo"]:w["hi"]]
+    g = po.pf_gradient_estimate("svm", obs, svm_theta(), rng, subsequence_start=w["start"] - w["lo"],
+                                subsequence_end=w["start"] - w["lo"] + SUBSEQ, weights=w["weights"],
+                                pf="poyiadjis_N", N=N_PARTICLES)
+    return obs.shape[0] * N_PARTICLES, [g["LRinv_vec"], g["LQinv_vec"], g["A"]]
+
+
+def cpu_rate(y, windows, cores, steps, warmup):
+    """particle-steps/s of the numpy port: each step = `cores` independent subsequence gradients, one per
+    process (the reference itself is single-threaded; independent processes are its fair multi-core use)."""
+    import multiprocessing as mp
+    per_step = cores
+    jobs = [(y, windows[i % len(windows)], 1000 + i) for i in range((steps + warmup) * per_step)]
+    if cores == 1:
+        for j in jobs[:warmup * per_step]:
+            _cpu_one_gradient(j)
+        t0 = time.perf_counter()
+        done = sum(_cpu_one_gradient(j)[0] for j in jobs[warmup * per_step:])
+        dt = time.perf_counter() - t0
+    else:
+        with mp.get_context("fork").Pool(cores) as pool:
+            if warmup:
+                pool.map(_cpu_one_gradient, jobs[:warmup * per_step], chunksize=1)
+            t0 = time.perf_counter()
+            done = sum(r[0] for r in pool.map(_cpu_one_gradient, jobs[warmup * per_step:], chunksize=1))
+            dt = time.perf_counter() - t0
+    return done / dt, dt, done
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    for k in ("OMP_NUM_THREADS", "MKL_NUM_THREADS", "OPENBLAS_NUM_THREADS"):
+        os.environ.setdefault(k, "1")
+    cores = os.cpu_count() or 1
+    y = svm_series()
+    windows = draw_windows(256)
+    rate, dt, done = cpu_rate(y, windows, cores, args.steps, min(args.warmup, 1))
+    sample = "{0} independent subsequence gradients per step (one per core), N=2^16, T_buf<=60".format(cores)
+    line = {"metric": METRIC, "value": rate, "unit": UNIT, "impl": "reference", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": min(args.warmup, 1), "ms_per_step": 1e3 * dt / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(args.gpus, args.minibatch),
+            "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def workload_config(world, M):
+    return {"workload": "SVM synthetic T=10000 (A,Q,R)=(0.95,0.5,0.5), buffered PF gradient, pf=poyiadjis_N, "
+                        "N=65536 particles/subsequence, subsequence 40 + buffer 10 (T_buf<=60), "
+                        "minibatch {0} subsequences/GPU x {1} GPU".format(M, world),
+            "minibatch_per_gpu": M, "n_particles": N_PARTICLES, "subsequence_length": SUBSEQ,
+            "buffer_length": BUFFER, "pf": "poyiadjis_N", "resample": "multinomial_sorted", "rng": "philox",
+            "parallelism": "items sharded over {0} GPU, one NCCL all-reduce of gradient sums per step".format(world),
+            "l2": "particle state per GPU = M*N*(16+4)B*2 buffers >> 126 MB L2 (inputs larger than L2)"}
+
+
+# ------------------------------------------------------------------------------------------------------
+class ClockSampler(object):
+    """nvidia-smi sampling during the timed region (B200_PROFILING.md clocks line)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows if len(r) >= 9 for n, v in zip(names, r[5:9]) if v.lower() == "active"})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def run_gpu(args):
+    import torch
+    import sgmcmc_ssm_b200 as sg
+    from sgmcmc_ssm_b200 import parallel
+    from sgmcmc_ssm_b200.models.svm import SVMSampler, SVMParameters
+    rank, world, local = parallel.init_distributed()
+    dev = torch.device("cuda", torch.cuda.current_device())
+    M = args.minibatch
+    y = svm_series()
+    windows_all = draw_windows(M * world)
+    lo, hi = parallel.shard_bounds(len(windows_all))
+    th = svm_theta()
+    theta = [th[k] for k in ("A", "LQinv", "Qinv", "LRinv", "Rinv")]
+    sg.set_seed(12345)
+
+    # ---- (A) device-resident: inputs packed and uploaded once, K timed launches -----------------------
+    items = sg.PFItems()
+    for w in windows_all[lo:hi]:
+        items.add(y[w["lo"]:w["hi"]], theta, t1=w["start"] - w["lo"], tL=w["start"] - w["lo"] + SUBSEQ,
+                  weights=w["weights"], prior_mean=0.0, prior_var=10.0)
+    prep = sg.engine.PreparedPF("svm", "prior", "poyiadjis_N", items, N_PARTICLES, dtype="f32", rng="philox",
+                                resample="multinomial_sorted", item_id_base=lo)
+    prep.upload()
+    st = prep.st
+    so = prep.base_out - st.dev_out.data_ptr()
+    grad_view = st.dev_out[so:so + prep.B * 64].view(torch.float64).view(prep.B, 8)
+    gsum = torch.zeros(8, dtype=torch.float64, device=dev)
+
+    def one_step(k, events=None):
+        prep.launch(offset=k + 1, step_events=events)
+        torch.sum(grad_view, dim=0, out=gsum)
+        if world > 1:
+            torch.distributed.all_reduce(gsum)
+
+    for k in range(args.warmup):
+        one_step(k)
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    for a, b in ev:           # create the handles
+        a.record(); b.record()
+    torch.cuda.synchronize()
+    parallel.barrier()
+    clocks = ClockSampler(torch.cuda.current_device())
+    if rank == 0:
+        clocks.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for k in range(args.steps):
+        one_step(args.warmup + k, ev[k])
+    e1.record()
+    torch.cuda.synchronize()
+    parallel.barrier()
+    dev_ms = parallel.allreduce_max(e0.elapsed_time(e1))
+    clk = clocks.stop() if rank == 0 else None
+    step_kernel_ms = float(np.mean([a.elapsed_time(b) for a, b in ev])) / prep.max_T     # avg pf_step_kernel launch
+    step_kernel_ms = parallel.allreduce_max(step_kernel_ms)
+    local_ps = prep.particle_steps
+    total_ps = parallel.allreduce_sum(np.array([float(local_ps)]))[0]
+    value = total_ps * args.steps / (dev_ms * 1e-3)
+    res = prep.download().wait()
+    assert np.all(np.isfinite(res.grad)) and np.all(res.status == 0), "bench produced non-finite gradients"
+    launches_per_step = prep.launches + 1 + (1 if world > 1 else 0)
+
+    # ---- (B) end to end through the public API, host buffers -----------------------------------------
+    params = SVMParameters(A=np.eye(1) * 0.95, LQinv=np.eye(1) * th["LQinv"], LRinv=np.eye(1) * th["LRinv"])
+    sampler = SVMSampler(n=1, m=1, observations=y, parameters=params)
+    np.random.seed(4242)                                   # identical subsequence draws on every rank
+    api_kw = dict(kind="pf", pf="poyiadjis_N", N=N_PARTICLES, subsequence_length=SUBSEQ, buffer_length=BUFFER,
+                  minibatch_size=M * world, dtype="f32", rng="philox", resample="multinomial_sorted",
+                  distributed=(world > 1))
+    for _ in range(max(1, min(args.warmup, 2))):
+        sampler.noisy_gradient(**api_kw)
+    torch.cuda.synchronize()
+    parallel.barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        g = sampler.noisy_gradient(**api_kw)
+    torch.cuda.synchronize()
+    parallel.barrier()
+    e2e_s = parallel.allreduce_max(time.perf_counter() - t0)
+    e2e_ps = M * world * N_PARTICLES * (SUBSEQ + 2 * BUFFER)      # interior windows; edge windows are shorter
+    e2e_value = e2e_ps * args.steps / e2e_s
+
+    if rank != 0:
+        return 0
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm = float(peaks.get("hbm_gbs", 6650.0))
+    achieved = ALG_BYTES * prep.B * N_PARTICLES / (step_kernel_ms * 1e-3) / 1e9
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "step_kernel_traffic.json")))["dram_bytes_per_launch"]
+    except Exception:
+        pass
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic", "config": workload_config(world, M),
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(res.h2d_bytes),
+                "d2h_bytes_per_step": int(res.d2h_bytes), "ms_per_step": 1e3 * e2e_s / args.steps,
+                "api": "SVMSampler.noisy_gradient(kind='pf', minibatch_size=M*n_gpus, ...)"},
+        "gpu_launches": int(launches_per_step * args.steps),
+        "clocks": clk,
+        "roofline": {"bound": "hbm", "kernel": "pf_step_kernel<float, SvmPrior>", "achieved": achieved, "peak": hbm,
+                     "unit": "GB/s", "frac": achieved / hbm, "traffic": traffic,
+                     "peak_source": "MEASURED_PEAKS.json (measured)" if peaks else "fallback 6650 GB/s",
+                     "alg_bytes_per_particle_step": ALG_BYTES, "particles_per_launch": prep.B * N_PARTICLES,
+                     "avg_launch_ms": step_kernel_ms, "step_kernel_share_of_step": step_kernel_ms * prep.max_T * args.steps / dev_ms},
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        windows = draw_windows(8, seed=99)
+        n_grad = max(1, int(args.cpu_seconds // 3))
+        rate, dt, done = cpu_rate(y, windows, 1, n_grad, 0)
+        line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": 1, "kind": "port",
+                                "sample": "{0} subsequence gradient(s) of the same workload (N=2^16, T_buf<=60), "
+                                          "numpy oracle port incl. np.random.choice, {1:.1f} s; host has {2} cores".format(
+                                              n_grad, dt, os.cpu_count())}
+    if world == 1 and not args.no_extras:
+        line["extra"] = extras(sg, y, theta, windows_all, torch)
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def extras(sg, y, theta, windows, torch):
+    """Secondary numbers: single-subsequence latency (the reference script's minibatch_size=1) and SGLD iters/sec."""
+    out = {}
+    w = windows[0]
+    it = sg.PFItems().add(y[w["lo"]:w["hi"]], theta, t1=w["start"] - w["lo"], tL=w["start"] - w["lo"] + SUBSEQ,
+                          weights=w["weights"], prior_mean=0.0, prior_var=10.0)
+    prep = sg.engine.PreparedPF("svm", "prior", "poyiadjis_N", it, N_PARTICLES, dtype="f32", rng="philox",
+                                resample="multinomial_sorted").upload()
+    for k in range(3):
+        prep.launch(offset=k)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for k in range(20):
+        prep.launch(offset=10 + k)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 20
+    out["minibatch1_ms_per_gradient"] = ms
+    out["minibatch1_particle_steps_per_sec"] = prep.particle_steps / (ms * 1e-3)
+    # SGLD iterations / s, BASELINE configs[0]: LGSSM T=1000, N=1000, S=40, B=10, minibatch 1
+    from sgmcmc_ssm_b200.models.lgssm import LGSSMSampler, LGSSMParameters, generate_lgssm_data
+    np.random.seed(12345)
+    p = LGSSMParameters(A=np.eye(1) * 0.9, C=np.eye(1), LQinv=np.eye(1) * np.sqrt(10.0), LRinv=np.eye(1))
+    data = generate_lgssm_data(T=1000, parameters=p)
+    s = LGSSMSampler(n=1, m=1, observations=data["observations"], parameters=p.copy())
+    kw = dict(epsilon=0.01, kind="pf", pf="poyiadjis_N", N=1000, subsequence_length=40, buffer_length=10, minibatch_size=1)
+    for _ in range(5):
+        s.sample_sgld(**kw); s.project_parameters()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(100):
+        s.sample_sgld(**kw); s.project_parameters()
+    torch.cuda.synchronize()
+    out["sgld_iters_per_sec_lgssm_T1000_N1000"] = 100 / (time.perf_counter() - t0)
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--minibatch", type=int, default=256, help="subsequences per GPU per step")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_gpu(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

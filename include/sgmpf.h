@@ -122,6 +122,8 @@ typedef struct sgm_pf_desc {
 
     void* workspace;               /* >= sgm_pf_workspace_bytes(desc), 256-byte aligned             */
     uint64_t workspace_bytes;
+    void* ev_steps_begin;          /* optional cudaEvent_t recorded on `stream` before the first ...  */
+    void* ev_steps_end;            /* ... and after the last step-kernel launch (bench roofline timing) */
 } sgm_pf_desc;
 
 /* library version (SGM_VERSION) */

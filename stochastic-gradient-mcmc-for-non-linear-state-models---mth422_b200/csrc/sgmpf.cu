@@ -136,11 +136,13 @@ int run_impl(const sgm_pf_desc* d, cudaStream_t stream) {
         gamma_prefix_kernel<<<dim3(a.max_T, a.B), block, 0, stream>>>(a, gam); ++launches;
     }
     pf_init_kernel<R, Model><<<grid, block, 0, stream>>>(a); ++launches;
+    if (d->ev_steps_begin) cudaEventRecord(reinterpret_cast<cudaEvent_t>(d->ev_steps_begin), stream);
     for (int t = 0; t < a.max_T; ++t) {
         pf_step_kernel<R, Model><<<grid, block, 0, stream>>>(a, t); ++launches;
         if (d->pf == SGM_PF_POY_N2) launches += launch_poyiadjis_n2<R, Model>(a, t, stream);
         else if (d->pf == SGM_PF_PARIS) launches += launch_paris<R, Model>(a, t, stream);
     }
+    if (d->ev_steps_end) cudaEventRecord(reinterpret_cast<cudaEvent_t>(d->ev_steps_end), stream);
     pf_final_kernel<R, Model><<<a.B, block, 0, stream>>>(a); ++launches;
     if (d->out_x || d->out_lw || d->out_stats) {
         pf_export_kernel<R, Model><<<dim3((a.N + NT - 1) / NT, a.B), block, 0, stream>>>(a); ++launches;

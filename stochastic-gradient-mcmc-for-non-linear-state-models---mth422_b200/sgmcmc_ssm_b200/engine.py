@@ -153,163 +153,197 @@ class PFResult(object):
         return self._extra[name]
 
 
-def run_pf(model, kernel, pf, items, N, dtype=None, rng=None, resample=None, stat_kind="score",
-           lambduh=None, Ntilde=2, accept_reject=True, max_accept_reject=None,
-           manual_sample_threshold=None, seed=None, offset=None, item_id_base=0, injected=None,
-           want=(), device=None, sync=True, check=True):
-    """Run the buffered particle filter / smoother for a batch of work items on the GPU.
+class PreparedPF(object):
+    """A packed batch: host staging buffer filled, descriptor built.  `upload()` issues the single
+    H2D copy, `launch()` calls sgm_pf_run on the current stream (re-launchable: the bench times
+    launches with inputs resident in HBM), `download()` issues the single D2H copy."""
+
+    def __init__(self, model, kernel, pf, items, N, dtype=None, rng=None, resample=None, stat_kind="score",
+                 lambduh=None, Ntilde=2, accept_reject=True, max_accept_reject=None,
+                 manual_sample_threshold=None, seed=None, offset=None, item_id_base=0, injected=None,
+                 want=(), device=None):
+        lib = self.lib = nat.load()
+        device = self.device = _device(device)
+        st = self.st = _state(device)
+        dtype = dtype or config.dtype
+        rng = rng or config.rng
+        resample = resample or config.resample
+        if pf not in nat.PF:
+            raise ValueError("Unrecognized pf = {0}".format(pf))
+        if lambduh is None:
+            lambduh = 0.95                                           # pf.py:140
+        if pf == "poyiadjis_N":
+            lambduh = 1.0                                            # buffered_smoother.py:175-180
+        B = self.B = len(items)
+        if B == 0:
+            raise ValueError("empty batch")
+        N = self.N = int(N)
+        model_id, kernel_id = nat.MODEL[model], nat.KERNEL[kernel]
+        self.p = lib.sgm_stat_dim(model_id, nat.STAT[stat_kind])
+        self.n = n = lib.sgm_state_dim(model_id)
+        NPrec = lib.sgm_stat_dim(model_id, 0)
+        T_buf = self.T_buf = np.array([o.shape[0] for o in items.obs], dtype=np.int32)
+        max_T = self.max_T = int(T_buf.max())
+        t_real = torch.float64 if dtype == "f64" else torch.float32
+
+        # ---- layout of the packed host buffer ----------------------------------------------------
+        obs_off = np.zeros(B, dtype=np.int64)
+        obs_off[1:] = np.cumsum(T_buf[:-1])
+        n_obs = int(T_buf.sum())
+        has_w = any(w is not None for w in items.weights)
+        wts_off = np.full(B, -1, dtype=np.int64)
+        wlen = 0
+        if has_w:
+            for b, w in enumerate(items.weights):
+                if w is not None:
+                    wts_off[b] = wlen
+                    wlen += w.shape[0]
+        sections = [("obs", n_obs * 8), ("wts", max(wlen, 1) * 8), ("theta", B * nat.THETA_STRIDE * 8),
+                    ("prior_mean", B * 8), ("prior_var", B * 8), ("obs_off", B * 8), ("wts_off", B * 8),
+                    ("T_buf", B * 4), ("t1", B * 4), ("tL", B * 4)]
+        offs, tot = {}, 0
+        for name, nb in sections:
+            offs[name] = tot
+            tot = _align(tot + nb, 16)
+        self.in_bytes, self.out_bytes = tot, B * 76 + 64
+
+        desc = self.desc = nat.SgmPfDesc()
+        desc.struct_bytes = ctypes.sizeof(nat.SgmPfDesc)
+        desc.model, desc.kernel, desc.pf, desc.dtype = model_id, kernel_id, nat.PF[pf], nat.DTYPE[dtype]
+        desc.rng_mode, desc.resample, desc.stat_kind = nat.RNG[rng], nat.RESAMPLE[resample], nat.STAT[stat_kind]
+        desc.n_items, desc.n_particles, desc.max_T = B, N, max_T
+        desc.Ntilde, desc.accept_reject = int(Ntilde), int(bool(accept_reject))
+        desc.max_accept_reject = -1 if max_accept_reject is None else int(max_accept_reject)
+        desc.manual_sample_threshold = -1 if manual_sample_threshold is None else int(manual_sample_threshold)
+        desc.item_id_base = int(item_id_base)
+        desc.lambduh = float(lambduh)
+        if seed is None or offset is None:
+            s_, o_ = _next_seed_offset()
+            seed = s_ if seed is None else seed
+            offset = o_ if offset is None else offset
+        desc.seed, desc.offset = int(seed) & (2 ** 64 - 1), int(offset)
+
+        with torch.cuda.device(device):
+            extra = self.extra = {}
+
+            def opt(name, shape, tdtype):
+                if name in want:
+                    extra[name] = torch.empty(shape, dtype=tdtype, device=device)
+                    return extra[name].data_ptr()
+                return None
+
+            desc.out_x = opt("x", (B, N, n), t_real)
+            desc.out_lw = opt("lw", (B, N), t_real)
+            desc.out_stats = opt("stats", (B, N, NPrec), t_real)       # record width
+            desc.trace_anc = opt("anc", (B, max_T, N), torch.int32)
+            desc.trace_x = opt("trace_x", (B, max_T + 1, N, n), t_real)
+            desc.trace_lw = opt("trace_lw", (B, max_T + 1, N), t_real)
+            desc.trace_J = opt("J", (B, max_T, N, int(Ntilde)), torch.int32)
+
+            keep = self.keep = []
+            if rng == "injected":
+                if injected is None:
+                    raise ValueError("rng='injected' needs the recorded randoms")
+
+                def dev64(a, shape):
+                    a = np.ascontiguousarray(np.asarray(a, dtype=np.float64)).reshape(shape)
+                    tns = torch.from_numpy(a).to(device)
+                    keep.append(tns)
+                    return tns.data_ptr()
+
+                desc.inj_z0 = dev64(injected["z0"], (B, N))
+                desc.inj_u = dev64(injected["u"], (B, max_T, N))
+                desc.inj_z = dev64(injected["z"], (B, max_T, N))
+                if injected.get("extra") is not None:
+                    flat = np.concatenate([np.asarray(e, dtype=np.float64).ravel() for e in injected["extra"]] + [np.zeros(1)])
+                    lens = np.array([np.asarray(e).size for e in injected["extra"]], dtype=np.int64)
+                    eoff = np.zeros(B * max_T, dtype=np.int64)
+                    eoff[1:] = np.cumsum(lens)[:-1]
+                    desc.inj_extra = dev64(flat, (-1,))
+                    toff = torch.from_numpy(eoff).to(device)
+                    keep.append(toff)
+                    desc.inj_extra_off = toff.data_ptr()
+
+            # workspace size depends on the scalar fields and on which optional outputs are set
+            desc.obs = desc.obs_off = desc.T_buf = desc.t1 = desc.tL = desc.theta = desc.prior_mean = desc.prior_var = 1
+            desc.grad = desc.loglik = desc.status = 1
+            ws_bytes = self.ws_bytes = int(lib.sgm_pf_workspace_bytes(ctypes.byref(desc)))
+            if ws_bytes == 0:
+                nat.check(lib.sgm_pf_run(ctypes.byref(desc), None) or -1)
+            st.buffers(ws_bytes, self.in_bytes, self.out_bytes)
+
+            host = st.pin_in.numpy()
+
+            def view(name, dt, count):
+                return host[offs[name]:offs[name] + count * np.dtype(dt).itemsize].view(dt)
+
+            view("obs", np.float64, n_obs)[:] = np.concatenate(items.obs)
+            if has_w:
+                view("wts", np.float64, wlen)[:] = np.concatenate([w for w in items.weights if w is not None])
+            view("theta", np.float64, B * nat.THETA_STRIDE)[:] = np.concatenate(items.theta)
+            view("prior_mean", np.float64, B)[:] = items.prior_mean
+            view("prior_var", np.float64, B)[:] = items.prior_var
+            view("obs_off", np.int64, B)[:] = obs_off
+            view("wts_off", np.int64, B)[:] = wts_off
+            view("T_buf", np.int32, B)[:] = T_buf
+            view("t1", np.int32, B)[:] = items.t1
+            view("tL", np.int32, B)[:] = items.tL
+
+            base_in = self.base_in = _aligned_ptr(st.dev_in)
+            for name in ("obs", "theta", "prior_mean", "prior_var", "obs_off", "wts_off", "T_buf", "t1", "tL"):
+                setattr(desc, name, base_in + offs[name])
+            desc.step_weights = (base_in + offs["wts"]) if has_w else None
+            base_out = self.base_out = _aligned_ptr(st.dev_out)
+            desc.grad, desc.loglik, desc.status = base_out, base_out + B * 64, base_out + B * 72
+            desc.workspace = _aligned_ptr(st.workspace)
+            desc.workspace_bytes = ws_bytes
+        self.launches = 0
+        self.particle_steps = int(N) * int(T_buf.sum())
+
+    def upload(self):
+        st = self.st
+        with torch.cuda.device(self.device):
+            sh = self.base_in - st.dev_in.data_ptr()
+            st.dev_in[sh:sh + self.in_bytes].copy_(st.pin_in[:self.in_bytes], non_blocking=True)
+        return self
+
+    def launch(self, offset=None, step_events=None):
+        """sgm_pf_run on the current stream.  step_events = (begin, end) torch events recorded around
+        the step-kernel launches (they must have been recorded once so their handles exist)."""
+        if offset is not None:
+            self.desc.offset = int(offset)
+        if step_events is not None:
+            self.desc.ev_steps_begin, self.desc.ev_steps_end = step_events[0].cuda_event, step_events[1].cuda_event
+        else:
+            self.desc.ev_steps_begin = self.desc.ev_steps_end = None
+        with torch.cuda.device(self.device):
+            stream = torch.cuda.current_stream(self.device)
+            nat.check(self.lib.sgm_pf_run(ctypes.byref(self.desc), ctypes.c_void_p(stream.cuda_stream)))
+        self.launches = int(self.lib.sgm_last_launch_count())
+        return self
+
+    def download(self):
+        st = self.st
+        with torch.cuda.device(self.device):
+            stream = torch.cuda.current_stream(self.device)
+            so = self.base_out - st.dev_out.data_ptr()
+            st.pin_out[:self.out_bytes].copy_(st.dev_out[so:so + self.out_bytes], non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(stream)
+        return PFResult(B=self.B, N=self.N, p=self.p, n=self.n, max_T=self.max_T, T_buf=self.T_buf, _event=ev,
+                        _pin_out=st.pin_out, _extra=self.extra, _keep=self.keep, launches=self.launches,
+                        h2d_bytes=self.in_bytes, d2h_bytes=self.out_bytes, particle_steps=self.particle_steps,
+                        ws_bytes=self.ws_bytes)
+
+
+def run_pf(model, kernel, pf, items, N, sync=True, check=True, **kwargs):
+    """Run the buffered particle filter / smoother for a batch of work items on the GPU: pack, one H2D
+    copy, the whole t-loop through the C-ABI, one D2H copy.
 
     Mirrors particle_filters/buffered_smoother.py:156-199 (`pf` dispatch) for a whole batch.
-    Returns a PFResult with .grad (B, p), .loglik (B,), .status (B,).
-    """
-    lib = nat.load()
-    device = _device(device)
-    st = _state(device)
-    dtype = dtype or config.dtype
-    rng = rng or config.rng
-    resample = resample or config.resample
-    if pf not in nat.PF:
-        raise ValueError("Unrecognized pf = {0}".format(pf))
-    if lambduh is None:
-        lambduh = 1.0 if pf == "poyiadjis_N" else 0.95          # buffered_smoother.py:175-180, pf.py:140
-    if pf == "poyiadjis_N":
-        lambduh = 1.0
-    B = len(items)
-    if B == 0:
-        raise ValueError("empty batch")
-    N = int(N)
-    model_id, kernel_id = nat.MODEL[model], nat.KERNEL[kernel]
-    p = lib.sgm_stat_dim(model_id, nat.STAT[stat_kind])
-    n = lib.sgm_state_dim(model_id)
-    T_buf = np.array([o.shape[0] for o in items.obs], dtype=np.int32)
-    max_T = int(T_buf.max())
-    np_real = np.float64 if dtype == "f64" else np.float32
-    t_real = torch.float64 if dtype == "f64" else torch.float32
-
-    # ---- pack the host buffer ------------------------------------------------------------------
-    obs_off = np.zeros(B, dtype=np.int64)
-    obs_off[1:] = np.cumsum(T_buf[:-1])
-    n_obs = int(T_buf.sum())
-    has_w = any(w is not None for w in items.weights)
-    wts_off = np.full(B, -1, dtype=np.int64)
-    wlen = 0
-    if has_w:
-        for b, w in enumerate(items.weights):
-            if w is not None:
-                wts_off[b] = wlen
-                wlen += w.shape[0]
-    sections = [("obs", n_obs * 8), ("wts", max(wlen, 1) * 8), ("theta", B * nat.THETA_STRIDE * 8),
-                ("prior_mean", B * 8), ("prior_var", B * 8), ("obs_off", B * 8), ("wts_off", B * 8),
-                ("T_buf", B * 4), ("t1", B * 4), ("tL", B * 4)]
-    offs, tot = {}, 0
-    for name, nb in sections:
-        offs[name] = tot
-        tot = _align(tot + nb, 16)
-    in_bytes, out_bytes = tot, B * 76 + 64
-
-    desc = nat.SgmPfDesc()
-    desc.struct_bytes = ctypes.sizeof(nat.SgmPfDesc)
-    desc.model, desc.kernel, desc.pf, desc.dtype = model_id, kernel_id, nat.PF[pf], nat.DTYPE[dtype]
-    desc.rng_mode, desc.resample, desc.stat_kind = nat.RNG[rng], nat.RESAMPLE[resample], nat.STAT[stat_kind]
-    desc.n_items, desc.n_particles, desc.max_T = B, N, max_T
-    desc.Ntilde, desc.accept_reject = int(Ntilde), int(bool(accept_reject))
-    desc.max_accept_reject = -1 if max_accept_reject is None else int(max_accept_reject)
-    desc.manual_sample_threshold = -1 if manual_sample_threshold is None else int(manual_sample_threshold)
-    desc.item_id_base = int(item_id_base)
-    desc.lambduh = float(lambduh)
-    if seed is None or offset is None:
-        s, o = _next_seed_offset()
-        seed = s if seed is None else seed
-        offset = o if offset is None else offset
-    desc.seed, desc.offset = int(seed) & (2 ** 64 - 1), int(offset)
-
-    with torch.cuda.device(device):
-        extra = {}
-
-        def opt(name, shape, tdtype):
-            if name in want:
-                extra[name] = torch.empty(shape, dtype=tdtype, device=device)
-                return extra[name].data_ptr()
-            return None
-
-        desc.out_x = opt("x", (B, N, n), t_real)
-        desc.out_lw = opt("lw", (B, N), t_real)
-        desc.out_stats = opt("stats", (B, N, lib.sgm_stat_dim(model_id, 0)), t_real)   # record width
-        desc.trace_anc = opt("anc", (B, max_T, N), torch.int32)
-        desc.trace_x = opt("trace_x", (B, max_T + 1, N, n), t_real)
-        desc.trace_lw = opt("trace_lw", (B, max_T + 1, N), t_real)
-        desc.trace_J = opt("J", (B, max_T, N, int(Ntilde)), torch.int32)
-        keep = []
-        if rng == "injected":
-            if injected is None:
-                raise ValueError("rng='injected' needs the recorded randoms")
-
-            def dev64(a, shape):
-                a = np.ascontiguousarray(np.asarray(a, dtype=np.float64)).reshape(shape)
-                tns = torch.from_numpy(a).to(device)
-                keep.append(tns)
-                return tns.data_ptr()
-
-            desc.inj_z0 = dev64(injected["z0"], (B, N))
-            desc.inj_u = dev64(injected["u"], (B, max_T, N))
-            desc.inj_z = dev64(injected["z"], (B, max_T, N))
-            if "extra" in injected and injected["extra"] is not None:
-                flat = np.concatenate([np.asarray(e, dtype=np.float64).ravel() for e in injected["extra"]] + [np.zeros(1)])
-                lens = np.array([np.asarray(e).size for e in injected["extra"]], dtype=np.int64)
-                eoff = np.zeros(B * max_T, dtype=np.int64)
-                eoff[1:] = np.cumsum(lens)[:-1]
-                desc.inj_extra = dev64(flat, (-1,))
-                toff = torch.from_numpy(eoff).to(device)
-                keep.append(toff)
-                desc.inj_extra_off = toff.data_ptr()
-
-        # workspace size needs only the scalar fields (+ which optional outputs are set)
-        desc.obs = desc.obs_off = desc.T_buf = desc.t1 = desc.tL = desc.theta = desc.prior_mean = desc.prior_var = 1
-        desc.grad = desc.loglik = desc.status = 1
-        ws_bytes = lib.sgm_pf_workspace_bytes(ctypes.byref(desc))
-        if ws_bytes == 0:
-            nat.check(lib.sgm_pf_run(ctypes.byref(desc), None) or -1)
-        st.buffers(ws_bytes, in_bytes, out_bytes)
-
-        host = st.pin_in.numpy()
-
-        def view(name, dt, count):
-            return host[offs[name]:offs[name] + count * np.dtype(dt).itemsize].view(dt)
-
-        view("obs", np.float64, n_obs)[:] = np.concatenate(items.obs)
-        if has_w:
-            view("wts", np.float64, wlen)[:] = np.concatenate([w for w in items.weights if w is not None])
-        view("theta", np.float64, B * nat.THETA_STRIDE)[:] = np.concatenate(items.theta)
-        view("prior_mean", np.float64, B)[:] = items.prior_mean
-        view("prior_var", np.float64, B)[:] = items.prior_var
-        view("obs_off", np.int64, B)[:] = obs_off
-        view("wts_off", np.int64, B)[:] = wts_off
-        view("T_buf", np.int32, B)[:] = T_buf
-        view("t1", np.int32, B)[:] = items.t1
-        view("tL", np.int32, B)[:] = items.tL
-
-        base_in = _aligned_ptr(st.dev_in)
-        sh = base_in - st.dev_in.data_ptr()
-        st.dev_in[sh:sh + in_bytes].copy_(st.pin_in[:in_bytes], non_blocking=True)
-        for name in ("obs", "theta", "prior_mean", "prior_var", "obs_off", "wts_off", "T_buf", "t1", "tL"):
-            setattr(desc, name, base_in + offs[name])
-        desc.step_weights = (base_in + offs["wts"]) if has_w else None
-        base_out = _aligned_ptr(st.dev_out)
-        desc.grad, desc.loglik, desc.status = base_out, base_out + B * 64, base_out + B * 72
-        desc.workspace = _aligned_ptr(st.workspace)
-        desc.workspace_bytes = ws_bytes
-
-        stream = torch.cuda.current_stream(device)
-        nat.check(lib.sgm_pf_run(ctypes.byref(desc), ctypes.c_void_p(stream.cuda_stream)))
-        launches = int(lib.sgm_last_launch_count())
-        so = base_out - st.dev_out.data_ptr()
-        st.pin_out[:out_bytes].copy_(st.dev_out[so:so + out_bytes], non_blocking=True)
-        ev = torch.cuda.Event()
-        ev.record(stream)
-
-    res = PFResult(B=B, N=N, p=p, n=n, max_T=max_T, T_buf=T_buf, _event=ev, _pin_out=st.pin_out, _extra=extra,
-                   _keep=keep, launches=launches, h2d_bytes=in_bytes, d2h_bytes=out_bytes,
-                   particle_steps=int(N) * int(T_buf.sum()), ws_bytes=int(ws_bytes))
+    Returns a PFResult with .grad (B, p), .loglik (B,), .status (B,).  One call may be outstanding per
+    device (staging buffers are shared)."""
+    res = PreparedPF(model, kernel, pf, items, N, **kwargs).upload().launch().download()
     if sync:
         res.wait(check=check)
     return res

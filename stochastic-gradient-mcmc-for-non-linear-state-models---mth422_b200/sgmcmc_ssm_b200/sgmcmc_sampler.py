@@ -182,11 +182,26 @@ class SGMCMCSampler(object):
         windows = self._pf_windows(subsequence_length, minibatch_size, buffer_length, observations, buffer_dicts)
         if kwargs.get("N", None) is None:
             kwargs["N"] = num_samples
-        grads, _ = self.message_helper.pf_gradient_estimate_batch(windows, self.parameters, **kwargs)
         noisy_grad = {var: np.zeros_like(value) for var, value in self.parameters.as_dict().items()}
-        for g in grads:
-            for var in noisy_grad:
-                noisy_grad[var] += g[var] * 1.0 / minibatch_size
+        if kwargs.pop("distributed", False):
+            # every rank holds the same sampler state and numpy stream, hence the same windows; rank r
+            # filters its contiguous shard and ONE all-reduce sums the per-rank gradient sums
+            from . import parallel
+            lo, hi = parallel.shard_bounds(len(windows))
+            keys = list(noisy_grad)
+            local = np.zeros(len(keys))
+            if hi > lo:
+                grads, _ = self.message_helper.pf_gradient_estimate_batch(
+                    windows[lo:hi], self.parameters, item_id_base=lo, **kwargs)
+                local = np.array([sum(float(np.ravel(g[k])[0]) for g in grads) for k in keys])
+            total = parallel.allreduce_sum(local)
+            for k, v in zip(keys, total):
+                noisy_grad[k] += v / minibatch_size
+        else:
+            grads, _ = self.message_helper.pf_gradient_estimate_batch(windows, self.parameters, **kwargs)
+            for g in grads:
+                for var in noisy_grad:
+                    noisy_grad[var] += g[var] * 1.0 / minibatch_size
         for var in noisy_grad:
             if np.any(np.isnan(noisy_grad[var])):
                 raise ValueError("NaNs in gradient of {0}".format(var))
