@@ -39,7 +39,7 @@ __global__ void __launch_bounds__(NT) poyiadjis_n2_kernel(KArgs a, int t) {
     const size_t item_off = (size_t)b * N;
     const int i = blockIdx.x * NT + tid;
     const bool valid = i < N;
-    const typename Model::template Theta<R> th = Model::template load<R>(a.theta + (size_t)b * SGM_THETA_STRIDE);
+    const typename Model::template Theta<R> th = load_thc<R, Model>(a, b);
     const R y = (R)a.obs[a.obs_off[b] + t];
     const bool in_sub = (t >= a.t1[b]) && (t < a.tL[b]);
     const R wt = in_sub ? ((a.wts_off && a.wts_off[b] >= 0) ? (R)a.step_weights[a.wts_off[b] + (t - a.t1[b])] : (R)1) : (R)0;
@@ -200,7 +200,8 @@ __global__ void __launch_bounds__(NT) paris_ar_kernel(KArgs a, int t) {
     const int N = a.N, G = a.G, par = t & 1;
     const size_t item_off = (size_t)b * N;
     build_cdf_header(a.part[par] + (size_t)b * G * PSTRIDE, G, 0, hdr);
-    const typename Model::template Theta<R> th = Model::template load<R>(a.theta + (size_t)b * SGM_THETA_STRIDE);
+    __syncthreads();
+    const typename Model::template Theta<R> th = load_thc<R, Model>(a, b);
     const R ltmax = Model::log_trans_max(th);
     const R* fine_old = reinterpret_cast<const R*>(a.fine[par]) + item_off;
     RngKey key = a.key; key.item += (uint32_t)b;
@@ -240,7 +241,7 @@ __global__ void __launch_bounds__(NT) paris_exact_kernel(KArgs a, int t) {
     const size_t item_off = (size_t)b * N;
     const int count = a.counters[b * 16];
     if (count > 0 && blockIdx.x == 0 && threadIdx.x == 0 && a.accept_reject) a.status[b] |= SGM_STATUS_AR_OVERFLOW;
-    const typename Model::template Theta<R> th = Model::template load<R>(a.theta + (size_t)b * SGM_THETA_STRIDE);
+    const typename Model::template Theta<R> th = load_thc<R, Model>(a, b);
     RngKey key = a.key; key.item += (uint32_t)b;
     for (int e = blockIdx.x; e < count; e += gridDim.x) {
         const int entry = a.Llist[0][item_off * a.Ntilde + e];
@@ -267,7 +268,8 @@ __global__ void __launch_bounds__(NT) paris_injected_kernel(KArgs a, int t) {
     const int N = a.N, G = a.G, par = t & 1, Nt = a.Ntilde;
     const size_t item_off = (size_t)b * N;
     build_cdf_header(a.part[par] + (size_t)b * G * PSTRIDE, G, 0, hdr);
-    const typename Model::template Theta<R> th = Model::template load<R>(a.theta + (size_t)b * SGM_THETA_STRIDE);
+    __syncthreads();
+    const typename Model::template Theta<R> th = load_thc<R, Model>(a, b);
     const R ltmax = Model::log_trans_max(th);
     const R* fine_old = reinterpret_cast<const R*>(a.fine[par]) + item_off;
     const double* extra = a.inj_extra + a.inj_extra_off[(size_t)b * a.max_T + t];
@@ -340,7 +342,7 @@ __global__ void __launch_bounds__(NT) paris_update_kernel(KArgs a, int t) {
     const int i = blockIdx.x * NT + tid;
     if (blockIdx.x == 0 && tid == 0) a.counters[b * 16] = 0;
     if (i >= N) return;
-    const typename Model::template Theta<R> th = Model::template load<R>(a.theta + (size_t)b * SGM_THETA_STRIDE);
+    const typename Model::template Theta<R> th = load_thc<R, Model>(a, b);
     const R y = (R)a.obs[a.obs_off[b] + t];
     const bool in_sub = (t >= a.t1[b]) && (t < a.tL[b]);
     const R wt = in_sub ? ((a.wts_off && a.wts_off[b] >= 0) ? (R)a.step_weights[a.wts_off[b] + (t - a.t1[b])] : (R)1) : (R)0;

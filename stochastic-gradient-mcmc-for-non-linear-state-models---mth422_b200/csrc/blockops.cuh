@@ -23,15 +23,17 @@ template <class T> __device__ __forceinline__ T warp_sum(T v) {
     for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(FULL, v, d);
     return v;
 }
-__device__ __forceinline__ float nan_max(float a, float b) { return (a != a || b != b) ? (a + b) : fmaxf(a, b); }
-__device__ __forceinline__ double nan_max(double a, double b) { return (a != a || b != b) ? (a + b) : fmax(a, b); }
+// NaN handling: fmax drops NaNs, which is fine here -- a NaN (or +inf) log-weight still poisons the tile
+// sum through exp(lw - m), and the degenerate-weight status flag is raised from the sum.
+__device__ __forceinline__ float nan_max(float a, float b) { return fmaxf(a, b); }
+__device__ __forceinline__ double nan_max(double a, double b) { return fmax(a, b); }
 template <class T> __device__ __forceinline__ T warp_max(T v) {
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) v = nan_max(v, __shfl_xor_sync(FULL, v, d));
     return v;
 }
 
-// Block max (NaN-propagating).  `sh` needs NWARP elements.  Result valid in all threads.
+// Block max.  `sh` needs NWARP elements.  Result valid in all threads.
 template <class T> __device__ __forceinline__ T block_max(T v, T* sh) {
     v = warp_max(v);
     __syncthreads();                      // protect sh from a previous use

@@ -9,10 +9,20 @@ namespace sgm {
 
 template <class R> struct Mth;
 template <> struct Mth<float> {
-    static __device__ __forceinline__ float exp(float x) { return __expf(x); }
-    static __device__ __forceinline__ float log(float x) { return __logf(x); }
-    static __device__ __forceinline__ float sqrt(float x) { return sqrtf(x); }
-    static __device__ __forceinline__ float rcp(float x) { return __frcp_rn(x); }
+    // single MUFU instructions (flush-to-zero, ~2 ulp): the f32 path is the throughput path; the f64
+    // instantiation below is the parity path
+    static __device__ __forceinline__ float exp(float x) {
+        float r; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x * 1.4426950408889634f)); return r;
+    }
+    static __device__ __forceinline__ float log(float x) {
+        float r; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r * 0.6931471805599453f;
+    }
+    static __device__ __forceinline__ float sqrt(float x) {
+        float r; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r;
+    }
+    static __device__ __forceinline__ float rcp(float x) {
+        float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r;
+    }
     static __device__ __forceinline__ float inf() { return __int_as_float(0x7f800000); }
 };
 template <> struct Mth<double> {
@@ -31,7 +41,7 @@ constexpr double LOG_2PI_D = 1.8378770664093453;
 template <class R> struct GaussTheta {
     R A, LQinv, Qinv, C, LRinv, Rinv;
     R invLQ, invLR, logLQinv, logLRinv;     // LQinv**-1, LRinv**-1, log LQinv, log LRinv
-    R opt_sd, opt_iprec, opt_var, opt_lvar; // LGSSM optimal kernel: prec**-0.5, 1/prec, 1/Qinv+1/Rinv, log of it
+    R opt_sd, opt_iprec, opt_ivar, opt_lvar; // LGSSM optimal kernel: prec**-0.5, 1/prec, 1/(1/Qinv+1/Rinv), log(1/Qinv+1/Rinv)
 };
 
 struct SvmPrior {
@@ -41,7 +51,7 @@ struct SvmPrior {
         Theta<R> t;   // theta: A, LQinv, Qinv, LRinv, Rinv
         t.A = (R)th[0]; t.LQinv = (R)th[1]; t.Qinv = (R)th[2]; t.LRinv = (R)th[3]; t.Rinv = (R)th[4]; t.C = (R)1;
         t.invLQ = (R)(1.0 / th[1]); t.invLR = (R)(1.0 / th[3]); t.logLQinv = (R)::log(th[1]); t.logLRinv = (R)::log(th[3]);
-        t.opt_sd = t.opt_iprec = t.opt_var = t.opt_lvar = (R)0;
+        t.opt_sd = t.opt_iprec = t.opt_ivar = t.opt_lvar = (R)0;
         return t;
     }
     // svm/kernels.py:34-37
@@ -93,7 +103,7 @@ struct LgssmPrior {
         t.invLQ = (R)(1.0 / th[1]); t.invLR = (R)(1.0 / th[4]); t.logLQinv = (R)::log(th[1]); t.logLRinv = (R)::log(th[4]);
         const double prec = th[2] + th[3] * th[3] * th[5];          // lgssm/kernels.py:91-93
         const double var = 1.0 / th[2] + 1.0 / th[5];                // lgssm/kernels.py:118
-        t.opt_sd = (R)(1.0 / ::sqrt(prec)); t.opt_iprec = (R)(1.0 / prec); t.opt_var = (R)var; t.opt_lvar = (R)::log(var);
+        t.opt_sd = (R)(1.0 / ::sqrt(prec)); t.opt_iprec = (R)(1.0 / prec); t.opt_ivar = (R)(1.0 / var); t.opt_lvar = (R)::log(var);
         return t;
     }
     // lgssm/kernels.py:29-33
@@ -135,7 +145,7 @@ struct LgssmOptimal : LgssmPrior {
     // lgssm/kernels.py:117-120 (ignores C, as the reference does)
     template <class R> static __device__ __forceinline__ R log_weight(const Theta<R>& t, const R* xa, const R* xn, R y) {
         const R d = y - t.A * xa[0];
-        return (R)-0.5 * (d * d) / t.opt_var - (R)(0.5 * LOG_2PI_D) - (R)0.5 * t.opt_lvar;
+        return (R)-0.5 * (d * d) * t.opt_ivar - (R)(0.5 * LOG_2PI_D) - (R)0.5 * t.opt_lvar;
     }
 };
 
@@ -174,7 +184,8 @@ struct GarchPrior {
     // garch/helper.py:350-372 ; order [dLRinv, dlog_mu, dlogit_phi, dlogit_lambduh]
     template <class R> static __device__ __forceinline__ void score(const Theta<R>& t, const R* xa, const R* xn, R y, R* h) {
         const R v = xn[1];
-        const R gv = (R)-0.5 * (v - xn[0] * xn[0]) / (v * v);
+        const R iv = Mth<R>::rcp(v);
+        const R gv = (R)-0.5 * (v - xn[0] * xn[0]) * (iv * iv);
         const R xa2 = xa[0] * xa[0];
         h[1] = gv * ((R)1 - t.phi) * t.mu;
         h[2] = gv * (-t.mu + t.lam * xa2 + ((R)1 - t.lam) * xa[1]) * ((R)1 - t.phi) * t.phi;
@@ -185,12 +196,12 @@ struct GarchPrior {
     // garch/kernels.py:28-34 : sigma2 from the candidate parent
     template <class R> static __device__ __forceinline__ R log_trans(const Theta<R>& t, const R* xa, const R* xn) {
         const R s2 = sigma2_next(t, xa);
-        return (R)-0.5 * (xn[0] * xn[0]) / s2 - (R)(0.5 * LOG_2PI_D) - (R)0.5 * Mth<R>::log(s2);
+        return (R)-0.5 * (xn[0] * xn[0]) * Mth<R>::rcp(s2) - (R)(0.5 * LOG_2PI_D) - (R)0.5 * Mth<R>::log(s2);
     }
     template <class R> static __device__ __forceinline__ R log_trans_max(const Theta<R>& t) { return t.ltmax; }
     template <class R> static __device__ __forceinline__ void jkey(const Theta<R>& t, const R* xa, R* k) {
         const R s2 = sigma2_next(t, xa);
-        k[0] = (R)1 / s2; k[1] = -(R)(0.5 * LOG_2PI_D) - (R)0.5 * Mth<R>::log(s2);
+        k[0] = Mth<R>::rcp(s2); k[1] = -(R)(0.5 * LOG_2PI_D) - (R)0.5 * Mth<R>::log(s2);
     }
     template <class R> static __device__ __forceinline__ R log_trans_key(const Theta<R>& t, const R* k, const R* xn) {
         return (R)-0.5 * (xn[0] * xn[0]) * k[0] + k[1];
@@ -208,7 +219,7 @@ struct GarchOptimal : GarchPrior {
     // garch/kernels.py:147-158
     template <class R> static __device__ __forceinline__ void propagate(const Theta<R>& t, const R* xa, R y, R z, R* xn) {
         const R s2 = sigma2_next(t, xa);
-        const R var = (R)1 / (t.Rinv + (R)1 / s2);
+        const R var = Mth<R>::rcp(t.Rinv + Mth<R>::rcp(s2));
         const R mean = var * (y * t.Rinv);
         xn[0] = mean + Mth<R>::sqrt(var) * z;
         xn[1] = s2;
@@ -216,7 +227,7 @@ struct GarchOptimal : GarchPrior {
     // garch/kernels.py:172-180
     template <class R> static __device__ __forceinline__ R log_weight(const Theta<R>& t, const R* xa, const R* xn, R y) {
         const R var = xn[1] + t.Rv;
-        return (R)(-0.5 * LOG_2PI_D) + (R)-0.5 * (y * y) / var + (R)-0.5 * Mth<R>::log(var);
+        return (R)(-0.5 * LOG_2PI_D) + (R)-0.5 * (y * y) * Mth<R>::rcp(var) + (R)-0.5 * Mth<R>::log(var);
     }
 };
 

@@ -26,6 +26,7 @@ constexpr int MAX_TILES = 512;         // N <= 2^20
 constexpr int CAP = 4096;              // parents staged in shared memory per CTA (sorted resampling)
 constexpr int PSTRIDE = 8;             // doubles per `part` entry
 constexpr int ACC_STRIDE = 8;          // doubles per `acc` entry
+constexpr int THC_BYTES = 128;         // per-item slot for the model's derived constants
 
 struct KArgs {
     int B, N, G, max_T;
@@ -40,6 +41,8 @@ struct KArgs {
     void* rec[2]; void* tail[2]; void* fine[2]; void* lw[2]; double* part[2]; double* acc;
     int32_t* Jidx; int32_t* Llist[2]; int32_t* counters;
     const double* gam;     // [B][max_T][G + 2] exclusive prefix of per-tile Gamma draws (sorted multinomial)
+    char* thc;             // [B][THC_BYTES]   Model::Theta<R> (derived constants) written by the init kernel
+    void* yw;              // [B][max_T][2] R  (y_t, statistic weight of step t: w_t inside [t1, tL), else 0)
     double* grad; double* loglik; int32_t* status;
     void* out_x; void* out_lw; void* out_stats; int32_t* trace_anc; void* trace_x; void* trace_lw; int32_t* trace_J;
 };
@@ -69,7 +72,7 @@ struct CdfHeader {
     double sbar[4];
 };
 
-// Built by warp 0 with shuffles only (one block barrier at the end).  hdr.sbar[k] receives
+// Built by warp 0 with shuffles only; the CALLER issues the __syncthreads() that publishes it.  hdr.sbar[k] receives
 // sum_g e_g * ws_g[k] / total for k < nws.  Fixed summation order -> deterministic.
 __device__ __forceinline__ void build_cdf_header(const double* __restrict__ part, int G, int nws, CdfHeader& hdr) {
     if (threadIdx.x < 32) {
@@ -97,7 +100,6 @@ __device__ __forceinline__ void build_cdf_header(const double* __restrict__ part
         }
         if (lane == 0) { hdr.coarse[G] = carry; hdr.M = M; hdr.total = carry; }
     }
-    __syncthreads();
 }
 
 // tile g with coarse[g] <= target < coarse[g + 1]  (branch-free, CTA-uniform trip count)
@@ -159,7 +161,8 @@ __device__ __forceinline__ void tile_epilogue(const R* lwn, int i0, int N, R* fi
     R w[KPT], run = (R)0;
 #pragma unroll
     for (int c = 0; c < KPT; ++c) {
-        w[c] = (i0 + c < N) ? ((m == -Mth<R>::inf()) ? (R)0 : Mth<R>::exp(lwn[c] - m)) : (R)0;
+        // m == -inf: every weight of the tile is zero (or NaN: keep the NaN so that the item is flagged)
+        w[c] = (i0 + c < N) ? ((m == -Mth<R>::inf()) ? ((lwn[c] != lwn[c]) ? lwn[c] : (R)0) : Mth<R>::exp(lwn[c] - m)) : (R)0;
         run += w[c];
     }
     R total;
@@ -234,11 +237,30 @@ __global__ void __launch_bounds__(NT) pf_init_kernel(KArgs a) {
     tile_epilogue<R, W, NP>(lwn, i0, N, reinterpret_cast<R*>(a.fine[0]) + item_off,
                             a.part[0] + ((size_t)b * a.G + g) * PSTRIDE, a.rec[0], a.tail[0], item_off,
                             false, 0, sh_r, sh_d);
-    if (g == 0 && tid == 0) {
-        for (int q = 0; q < ACC_STRIDE; ++q) a.acc[(size_t)b * ACC_STRIDE + q] = 0.0;
-        a.status[b] = 0;
-        if (a.counters) a.counters[b * 16] = 0;
+    if (g == 0) {
+        // per-item derived constants and per-step (observation, statistic weight) pairs, read by every
+        // later kernel with one vector load instead of pointer chasing + double-precision log / div
+        const int Tb = a.T_buf[b];
+        for (int t = tid; t < Tb; t += NT) {
+            const bool in_sub = (t >= a.t1[b]) && (t < a.tL[b]);
+            const double wt = in_sub ? ((a.wts_off && a.wts_off[b] >= 0) ? a.step_weights[a.wts_off[b] + (t - a.t1[b])] : 1.0) : 0.0;
+            R* yw = reinterpret_cast<R*>(a.yw) + ((size_t)b * a.max_T + t) * 2;
+            yw[0] = (R)a.obs[a.obs_off[b] + t];
+            yw[1] = (R)wt;
+        }
+        if (tid == 0) {
+            *reinterpret_cast<typename Model::template Theta<R>*>(a.thc + (size_t)b * THC_BYTES) =
+                Model::template load<R>(a.theta + (size_t)b * SGM_THETA_STRIDE);
+            for (int q = 0; q < ACC_STRIDE; ++q) a.acc[(size_t)b * ACC_STRIDE + q] = 0.0;
+            a.status[b] = 0;
+            if (a.counters) a.counters[b * 16] = 0;
+        }
     }
+}
+
+template <class R, class Model>
+__device__ __forceinline__ typename Model::template Theta<R> load_thc(const KArgs& a, int b) {
+    return *reinterpret_cast<const typename Model::template Theta<R>*>(a.thc + (size_t)b * THC_BYTES);
 }
 
 // Bookkeeping done once per item per step by (tile 0, thread 0): log-likelihood increment of the step
@@ -257,22 +279,87 @@ __device__ __forceinline__ void item_bookkeeping(const KArgs& a, int b, int t_do
     if (a.pf == SGM_PF_FILTER) for (int q = 0; q < nws; ++q) acc[1 + q] += hdr.sbar[q];
 }
 
-// ---- one resample -> propagate -> reweight -> statistic-update step (pf.py:7-38, 138-181, 40-82) ---
-// Resampling search, two paths:
-//   sorted targets (order-statistics multinomial / systematic / stratified, or INJECTED uniforms the
-//   caller declares ascending): the CTA's 2048 children hit one contiguous parent range [lo, hi]; two
-//   warp-cooperative searches find it, the CDF of that range is staged in shared memory in global
-//   units, and each thread merges its 8 consecutive children against it (streaming gather).
-//   iid targets (reference semantics): per-child coarse (shared) + fine (global) branch-free binary
-//   searches, the 8 children of a thread interleaved for memory-level parallelism.
+// ---- gather parents -> propagate -> reweight -> statistic update -> store (pf.py:30-36, 168-179) -----
+template <class R, class Model>
+__device__ __forceinline__ void propagate_store(const KArgs& a, int b, int t, int par, int i0, size_t item_off,
+                                                const int* anc, const R* z, const CdfHeader& hdr, int nws,
+                                                bool carries, bool shrink, R* lwn) {
+    constexpr int NX = Model::NX, NP = Model::NP, W = NX + NP;
+    const int N = a.N;
+    const typename Model::template Theta<R> th = load_thc<R, Model>(a, b);
+    const R* ywp = reinterpret_cast<const R*>(a.yw) + ((size_t)b * a.max_T + t) * 2;
+    const R y = ywp[0], wt = ywp[1];
+    const bool in_sub = (t >= a.t1[b]) && (t < a.tL[b]);
+    const R lam = (R)a.lambduh;
+    R sbar[4] = {(R)0, (R)0, (R)0, (R)0};
+    if (shrink) for (int q = 0; q < nws; ++q) sbar[q] = (R)((1.0 - a.lambduh) * hdr.sbar[q]);
+    const bool tracing = a.need_lw || a.trace_anc || a.trace_x || a.trace_lw;
+    const int mode = carries ? (shrink ? 1 : 0) : (a.pf == SGM_PF_FILTER ? 2 : 3);
+    const int stat_kind = in_sub ? a.stat_kind : SGM_STAT_NONE;
+    const void* rec_old = a.rec[par];
+    const void* tail_old = a.tail[par];
+    void* rec_new = a.rec[par ^ 1];
+    void* tail_new = a.tail[par ^ 1];
+#pragma unroll
+    for (int h0 = 0; h0 < KPT; h0 += 4) {
+        R ra[4][W];
+#pragma unroll
+        for (int c = 0; c < 4; ++c)                       // four independent parent gathers in flight
+            if (i0 + h0 + c < N) load_rec<R, W>(rec_old, tail_old, item_off + anc[h0 + c], ra[c]);
+#pragma unroll
+        for (int c4 = 0; c4 < 4; ++c4) {
+            const int c = h0 + c4, i = i0 + c;
+            lwn[c] = (R)0;
+            if (i < N) {
+                R rn[W];
+                Model::propagate(th, ra[c4] + NP, y, z[c], rn + NP);
+                lwn[c] = Model::log_weight(th, ra[c4] + NP, rn + NP, y);
+                R h[4] = {(R)0, (R)0, (R)0, (R)0};
+                if (stat_kind == SGM_STAT_SCORE) Model::score(th, ra[c4] + NP, rn + NP, y, h);
+                else if (stat_kind == SGM_STAT_SUFF) Model::suff(ra[c4] + NP, rn + NP, h);
+#pragma unroll
+                for (int q = 0; q < NP; ++q) {
+                    if (mode == 0) rn[q] = ra[c4][q] + h[q] * wt;                          // pf.py:175-179, lambduh = 1
+                    else if (mode == 1) rn[q] = lam * ra[c4][q] + sbar[q] + h[q] * wt;      // pf.py:175-179
+                    else if (mode == 2) rn[q] = h[q] * wt;                                  // pf.py:70-71
+                    else rn[q] = (R)0;                                                      // set by the backward kernel
+                }
+                store_rec<R, W>(rec_new, tail_new, item_off + i, rn);
+                if (tracing) {
+                    if (a.need_lw) reinterpret_cast<R*>(a.lw[par ^ 1])[item_off + i] = lwn[c];
+                    if (a.trace_anc) a.trace_anc[((size_t)b * a.max_T + t) * N + i] = anc[c];
+                    if (a.trace_x) {
+                        R* tx = reinterpret_cast<R*>(a.trace_x) + (((size_t)b * (a.max_T + 1) + t + 1) * N + i) * NX;
+                        for (int q = 0; q < NX; ++q) tx[q] = rn[NP + q];
+                    }
+                    if (a.trace_lw) reinterpret_cast<R*>(a.trace_lw)[((size_t)b * (a.max_T + 1) + t + 1) * N + i] = lwn[c];
+                }
+            }
+        }
+    }
+}
+
+template <class R>
+__device__ __forceinline__ void draw_normals(const KArgs& a, const RngKey& key, int b, int t, int i0, R* z) {
+    if (a.rng_mode == SGM_RNG_INJECTED) {
+        const double* zz = a.inj_z + ((size_t)b * a.max_T + t) * a.N;
+#pragma unroll
+        for (int c = 0; c < KPT; ++c) z[c] = (i0 + c < a.N) ? (R)zz[i0 + c] : (R)0;
+    } else {
+        rng_normal4(key, (uint32_t)(i0 >> 2), (uint32_t)t, z);
+        rng_normal4(key, (uint32_t)(i0 >> 2) + 1u, (uint32_t)t, z + 4);
+    }
+}
+
+// ---- step kernel, iid resampling uniforms (reference semantics, pf.py:27-29) --------------------------
+// Per-child coarse (shared) + fine (global) branch-free binary searches, the 8 children of a thread
+// interleaved for memory-level parallelism.
 template <class R, class Model>
 __global__ void __launch_bounds__(NT) pf_step_kernel(KArgs a, int t) {
-    constexpr int NX = Model::NX, NP = Model::NP, W = NX + NP;
+    constexpr int NP = Model::NP, W = Model::NX + NP;
     __shared__ CdfHeader hdr;
-    __shared__ R s_cdf[CAP];
     __shared__ R sh_r[NWARP];
     __shared__ double sh_d[NWARP];
-    __shared__ int s_range[2];
     const int b = blockIdx.y, g = blockIdx.x, tid = threadIdx.x;
     const int Tb = a.T_buf[b];
     if (t >= Tb) return;
@@ -284,109 +371,34 @@ __global__ void __launch_bounds__(NT) pf_step_kernel(KArgs a, int t) {
     const bool hdr_ws = shrink || (a.pf == SGM_PF_FILTER);
 
     build_cdf_header(a.part[par] + (size_t)b * G * PSTRIDE, G, hdr_ws ? nws : 0, hdr);
+    __syncthreads();
     if (g == 0 && tid == 0) item_bookkeeping(a, b, t - 1, hdr, nws);
 
     const R* __restrict__ fine_old = reinterpret_cast<const R*>(a.fine[par]) + item_off;
     const int i0 = g * TILE + tid * KPT;
-    const int n_valid = min(TILE, N - g * TILE);             // children in this tile
     RngKey key = a.key; key.item += (uint32_t)b;
     const double total = hdr.total;
 
-    // ---- resampling targets  u_i * total ------------------------------------------------------------
     double target[KPT];
     if (a.rng_mode == SGM_RNG_INJECTED) {
         const double* u = a.inj_u + ((size_t)b * a.max_T + t) * N;
 #pragma unroll
         for (int c = 0; c < KPT; ++c) target[c] = (i0 + c < N) ? u[i0 + c] * total : 0.0;
-    } else if (a.resample == SGM_RESAMPLE_MULTINOMIAL) {
+    } else {
         R u[KPT];
         rng_uniform4(key, (uint32_t)(i0 >> 2), (uint32_t)t, STREAM_UNIFORM, u);
         rng_uniform4(key, (uint32_t)(i0 >> 2) + 1u, (uint32_t)t, STREAM_UNIFORM, u + 4);
 #pragma unroll
         for (int c = 0; c < KPT; ++c) target[c] = (double)u[c] * total;
-    } else if (a.resample == SGM_RESAMPLE_MULTINOMIAL_SORTED) {
-        // Order statistics of N iid uniforms via exponential spacings.  Within a tile the normalised
-        // partial sums of P Exp(1) draws are independent of their total, which is Gamma(P, 1); the tile
-        // totals are therefore drawn directly (gamma_prefix_kernel) and no cross-tile scan is needed.
-        R e[KPT], run = (R)0;
-        rng_uniform4(key, (uint32_t)(i0 >> 2), (uint32_t)t, STREAM_UNIFORM, e);
-        rng_uniform4(key, (uint32_t)(i0 >> 2) + 1u, (uint32_t)t, STREAM_UNIFORM, e + 4);
-#pragma unroll
-        for (int c = 0; c < KPT; ++c) { e[c] = (i0 + c < N) ? -Mth<R>::log(e[c]) : (R)0; run += e[c]; }
-        R tile_sum;
-        R pre = block_excl_scan(run, sh_r, tile_sum);
-        const double* gam = a.gam + ((size_t)b * a.max_T + t) * (G + 2);
-        const double gl = gam[g], gmine = (gam[g + 1] - gam[g]) / (double)tile_sum, scale = total / gam[G + 1];
-#pragma unroll
-        for (int c = 0; c < KPT; ++c) { pre += e[c]; target[c] = (gl + gmine * (double)pre) * scale; }
-    } else {
-        // systematic: u_i = (i + U) / N with one U per item-step; stratified: u_i = (i + U_i) / N
-        R u[KPT];
-        if (a.resample == SGM_RESAMPLE_SYSTEMATIC) {
-            R u4[4];
-            rng_uniform4(key, 0u, (uint32_t)t, STREAM_GAMMA, u4);
-#pragma unroll
-            for (int c = 0; c < KPT; ++c) u[c] = u4[0];
-        } else {
-            rng_uniform4(key, (uint32_t)(i0 >> 2), (uint32_t)t, STREAM_UNIFORM, u);
-            rng_uniform4(key, (uint32_t)(i0 >> 2) + 1u, (uint32_t)t, STREAM_UNIFORM, u + 4);
-        }
-#pragma unroll
-        for (int c = 0; c < KPT; ++c) target[c] = ((double)(i0 + c) + (double)u[c]) / (double)N * total;
     }
-#pragma unroll
-    for (int c = 0; c < KPT; ++c) if (!(target[c] < total)) target[c] = total * (1.0 - 1.2e-16);
-
-    // ---- ancestor search ----------------------------------------------------------------------------
     int anc[KPT];
-    bool staged = false;
-    if (a.resample != SGM_RESAMPLE_MULTINOMIAL) {
-        const int last = n_valid - 1, w_last = (last / KPT) >> 5, l_last = (last / KPT) & 31, c_last = last % KPT;
-        const int warp = tid >> 5;
-        if (warp == 0) {
-            const int lo = warp_search_cdf<R>(__shfl_sync(FULL, target[0], 0), hdr, G, fine_old, N);
-            if (tid == 0) s_range[0] = lo;
-        }
-        if (warp == w_last) {
-            double tl = target[0];
-#pragma unroll
-            for (int c = 1; c < KPT; ++c) if (c == c_last) tl = target[c];
-            const int hi = warp_search_cdf<R>(__shfl_sync(FULL, tl, l_last), hdr, G, fine_old, N);
-            if ((tid & 31) == 0) s_range[1] = hi;
-        }
-        __syncthreads();
-        const int lo = s_range[0], range = s_range[1] - lo + 1;
-        if (range >= 1 && range <= CAP) {
-            staged = true;
-            const double cbase = hdr.coarse[lo / TILE];
-            for (int k = tid; k < range; k += NT) {
-                const int p = lo + k, gp = p / TILE;
-                s_cdf[k] = (R)((hdr.coarse[gp] - cbase) + (double)fine_old[p] * hdr.e[gp]);
-            }
-            __syncthreads();
-            // first child: branch-free binary search over the staged range; the rest merge forward
-            int pos = 0;
-            {
-                const R rt = (R)(target[0] - cbase);
-                for (int step = pow2_floor(range); step > 0; step >>= 1)
-                    if (pos + step <= range && s_cdf[pos + step - 1] <= rt) pos += step;
-                pos = min(pos, range - 1);
-            }
-            anc[0] = lo + pos;
-#pragma unroll
-            for (int c = 1; c < KPT; ++c) {
-                const R rt = (R)(target[c] - cbase);
-                if (i0 + c < N) while (pos < range - 1 && s_cdf[pos] <= rt) ++pos;
-                anc[c] = lo + pos;
-            }
-        }
-    }
-    if (!staged) {
+    {
         int gsel[KPT], pos[KPT], len[KPT];
         R rr[KPT];
         const int step0 = pow2_floor(G);
 #pragma unroll
         for (int c = 0; c < KPT; ++c) {
+            if (!(target[c] < total)) target[c] = total * (1.0 - 1.2e-16);
             gsel[c] = coarse_search(target[c], hdr, G, step0);
             rr[c] = (R)((target[c] - hdr.coarse[gsel[c]]) * hdr.einv[gsel[c]]);
             len[c] = min(TILE, N - gsel[c] * TILE);
@@ -403,70 +415,155 @@ __global__ void __launch_bounds__(NT) pf_step_kernel(KArgs a, int t) {
 #pragma unroll
         for (int c = 0; c < KPT; ++c) anc[c] = gsel[c] * TILE + min(pos[c], len[c] - 1);
     }
-
-    // ---- proposal normals ------------------------------------------------------------------------
-    R z[KPT];
-    if (a.rng_mode == SGM_RNG_INJECTED) {
-        const double* zz = a.inj_z + ((size_t)b * a.max_T + t) * N;
-#pragma unroll
-        for (int c = 0; c < KPT; ++c) z[c] = (i0 + c < N) ? (R)zz[i0 + c] : (R)0;
-    } else {
-        rng_normal4(key, (uint32_t)(i0 >> 2), (uint32_t)t, z);
-        rng_normal4(key, (uint32_t)(i0 >> 2) + 1u, (uint32_t)t, z + 4);
-    }
-
-    const typename Model::template Theta<R> th = Model::template load<R>(a.theta + (size_t)b * SGM_THETA_STRIDE);
-    const R y = (R)a.obs[a.obs_off[b] + t];
-    const bool in_sub = (t >= a.t1[b]) && (t < a.tL[b]);
-    const R wt = in_sub ? ((a.wts_off && a.wts_off[b] >= 0) ? (R)a.step_weights[a.wts_off[b] + (t - a.t1[b])] : (R)1) : (R)0;
-    const R lam = (R)a.lambduh;
-    R sbar[4] = {(R)0, (R)0, (R)0, (R)0};
-    if (shrink) for (int q = 0; q < nws; ++q) sbar[q] = (R)((1.0 - a.lambduh) * hdr.sbar[q]);
-
-    const void* rec_old = a.rec[par];
-    const void* tail_old = a.tail[par];
-    void* rec_new = a.rec[par ^ 1];
-    void* tail_new = a.tail[par ^ 1];
-    R lwn[KPT];
-#pragma unroll
-    for (int h0 = 0; h0 < KPT; h0 += 4) {
-        R ra[4][W];
-#pragma unroll
-        for (int c = 0; c < 4; ++c)                       // four independent parent gathers in flight
-            if (i0 + h0 + c < N) load_rec<R, W>(rec_old, tail_old, item_off + anc[h0 + c], ra[c]);
-#pragma unroll
-        for (int c4 = 0; c4 < 4; ++c4) {
-            const int c = h0 + c4, i = i0 + c;
-            lwn[c] = (R)0;
-            if (i < N) {
-                R rn[W];
-                Model::propagate(th, ra[c4] + NP, y, z[c], rn + NP);
-                lwn[c] = Model::log_weight(th, ra[c4] + NP, rn + NP, y);
-                R h[4] = {(R)0, (R)0, (R)0, (R)0};
-                if (in_sub) {
-                    if (a.stat_kind == SGM_STAT_SCORE) Model::score(th, ra[c4] + NP, rn + NP, y, h);
-                    else if (a.stat_kind == SGM_STAT_SUFF) Model::suff(ra[c4] + NP, rn + NP, h);
-                }
-#pragma unroll
-                for (int q = 0; q < NP; ++q) {
-                    if (carries) rn[q] = shrink ? (lam * ra[c4][q] + sbar[q] + h[q] * wt) : (ra[c4][q] + h[q] * wt);   // pf.py:175-179
-                    else if (a.pf == SGM_PF_FILTER) rn[q] = h[q] * wt;                                               // pf.py:70-71
-                    else rn[q] = (R)0;                                                                                // set by the backward kernel
-                }
-                store_rec<R, W>(rec_new, tail_new, item_off + i, rn);
-                if (a.need_lw) reinterpret_cast<R*>(a.lw[par ^ 1])[item_off + i] = lwn[c];
-                if (a.trace_anc) a.trace_anc[((size_t)b * a.max_T + t) * N + i] = anc[c];
-                if (a.trace_x) {
-                    R* tx = reinterpret_cast<R*>(a.trace_x) + (((size_t)b * (a.max_T + 1) + t + 1) * N + i) * NX;
-                    for (int q = 0; q < NX; ++q) tx[q] = rn[NP + q];
-                }
-                if (a.trace_lw) reinterpret_cast<R*>(a.trace_lw)[((size_t)b * (a.max_T + 1) + t + 1) * N + i] = lwn[c];
-            }
-        }
-    }
+    R z[KPT], lwn[KPT];
+    draw_normals<R>(a, key, b, t, i0, z);
+    propagate_store<R, Model>(a, b, t, par, i0, item_off, anc, z, hdr, nws, carries, shrink, lwn);
     const bool need_ws = (nws > 0) && (a.pf == SGM_PF_FILTER || shrink || (carries && t == Tb - 1));
     tile_epilogue<R, W, NP>(lwn, i0, N, reinterpret_cast<R*>(a.fine[par ^ 1]) + item_off,
-                            a.part[par ^ 1] + ((size_t)b * G + g) * PSTRIDE, rec_new, tail_new, item_off,
+                            a.part[par ^ 1] + ((size_t)b * G + g) * PSTRIDE, a.rec[par ^ 1], a.tail[par ^ 1], item_off,
+                            need_ws, nws, sh_r, sh_d);
+}
+
+// ---- step kernel, ascending resampling targets ---------------------------------------------------------
+// (order-statistics multinomial / systematic / stratified, or INJECTED uniforms the caller declares
+// sorted).  The CTA's 2048 children hit ONE contiguous parent range [lo, hi]: two warp-cooperative
+// searches find it, the CDF of the range is staged in shared memory in global units, and every thread
+// merges its 8 consecutive children against it, so parent records are gathered as a stream.
+template <class R, class Model>
+__global__ void __launch_bounds__(NT, (sizeof(R) == 4 ? 4 : 2)) pf_step_sorted_kernel(KArgs a, int t) {
+    constexpr int NP = Model::NP, W = Model::NX + NP;
+    __shared__ CdfHeader hdr;
+    __shared__ R s_cdf[CAP];
+    __shared__ R sh_r[NWARP];
+    __shared__ double sh_d[NWARP];
+    __shared__ int s_range[2];
+    const int b = blockIdx.y, g = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int Tb = a.T_buf[b];
+    if (t >= Tb) return;
+    const int N = a.N, G = a.G, par = t & 1;
+    const size_t item_off = (size_t)b * N;
+    const int nws = stat_width<Model>(a.stat_kind);
+    const bool carries = (a.pf == SGM_PF_NEMETH);
+    const bool shrink = carries && (a.lambduh != 1.0);
+    const bool hdr_ws = shrink || (a.pf == SGM_PF_FILTER);
+    const R* __restrict__ fine_old = reinterpret_cast<const R*>(a.fine[par]) + item_off;
+    const int i0 = g * TILE + tid * KPT;
+    const int n_valid = min(TILE, N - g * TILE);
+    RngKey key = a.key; key.item += (uint32_t)b;
+
+    // warp 0 rebuilds the CDF header while the other warps draw their randoms
+    build_cdf_header(a.part[par] + (size_t)b * G * PSTRIDE, G, hdr_ws ? nws : 0, hdr);
+
+    // u[c]: tile-local position in (0, 1] of child c for the order-statistics sampler, else the uniform
+    R u[KPT], z[KPT];
+    double gl = 0.0, gw = 0.0, scale_over_total = 0.0;
+    const bool spacings = (a.rng_mode == SGM_RNG_PHILOX) && (a.resample == SGM_RESAMPLE_MULTINOMIAL_SORTED);
+    if (spacings) {
+        // Order statistics of N iid uniforms via exponential spacings.  Within a tile the normalised
+        // partial sums of P Exp(1) draws are independent of their total, which is Gamma(P, 1); the tile
+        // totals are drawn directly (gamma_prefix_kernel), so no cross-tile scan is needed.
+        const double* gam = a.gam + ((size_t)b * a.max_T + t) * (G + 2);
+        gl = gam[g]; gw = gam[g + 1] - gl; scale_over_total = 1.0 / gam[G + 1];
+        R run = (R)0;
+        rng_uniform4(key, (uint32_t)(i0 >> 2), (uint32_t)t, STREAM_UNIFORM, u);
+        rng_uniform4(key, (uint32_t)(i0 >> 2) + 1u, (uint32_t)t, STREAM_UNIFORM, u + 4);
+#pragma unroll
+        for (int c = 0; c < KPT; ++c) { run += (i0 + c < N) ? -Mth<R>::log(u[c]) : (R)0; u[c] = run; }
+        const R incl = warp_incl_scan(run);
+        if (lane == 31) sh_r[warp] = incl;
+        draw_normals<R>(a, key, b, t, i0, z);
+        __syncthreads();                                   // header + warp totals
+        R base = (R)0, tile_sum = (R)0;
+#pragma unroll
+        for (int k = 0; k < NWARP; ++k) { const R sk = sh_r[k]; if (k < warp) base += sk; tile_sum += sk; }
+        base += incl - run;
+        const R inv = Mth<R>::rcp(tile_sum);
+#pragma unroll
+        for (int c = 0; c < KPT; ++c) u[c] = (base + u[c]) * inv;
+    } else {
+        if (a.rng_mode == SGM_RNG_INJECTED) {
+#pragma unroll
+            for (int c = 0; c < KPT; ++c) u[c] = (R)0;            // targets come from inj_u (target_of)
+        } else if (a.resample == SGM_RESAMPLE_SYSTEMATIC) {
+            R u4[4];
+            rng_uniform4(key, 0u, (uint32_t)t, STREAM_GAMMA, u4);
+#pragma unroll
+            for (int c = 0; c < KPT; ++c) u[c] = u4[0];
+        } else {
+            rng_uniform4(key, (uint32_t)(i0 >> 2), (uint32_t)t, STREAM_UNIFORM, u);
+            rng_uniform4(key, (uint32_t)(i0 >> 2) + 1u, (uint32_t)t, STREAM_UNIFORM, u + 4);
+        }
+        draw_normals<R>(a, key, b, t, i0, z);
+        __syncthreads();                                   // header
+    }
+    if (g == 0 && tid == 0) item_bookkeeping(a, b, t - 1, hdr, nws);
+    const double total = hdr.total;
+
+    // target of child c in global CDF units
+    auto target_of = [&](int c) -> double {
+        double tg;
+        if (spacings) tg = (gl + gw * (double)u[c]) * (scale_over_total * total);
+        else if (a.rng_mode == SGM_RNG_INJECTED) tg = (i0 + c < N) ? a.inj_u[((size_t)b * a.max_T + t) * N + i0 + c] * total : 0.0;
+        else tg = ((double)(i0 + c) + (double)u[c]) / (double)N * total;
+        return (tg < total) ? tg : total * (1.0 - 1.2e-16);
+    };
+
+    // ---- parent range of this tile ---------------------------------------------------------------------
+    {
+        const int last = n_valid - 1, w_last = (last / KPT) >> 5, l_last = (last / KPT) & 31, c_last = last % KPT;
+        if (warp == 0) {
+            const int lo = warp_search_cdf<R>(__shfl_sync(FULL, target_of(0), 0), hdr, G, fine_old, N);
+            if (lane == 0) s_range[0] = lo;
+        }
+        if (warp == w_last) {
+            double tl = target_of(0);
+#pragma unroll
+            for (int c = 1; c < KPT; ++c) if (c == c_last) tl = target_of(c);
+            const int hi = warp_search_cdf<R>(__shfl_sync(FULL, tl, l_last), hdr, G, fine_old, N);
+            if (lane == 0) s_range[1] = hi;
+        }
+    }
+    __syncthreads();
+    const int lo = s_range[0], range = s_range[1] - lo + 1;
+    int anc[KPT];
+    if (range >= 1 && range <= CAP) {
+        const double cbase = hdr.coarse[lo / TILE];
+        for (int k = tid; k < range; k += NT) {
+            const int p = lo + k, gp = p / TILE;
+            s_cdf[k] = (R)((hdr.coarse[gp] - cbase) + (double)fine_old[p] * hdr.e[gp]);
+        }
+        __syncthreads();
+        // first child: branch-free binary search over the staged range; the others merge forward with a
+        // few unrolled probes (expected advance: one parent per child) and a loop only for long gaps
+        int pos = 0;
+        {
+            const R rt = (R)(target_of(0) - cbase);
+            for (int step = pow2_floor(range); step > 0; step >>= 1)
+                if (pos + step <= range && s_cdf[pos + step - 1] <= rt) pos += step;
+            pos = min(pos, range - 1);
+        }
+        anc[0] = lo + pos;
+        const int lastp = range - 1;
+#pragma unroll
+        for (int c = 1; c < KPT; ++c) {
+            const R rt = (R)(target_of(c) - cbase);
+            if (i0 + c < N) {
+#pragma unroll
+                for (int k = 0; k < 3; ++k) pos += (pos < lastp && s_cdf[pos] <= rt) ? 1 : 0;
+                while (pos < lastp && s_cdf[pos] <= rt) ++pos;
+            }
+            anc[c] = lo + pos;
+        }
+    } else {
+        // very uneven weights: the tile spans more parents than the staging buffer holds
+#pragma unroll 1
+        for (int c = 0; c < KPT; ++c) anc[c] = search_cdf<R>(target_of(c), hdr, G, fine_old, N);
+    }
+    R lwn[KPT];
+    propagate_store<R, Model>(a, b, t, par, i0, item_off, anc, z, hdr, nws, carries, shrink, lwn);
+    const bool need_ws = (nws > 0) && (a.pf == SGM_PF_FILTER || shrink || (carries && t == Tb - 1));
+    tile_epilogue<R, W, NP>(lwn, i0, N, reinterpret_cast<R*>(a.fine[par ^ 1]) + item_off,
+                            a.part[par ^ 1] + ((size_t)b * G + g) * PSTRIDE, a.rec[par ^ 1], a.tail[par ^ 1], item_off,
                             need_ws, nws, sh_r, sh_d);
 }
 
@@ -503,6 +600,7 @@ __global__ void __launch_bounds__(NT) pf_final_kernel(KArgs a) {
     const int Tb = a.T_buf[b], par = Tb & 1, G = a.G;
     const int nws = stat_width<Model>(a.stat_kind);
     build_cdf_header(a.part[par] + (size_t)b * G * PSTRIDE, G, nws, hdr);
+    __syncthreads();
     if (tid == 0) {
         item_bookkeeping(a, b, Tb - 1, hdr, nws);
         const double* acc = a.acc + (size_t)b * ACC_STRIDE;

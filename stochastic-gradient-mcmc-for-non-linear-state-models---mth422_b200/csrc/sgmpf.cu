@@ -25,7 +25,7 @@ int fail(int code, const char* fmt, const char* extra = "") {
 size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
 
 struct Layout {
-    size_t rec[2], tail[2], fine[2], lw[2], part[2], acc, gam, Jidx, Llist[2], counters, total;
+    size_t rec[2], tail[2], fine[2], lw[2], part[2], acc, thc, yw, gam, Jidx, Llist[2], counters, total;
 };
 
 bool backward_pf(int pf) { return pf == SGM_PF_POY_N2 || pf == SGM_PF_PARIS; }
@@ -75,6 +75,8 @@ Layout make_layout(const sgm_pf_desc* d) {
     for (int k = 0; k < 2; ++k) { L.lw[k] = off; off = align_up(off + (need_lw ? B * N * es : 0)); }
     for (int k = 0; k < 2; ++k) { L.part[k] = off; off = align_up(off + B * G * PSTRIDE * 8); }
     L.acc = off; off = align_up(off + B * ACC_STRIDE * 8);
+    L.thc = off; off = align_up(off + B * THC_BYTES);
+    L.yw = off; off = align_up(off + B * (size_t)(d->max_T > 0 ? d->max_T : 1) * 2 * es);
     if (d->rng_mode == SGM_RNG_PHILOX && d->resample == SGM_RESAMPLE_MULTINOMIAL_SORTED) {
         L.gam = off; off = align_up(off + B * (size_t)d->max_T * (G + 2) * 8);
     }
@@ -120,6 +122,8 @@ int run_impl(const sgm_pf_desc* d, cudaStream_t stream) {
         if (d->pf == SGM_PF_PARIS) a.Llist[k] = reinterpret_cast<int32_t*>(ws + L.Llist[k]);
     }
     a.acc = reinterpret_cast<double*>(ws + L.acc);
+    a.thc = ws + L.thc;
+    a.yw = ws + L.yw;
     if (d->pf == SGM_PF_PARIS) {
         a.Jidx = reinterpret_cast<int32_t*>(ws + L.Jidx);
         a.counters = reinterpret_cast<int32_t*>(ws + L.counters);
@@ -138,7 +142,9 @@ int run_impl(const sgm_pf_desc* d, cudaStream_t stream) {
     pf_init_kernel<R, Model><<<grid, block, 0, stream>>>(a); ++launches;
     if (d->ev_steps_begin) cudaEventRecord(reinterpret_cast<cudaEvent_t>(d->ev_steps_begin), stream);
     for (int t = 0; t < a.max_T; ++t) {
-        pf_step_kernel<R, Model><<<grid, block, 0, stream>>>(a, t); ++launches;
+        if (d->resample == SGM_RESAMPLE_MULTINOMIAL) pf_step_kernel<R, Model><<<grid, block, 0, stream>>>(a, t);
+        else pf_step_sorted_kernel<R, Model><<<grid, block, 0, stream>>>(a, t);
+        ++launches;
         if (d->pf == SGM_PF_POY_N2) launches += launch_poyiadjis_n2<R, Model>(a, t, stream);
         else if (d->pf == SGM_PF_PARIS) launches += launch_paris<R, Model>(a, t, stream);
     }
