@@ -154,15 +154,18 @@ template <class R, int W, int NP>
 __device__ __forceinline__ void tile_epilogue(const R* lwn, int i0, int N, R* fine_out, double* part_out,
                                               const void* rec_new, const void* tail_new, size_t item_off,
                                               bool need_ws, int nws, R* sh_r, double* sh_d) {
+    // callers set lwn[c] = -inf for children beyond N, so they carry zero weight below
     R m = -Mth<R>::inf();
 #pragma unroll
-    for (int c = 0; c < KPT; ++c) if (i0 + c < N) m = nan_max(m, lwn[c]);
+    for (int c = 0; c < KPT; ++c) m = nan_max(m, lwn[c]);
     m = block_max(m, sh_r);
+    // m == -inf (every weight of the tile zero): shift by 0 instead, exp(-inf) = 0 and a NaN log-weight
+    // still poisons the tile sum so that the item gets flagged
+    const R msafe = (m == -Mth<R>::inf()) ? (R)0 : m;
     R w[KPT], run = (R)0;
 #pragma unroll
     for (int c = 0; c < KPT; ++c) {
-        // m == -inf: every weight of the tile is zero (or NaN: keep the NaN so that the item is flagged)
-        w[c] = (i0 + c < N) ? ((m == -Mth<R>::inf()) ? ((lwn[c] != lwn[c]) ? lwn[c] : (R)0) : Mth<R>::exp(lwn[c] - m)) : (R)0;
+        w[c] = Mth<R>::exp(lwn[c] - msafe);
         run += w[c];
     }
     R total;
@@ -218,8 +221,8 @@ __global__ void __launch_bounds__(NT) pf_init_kernel(KArgs a) {
     }
 #pragma unroll
     for (int c = 0; c < KPT; ++c) {
-        lwn[c] = (R)0;
         const int i = i0 + c;
+        lwn[c] = (i < N) ? (R)0 : -Mth<R>::inf();
         if (i < N) {
             R r[W];
 #pragma unroll
@@ -294,8 +297,12 @@ __device__ __forceinline__ void propagate_store(const KArgs& a, int b, int t, in
     R sbar[4] = {(R)0, (R)0, (R)0, (R)0};
     if (shrink) for (int q = 0; q < nws; ++q) sbar[q] = (R)((1.0 - a.lambduh) * hdr.sbar[q]);
     const bool tracing = a.need_lw || a.trace_anc || a.trace_x || a.trace_lw;
-    const int mode = carries ? (shrink ? 1 : 0) : (a.pf == SGM_PF_FILTER ? 2 : 3);
-    const int stat_kind = in_sub ? a.stat_kind : SGM_STAT_NONE;
+    // new statistic = keep * parent statistic + sbar + h * hs   (one FMA chain for every smoother):
+    //   Poyiadjis O(N)/Nemeth: keep = lambduh, hs = w_t (pf.py:175-179); filter: keep = 0, hs = w_t
+    //   (pf.py:70-71); O(N^2)/PaRIS: keep = hs = 0 (the backward kernel writes the statistic)
+    const R keep = carries ? (shrink ? lam : (R)1) : (R)0;
+    const R hs = (carries || a.pf == SGM_PF_FILTER) ? wt : (R)0;
+    const int stat_kind = (in_sub && hs != (R)0) ? a.stat_kind : SGM_STAT_NONE;
     const void* rec_old = a.rec[par];
     const void* tail_old = a.tail[par];
     void* rec_new = a.rec[par ^ 1];
@@ -309,7 +316,7 @@ __device__ __forceinline__ void propagate_store(const KArgs& a, int b, int t, in
 #pragma unroll
         for (int c4 = 0; c4 < 4; ++c4) {
             const int c = h0 + c4, i = i0 + c;
-            lwn[c] = (R)0;
+            lwn[c] = -Mth<R>::inf();
             if (i < N) {
                 R rn[W];
                 Model::propagate(th, ra[c4] + NP, y, z[c], rn + NP);
@@ -318,12 +325,7 @@ __device__ __forceinline__ void propagate_store(const KArgs& a, int b, int t, in
                 if (stat_kind == SGM_STAT_SCORE) Model::score(th, ra[c4] + NP, rn + NP, y, h);
                 else if (stat_kind == SGM_STAT_SUFF) Model::suff(ra[c4] + NP, rn + NP, h);
 #pragma unroll
-                for (int q = 0; q < NP; ++q) {
-                    if (mode == 0) rn[q] = ra[c4][q] + h[q] * wt;                          // pf.py:175-179, lambduh = 1
-                    else if (mode == 1) rn[q] = lam * ra[c4][q] + sbar[q] + h[q] * wt;      // pf.py:175-179
-                    else if (mode == 2) rn[q] = h[q] * wt;                                  // pf.py:70-71
-                    else rn[q] = (R)0;                                                      // set by the backward kernel
-                }
+                for (int q = 0; q < NP; ++q) rn[q] = keep * ra[c4][q] + (sbar[q] + h[q] * hs);
                 store_rec<R, W>(rec_new, tail_new, item_off + i, rn);
                 if (tracing) {
                     if (a.need_lw) reinterpret_cast<R*>(a.lw[par ^ 1])[item_off + i] = lwn[c];
@@ -433,7 +435,7 @@ template <class R, class Model>
 __global__ void __launch_bounds__(NT, (sizeof(R) == 4 ? 4 : 2)) pf_step_sorted_kernel(KArgs a, int t) {
     constexpr int NP = Model::NP, W = Model::NX + NP;
     __shared__ CdfHeader hdr;
-    __shared__ R s_cdf[CAP];
+    __shared__ R s_cdf[CAP + 16];
     __shared__ R sh_r[NWARP];
     __shared__ double sh_d[NWARP];
     __shared__ int s_range[2];
@@ -499,12 +501,15 @@ __global__ void __launch_bounds__(NT, (sizeof(R) == 4 ? 4 : 2)) pf_step_sorted_k
     if (g == 0 && tid == 0) item_bookkeeping(a, b, t - 1, hdr, nws);
     const double total = hdr.total;
 
-    // target of child c in global CDF units
+    // target of child c in global CDF units: tA + tB * u[c]  (f64; only used for the two range searches)
+    double tA, tB;
+    if (spacings) { tB = gw * (scale_over_total * total); tA = gl * (scale_over_total * total); }
+    else { tB = total / (double)N; tA = (double)i0 * tB; }
     auto target_of = [&](int c) -> double {
         double tg;
-        if (spacings) tg = (gl + gw * (double)u[c]) * (scale_over_total * total);
-        else if (a.rng_mode == SGM_RNG_INJECTED) tg = (i0 + c < N) ? a.inj_u[((size_t)b * a.max_T + t) * N + i0 + c] * total : 0.0;
-        else tg = ((double)(i0 + c) + (double)u[c]) / (double)N * total;
+        if (a.rng_mode == SGM_RNG_INJECTED) tg = (i0 + c < N) ? a.inj_u[((size_t)b * a.max_T + t) * N + i0 + c] * total : 0.0;
+        else if (spacings) tg = tA + tB * (double)u[c];
+        else tg = tA + tB * ((double)c + (double)u[c]);
         return (tg < total) ? tg : total * (1.0 - 1.2e-16);
     };
 
@@ -526,32 +531,46 @@ __global__ void __launch_bounds__(NT, (sizeof(R) == 4 ? 4 : 2)) pf_step_sorted_k
     __syncthreads();
     const int lo = s_range[0], range = s_range[1] - lo + 1;
     int anc[KPT];
-    if (range >= 1 && range <= CAP) {
-        const double cbase = hdr.coarse[lo / TILE];
-        for (int k = tid; k < range; k += NT) {
-            const int p = lo + k, gp = p / TILE;
-            s_cdf[k] = (R)((hdr.coarse[gp] - cbase) + (double)fine_old[p] * hdr.e[gp]);
+    if (range >= 1 && range <= CAP - 16) {
+        // stage the CDF of [lo, hi] in global units relative to cbase (f32 is enough: the range spans a
+        // few tiles at most), padded with +inf up to a power of two so the searches need no bound checks
+        const int g_lo = lo / TILE;
+        const double cbase = hdr.coarse[g_lo];
+        for (int k = tid; k < range + 16; k += NT) {                 // 16 sentinels for the windowed probes
+            R v = Mth<R>::inf();
+            if (k < range) {
+                const int p = lo + k, gp = p / TILE;
+                v = (R)(hdr.coarse[gp] - cbase) + fine_old[p] * (R)hdr.e[gp];
+            }
+            s_cdf[k] = v;
         }
         __syncthreads();
-        // first child: branch-free binary search over the staged range; the others merge forward with a
-        // few unrolled probes (expected advance: one parent per child) and a loop only for long gaps
-        int pos = 0;
-        {
-            const R rt = (R)(target_of(0) - cbase);
-            for (int step = pow2_floor(range); step > 0; step >>= 1)
-                if (pos + step <= range && s_cdf[pos + step - 1] <= rt) pos += step;
-            pos = min(pos, range - 1);
+        // relative targets in f32: rA + rB * u
+        R rt[KPT];
+        if (a.rng_mode == SGM_RNG_INJECTED) {
+#pragma unroll
+            for (int c = 0; c < KPT; ++c) rt[c] = (R)(target_of(c) - cbase);
+        } else {
+            const R rA = (R)(tA - cbase), rB = (R)tB;
+#pragma unroll
+            for (int c = 0; c < KPT; ++c) rt[c] = spacings ? (rA + rB * u[c]) : (rA + rB * ((R)c + u[c]));
         }
-        anc[0] = lo + pos;
+        // first child: branch-free binary search over the range; every further child advances from its
+        // predecessor (expected: one parent) with a fixed 4-step search of the next 16 entries -- no
+        // warp divergence -- and a loop only when the gap is longer than that
         const int lastp = range - 1;
+        int pos = 0;
+        for (int step = pow2_floor(range); step > 0; step >>= 1)
+            if (pos + step <= range && s_cdf[pos + step - 1] <= rt[0]) pos += step;
+        pos = min(pos, lastp);
+        anc[0] = lo + pos;
 #pragma unroll
         for (int c = 1; c < KPT; ++c) {
-            const R rt = (R)(target_of(c) - cbase);
-            if (i0 + c < N) {
 #pragma unroll
-                for (int k = 0; k < 3; ++k) pos += (pos < lastp && s_cdf[pos] <= rt) ? 1 : 0;
-                while (pos < lastp && s_cdf[pos] <= rt) ++pos;
-            }
+            for (int step = 8; step > 0; step >>= 1)
+                if (s_cdf[pos + step - 1] <= rt[c]) pos += step;
+            while (pos < lastp && s_cdf[pos] <= rt[c]) ++pos;
+            pos = min(pos, lastp);
             anc[c] = lo + pos;
         }
     } else {
