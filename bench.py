@@ -256,6 +256,8 @@ def run_gpu(args):
     e2e_ps = M * world * N_PARTICLES * (SUBSEQ + 2 * BUFFER)      # interior windows; edge windows are shorter
     e2e_value = e2e_ps * args.steps / e2e_s
 
+    if world > 1:
+        torch.distributed.destroy_process_group()
     if rank != 0:
         return 0
     peaks = {}
@@ -279,7 +281,7 @@ def run_gpu(args):
                 "api": "SVMSampler.noisy_gradient(kind='pf', minibatch_size=M*n_gpus, ...)"},
         "gpu_launches": int(launches_per_step * args.steps),
         "clocks": clk,
-        "roofline": {"bound": "hbm", "kernel": "pf_step_kernel<float, SvmPrior>", "achieved": achieved, "peak": hbm,
+        "roofline": {"bound": "hbm", "kernel": "pf_step_sorted_kernel<float, SvmPrior>", "achieved": achieved, "peak": hbm,
                      "unit": "GB/s", "frac": achieved / hbm, "traffic": traffic,
                      "peak_source": "MEASURED_PEAKS.json (measured)" if peaks else "fallback 6650 GB/s",
                      "alg_bytes_per_particle_step": ALG_BYTES, "particles_per_launch": prep.B * N_PARTICLES,
