@@ -104,32 +104,35 @@ __global__ void __launch_bounds__(NT) poyiadjis_n2_kernel(KArgs a, int t) {
     }
 }
 
-// Per-tile weighted statistic sums for the final average (only on an item's last step).
+// Per-warp-tile weighted statistic sums for the final average (only on an item's last step).
 template <class R, class Model>
 __global__ void __launch_bounds__(NT) stat_ws_kernel(KArgs a, int t) {
     constexpr int NX = Model::NX, NP = Model::NP, W = NX + NP;
-    __shared__ double sh_d[NWARP];
-    const int b = blockIdx.y, g = blockIdx.x, tid = threadIdx.x;
+    const int b = blockIdx.y, g = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (t != a.T_buf[b] - 1) return;
+    const int q_me = g * NWARP + warp;
+    if (q_me >= a.Q) return;
     const int N = a.N, par = (t & 1) ^ 1;          // buffers written by step t
     const size_t item_off = (size_t)b * N;
     const int nws = stat_width<Model>(a.stat_kind);
-    double* part = a.part[par] + ((size_t)b * a.G + g) * PSTRIDE;
-    const R m = (R)part[0];
+    double* sub = a.sub[par] + ((size_t)b * a.Q + q_me) * SSTRIDE;
+    const R m = (R)sub[0];
+    const R msafe = (m == -Mth<R>::inf()) ? (R)0 : m;
     const R* lw = reinterpret_cast<const R*>(a.lw[par]) + item_off;
-    const int i0 = g * TILE + tid * KPT;
+    const int i0 = q_me * WT + lane * KPT;
     double ws[4] = {0.0, 0.0, 0.0, 0.0};
     for (int c = 0; c < KPT; ++c) {
         const int i = i0 + c;
         if (i < N) {
             R r[W];
             load_rec<R, W>(a.rec[par], a.tail[par], item_off + i, r);
-            const R w = (m == -Mth<R>::inf()) ? (R)0 : Mth<R>::exp(lw[i] - m);
+            const R w = Mth<R>::exp(lw[i] - msafe);
             for (int q = 0; q < nws; ++q) ws[q] += (double)(r[q] * w);
         }
     }
-    for (int q = 0; q < nws; ++q) ws[q] = block_sum(ws[q], sh_d);
-    if (tid == 0) for (int q = 0; q < 4; ++q) part[2 + q] = ws[q];
+    for (int q = 0; q < nws; ++q) ws[q] = warp_sum(ws[q]);
+    __syncwarp();
+    if (lane == 0) for (int q = 0; q < 4; ++q) sub[2 + q] = ws[q];
 }
 
 template <class R, class Model>
@@ -194,13 +197,11 @@ __device__ __forceinline__ void exact_backward_sample(const KArgs& a, const type
 template <class R, class Model>
 __global__ void __launch_bounds__(NT) paris_ar_kernel(KArgs a, int t) {
     constexpr int NX = Model::NX, NP = Model::NP, W = NX + NP;
-    __shared__ CdfHeader hdr;
     const int b = blockIdx.y, g = blockIdx.x, tid = threadIdx.x;
     if (t >= a.T_buf[b]) return;
-    const int N = a.N, G = a.G, par = t & 1;
+    const int N = a.N, par = t & 1;
     const size_t item_off = (size_t)b * N;
-    build_cdf_header(a.part[par] + (size_t)b * G * PSTRIDE, G, 0, hdr);
-    __syncthreads();
+    const ItemHdr hdr = load_hdr(a, b);            // header of the OLD weights (built before step t)
     const typename Model::template Theta<R> th = load_thc<R, Model>(a, b);
     const R ltmax = Model::log_trans_max(th);
     const R* fine_old = reinterpret_cast<const R*>(a.fine[par]) + item_off;
@@ -215,7 +216,7 @@ __global__ void __launch_bounds__(NT) paris_ar_kernel(KArgs a, int t) {
             int J = -1;
             for (int r = 0; r < tries; ++r) {
                 const uint4 raw = rng_raw(key, (uint32_t)i, (uint32_t)t, STREAM_PARIS, (uint32_t)(jt * a.max_ar + r));
-                const int I = search_cdf<R>(u01d(raw.x, raw.y) * hdr.total, hdr, G, fine_old, N);
+                const int I = search_hdr<R>(u01d(raw.x, raw.y) * hdr.total, hdr, fine_old, N);
                 R ra[W];
                 load_rec<R, W>(a.rec[par], a.tail[par], item_off + I, ra);
                 const R thr = Mth<R>::exp(Model::log_trans(th, ra + NP, rn + NP) - ltmax);
@@ -259,16 +260,14 @@ __global__ void __launch_bounds__(NT) paris_exact_kernel(KArgs a, int t) {
 template <class R, class Model>
 __global__ void __launch_bounds__(NT) paris_injected_kernel(KArgs a, int t) {
     constexpr int NX = Model::NX, NP = Model::NP, W = NX + NP;
-    __shared__ CdfHeader hdr;
     __shared__ R sh_r[NWARP];
     __shared__ double sh_d[NWARP];
     __shared__ int sh_i[NWARP];
     const int b = blockIdx.x, tid = threadIdx.x;
     if (t >= a.T_buf[b]) return;
-    const int N = a.N, G = a.G, par = t & 1, Nt = a.Ntilde;
+    const int N = a.N, par = t & 1, Nt = a.Ntilde;
     const size_t item_off = (size_t)b * N;
-    build_cdf_header(a.part[par] + (size_t)b * G * PSTRIDE, G, 0, hdr);
-    __syncthreads();
+    const ItemHdr hdr = load_hdr(a, b);            // header of the OLD weights (built before step t)
     const typename Model::template Theta<R> th = load_thc<R, Model>(a, b);
     const R ltmax = Model::log_trans_max(th);
     const R* fine_old = reinterpret_cast<const R*>(a.fine[par]) + item_off;
@@ -300,7 +299,7 @@ __global__ void __launch_bounds__(NT) paris_injected_kernel(KArgs a, int t) {
                 int flag = 0, i = 0;
                 if (k < size_L) {
                     i = Lcur[k];
-                    const int I = search_cdf<R>(extra[off + k] * hdr.total, hdr, G, fine_old, N);
+                    const int I = search_hdr<R>(extra[off + k] * hdr.total, hdr, fine_old, N);
                     R ra[W], rn[W];
                     load_rec<R, W>(a.rec[par], a.tail[par], item_off + I, ra);
                     load_rec<R, W>(a.rec[par ^ 1], a.tail[par ^ 1], item_off + i, rn);

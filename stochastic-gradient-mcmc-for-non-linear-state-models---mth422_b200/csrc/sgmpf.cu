@@ -25,7 +25,7 @@ int fail(int code, const char* fmt, const char* extra = "") {
 size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
 
 struct Layout {
-    size_t rec[2], tail[2], fine[2], lw[2], part[2], acc, thc, yw, gam, Jidx, Llist[2], counters, total;
+    size_t rec[2], tail[2], fine[2], lw[2], sub[2], hdr, acc, thc, yw, Jidx, Llist[2], counters, total;
 };
 
 bool backward_pf(int pf) { return pf == SGM_PF_POY_N2 || pf == SGM_PF_PARIS; }
@@ -42,7 +42,7 @@ int validate(const sgm_pf_desc* d) {
     if (d->resample < 0 || d->resample > SGM_RESAMPLE_STRATIFIED) return fail(SGM_ERR_INVALID, "unknown resample");
     if (d->stat_kind < 0 || d->stat_kind > SGM_STAT_NONE) return fail(SGM_ERR_INVALID, "unknown stat_kind");
     if (d->n_items < 1 || d->n_items > 65535) return fail(SGM_ERR_INVALID, "n_items must be in [1, 65535]");
-    if (d->n_particles < 1 || d->n_particles > TILE * MAX_TILES) return fail(SGM_ERR_INVALID, "n_particles must be in [1, 2^20]");
+    if (d->n_particles < 1 || d->n_particles > WT * MAX_Q) return fail(SGM_ERR_INVALID, "n_particles must be in [1, 2^20]");
     if (d->max_T < 0 || d->max_T > 65000) return fail(SGM_ERR_INVALID, "max_T out of range");
     if (!d->obs || !d->obs_off || !d->T_buf || !d->t1 || !d->tL || !d->theta || !d->prior_mean || !d->prior_var)
         return fail(SGM_ERR_INVALID, "missing per-item input array");
@@ -65,7 +65,7 @@ Layout make_layout(const sgm_pf_desc* d) {
     Layout L;
     memset(&L, 0, sizeof(L));
     const size_t es = d->dtype == SGM_F64 ? 8 : 4;
-    const size_t B = d->n_items, N = d->n_particles, G = (N + TILE - 1) / TILE;
+    const size_t B = d->n_items, N = d->n_particles, Q = (N + WT - 1) / WT;
     const size_t KT = state_dim(d->model) + score_dim(d->model) - 4;
     const bool need_lw = backward_pf(d->pf) || d->out_lw || d->trace_lw;
     size_t off = 0;
@@ -73,13 +73,11 @@ Layout make_layout(const sgm_pf_desc* d) {
     for (int k = 0; k < 2; ++k) { L.tail[k] = off; off = align_up(off + B * N * KT * es); }
     for (int k = 0; k < 2; ++k) { L.fine[k] = off; off = align_up(off + B * N * es); }
     for (int k = 0; k < 2; ++k) { L.lw[k] = off; off = align_up(off + (need_lw ? B * N * es : 0)); }
-    for (int k = 0; k < 2; ++k) { L.part[k] = off; off = align_up(off + B * G * PSTRIDE * 8); }
+    for (int k = 0; k < 2; ++k) { L.sub[k] = off; off = align_up(off + B * Q * SSTRIDE * 8); }
+    L.hdr = off; off = align_up(off + B * hdr_stride((int)Q) * 8);
     L.acc = off; off = align_up(off + B * ACC_STRIDE * 8);
     L.thc = off; off = align_up(off + B * THC_BYTES);
     L.yw = off; off = align_up(off + B * (size_t)(d->max_T > 0 ? d->max_T : 1) * 2 * es);
-    if (d->rng_mode == SGM_RNG_PHILOX && d->resample == SGM_RESAMPLE_MULTINOMIAL_SORTED) {
-        L.gam = off; off = align_up(off + B * (size_t)d->max_T * (G + 2) * 8);
-    }
     if (d->pf == SGM_PF_PARIS) {
         L.Jidx = off; off = align_up(off + B * N * (size_t)d->Ntilde * 4);
         L.Llist[0] = off; off = align_up(off + B * N * (size_t)d->Ntilde * 4);
@@ -98,7 +96,7 @@ int run_impl(const sgm_pf_desc* d, cudaStream_t stream) {
     char* ws = reinterpret_cast<char*>(d->workspace);
     KArgs a;
     memset(&a, 0, sizeof(a));
-    a.B = d->n_items; a.N = d->n_particles; a.G = (a.N + TILE - 1) / TILE; a.max_T = d->max_T;
+    a.B = d->n_items; a.N = d->n_particles; a.G = (a.N + TILE - 1) / TILE; a.Q = (a.N + WT - 1) / WT; a.max_T = d->max_T;
     a.pf = d->pf; a.rng_mode = d->rng_mode; a.resample = d->resample; a.stat_kind = d->stat_kind;
     a.Ntilde = d->Ntilde; a.accept_reject = d->accept_reject;
     const double l10 = log10((double)a.N / 10.0);
@@ -118,10 +116,11 @@ int run_impl(const sgm_pf_desc* d, cudaStream_t stream) {
     a.inj_z0 = d->inj_z0; a.inj_u = d->inj_u; a.inj_z = d->inj_z; a.inj_extra = d->inj_extra; a.inj_extra_off = d->inj_extra_off;
     for (int k = 0; k < 2; ++k) {
         a.rec[k] = ws + L.rec[k]; a.tail[k] = ws + L.tail[k]; a.fine[k] = ws + L.fine[k]; a.lw[k] = ws + L.lw[k];
-        a.part[k] = reinterpret_cast<double*>(ws + L.part[k]);
+        a.sub[k] = reinterpret_cast<double*>(ws + L.sub[k]);
         if (d->pf == SGM_PF_PARIS) a.Llist[k] = reinterpret_cast<int32_t*>(ws + L.Llist[k]);
     }
     a.acc = reinterpret_cast<double*>(ws + L.acc);
+    a.hdr = reinterpret_cast<double*>(ws + L.hdr);
     a.thc = ws + L.thc;
     a.yw = ws + L.yw;
     if (d->pf == SGM_PF_PARIS) {
@@ -134,22 +133,18 @@ int run_impl(const sgm_pf_desc* d, cudaStream_t stream) {
 
     const dim3 grid(a.G, a.B), block(NT);
     int64_t launches = 0;
-    if (d->rng_mode == SGM_RNG_PHILOX && d->resample == SGM_RESAMPLE_MULTINOMIAL_SORTED && a.max_T > 0) {
-        double* gam = reinterpret_cast<double*>(ws + L.gam);
-        a.gam = gam;
-        gamma_prefix_kernel<<<dim3(a.max_T, a.B), block, 0, stream>>>(a, gam); ++launches;
-    }
     pf_init_kernel<R, Model><<<grid, block, 0, stream>>>(a); ++launches;
     if (d->ev_steps_begin) cudaEventRecord(reinterpret_cast<cudaEvent_t>(d->ev_steps_begin), stream);
     for (int t = 0; t < a.max_T; ++t) {
-        if (d->resample == SGM_RESAMPLE_MULTINOMIAL) pf_step_kernel<R, Model><<<grid, block, 0, stream>>>(a, t);
-        else pf_step_sorted_kernel<R, Model><<<grid, block, 0, stream>>>(a, t);
+        pf_header_kernel<R, Model><<<a.B, block, 0, stream>>>(a, t, 0); ++launches;
+        if (d->resample == SGM_RESAMPLE_MULTINOMIAL) pf_step_kernel<R, Model, false><<<grid, block, 0, stream>>>(a, t);
+        else pf_step_kernel<R, Model, true><<<grid, block, 0, stream>>>(a, t);
         ++launches;
         if (d->pf == SGM_PF_POY_N2) launches += launch_poyiadjis_n2<R, Model>(a, t, stream);
         else if (d->pf == SGM_PF_PARIS) launches += launch_paris<R, Model>(a, t, stream);
     }
     if (d->ev_steps_end) cudaEventRecord(reinterpret_cast<cudaEvent_t>(d->ev_steps_end), stream);
-    pf_final_kernel<R, Model><<<a.B, block, 0, stream>>>(a); ++launches;
+    pf_header_kernel<R, Model><<<a.B, block, 0, stream>>>(a, a.max_T, 1); ++launches;
     if (d->out_x || d->out_lw || d->out_stats) {
         pf_export_kernel<R, Model><<<dim3((a.N + NT - 1) / NT, a.B), block, 0, stream>>>(a); ++launches;
     }
