@@ -147,6 +147,47 @@ __device__ __forceinline__ int warp_search_hdr(double target, const ItemHdr& h, 
     return base + min(res, lenf - 1);
 }
 
+// Two searches at once (first and last child of a warp tile), all loads of a level issued together so
+// the two dependent-load chains overlap.  `c1` is the level-1 coarse probe off[lane * s1c] (+inf beyond Q),
+// prefetched by the caller before it draws its randoms.
+template <class R>
+__device__ __forceinline__ void warp_search_pair(double ta, double tb, double c1, int s1c, const ItemHdr& h,
+                                                 const R* __restrict__ fine, int N, int lane, int& ia, int& ib) {
+    const double tmax = h.total * (1.0 - 1.2e-16);
+    if (!(ta < h.total)) ta = tmax;
+    if (!(tb < h.total)) tb = tmax;
+    int qa = (max(__popc(__ballot_sync(FULL, c1 <= ta)), 1) - 1) * s1c;
+    int qb = (max(__popc(__ballot_sync(FULL, c1 <= tb)), 1) - 1) * s1c;
+    int la = min(s1c, h.Q - qa), lb = min(s1c, h.Q - qb);
+    while (la > 1 || lb > 1) {
+        const int sa = (la + 31) >> 5, sb = (lb + 31) >> 5;
+        const double va = (la > 1 && lane * sa < la) ? h.off[qa + lane * sa] : Mth<double>::inf();
+        const double vb = (lb > 1 && lane * sb < lb) ? h.off[qb + lane * sb] : Mth<double>::inf();
+        if (la > 1) {
+            const int adv = (max(__popc(__ballot_sync(FULL, va <= ta)), 1) - 1) * sa;
+            la = min(sa, la - adv); qa += adv;
+        }
+        if (lb > 1) {
+            const int adv = (max(__popc(__ballot_sync(FULL, vb <= tb)), 1) - 1) * sb;
+            lb = min(sb, lb - adv); qb += adv;
+        }
+    }
+    const double oa = h.off[qa], ob = h.off[qb], sca = h.sc[qa], scb = h.sc[qb];
+    const R ra = (R)((ta - oa) / sca), rb = (R)((tb - ob) / scb);
+    const int ba = qa * WT, bb = qb * WT;
+    const int na = min(WT, N - ba), nb = min(WT, N - bb);
+    const R* fa = fine + ba;
+    const R* fb = fine + bb;
+    const R pa = (lane * KPT < na) ? fa[min(na, (lane + 1) * KPT) - 1] : Mth<R>::inf();
+    const R pb = (lane * KPT < nb) ? fb[min(nb, (lane + 1) * KPT) - 1] : Mth<R>::inf();
+    const int s1a = __popc(__ballot_sync(FULL, pa <= ra)) * KPT;
+    const int s1b = __popc(__ballot_sync(FULL, pb <= rb)) * KPT;
+    const R pa2 = (lane < KPT && s1a + lane < na) ? fa[s1a + lane] : Mth<R>::inf();
+    const R pb2 = (lane < KPT && s1b + lane < nb) ? fb[s1b + lane] : Mth<R>::inf();
+    ia = ba + min(s1a + __popc(__ballot_sync(FULL, pa2 <= ra)), na - 1);
+    ib = bb + min(s1b + __popc(__ballot_sync(FULL, pb2 <= rb)), nb - 1);
+}
+
 // ---- per-warp-tile epilogue: tile max, tile-local scan of exp(lw - m), per-tile partials ---------------
 // Callers set lwn[c] = -inf for children beyond N, so they carry zero weight.
 template <class R, int W>
@@ -356,13 +397,11 @@ __global__ void __launch_bounds__(NT) pf_header_kernel(KArgs a, int t, int final
 template <class R, class Model>
 __device__ __forceinline__ void propagate_store(const KArgs& a, int b, int t, int par, int i0, size_t item_off,
                                                 const int* anc, const R* z, const ItemHdr& hdr, int nws,
-                                                bool carries, bool shrink, R* lwn) {
+                                                bool carries, bool shrink, R* lwn,
+                                                const typename Model::template Theta<R>& th, R y, R wt) {
     constexpr int NX = Model::NX, NP = Model::NP, W = NX + NP;
     const int N = a.N;
-    const typename Model::template Theta<R> th = load_thc<R, Model>(a, b);
-    const R* ywp = reinterpret_cast<const R*>(a.yw) + ((size_t)b * a.max_T + t) * 2;
-    const R y = ywp[0], wt = ywp[1];
-    const bool in_sub = (t >= a.t1[b]) && (t < a.tL[b]);
+    const bool in_sub = wt != (R)0;               // yw[1] is zero outside [t1, tL)
     const R lam = (R)a.lambduh;
     R sbar[4] = {(R)0, (R)0, (R)0, (R)0};
     if (shrink) for (int q = 0; q < nws; ++q) sbar[q] = (R)((1.0 - a.lambduh) * hdr.base[H_SBAR + q]);
@@ -437,11 +476,22 @@ __global__ void __launch_bounds__(NT, (sizeof(R) == 4 ? 4 : 2)) pf_step_kernel(K
     __shared__ R s_cdf_all[SORTED ? NWARP : 1][SORTED ? (CAPW + 16) : 1];
     __shared__ R s_conv_all[SORTED ? NWARP : 1][SORTED ? 8 : 1][2];
     const int b = blockIdx.y, g = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int Tb = a.T_buf[b];
-    if (t >= Tb) return;
     const int N = a.N, par = t & 1;
     const int q_me = g * NWARP + warp;
     if (q_me >= a.Q) return;
+    // every load that does not depend on the randoms is issued up front (one round trip for all of them):
+    // activity flag, item header scalars, level-1 coarse probe, Gamma prefix, (y_t, w_t), model constants
+    const int Tb = a.T_buf[b];
+    const ItemHdr hdr = load_hdr(a, b);
+    const int s1c = (a.Q + 31) >> 5;
+    const double c1 = (SORTED && lane * s1c < a.Q) ? hdr.off[lane * s1c] : Mth<double>::inf();
+    const R* ywp = reinterpret_cast<const R*>(a.yw) + ((size_t)b * a.max_T + min(t, a.max_T - 1)) * 2;
+    const R y_t = ywp[0], w_t = ywp[1];
+    const typename Model::template Theta<R> th = load_thc<R, Model>(a, b);
+    const double gam_lo = (SORTED && uses_spacings(a)) ? hdr.gam[q_me] : 0.0;
+    const double gam_hi = (SORTED && uses_spacings(a)) ? hdr.gam[q_me + 1] : 0.0;
+    const double gam_tot = (SORTED && uses_spacings(a)) ? hdr.gam[a.Q + 1] : 1.0;
+    if (t >= Tb) return;
     const size_t item_off = (size_t)b * N;
     const int nws = stat_width<Model>(a.stat_kind);
     const bool carries = (a.pf == SGM_PF_NEMETH);            // stats follow the resampled genealogy here
@@ -450,7 +500,6 @@ __global__ void __launch_bounds__(NT, (sizeof(R) == 4 ? 4 : 2)) pf_step_kernel(K
     const int i0 = q_me * WT + lane * KPT;
     const int n_valid = min(WT, N - q_me * WT);
     RngKey key = a.key; key.item += (uint32_t)b;
-    const ItemHdr hdr = load_hdr(a, b);
     const double total = hdr.total;
     int anc[KPT];
     R z[KPT];
@@ -506,7 +555,7 @@ __global__ void __launch_bounds__(NT, (sizeof(R) == 4 ? 4 : 2)) pf_step_kernel(K
             // Order statistics of N iid uniforms via exponential spacings.  Within a tile the normalised
             // partial sums of P Exp(1) draws are independent of their total, which is Gamma(P, 1); the tile
             // totals are drawn directly (pf_header_kernel), so no cross-tile scan is needed.
-            const double gl = hdr.gam[q_me], gw = hdr.gam[q_me + 1] - gl, k = total / hdr.gam[hdr.Q + 1];
+            const double gl = gam_lo, gw = gam_hi - gam_lo, k = total / gam_tot;
             R run = (R)0;
             rng_uniform4(key, (uint32_t)(i0 >> 2), (uint32_t)t, STREAM_UNIFORM, u);
             rng_uniform4(key, (uint32_t)(i0 >> 2) + 1u, (uint32_t)t, STREAM_UNIFORM, u + 4);
@@ -548,8 +597,8 @@ __global__ void __launch_bounds__(NT, (sizeof(R) == 4 ? 4 : 2)) pf_step_kernel(K
 #pragma unroll
         for (int c = 1; c < KPT; ++c) if (c == c_last) tl = target_of(c);
         tl = __shfl_sync(FULL, tl, l_last);
-        const int lo = warp_search_hdr<R>(tf, hdr, fine_old, N, lane);
-        const int hi = warp_search_hdr<R>(tl, hdr, fine_old, N, lane);
+        int lo, hi;
+        warp_search_pair<R>(tf, tl, c1, s1c, hdr, fine_old, N, lane, lo, hi);
         const int range = hi - lo + 1, q_lo = lo / WT, nq = hi / WT - q_lo + 1;
         if (range >= 1 && range <= CAPW && nq <= 8) {
             // stage the CDF of [lo, hi] in global units relative to cbase (f32 is enough: the range spans a
@@ -600,7 +649,7 @@ __global__ void __launch_bounds__(NT, (sizeof(R) == 4 ? 4 : 2)) pf_step_kernel(K
         }
     }
     R lwn[KPT];
-    propagate_store<R, Model>(a, b, t, par, i0, item_off, anc, z, hdr, nws, carries, shrink, lwn);
+    propagate_store<R, Model>(a, b, t, par, i0, item_off, anc, z, hdr, nws, carries, shrink, lwn, th, y_t, w_t);
     const bool need_ws = (nws > 0) && (a.pf == SGM_PF_FILTER || shrink || (carries && t == Tb - 1));
     warp_tile_epilogue<R, W>(lwn, i0, N, lane, reinterpret_cast<R*>(a.fine[par ^ 1]) + item_off,
                              a.sub[par ^ 1] + ((size_t)b * a.Q + q_me) * SSTRIDE, a.rec[par ^ 1], a.tail[par ^ 1],
