@@ -119,10 +119,9 @@ __global__ void __launch_bounds__(NT) stat_ws_kernel(KArgs a, int t) {
     const R m = (R)sub[0];
     const R msafe = (m == -Mth<R>::inf()) ? (R)0 : m;
     const R* lw = reinterpret_cast<const R*>(a.lw[par]) + item_off;
-    const int i0 = q_me * WT + lane * KPT;
     double ws[4] = {0.0, 0.0, 0.0, 0.0};
     for (int c = 0; c < KPT; ++c) {
-        const int i = i0 + c;
+        const int i = q_me * WT + 32 * c + lane;
         if (i < N) {
             R r[W];
             load_rec<R, W>(a.rec[par], a.tail[par], item_off + i, r);

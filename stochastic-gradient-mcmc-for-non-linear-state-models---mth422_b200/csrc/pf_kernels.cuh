@@ -1,6 +1,8 @@
 // Kernels of the batched buffered particle filter / smoother (O(N) paths).
 //
-// Work decomposition: the unit of work is a WARP TILE of WT = 256 consecutive particles (8 per lane).
+// Work decomposition: the unit of work is a WARP TILE of WT = 256 consecutive particles.  Lane l owns the
+// particles 32 * c + l (c = 0..7) of its tile, so every warp-level load / store of particle data is one
+// contiguous 128..512-byte access (the L1 data pipe, not HBM, was the first bound of a lane-contiguous layout).
 // A warp does everything for its tile -- draw randoms, find its parents, gather, propose, reweight,
 // update statistics, tile-local scan of the new weights -- with shuffles and __syncwarp only: the step
 // kernel contains NO block barrier, so the 32+ resident warps of an SM hide each other's memory latency.
@@ -189,9 +191,9 @@ __device__ __forceinline__ void warp_search_pair(double ta, double tb, double c1
 }
 
 // ---- per-warp-tile epilogue: tile max, tile-local scan of exp(lw - m), per-tile partials ---------------
-// Callers set lwn[c] = -inf for children beyond N, so they carry zero weight.
+// lwn[c] belongs to particle tile_base + 32 c + lane; callers set -inf beyond N (zero weight).
 template <class R, int W>
-__device__ __forceinline__ void warp_tile_epilogue(const R* lwn, int i0, int N, int lane, R* fine_out, double* sub_out,
+__device__ __forceinline__ void warp_tile_epilogue(const R* lwn, int tile_base, int N, int lane, R* fine_out, double* sub_out,
                                                    const void* rec_new, const void* tail_new, size_t item_off,
                                                    bool need_ws, int nws) {
     R m = -Mth<R>::inf();
@@ -201,27 +203,23 @@ __device__ __forceinline__ void warp_tile_epilogue(const R* lwn, int i0, int N, 
     // m == -inf (every weight of the tile zero): shift by 0 instead; exp(-inf) = 0, and a NaN log-weight
     // still poisons the tile sum so that the item gets flagged
     const R msafe = (m == -Mth<R>::inf()) ? (R)0 : m;
-    R w[KPT], run = (R)0;
+    R w[KPT], carry = (R)0;
 #pragma unroll
-    for (int c = 0; c < KPT; ++c) {
+    for (int c = 0; c < KPT; ++c) {                  // row c = 32 consecutive particles: shuffle scan + carry
         w[c] = Mth<R>::exp(lwn[c] - msafe);
-        run += w[c];
-    }
-    const R incl = warp_incl_scan(run);
-    R pre = incl - run;
-    const R total = __shfl_sync(FULL, incl, 31);
-#pragma unroll
-    for (int c = 0; c < KPT; ++c) {
-        pre += w[c];
-        if (i0 + c < N) fine_out[i0 + c] = pre;
+        const R incl = warp_incl_scan(w[c]);
+        const int i = tile_base + 32 * c + lane;
+        if (i < N) fine_out[i] = carry + incl;
+        carry += __shfl_sync(FULL, incl, 31);
     }
     double ws[4] = {0.0, 0.0, 0.0, 0.0};
     if (need_ws) {
 #pragma unroll
         for (int c = 0; c < KPT; ++c) {
-            if (i0 + c < N) {
+            const int i = tile_base + 32 * c + lane;
+            if (i < N) {
                 R r[W];
-                load_rec<R, W>(rec_new, tail_new, item_off + i0 + c, r);
+                load_rec<R, W>(rec_new, tail_new, item_off + i, r);
                 for (int q = 0; q < nws; ++q) ws[q] += (double)(r[q] * w[c]);
             }
         }
@@ -229,7 +227,7 @@ __device__ __forceinline__ void warp_tile_epilogue(const R* lwn, int i0, int N, 
     }
     if (lane == 0) {
         sub_out[0] = (double)m;
-        sub_out[1] = (double)total;
+        sub_out[1] = (double)carry;
         for (int q = 0; q < 4; ++q) sub_out[2 + q] = ws[q];
     }
 }
@@ -262,21 +260,21 @@ __global__ void __launch_bounds__(NT) pf_init_kernel(KArgs a) {
     }
     const int q_me = g * NWARP + warp;
     if (q_me >= a.Q) return;
-    const int i0 = q_me * WT + lane * KPT;
+    const int tile_base = q_me * WT;
     RngKey key = a.key; key.item += (uint32_t)b;
     const R mean = (R)a.prior_mean[b], sd = (R)::sqrt(a.prior_var[b]);
     R lwn[KPT];
     R z[KPT];
     if (a.rng_mode == SGM_RNG_PHILOX) {
-        rng_normal4(key, (uint32_t)(i0 >> 2), 0xffffu, z);
-        rng_normal4(key, (uint32_t)(i0 >> 2) + 1u, 0xffffu, z + 4);
+        rng_normal4(key, (uint32_t)(q_me * 64 + lane * 2), 0xffffu, z);
+        rng_normal4(key, (uint32_t)(q_me * 64 + lane * 2 + 1), 0xffffu, z + 4);
     } else {
 #pragma unroll
-        for (int c = 0; c < KPT; ++c) z[c] = (i0 + c < N) ? (R)a.inj_z0[item_off + i0 + c] : (R)0;
+        for (int c = 0; c < KPT; ++c) { const int i = tile_base + 32 * c + lane; z[c] = (i < N) ? (R)a.inj_z0[item_off + i] : (R)0; }
     }
 #pragma unroll
     for (int c = 0; c < KPT; ++c) {
-        const int i = i0 + c;
+        const int i = tile_base + 32 * c + lane;
         lwn[c] = (i < N) ? (R)0 : -Mth<R>::inf();
         if (i < N) {
             R r[W];
@@ -292,7 +290,7 @@ __global__ void __launch_bounds__(NT) pf_init_kernel(KArgs a) {
             if (a.trace_lw) reinterpret_cast<R*>(a.trace_lw)[(size_t)b * (a.max_T + 1) * N + i] = (R)0;
         }
     }
-    warp_tile_epilogue<R, W>(lwn, i0, N, lane, reinterpret_cast<R*>(a.fine[0]) + item_off,
+    warp_tile_epilogue<R, W>(lwn, tile_base, N, lane, reinterpret_cast<R*>(a.fine[0]) + item_off,
                              a.sub[0] + ((size_t)b * a.Q + q_me) * SSTRIDE, a.rec[0], a.tail[0], item_off, false, 0);
 }
 
@@ -394,8 +392,10 @@ __global__ void __launch_bounds__(NT) pf_header_kernel(KArgs a, int t, int final
 }
 
 // ---- gather parents -> propagate -> reweight -> statistic update -> store (pf.py:30-36, 168-179) -----
+// Row c of the warp tile = particles tile_base + 32 c + lane: coalesced stores, and with ascending
+// ancestors the parent gathers of a row are (nearly) contiguous too.
 template <class R, class Model>
-__device__ __forceinline__ void propagate_store(const KArgs& a, int b, int t, int par, int i0, size_t item_off,
+__device__ __forceinline__ void propagate_store(const KArgs& a, int b, int t, int par, int tile_base, int lane, size_t item_off,
                                                 const int* anc, const R* z, const ItemHdr& hdr, int nws,
                                                 bool carries, bool shrink, R* lwn,
                                                 const typename Model::template Theta<R>& th, R y, R wt) {
@@ -421,10 +421,10 @@ __device__ __forceinline__ void propagate_store(const KArgs& a, int b, int t, in
         R ra[4][W];
 #pragma unroll
         for (int c = 0; c < 4; ++c)                       // four independent parent gathers in flight
-            if (i0 + h0 + c < N) load_rec<R, W>(rec_old, tail_old, item_off + anc[h0 + c], ra[c]);
+            if (tile_base + 32 * (h0 + c) + lane < N) load_rec<R, W>(rec_old, tail_old, item_off + anc[h0 + c], ra[c]);
 #pragma unroll
         for (int c4 = 0; c4 < 4; ++c4) {
-            const int c = h0 + c4, i = i0 + c;
+            const int c = h0 + c4, i = tile_base + 32 * c + lane;
             lwn[c] = -Mth<R>::inf();
             if (i < N) {
                 R rn[W];
@@ -450,16 +450,23 @@ __device__ __forceinline__ void propagate_store(const KArgs& a, int b, int t, in
     }
 }
 
+// Random numbers of a warp tile: one Philox call yields the values of rows 4h..4h+3 of a lane
+// (counter index = 64 q + 2 lane + h: a function of the particle index only).
 template <class R>
-__device__ __forceinline__ void draw_normals(const KArgs& a, const RngKey& key, int b, int t, int i0, R* z) {
+__device__ __forceinline__ void draw_normals(const KArgs& a, const RngKey& key, int b, int t, int q_me, int lane, R* z) {
     if (a.rng_mode == SGM_RNG_INJECTED) {
         const double* zz = a.inj_z + ((size_t)b * a.max_T + t) * a.N;
 #pragma unroll
-        for (int c = 0; c < KPT; ++c) z[c] = (i0 + c < a.N) ? (R)zz[i0 + c] : (R)0;
+        for (int c = 0; c < KPT; ++c) { const int i = q_me * WT + 32 * c + lane; z[c] = (i < a.N) ? (R)zz[i] : (R)0; }
     } else {
-        rng_normal4(key, (uint32_t)(i0 >> 2), (uint32_t)t, z);
-        rng_normal4(key, (uint32_t)(i0 >> 2) + 1u, (uint32_t)t, z + 4);
+        rng_normal4(key, (uint32_t)(q_me * 64 + lane * 2), (uint32_t)t, z);
+        rng_normal4(key, (uint32_t)(q_me * 64 + lane * 2 + 1), (uint32_t)t, z + 4);
     }
+}
+template <class R>
+__device__ __forceinline__ void draw_uniforms(const RngKey& key, int t, int q_me, int lane, R* u) {
+    rng_uniform4(key, (uint32_t)(q_me * 64 + lane * 2), (uint32_t)t, STREAM_UNIFORM, u);
+    rng_uniform4(key, (uint32_t)(q_me * 64 + lane * 2 + 1), (uint32_t)t, STREAM_UNIFORM, u + 4);
 }
 
 // ---- one resample -> propagate -> reweight -> statistic-update step (pf.py:7-38, 138-181, 40-82) ---
@@ -467,13 +474,13 @@ __device__ __forceinline__ void draw_normals(const KArgs& a, const RngKey& key, 
 //   search over the tile offsets and inside one tile, the 8 children of a lane interleaved.
 // SORTED = true : ascending targets (order-statistics multinomial / systematic / stratified, or INJECTED
 //   uniforms the caller declares sorted).  The warp's 256 children hit ONE contiguous parent range
-//   [lo, hi]: two warp-cooperative searches find it, the CDF of the range is staged in the warp's slice of
-//   shared memory in global units, and each lane merges its 8 consecutive children against it, so parent
-//   records are gathered as a stream.
+//   [lo, hi]: a paired warp-cooperative search finds it, the CDF of the range is staged in the warp's slice
+//   of shared memory in global units, each child binary-searches that slice (8 interleaved searches per
+//   lane, neighbouring lanes read neighbouring words), and parent records are gathered as a stream.
 template <class R, class Model, bool SORTED>
 __global__ void __launch_bounds__(NT, (sizeof(R) == 4 ? 4 : 2)) pf_step_kernel(KArgs a, int t) {
     constexpr int NP = Model::NP, W = Model::NX + NP;
-    __shared__ R s_cdf_all[SORTED ? NWARP : 1][SORTED ? (CAPW + 16) : 1];
+    __shared__ R s_cdf_all[SORTED ? NWARP : 1][SORTED ? CAPW : 1];
     __shared__ R s_conv_all[SORTED ? NWARP : 1][SORTED ? 8 : 1][2];
     const int b = blockIdx.y, g = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int N = a.N, par = t & 1;
@@ -488,19 +495,21 @@ __global__ void __launch_bounds__(NT, (sizeof(R) == 4 ? 4 : 2)) pf_step_kernel(K
     const R* ywp = reinterpret_cast<const R*>(a.yw) + ((size_t)b * a.max_T + min(t, a.max_T - 1)) * 2;
     const R y_t = ywp[0], w_t = ywp[1];
     const typename Model::template Theta<R> th = load_thc<R, Model>(a, b);
-    const double gam_lo = (SORTED && uses_spacings(a)) ? hdr.gam[q_me] : 0.0;
-    const double gam_hi = (SORTED && uses_spacings(a)) ? hdr.gam[q_me + 1] : 0.0;
-    const double gam_tot = (SORTED && uses_spacings(a)) ? hdr.gam[a.Q + 1] : 1.0;
+    const bool spacings = SORTED && uses_spacings(a);
+    const double gam_lo = spacings ? hdr.gam[q_me] : 0.0;
+    const double gam_hi = spacings ? hdr.gam[q_me + 1] : 0.0;
+    const double gam_tot = spacings ? hdr.gam[a.Q + 1] : 1.0;
     if (t >= Tb) return;
     const size_t item_off = (size_t)b * N;
     const int nws = stat_width<Model>(a.stat_kind);
     const bool carries = (a.pf == SGM_PF_NEMETH);            // stats follow the resampled genealogy here
     const bool shrink = carries && (a.lambduh != 1.0);
     const R* __restrict__ fine_old = reinterpret_cast<const R*>(a.fine[par]) + item_off;
-    const int i0 = q_me * WT + lane * KPT;
-    const int n_valid = min(WT, N - q_me * WT);
+    const int tile_base = q_me * WT;
+    const int n_valid = min(WT, N - tile_base);
     RngKey key = a.key; key.item += (uint32_t)b;
     const double total = hdr.total;
+    const double tmax = total * (1.0 - 1.2e-16);
     int anc[KPT];
     R z[KPT];
 
@@ -509,18 +518,17 @@ __global__ void __launch_bounds__(NT, (sizeof(R) == 4 ? 4 : 2)) pf_step_kernel(K
         if (a.rng_mode == SGM_RNG_INJECTED) {
             const double* u = a.inj_u + ((size_t)b * a.max_T + t) * N;
 #pragma unroll
-            for (int c = 0; c < KPT; ++c) target[c] = (i0 + c < N) ? u[i0 + c] * total : 0.0;
+            for (int c = 0; c < KPT; ++c) { const int i = tile_base + 32 * c + lane; target[c] = (i < N) ? u[i] * total : 0.0; }
         } else {
             R u[KPT];
-            rng_uniform4(key, (uint32_t)(i0 >> 2), (uint32_t)t, STREAM_UNIFORM, u);
-            rng_uniform4(key, (uint32_t)(i0 >> 2) + 1u, (uint32_t)t, STREAM_UNIFORM, u + 4);
+            draw_uniforms<R>(key, t, q_me, lane, u);
 #pragma unroll
             for (int c = 0; c < KPT; ++c) target[c] = (double)u[c] * total;
         }
         int qsel[KPT], pos[KPT], len[KPT];
         R rr[KPT];
 #pragma unroll
-        for (int c = 0; c < KPT; ++c) { if (!(target[c] < total)) target[c] = total * (1.0 - 1.2e-16); qsel[c] = 0; }
+        for (int c = 0; c < KPT; ++c) { if (!(target[c] < total)) target[c] = tmax; qsel[c] = 0; }
 #pragma unroll 1
         for (int step = pow2_floor(hdr.Q); step > 0; step >>= 1) {
 #pragma unroll
@@ -543,30 +551,32 @@ __global__ void __launch_bounds__(NT, (sizeof(R) == 4 ? 4 : 2)) pf_step_kernel(K
         }
 #pragma unroll
         for (int c = 0; c < KPT; ++c) anc[c] = qsel[c] * WT + min(pos[c], len[c] - 1);
-        draw_normals<R>(a, key, b, t, i0, z);
+        draw_normals<R>(a, key, b, t, q_me, lane, z);
     } else {
         R* s_cdf = s_cdf_all[SORTED ? warp : 0];
         R(*s_conv)[2] = s_conv_all[SORTED ? warp : 0];
-        // u[c]: tile-local position in (0, 1] of child c for the order-statistics sampler, else the uniform
+        // u[c]: for the order-statistics sampler the tile-local position in (0, 1] of child 32 c + lane,
+        // else its uniform.  target of that child = tA + tB * (u[c] (+ 32 c + lane))
         R u[KPT];
-        const bool spacings = uses_spacings(a);
-        double tA, tB;                                   // target of child c = tA + tB * (u[c] (+ c))
+        double tA, tB;
         if (spacings) {
             // Order statistics of N iid uniforms via exponential spacings.  Within a tile the normalised
             // partial sums of P Exp(1) draws are independent of their total, which is Gamma(P, 1); the tile
             // totals are drawn directly (pf_header_kernel), so no cross-tile scan is needed.
-            const double gl = gam_lo, gw = gam_hi - gam_lo, k = total / gam_tot;
-            R run = (R)0;
-            rng_uniform4(key, (uint32_t)(i0 >> 2), (uint32_t)t, STREAM_UNIFORM, u);
-            rng_uniform4(key, (uint32_t)(i0 >> 2) + 1u, (uint32_t)t, STREAM_UNIFORM, u + 4);
+            draw_uniforms<R>(key, t, q_me, lane, u);
+            R carry = (R)0;
 #pragma unroll
-            for (int c = 0; c < KPT; ++c) { run += (i0 + c < N) ? -Mth<R>::log(u[c]) : (R)0; u[c] = run; }
-            const R incl = warp_incl_scan(run);
-            const R inv = Mth<R>::rcp(__shfl_sync(FULL, incl, 31));
-            const R base = incl - run;
+            for (int c = 0; c < KPT; ++c) {
+                const R e = (tile_base + 32 * c + lane < N) ? -Mth<R>::log(u[c]) : (R)0;
+                const R incl = warp_incl_scan(e);
+                u[c] = carry + incl;
+                carry += __shfl_sync(FULL, incl, 31);
+            }
+            const R inv = Mth<R>::rcp(carry);
 #pragma unroll
-            for (int c = 0; c < KPT; ++c) u[c] = (base + u[c]) * inv;
-            tA = gl * k; tB = gw * k;
+            for (int c = 0; c < KPT; ++c) u[c] *= inv;
+            const double k = total / gam_tot;
+            tA = gam_lo * k; tB = (gam_hi - gam_lo) * k;
         } else {
             if (a.rng_mode == SGM_RNG_INJECTED) {
 #pragma unroll
@@ -577,21 +587,21 @@ __global__ void __launch_bounds__(NT, (sizeof(R) == 4 ? 4 : 2)) pf_step_kernel(K
 #pragma unroll
                 for (int c = 0; c < KPT; ++c) u[c] = u4[0];
             } else {
-                rng_uniform4(key, (uint32_t)(i0 >> 2), (uint32_t)t, STREAM_UNIFORM, u);
-                rng_uniform4(key, (uint32_t)(i0 >> 2) + 1u, (uint32_t)t, STREAM_UNIFORM, u + 4);
+                draw_uniforms<R>(key, t, q_me, lane, u);
             }
-            tB = total / (double)N; tA = (double)i0 * tB;
+            tB = total / (double)N; tA = (double)tile_base * tB;
         }
-        draw_normals<R>(a, key, b, t, i0, z);
+        draw_normals<R>(a, key, b, t, q_me, lane, z);
         auto target_of = [&](int c) -> double {
             double tg;
-            if (a.rng_mode == SGM_RNG_INJECTED) tg = (i0 + c < N) ? a.inj_u[((size_t)b * a.max_T + t) * N + i0 + c] * total : 0.0;
+            const int i = tile_base + 32 * c + lane;
+            if (a.rng_mode == SGM_RNG_INJECTED) tg = (i < N) ? a.inj_u[((size_t)b * a.max_T + t) * N + i] * total : 0.0;
             else if (spacings) tg = tA + tB * (double)u[c];
-            else tg = tA + tB * ((double)c + (double)u[c]);
-            return (tg < total) ? tg : total * (1.0 - 1.2e-16);
+            else tg = tA + tB * ((double)(32 * c + lane) + (double)u[c]);
+            return (tg < total) ? tg : tmax;
         };
-        // ---- parent range of this warp tile ---------------------------------------------------------------
-        const int last = n_valid - 1, l_last = last / KPT, c_last = last % KPT;
+        // ---- parent range of this warp tile: first child = (row 0, lane 0), last = particle n_valid - 1 ----
+        const int last = n_valid - 1, l_last = last & 31, c_last = last >> 5;
         double tl = target_of(0);
         const double tf = __shfl_sync(FULL, tl, 0);
 #pragma unroll
@@ -602,17 +612,13 @@ __global__ void __launch_bounds__(NT, (sizeof(R) == 4 ? 4 : 2)) pf_step_kernel(K
         const int range = hi - lo + 1, q_lo = lo / WT, nq = hi / WT - q_lo + 1;
         if (range >= 1 && range <= CAPW && nq <= 8) {
             // stage the CDF of [lo, hi] in global units relative to cbase (f32 is enough: the range spans a
-            // few tiles), followed by 16 +inf sentinels so the windowed probes need no bound checks
+            // few tiles)
             const double cbase = hdr.off[q_lo];
             if (lane < nq) { s_conv[lane][0] = (R)(hdr.off[q_lo + lane] - cbase); s_conv[lane][1] = (R)hdr.sc[q_lo + lane]; }
             __syncwarp();
-            for (int k = lane; k < range + 16; k += 32) {
-                R v = Mth<R>::inf();
-                if (k < range) {
-                    const int p = lo + k, j = p / WT - q_lo;
-                    v = s_conv[j][0] + fine_old[p] * s_conv[j][1];
-                }
-                s_cdf[k] = v;
+            for (int k = lane; k < range; k += 32) {
+                const int p = lo + k, j = p / WT - q_lo;
+                s_cdf[k] = s_conv[j][0] + fine_old[p] * s_conv[j][1];
             }
             __syncwarp();
             R rt[KPT];
@@ -622,26 +628,22 @@ __global__ void __launch_bounds__(NT, (sizeof(R) == 4 ? 4 : 2)) pf_step_kernel(K
             } else {
                 const R rA = (R)(tA - cbase), rB = (R)tB;
 #pragma unroll
-                for (int c = 0; c < KPT; ++c) rt[c] = spacings ? (rA + rB * u[c]) : (rA + rB * ((R)c + u[c]));
+                for (int c = 0; c < KPT; ++c) rt[c] = spacings ? (rA + rB * u[c]) : (rA + rB * ((R)(32 * c + lane) + u[c]));
             }
-            // first child: branch-free binary search over the range; every further child advances from its
-            // predecessor (expected: one parent) with a fixed 4-step search of the next 16 entries -- no
-            // warp divergence -- and a loop only when the gap is longer than that
-            const int lastp = range - 1;
-            int pos = 0;
-            for (int step = pow2_floor(range); step > 0; step >>= 1)
-                if (pos + step <= range && s_cdf[pos + step - 1] <= rt[0]) pos += step;
-            pos = min(pos, lastp);
-            anc[0] = lo + pos;
+            // 8 independent branch-free binary searches per lane, interleaved; pos = #{k : s_cdf[k] <= rt}
+            int pos[KPT];
 #pragma unroll
-            for (int c = 1; c < KPT; ++c) {
+            for (int c = 0; c < KPT; ++c) pos[c] = 0;
+#pragma unroll 1
+            for (int step = pow2_floor(range); step > 0; step >>= 1) {
 #pragma unroll
-                for (int step = 8; step > 0; step >>= 1)
-                    if (s_cdf[pos + step - 1] <= rt[c]) pos += step;
-                while (pos < lastp && s_cdf[pos] <= rt[c]) ++pos;
-                pos = min(pos, lastp);
-                anc[c] = lo + pos;
+                for (int c = 0; c < KPT; ++c) {
+                    const int idx = pos[c] + step;
+                    if (idx <= range && s_cdf[idx - 1] <= rt[c]) pos[c] = idx;
+                }
             }
+#pragma unroll
+            for (int c = 0; c < KPT; ++c) anc[c] = lo + min(pos[c], range - 1);
         } else {
             // very uneven weights: the tile spans more parents than the staging buffer holds
 #pragma unroll 1
@@ -649,9 +651,9 @@ __global__ void __launch_bounds__(NT, (sizeof(R) == 4 ? 4 : 2)) pf_step_kernel(K
         }
     }
     R lwn[KPT];
-    propagate_store<R, Model>(a, b, t, par, i0, item_off, anc, z, hdr, nws, carries, shrink, lwn, th, y_t, w_t);
+    propagate_store<R, Model>(a, b, t, par, tile_base, lane, item_off, anc, z, hdr, nws, carries, shrink, lwn, th, y_t, w_t);
     const bool need_ws = (nws > 0) && (a.pf == SGM_PF_FILTER || shrink || (carries && t == Tb - 1));
-    warp_tile_epilogue<R, W>(lwn, i0, N, lane, reinterpret_cast<R*>(a.fine[par ^ 1]) + item_off,
+    warp_tile_epilogue<R, W>(lwn, tile_base, N, lane, reinterpret_cast<R*>(a.fine[par ^ 1]) + item_off,
                              a.sub[par ^ 1] + ((size_t)b * a.Q + q_me) * SSTRIDE, a.rec[par ^ 1], a.tail[par ^ 1],
                              item_off, need_ws, nws);
 }
