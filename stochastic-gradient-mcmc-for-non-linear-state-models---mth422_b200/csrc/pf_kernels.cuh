@@ -616,9 +616,17 @@ __global__ void __launch_bounds__(NT, (sizeof(R) == 4 ? 4 : 2)) pf_step_kernel(K
             const double cbase = hdr.off[q_lo];
             if (lane < nq) { s_conv[lane][0] = (R)(hdr.off[q_lo + lane] - cbase); s_conv[lane][1] = (R)hdr.sc[q_lo + lane]; }
             __syncwarp();
-            for (int k = lane; k < range; k += 32) {
-                const int p = lo + k, j = p / WT - q_lo;
-                s_cdf[k] = s_conv[j][0] + fine_old[p] * s_conv[j][1];
+            // ... padded with +inf to a power of two (256 or 512) so the searches below need neither bound
+            // checks nor a run-time step: LDS [pos + immediate], compare, predicated add
+            const int p2 = (range <= CAPW / 2) ? CAPW / 2 : CAPW;
+#pragma unroll 4
+            for (int k = lane; k < p2; k += 32) {
+                R v = Mth<R>::inf();
+                if (k < range) {
+                    const int p = lo + k, j = p / WT - q_lo;
+                    v = s_conv[j][0] + fine_old[p] * s_conv[j][1];
+                }
+                s_cdf[k] = v;
             }
             __syncwarp();
             R rt[KPT];
@@ -634,13 +642,15 @@ __global__ void __launch_bounds__(NT, (sizeof(R) == 4 ? 4 : 2)) pf_step_kernel(K
             int pos[KPT];
 #pragma unroll
             for (int c = 0; c < KPT; ++c) pos[c] = 0;
-#pragma unroll 1
-            for (int step = pow2_floor(range); step > 0; step >>= 1) {
+            if (p2 == CAPW) {
 #pragma unroll
-                for (int c = 0; c < KPT; ++c) {
-                    const int idx = pos[c] + step;
-                    if (idx <= range && s_cdf[idx - 1] <= rt[c]) pos[c] = idx;
-                }
+                for (int c = 0; c < KPT; ++c) if (s_cdf[CAPW / 2 - 1] <= rt[c]) pos[c] = CAPW / 2;
+            }
+#pragma unroll
+            for (int step = CAPW / 4; step > 0; step >>= 1) {
+#pragma unroll
+                for (int c = 0; c < KPT; ++c)
+                    if (s_cdf[pos[c] + step - 1] <= rt[c]) pos[c] += step;
             }
 #pragma unroll
             for (int c = 0; c < KPT; ++c) anc[c] = lo + min(pos[c], range - 1);
