@@ -281,7 +281,7 @@ def run_gpu(args):
                 "api": "SVMSampler.noisy_gradient(kind='pf', minibatch_size=M*n_gpus, ...)"},
         "gpu_launches": int(launches_per_step * args.steps),
         "clocks": clk,
-        "roofline": {"bound": "hbm", "kernel": "pf_step_sorted_kernel<float, SvmPrior>", "achieved": achieved, "peak": hbm,
+        "roofline": {"bound": "hbm", "kernel": "pf_step_kernel<float, SvmPrior, SORTED=true> (+ pf_header_kernel, <2 % of the step)", "achieved": achieved, "peak": hbm,
                      "unit": "GB/s", "frac": achieved / hbm, "traffic": traffic,
                      "peak_source": "MEASURED_PEAKS.json (measured)" if peaks else "fallback 6650 GB/s",
                      "alg_bytes_per_particle_step": ALG_BYTES, "particles_per_launch": prep.B * N_PARTICLES,

@@ -1,4 +1,7 @@
-// Counter-based RNG: Philox4x32-10 (Salmon et al. 2011), uniform / normal / exponential transforms.
+// Counter-based RNG: Philox4x32 (Salmon et al. 2011), uniform / normal / exponential transforms.
+// PHILOX_ROUNDS = 7: the smallest round count the Random123 authors report as passing BigCrush
+// ("Philox4x32-7"); 10 is their conservative default.  The step kernel is instruction-issue bound and
+// Philox is ~15 % of its instructions, so the three extra rounds are not free.
 // Counter layout (rank- and launch-geometry-invariant, so sharding items over GPUs reproduces the
 // single-GPU stream):  c0 = index (particle quad, particle, or tile), c1 = step | stream<<16 | sub<<20,
 // c2 = global item id, c3 = call offset;  key = 64-bit seed.
@@ -12,10 +15,11 @@ enum : uint32_t { STREAM_NORMAL = 0, STREAM_UNIFORM = 1, STREAM_GAMMA = 2, STREA
 
 struct RngKey { uint32_t k0, k1, item, offset; };
 
-__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint32_t k0, uint32_t k1) {
+constexpr int PHILOX_ROUNDS = 7;
+__device__ __forceinline__ uint4 philox4x32(uint4 c, uint32_t k0, uint32_t k1) {
     constexpr uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
 #pragma unroll
-    for (int r = 0; r < 10; ++r) {
+    for (int r = 0; r < PHILOX_ROUNDS; ++r) {
         const uint32_t hi0 = __umulhi(M0, c.x), lo0 = M0 * c.x;
         const uint32_t hi1 = __umulhi(M1, c.z), lo1 = M1 * c.z;
         c = make_uint4(hi1 ^ c.y ^ k0, lo1, hi0 ^ c.w ^ k1, lo0);
@@ -24,7 +28,7 @@ __device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint32_t k0, uint32_t k1
     return c;
 }
 __device__ __forceinline__ uint4 rng_raw(const RngKey& k, uint32_t index, uint32_t step, uint32_t stream, uint32_t sub) {
-    return philox4x32_10(make_uint4(index, (step & 0xffffu) | (stream << 16) | (sub << 20), k.item, k.offset), k.k0, k.k1);
+    return philox4x32(make_uint4(index, (step & 0xffffu) | (stream << 16) | (sub << 20), k.item, k.offset), k.k0, k.k1);
 }
 // open-interval uniforms
 __device__ __forceinline__ float u01f(uint32_t x) { return ((float)(x >> 9) + 0.5f) * (1.0f / 8388608.0f); }             // (0,1), 23 bits
@@ -58,23 +62,25 @@ __device__ __forceinline__ void rng_normal4(const RngKey& k, uint32_t q, uint32_
     sincospi(2.0 * u01d(b.z, b.w), &s1, &c1);
     z[0] = r0 * c0; z[1] = r0 * s0; z[2] = r1 * c1; z[3] = r1 * s1;
 }
-// Gamma(shape, 1), shape >= 1 (Marsaglia & Tsang 2000), double precision, own sub-stream per attempt.
+// Gamma(shape, 1), shape >= 1 (Marsaglia & Tsang 2000) with their squeeze test (no logs ~98 % of the time);
+// the variate is generated in f32 (relative resolution 6e-8, far below its Monte-Carlo spread) and
+// returned as f64.  Own sub-stream per attempt.
 __device__ inline double rng_gamma(const RngKey& k, uint32_t index, uint32_t step, double shape) {
-    const double d = shape - 1.0 / 3.0, c = 1.0 / sqrt(9.0 * d);
+    const float d = (float)(shape - 1.0 / 3.0), c = rsqrtf(9.0f * d);
     for (uint32_t attempt = 0; attempt < 64; ++attempt) {
         const uint4 r = rng_raw(k, index, step, STREAM_GAMMA, attempt);
-        const double u1 = u01d(r.x, r.y), u2 = u01d(r.z, r.w);
-        double s, co;
-        sincospi(2.0 * u2, &s, &co);
-        const double x = sqrt(-2.0 * log(u1)) * co;
-        const uint4 r2 = rng_raw(k, index, step, STREAM_GAMMA, attempt + 2048u);
-        const double u = u01d(r2.x, r2.y);
-        double v = 1.0 + c * x;
-        if (v <= 0.0) continue;
+        float s, co;
+        __sincosf(6.28318530717958647692f * u01f(r.y), &s, &co);
+        const float x = sqrtf(-2.0f * __logf(u01f(r.x))) * co;
+        const float u = u01f(r.z);
+        float v = 1.0f + c * x;
+        if (v <= 0.0f) continue;
         v = v * v * v;
-        if (log(u) < 0.5 * x * x + d - d * v + d * log(v)) return d * v;
+        const float x2 = x * x;
+        if (u < 1.0f - 0.0331f * x2 * x2) return (double)(d * v);
+        if (__logf(u) < 0.5f * x2 + d * (1.0f - v + __logf(v))) return (double)(d * v);
     }
-    return d;   // unreachable in practice (acceptance > 95 % per attempt)
+    return (double)d;   // unreachable in practice (acceptance > 95 % per attempt)
 }
 
 }  // namespace sgm
