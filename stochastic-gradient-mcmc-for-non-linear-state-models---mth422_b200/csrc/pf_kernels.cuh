@@ -108,7 +108,7 @@ __device__ __forceinline__ ItemHdr load_hdr(const KArgs& a, int b) {
 // searchsorted(cdf, u, side='right') on the hierarchical CDF: first index whose cumulative mass exceeds
 // target = u * total.  One thread, dependent (cached) loads.
 template <class R>
-__device__ __forceinline__ int search_hdr(double target, const ItemHdr& h, const R* __restrict__ fine, int N) {
+__device__ __forceinline__ int search_hdr(double target, const ItemHdr& h, const R* fine, int N) {
     if (!(target < h.total)) target = h.total * (1.0 - 1.2e-16);
     int q = 0;
     for (int step = pow2_floor(h.Q); step > 0; step >>= 1)       // largest q with off[q] <= target
@@ -127,7 +127,7 @@ __device__ __forceinline__ int search_hdr(double target, const ItemHdr& h, const
 // The same search executed cooperatively by a full warp (all lanes pass the same target): 32-ary probing
 // with ballots -- 2-3 dependent loads for the tile, 2 inside it.
 template <class R>
-__device__ __forceinline__ int warp_search_hdr(double target, const ItemHdr& h, const R* __restrict__ fine, int N, int lane) {
+__device__ __forceinline__ int warp_search_hdr(double target, const ItemHdr& h, const R* fine, int N, int lane) {
     if (!(target < h.total)) target = h.total * (1.0 - 1.2e-16);
     int q = 0, len = h.Q;
     while (len > 1) {
@@ -154,7 +154,7 @@ __device__ __forceinline__ int warp_search_hdr(double target, const ItemHdr& h, 
 // prefetched by the caller before it draws its randoms.
 template <class R>
 __device__ __forceinline__ void warp_search_pair(double ta, double tb, double c1, int s1c, const ItemHdr& h,
-                                                 const R* __restrict__ fine, int N, int lane, int& ia, int& ib) {
+                                                 const R* fine, int N, int lane, int& ia, int& ib) {
     const double tmax = h.total * (1.0 - 1.2e-16);
     if (!(ta < h.total)) ta = tmax;
     if (!(tb < h.total)) tb = tmax;
@@ -234,9 +234,9 @@ __device__ __forceinline__ void warp_tile_epilogue(const R* lwn, int tile_base, 
 
 // ---- init: x0 ~ N(prior_mean, prior_var), lw = 0, stats = 0  (buffered_smoother.py:67-75) ----------
 template <class R, class Model>
-__global__ void __launch_bounds__(NT) pf_init_kernel(KArgs a) {
+__device__ __forceinline__ void init_body(const KArgs& a, int b, int g) {
     constexpr int NX = Model::NX, NP = Model::NP, W = NX + NP;
-    const int b = blockIdx.y, g = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int N = a.N;
     const size_t item_off = (size_t)b * N;
     if (g == 0) {
@@ -293,6 +293,8 @@ __global__ void __launch_bounds__(NT) pf_init_kernel(KArgs a) {
     warp_tile_epilogue<R, W>(lwn, tile_base, N, lane, reinterpret_cast<R*>(a.fine[0]) + item_off,
                              a.sub[0] + ((size_t)b * a.Q + q_me) * SSTRIDE, a.rec[0], a.tail[0], item_off, false, 0);
 }
+template <class R, class Model>
+__global__ void __launch_bounds__(NT) pf_init_kernel(KArgs a) { init_body<R, Model>(a, blockIdx.y, blockIdx.x); }
 
 // ---- per-item header: everything of a step that crosses tiles ----------------------------------------
 // One CTA per item, launched before step kernel t (final_pass = 0) and once after the last step (1):
@@ -303,9 +305,8 @@ __global__ void __launch_bounds__(NT) pf_init_kernel(KArgs a) {
 //   * exclusive prefix of the per-tile Gamma(P_q, 1) draws (+ one Exp(1)) of the order-statistics sampler
 //   * final: grad = average_statistic (buffered_smoother.py:151-154) or the filter statistic (pf.py:77-80)
 template <class R, class Model>
-__global__ void __launch_bounds__(NT) pf_header_kernel(KArgs a, int t, int final_pass) {
-    __shared__ double sh_d[NWARP];
-    const int b = blockIdx.x, tid = threadIdx.x;
+__device__ __forceinline__ void header_body(const KArgs& a, int b, int t, int final_pass, double* sh_d) {
+    const int tid = threadIdx.x;
     const int Tb = a.T_buf[b];
     if (!final_pass && t >= Tb) return;
     const int par = final_pass ? (Tb & 1) : (t & 1);
@@ -389,6 +390,12 @@ __global__ void __launch_bounds__(NT) pf_header_kernel(KArgs a, int t, int final
             for (int j = 0; j < nstat; ++j) a.grad[(size_t)b * 8 + j] = (a.pf == SGM_PF_FILTER) ? acc[1 + j] : sbar[j];
         }
     }
+}
+
+template <class R, class Model>
+__global__ void __launch_bounds__(NT) pf_header_kernel(KArgs a, int t, int final_pass) {
+    __shared__ double sh_d[NWARP];
+    header_body<R, Model>(a, blockIdx.x, t, final_pass, sh_d);
 }
 
 // ---- gather parents -> propagate -> reweight -> statistic update -> store (pf.py:30-36, 168-179) -----
@@ -478,13 +485,9 @@ __device__ __forceinline__ void draw_uniforms(const RngKey& key, int t, int q_me
 //   of shared memory in global units, each child binary-searches that slice (8 interleaved searches per
 //   lane, neighbouring lanes read neighbouring words), and parent records are gathered as a stream.
 template <class R, class Model, bool SORTED>
-__global__ void __launch_bounds__(NT, (sizeof(R) == 4 ? 4 : 2)) pf_step_kernel(KArgs a, int t) {
+__device__ __forceinline__ void step_body(const KArgs& a, int b, int t, int q_me, int lane, R* s_cdf, R (*s_conv)[2]) {
     constexpr int NP = Model::NP, W = Model::NX + NP;
-    __shared__ R s_cdf_all[SORTED ? NWARP : 1][SORTED ? CAPW : 1];
-    __shared__ R s_conv_all[SORTED ? NWARP : 1][SORTED ? 8 : 1][2];
-    const int b = blockIdx.y, g = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int N = a.N, par = t & 1;
-    const int q_me = g * NWARP + warp;
     if (q_me >= a.Q) return;
     // every load that does not depend on the randoms is issued up front (one round trip for all of them):
     // activity flag, item header scalars, level-1 coarse probe, Gamma prefix, (y_t, w_t), model constants
@@ -504,7 +507,7 @@ __global__ void __launch_bounds__(NT, (sizeof(R) == 4 ? 4 : 2)) pf_step_kernel(K
     const int nws = stat_width<Model>(a.stat_kind);
     const bool carries = (a.pf == SGM_PF_NEMETH);            // stats follow the resampled genealogy here
     const bool shrink = carries && (a.lambduh != 1.0);
-    const R* __restrict__ fine_old = reinterpret_cast<const R*>(a.fine[par]) + item_off;
+    const R* fine_old = reinterpret_cast<const R*>(a.fine[par]) + item_off;
     const int tile_base = q_me * WT;
     const int n_valid = min(WT, N - tile_base);
     RngKey key = a.key; key.item += (uint32_t)b;
@@ -553,8 +556,6 @@ __global__ void __launch_bounds__(NT, (sizeof(R) == 4 ? 4 : 2)) pf_step_kernel(K
         for (int c = 0; c < KPT; ++c) anc[c] = qsel[c] * WT + min(pos[c], len[c] - 1);
         draw_normals<R>(a, key, b, t, q_me, lane, z);
     } else {
-        R* s_cdf = s_cdf_all[SORTED ? warp : 0];
-        R(*s_conv)[2] = s_conv_all[SORTED ? warp : 0];
         // u[c]: for the order-statistics sampler the tile-local position in (0, 1] of child 32 c + lane,
         // else its uniform.  target of that child = tA + tB * (u[c] (+ 32 c + lane))
         R u[KPT];
@@ -666,6 +667,37 @@ __global__ void __launch_bounds__(NT, (sizeof(R) == 4 ? 4 : 2)) pf_step_kernel(K
     warp_tile_epilogue<R, W>(lwn, tile_base, N, lane, reinterpret_cast<R*>(a.fine[par ^ 1]) + item_off,
                              a.sub[par ^ 1] + ((size_t)b * a.Q + q_me) * SSTRIDE, a.rec[par ^ 1], a.tail[par ^ 1],
                              item_off, need_ws, nws);
+}
+
+template <class R, class Model, bool SORTED>
+__global__ void __launch_bounds__(NT, (sizeof(R) == 4 ? 4 : 2)) pf_step_kernel(KArgs a, int t) {
+    __shared__ R s_cdf_all[SORTED ? NWARP : 1][SORTED ? CAPW : 1];
+    __shared__ R s_conv_all[SORTED ? NWARP : 1][SORTED ? 8 : 1][2];
+    const int warp = threadIdx.x >> 5;
+    step_body<R, Model, SORTED>(a, blockIdx.y, t, blockIdx.x * NWARP + warp, threadIdx.x & 31,
+                                s_cdf_all[SORTED ? warp : 0], s_conv_all[SORTED ? warp : 0]);
+}
+
+// ---- fused kernel for small particle counts (N <= 2048: the item fits one CTA) -----------------------------
+// One CTA per item runs init, every (header, step) pair and the final header in ONE launch; the block
+// barrier replaces the kernel boundary (all global-memory traffic of an item stays on one SM, whose L1 is
+// coherent for its own writes).  This is the SGLD-with-N~1000 regime, where launch latency dominated.
+template <class R, class Model, bool SORTED>
+__global__ void __launch_bounds__(NT, (sizeof(R) == 4 ? 4 : 2)) pf_fused_kernel(KArgs a) {
+    __shared__ R s_cdf_all[SORTED ? NWARP : 1][SORTED ? CAPW : 1];
+    __shared__ R s_conv_all[SORTED ? NWARP : 1][SORTED ? 8 : 1][2];
+    __shared__ double sh_d[NWARP];
+    const int b = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    init_body<R, Model>(a, b, 0);
+    __syncthreads();
+    const int Tb = a.T_buf[b];
+    for (int t = 0; t < Tb; ++t) {
+        header_body<R, Model>(a, b, t, 0, sh_d);
+        __syncthreads();
+        step_body<R, Model, SORTED>(a, b, t, warp, lane, s_cdf_all[SORTED ? warp : 0], s_conv_all[SORTED ? warp : 0]);
+        __syncthreads();
+    }
+    header_body<R, Model>(a, b, Tb, 1, sh_d);
 }
 
 // ---- optional export of the final particle system (out['x_t'], ['log_weights'], ['statistics']) ---

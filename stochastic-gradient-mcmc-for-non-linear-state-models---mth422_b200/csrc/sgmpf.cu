@@ -133,18 +133,28 @@ int run_impl(const sgm_pf_desc* d, cudaStream_t stream) {
 
     const dim3 grid(a.G, a.B), block(NT);
     int64_t launches = 0;
-    pf_init_kernel<R, Model><<<grid, block, 0, stream>>>(a); ++launches;
-    if (d->ev_steps_begin) cudaEventRecord(reinterpret_cast<cudaEvent_t>(d->ev_steps_begin), stream);
-    for (int t = 0; t < a.max_T; ++t) {
-        pf_header_kernel<R, Model><<<a.B, block, 0, stream>>>(a, t, 0); ++launches;
-        if (d->resample == SGM_RESAMPLE_MULTINOMIAL) pf_step_kernel<R, Model, false><<<grid, block, 0, stream>>>(a, t);
-        else pf_step_kernel<R, Model, true><<<grid, block, 0, stream>>>(a, t);
+    const bool fused = (a.Q <= NWARP) && !backward_pf(d->pf);
+    if (fused) {
+        // small N: the whole time loop of an item in one launch (one CTA per item)
+        if (d->ev_steps_begin) cudaEventRecord(reinterpret_cast<cudaEvent_t>(d->ev_steps_begin), stream);
+        if (d->resample == SGM_RESAMPLE_MULTINOMIAL) pf_fused_kernel<R, Model, false><<<a.B, block, 0, stream>>>(a);
+        else pf_fused_kernel<R, Model, true><<<a.B, block, 0, stream>>>(a);
         ++launches;
-        if (d->pf == SGM_PF_POY_N2) launches += launch_poyiadjis_n2<R, Model>(a, t, stream);
-        else if (d->pf == SGM_PF_PARIS) launches += launch_paris<R, Model>(a, t, stream);
+        if (d->ev_steps_end) cudaEventRecord(reinterpret_cast<cudaEvent_t>(d->ev_steps_end), stream);
+    } else {
+        pf_init_kernel<R, Model><<<grid, block, 0, stream>>>(a); ++launches;
+        if (d->ev_steps_begin) cudaEventRecord(reinterpret_cast<cudaEvent_t>(d->ev_steps_begin), stream);
+        for (int t = 0; t < a.max_T; ++t) {
+            pf_header_kernel<R, Model><<<a.B, block, 0, stream>>>(a, t, 0); ++launches;
+            if (d->resample == SGM_RESAMPLE_MULTINOMIAL) pf_step_kernel<R, Model, false><<<grid, block, 0, stream>>>(a, t);
+            else pf_step_kernel<R, Model, true><<<grid, block, 0, stream>>>(a, t);
+            ++launches;
+            if (d->pf == SGM_PF_POY_N2) launches += launch_poyiadjis_n2<R, Model>(a, t, stream);
+            else if (d->pf == SGM_PF_PARIS) launches += launch_paris<R, Model>(a, t, stream);
+        }
+        if (d->ev_steps_end) cudaEventRecord(reinterpret_cast<cudaEvent_t>(d->ev_steps_end), stream);
+        pf_header_kernel<R, Model><<<a.B, block, 0, stream>>>(a, a.max_T, 1); ++launches;
     }
-    if (d->ev_steps_end) cudaEventRecord(reinterpret_cast<cudaEvent_t>(d->ev_steps_end), stream);
-    pf_header_kernel<R, Model><<<a.B, block, 0, stream>>>(a, a.max_T, 1); ++launches;
     if (d->out_x || d->out_lw || d->out_stats) {
         pf_export_kernel<R, Model><<<dim3((a.N + NT - 1) / NT, a.B), block, 0, stream>>>(a); ++launches;
     }
