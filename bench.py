@@ -178,6 +178,8 @@ def run_gpu(args):
     import sgmcmc_ssm_b200 as sg
     from sgmcmc_ssm_b200 import parallel
     from sgmcmc_ssm_b200.models.svm import SVMSampler, SVMParameters
+    if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+        os.environ["NCCL_DEBUG"] = "WARN"          # keep stdout to the one JSON line
     rank, world, local = parallel.init_distributed()
     dev = torch.device("cuda", torch.cuda.current_device())
     M = args.minibatch
