@@ -203,7 +203,7 @@ __global__ void __launch_bounds__(NT) paris_ar_kernel(KArgs a, int t) {
     const ItemHdr hdr = load_hdr(a, b);            // header of the OLD weights (built before step t)
     const typename Model::template Theta<R> th = load_thc<R, Model>(a, b);
     const R ltmax = Model::log_trans_max(th);
-    const R* fine_old = reinterpret_cast<const R*>(a.fine[par]) + item_off;
+    const R* fine_old = reinterpret_cast<const R*>(a.fine[par]) + (size_t)b * a.Q * WT;
     RngKey key = a.key; key.item += (uint32_t)b;
     const int tries = a.accept_reject ? a.max_ar : 0;
     for (int c = 0; c < KPT; ++c) {
@@ -269,7 +269,7 @@ __global__ void __launch_bounds__(NT) paris_injected_kernel(KArgs a, int t) {
     const ItemHdr hdr = load_hdr(a, b);            // header of the OLD weights (built before step t)
     const typename Model::template Theta<R> th = load_thc<R, Model>(a, b);
     const R ltmax = Model::log_trans_max(th);
-    const R* fine_old = reinterpret_cast<const R*>(a.fine[par]) + item_off;
+    const R* fine_old = reinterpret_cast<const R*>(a.fine[par]) + (size_t)b * a.Q * WT;
     const double* extra = a.inj_extra + a.inj_extra_off[(size_t)b * a.max_T + t];
     int32_t* Jb = a.Jidx + item_off * Nt;
     int64_t off = 0;

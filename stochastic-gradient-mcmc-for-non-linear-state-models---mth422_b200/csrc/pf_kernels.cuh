@@ -12,7 +12,7 @@
 // Data layout in HBM (caller workspace; B items, N particles, Q = ceil(N / 256) warp tiles per item):
 //   rec [2][B][N][4]   R   first four components of the particle record  (stats..., then state)
 //   tail[2][B][N][KT]  R   remaining KT = NX + NP - 4 components (SVM 0, LGSSM 1, GARCH 2)
-//   fine[2][B][N]      R   tile-local inclusive scan of exp(lw - m_tile)   ("fine" CDF)
+//   fine[2][B][Q*256]  R   tile-local inclusive scan of exp(lw - m_tile)   ("fine" CDF), padded to whole tiles
 //   lw  [2][B][N]      R   log-weights (only written when a consumer needs them)
 //   sub [2][B][Q][8]   f64 per warp tile: m_tile, s_tile = sum exp(lw - m_tile), ws[0..3]
 //   hdr [B][8+3(Q+2)]  f64 per item, rebuilt every step: M, total, sbar[4]; off[Q+1] exclusive prefix of
@@ -33,7 +33,7 @@ constexpr int KPT = 8;                 // consecutive particles per lane
 constexpr int WT = 32 * KPT;           // 256 particles per warp tile
 constexpr int TILE = NT * KPT;         // 2048 particles per CTA (8 warp tiles)
 constexpr int MAX_Q = 4096;            // N <= 2^20
-constexpr int CAPW = 512;              // parents staged in shared memory per warp (sorted resampling)
+constexpr int WIN_BYTES = 4096;        // per-warp shared-memory window of the staged parent CDF (sorted resampling)
 constexpr int SSTRIDE = 8;             // doubles per `sub` entry
 constexpr int ACC_STRIDE = 8;          // doubles per `acc` entry
 constexpr int THC_BYTES = 128;         // per-item slot for the model's derived constants
@@ -124,42 +124,14 @@ __device__ __forceinline__ int search_hdr(double target, const ItemHdr& h, const
     return base + min(pos, len - 1);
 }
 
-// The same search executed cooperatively by a full warp (all lanes pass the same target): 32-ary probing
-// with ballots -- 2-3 dependent loads for the tile, 2 inside it.
-template <class R>
-__device__ __forceinline__ int warp_search_hdr(double target, const ItemHdr& h, const R* fine, int N, int lane) {
-    if (!(target < h.total)) target = h.total * (1.0 - 1.2e-16);
-    int q = 0, len = h.Q;
-    while (len > 1) {
-        const int s = (len + 31) >> 5;
-        const bool pred = (lane * s < len) && (h.off[q + lane * s] <= target);
-        const int cnt = __popc(__ballot_sync(FULL, pred));
-        const int adv = (max(cnt, 1) - 1) * s;
-        len = min(s, len - adv);
-        q += adv;
-    }
-    const R r = (R)((target - h.off[q]) / h.sc[q]);
-    const int base = q * WT;
-    const int lenf = min(WT, N - base);
-    const R* f = fine + base;
-    bool le = (lane * KPT < lenf) ? (f[min(lenf, (lane + 1) * KPT) - 1] <= r) : false;
-    const int s1 = __popc(__ballot_sync(FULL, le)) * KPT;
-    le = (lane < KPT && s1 + lane < lenf) ? (f[s1 + lane] <= r) : false;
-    const int res = s1 + __popc(__ballot_sync(FULL, le));
-    return base + min(res, lenf - 1);
-}
-
-// Two searches at once (first and last child of a warp tile), all loads of a level issued together so
-// the two dependent-load chains overlap.  `c1` is the level-1 coarse probe off[lane * s1c] (+inf beyond Q),
-// prefetched by the caller before it draws its randoms.
-template <class R>
-__device__ __forceinline__ void warp_search_pair(double ta, double tb, double c1, int s1c, const ItemHdr& h,
-                                                 const R* fine, int N, int lane, int& ia, int& ib) {
-    const double tmax = h.total * (1.0 - 1.2e-16);
-    if (!(ta < h.total)) ta = tmax;
-    if (!(tb < h.total)) tb = tmax;
-    int qa = (max(__popc(__ballot_sync(FULL, c1 <= ta)), 1) - 1) * s1c;
-    int qb = (max(__popc(__ballot_sync(FULL, c1 <= tb)), 1) - 1) * s1c;
+// Coarse searches of two targets at once (first and last child of a warp tile): largest tile q with
+// off[q] <= target, by 32-ary probing with ballots; all loads of a level are issued together so the two
+// dependent-load chains overlap.  `c1` is the level-1 probe off[lane * s1c] (+inf beyond Q), prefetched by
+// the caller before it draws its randoms.
+__device__ __forceinline__ void warp_search_tiles(double ta, double tb, double c1, int s1c, const ItemHdr& h,
+                                                  int lane, int& qa, int& qb) {
+    qa = (max(__popc(__ballot_sync(FULL, c1 <= ta)), 1) - 1) * s1c;
+    qb = (max(__popc(__ballot_sync(FULL, c1 <= tb)), 1) - 1) * s1c;
     int la = min(s1c, h.Q - qa), lb = min(s1c, h.Q - qb);
     while (la > 1 || lb > 1) {
         const int sa = (la + 31) >> 5, sb = (lb + 31) >> 5;
@@ -174,20 +146,6 @@ __device__ __forceinline__ void warp_search_pair(double ta, double tb, double c1
             lb = min(sb, lb - adv); qb += adv;
         }
     }
-    const double oa = h.off[qa], ob = h.off[qb], sca = h.sc[qa], scb = h.sc[qb];
-    const R ra = (R)((ta - oa) / sca), rb = (R)((tb - ob) / scb);
-    const int ba = qa * WT, bb = qb * WT;
-    const int na = min(WT, N - ba), nb = min(WT, N - bb);
-    const R* fa = fine + ba;
-    const R* fb = fine + bb;
-    const R pa = (lane * KPT < na) ? fa[min(na, (lane + 1) * KPT) - 1] : Mth<R>::inf();
-    const R pb = (lane * KPT < nb) ? fb[min(nb, (lane + 1) * KPT) - 1] : Mth<R>::inf();
-    const int s1a = __popc(__ballot_sync(FULL, pa <= ra)) * KPT;
-    const int s1b = __popc(__ballot_sync(FULL, pb <= rb)) * KPT;
-    const R pa2 = (lane < KPT && s1a + lane < na) ? fa[s1a + lane] : Mth<R>::inf();
-    const R pb2 = (lane < KPT && s1b + lane < nb) ? fb[s1b + lane] : Mth<R>::inf();
-    ia = ba + min(s1a + __popc(__ballot_sync(FULL, pa2 <= ra)), na - 1);
-    ib = bb + min(s1b + __popc(__ballot_sync(FULL, pb2 <= rb)), nb - 1);
 }
 
 // ---- per-warp-tile epilogue: tile max, tile-local scan of exp(lw - m), per-tile partials ---------------
@@ -209,7 +167,7 @@ __device__ __forceinline__ void warp_tile_epilogue(const R* lwn, int tile_base, 
         w[c] = Mth<R>::exp(lwn[c] - msafe);
         const R incl = warp_incl_scan(w[c]);
         const int i = tile_base + 32 * c + lane;
-        if (i < N) fine_out[i] = carry + incl;
+        fine_out[i] = carry + incl;                   // `fine` is padded to whole tiles (entries >= N repeat the total)
         carry += __shfl_sync(FULL, incl, 31);
     }
     double ws[4] = {0.0, 0.0, 0.0, 0.0};
@@ -290,7 +248,7 @@ __device__ __forceinline__ void init_body(const KArgs& a, int b, int g) {
             if (a.trace_lw) reinterpret_cast<R*>(a.trace_lw)[(size_t)b * (a.max_T + 1) * N + i] = (R)0;
         }
     }
-    warp_tile_epilogue<R, W>(lwn, tile_base, N, lane, reinterpret_cast<R*>(a.fine[0]) + item_off,
+    warp_tile_epilogue<R, W>(lwn, tile_base, N, lane, reinterpret_cast<R*>(a.fine[0]) + (size_t)b * a.Q * WT,
                              a.sub[0] + ((size_t)b * a.Q + q_me) * SSTRIDE, a.rec[0], a.tail[0], item_off, false, 0);
 }
 template <class R, class Model>
@@ -485,7 +443,7 @@ __device__ __forceinline__ void draw_uniforms(const RngKey& key, int t, int q_me
 //   of shared memory in global units, each child binary-searches that slice (8 interleaved searches per
 //   lane, neighbouring lanes read neighbouring words), and parent records are gathered as a stream.
 template <class R, class Model, bool SORTED>
-__device__ __forceinline__ void step_body(const KArgs& a, int b, int t, int q_me, int lane, R* s_cdf, R (*s_conv)[2]) {
+__device__ __forceinline__ void step_body(const KArgs& a, int b, int t, int q_me, int lane, R* s_cdf) {
     constexpr int NP = Model::NP, W = Model::NX + NP;
     const int N = a.N, par = t & 1;
     if (q_me >= a.Q) return;
@@ -507,7 +465,7 @@ __device__ __forceinline__ void step_body(const KArgs& a, int b, int t, int q_me
     const int nws = stat_width<Model>(a.stat_kind);
     const bool carries = (a.pf == SGM_PF_NEMETH);            // stats follow the resampled genealogy here
     const bool shrink = carries && (a.lambduh != 1.0);
-    const R* fine_old = reinterpret_cast<const R*>(a.fine[par]) + item_off;
+    const R* fine_old = reinterpret_cast<const R*>(a.fine[par]) + (size_t)b * a.Q * WT;      // padded to whole tiles
     const int tile_base = q_me * WT;
     const int n_valid = min(WT, N - tile_base);
     RngKey key = a.key; key.item += (uint32_t)b;
@@ -601,33 +559,57 @@ __device__ __forceinline__ void step_body(const KArgs& a, int b, int t, int q_me
             else tg = tA + tB * ((double)(32 * c + lane) + (double)u[c]);
             return (tg < total) ? tg : tmax;
         };
-        // ---- parent range of this warp tile: first child = (row 0, lane 0), last = particle n_valid - 1 ----
+        // ---- parent tiles of this warp tile: first child = (row 0, lane 0), last = particle n_valid - 1 ----
         const int last = n_valid - 1, l_last = last & 31, c_last = last >> 5;
         double tl = target_of(0);
         const double tf = __shfl_sync(FULL, tl, 0);
 #pragma unroll
         for (int c = 1; c < KPT; ++c) if (c == c_last) tl = target_of(c);
         tl = __shfl_sync(FULL, tl, l_last);
-        int lo, hi;
-        warp_search_pair<R>(tf, tl, c1, s1c, hdr, fine_old, N, lane, lo, hi);
-        const int range = hi - lo + 1, q_lo = lo / WT, nq = hi / WT - q_lo + 1;
-        if (range >= 1 && range <= CAPW && nq <= 8) {
-            // stage the CDF of [lo, hi] in global units relative to cbase (f32 is enough: the range spans a
-            // few tiles)
+        int q_lo, q_hi;
+        warp_search_tiles(tf, tl, c1, s1c, hdr, lane, q_lo, q_hi);
+        constexpr int MAXT = WIN_BYTES / (int)(WT * sizeof(R));         // tiles the window holds: f32 4, f64 2
+        const int nst = q_hi - q_lo + 1;
+        if (nst >= 1 && nst <= MAXT) {
+            // Stage the CDF of whole parent tiles q_lo .. q_lo + wt - 1 (wt = 1, 2 or 4: a power-of-two window, so
+            // the searches below need neither bound checks nor a run-time step) in global units relative to
+            // cbase = off[q_lo]; f32 is enough, the window spans a few tiles.  `fine` is padded to whole tiles, so
+            // every tile is 2 aligned vector loads per lane; tiles beyond the item read as +inf.
+            const int wt = (nst <= 1) ? 1 : ((nst <= 2) ? 2 : 4);
             const double cbase = hdr.off[q_lo];
-            if (lane < nq) { s_conv[lane][0] = (R)(hdr.off[q_lo + lane] - cbase); s_conv[lane][1] = (R)hdr.sc[q_lo + lane]; }
-            __syncwarp();
-            // ... padded with +inf to a power of two (256 or 512) so the searches below need neither bound
-            // checks nor a run-time step: LDS [pos + immediate], compare, predicated add
-            const int p2 = (range <= CAPW / 2) ? CAPW / 2 : CAPW;
-#pragma unroll 4
-            for (int k = lane; k < p2; k += 32) {
-                R v = Mth<R>::inf();
-                if (k < range) {
-                    const int p = lo + k, j = p / WT - q_lo;
-                    v = s_conv[j][0] + fine_old[p] * s_conv[j][1];
+            const Vec4T<R>* src = reinterpret_cast<const Vec4T<R>*>(fine_old + (size_t)q_lo * WT);
+            Vec4T<R>* dst = reinterpret_cast<Vec4T<R>*>(s_cdf);
+#pragma unroll
+            for (int j0 = 0; j0 < MAXT; j0 += 2) {
+                if (j0 < wt) {
+                    Vec4T<R> f[2][2];
+                    R o[2], sc[2];
+#pragma unroll
+                    for (int j = 0; j < 2; ++j) {
+                        const bool live = (j0 + j < wt) && (q_lo + j0 + j < a.Q);
+                        o[j] = Mth<R>::inf(); sc[j] = (R)0;
+#pragma unroll
+                        for (int h = 0; h < 2; ++h) { f[j][h].x = f[j][h].y = f[j][h].z = f[j][h].w = (R)0; }
+                        if (live) {
+                            f[j][0] = src[(j0 + j) * (WT / 4) + lane];
+                            f[j][1] = src[(j0 + j) * (WT / 4) + 32 + lane];
+                            o[j] = (R)(hdr.off[q_lo + j0 + j] - cbase);
+                            sc[j] = (R)hdr.sc[q_lo + j0 + j];
+                        }
+                    }
+#pragma unroll
+                    for (int j = 0; j < 2; ++j) {
+                        if (j0 + j < wt) {
+#pragma unroll
+                            for (int h = 0; h < 2; ++h) {
+                                Vec4T<R> v;
+                                v.x = o[j] + f[j][h].x * sc[j]; v.y = o[j] + f[j][h].y * sc[j];
+                                v.z = o[j] + f[j][h].z * sc[j]; v.w = o[j] + f[j][h].w * sc[j];
+                                dst[(j0 + j) * (WT / 4) + 32 * h + lane] = v;
+                            }
+                        }
+                    }
                 }
-                s_cdf[k] = v;
             }
             __syncwarp();
             R rt[KPT];
@@ -639,24 +621,30 @@ __device__ __forceinline__ void step_body(const KArgs& a, int b, int t, int q_me
 #pragma unroll
                 for (int c = 0; c < KPT; ++c) rt[c] = spacings ? (rA + rB * u[c]) : (rA + rB * ((R)(32 * c + lane) + u[c]));
             }
-            // 8 independent branch-free binary searches per lane, interleaved; pos = #{k : s_cdf[k] <= rt}
+            // 8 independent branch-free binary searches per lane, interleaved; pos = #{k : s_cdf[k] <= rt}:
+            // LDS [pos + immediate], compare, predicated add
             int pos[KPT];
 #pragma unroll
             for (int c = 0; c < KPT; ++c) pos[c] = 0;
-            if (p2 == CAPW) {
+            if (MAXT >= 4 && wt == 4) {
 #pragma unroll
-                for (int c = 0; c < KPT; ++c) if (s_cdf[CAPW / 2 - 1] <= rt[c]) pos[c] = CAPW / 2;
+                for (int c = 0; c < KPT; ++c) if (s_cdf[2 * WT - 1] <= rt[c]) pos[c] = 2 * WT;
+            }
+            if (wt >= 2) {
+#pragma unroll
+                for (int c = 0; c < KPT; ++c) if (s_cdf[pos[c] + WT - 1] <= rt[c]) pos[c] += WT;
             }
 #pragma unroll
-            for (int step = CAPW / 4; step > 0; step >>= 1) {
+            for (int step = WT / 2; step > 0; step >>= 1) {
 #pragma unroll
                 for (int c = 0; c < KPT; ++c)
                     if (s_cdf[pos[c] + step - 1] <= rt[c]) pos[c] += step;
             }
 #pragma unroll
-            for (int c = 0; c < KPT; ++c) anc[c] = lo + min(pos[c], range - 1);
+            for (int c = 0; c < KPT; ++c) anc[c] = min(q_lo * WT + pos[c], N - 1);
+            __syncwarp();                   // the window is reused by this warp's next tile (fused kernel)
         } else {
-            // very uneven weights: the tile spans more parents than the staging buffer holds
+            // very uneven weights: the tile spans more parent tiles than the staging window holds
 #pragma unroll 1
             for (int c = 0; c < KPT; ++c) anc[c] = search_hdr<R>(target_of(c), hdr, fine_old, N);
         }
@@ -664,18 +652,16 @@ __device__ __forceinline__ void step_body(const KArgs& a, int b, int t, int q_me
     R lwn[KPT];
     propagate_store<R, Model>(a, b, t, par, tile_base, lane, item_off, anc, z, hdr, nws, carries, shrink, lwn, th, y_t, w_t);
     const bool need_ws = (nws > 0) && (a.pf == SGM_PF_FILTER || shrink || (carries && t == Tb - 1));
-    warp_tile_epilogue<R, W>(lwn, tile_base, N, lane, reinterpret_cast<R*>(a.fine[par ^ 1]) + item_off,
+    warp_tile_epilogue<R, W>(lwn, tile_base, N, lane, reinterpret_cast<R*>(a.fine[par ^ 1]) + (size_t)b * a.Q * WT,
                              a.sub[par ^ 1] + ((size_t)b * a.Q + q_me) * SSTRIDE, a.rec[par ^ 1], a.tail[par ^ 1],
                              item_off, need_ws, nws);
 }
 
 template <class R, class Model, bool SORTED>
 __global__ void __launch_bounds__(NT, (sizeof(R) == 4 ? 4 : 2)) pf_step_kernel(KArgs a, int t) {
-    __shared__ R s_cdf_all[SORTED ? NWARP : 1][SORTED ? CAPW : 1];
-    __shared__ R s_conv_all[SORTED ? NWARP : 1][SORTED ? 8 : 1][2];
+    __shared__ __align__(32) R s_cdf_all[SORTED ? NWARP : 1][SORTED ? WIN_BYTES / sizeof(R) : 4];
     const int warp = threadIdx.x >> 5;
-    step_body<R, Model, SORTED>(a, blockIdx.y, t, blockIdx.x * NWARP + warp, threadIdx.x & 31,
-                                s_cdf_all[SORTED ? warp : 0], s_conv_all[SORTED ? warp : 0]);
+    step_body<R, Model, SORTED>(a, blockIdx.y, t, blockIdx.x * NWARP + warp, threadIdx.x & 31, s_cdf_all[SORTED ? warp : 0]);
 }
 
 // ---- fused kernel for small particle counts (N <= 2048: the item fits one CTA) -----------------------------
@@ -684,8 +670,7 @@ __global__ void __launch_bounds__(NT, (sizeof(R) == 4 ? 4 : 2)) pf_step_kernel(K
 // coherent for its own writes).  This is the SGLD-with-N~1000 regime, where launch latency dominated.
 template <class R, class Model, bool SORTED>
 __global__ void __launch_bounds__(NT, (sizeof(R) == 4 ? 4 : 2)) pf_fused_kernel(KArgs a) {
-    __shared__ R s_cdf_all[SORTED ? NWARP : 1][SORTED ? CAPW : 1];
-    __shared__ R s_conv_all[SORTED ? NWARP : 1][SORTED ? 8 : 1][2];
+    __shared__ __align__(32) R s_cdf_all[SORTED ? NWARP : 1][SORTED ? WIN_BYTES / sizeof(R) : 4];
     __shared__ double sh_d[NWARP];
     const int b = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     init_body<R, Model>(a, b, 0);
@@ -694,7 +679,7 @@ __global__ void __launch_bounds__(NT, (sizeof(R) == 4 ? 4 : 2)) pf_fused_kernel(
     for (int t = 0; t < Tb; ++t) {
         header_body<R, Model>(a, b, t, 0, sh_d);
         __syncthreads();
-        step_body<R, Model, SORTED>(a, b, t, warp, lane, s_cdf_all[SORTED ? warp : 0], s_conv_all[SORTED ? warp : 0]);
+        step_body<R, Model, SORTED>(a, b, t, warp, lane, s_cdf_all[SORTED ? warp : 0]);
         __syncthreads();
     }
     header_body<R, Model>(a, b, Tb, 1, sh_d);

@@ -71,7 +71,7 @@ Layout make_layout(const sgm_pf_desc* d) {
     size_t off = 0;
     for (int k = 0; k < 2; ++k) { L.rec[k] = off; off = align_up(off + B * N * 4 * es); }
     for (int k = 0; k < 2; ++k) { L.tail[k] = off; off = align_up(off + B * N * KT * es); }
-    for (int k = 0; k < 2; ++k) { L.fine[k] = off; off = align_up(off + B * N * es); }
+    for (int k = 0; k < 2; ++k) { L.fine[k] = off; off = align_up(off + B * Q * WT * es); }
     for (int k = 0; k < 2; ++k) { L.lw[k] = off; off = align_up(off + (need_lw ? B * N * es : 0)); }
     for (int k = 0; k < 2; ++k) { L.sub[k] = off; off = align_up(off + B * Q * SSTRIDE * 8); }
     L.hdr = off; off = align_up(off + B * hdr_stride((int)Q) * 8);
