@@ -17,6 +17,7 @@
 //   sub [2][B][Q][8]   f64 per warp tile: m_tile, s_tile = sum exp(lw - m_tile), ws[0..3]
 //   hdr [B][8+3(Q+2)]  f64 per item, rebuilt every step: M, total, sbar[4]; off[Q+1] exclusive prefix of
 //                          tile masses in units of exp(-M); sc[Q] = exp(m_tile - M); gam[Q+2] Gamma prefix
+//                          (order-statistics sampler: first target of every child tile, in units of exp(-M))
 //   acc [B][8]         f64 running log-likelihood (+ filter statistic)
 // rec / tail / fine / lw / sub are double-buffered on step parity: step t reads [t & 1], writes [(t+1) & 1].
 //
@@ -62,13 +63,13 @@ struct KArgs {
 // ---- record access ---------------------------------------------------------------------------
 template <class R> struct alignas(4 * sizeof(R)) Vec4T { R x, y, z, w; };
 
-template <class R, int W> __device__ __forceinline__ void load_rec(const void* rec, const void* tail, size_t idx, R* r) {
+template <class R, int W, class I> __device__ __forceinline__ void load_rec(const void* rec, const void* tail, I idx, R* r) {
     const Vec4T<R> v = reinterpret_cast<const Vec4T<R>*>(rec)[idx];
     r[0] = v.x; r[1] = v.y; r[2] = v.z; r[3] = v.w;
     if (W == 5) r[4] = reinterpret_cast<const R*>(tail)[idx];
     if (W == 6) { const R* t = reinterpret_cast<const R*>(tail) + 2 * idx; r[4] = t[0]; r[5] = t[1]; }
 }
-template <class R, int W> __device__ __forceinline__ void store_rec(void* rec, void* tail, size_t idx, const R* r) {
+template <class R, int W, class I> __device__ __forceinline__ void store_rec(void* rec, void* tail, I idx, const R* r) {
     Vec4T<R> v; v.x = r[0]; v.y = r[1]; v.z = r[2]; v.w = r[3];
     reinterpret_cast<Vec4T<R>*>(rec)[idx] = v;
     if (W == 5) reinterpret_cast<R*>(tail)[idx] = r[4];
@@ -148,12 +149,40 @@ __device__ __forceinline__ void warp_search_tiles(double ta, double tb, double c
     }
 }
 
+// ---- warp-tile scan helpers -------------------------------------------------------------------------------
+// A warp tile is an 8 x 32 matrix of particles, slot = 32 c + lane ("row-major": what the coalesced loads /
+// stores want).  A prefix scan in slot order is cheapest "lane-major" (lane l holds slots 8 l .. 8 l + 7: 7
+// serial adds, ONE shuffle scan of the lane totals, 8 offset adds, instead of 8 shuffle scans), so scans
+// transpose through the warp's slice `s_tr` (>= 256 R, 32-byte aligned) of shared memory.
+template <class R>
+__device__ __forceinline__ void lane_major_incl_scan(R* v, R& total) {           // v[k]: slot 8 lane + k, in place
+#pragma unroll
+    for (int k = 1; k < KPT; ++k) v[k] += v[k - 1];
+    const R incl = warp_incl_scan(v[KPT - 1]);
+    const R excl = incl - v[KPT - 1];
+#pragma unroll
+    for (int k = 0; k < KPT; ++k) v[k] += excl;
+    total = __shfl_sync(FULL, incl, 31);
+}
+template <class R>
+__device__ __forceinline__ void store_lane_major(R* dst, int lane, const R* v) {  // dst[8 lane + k] = v[k]
+    Vec4T<R> a, b;
+    a.x = v[0]; a.y = v[1]; a.z = v[2]; a.w = v[3]; b.x = v[4]; b.y = v[5]; b.z = v[6]; b.w = v[7];
+    reinterpret_cast<Vec4T<R>*>(dst)[2 * lane] = a;
+    reinterpret_cast<Vec4T<R>*>(dst)[2 * lane + 1] = b;
+}
+template <class R>
+__device__ __forceinline__ void load_lane_major(const R* src, int lane, R* v) {
+    const Vec4T<R> a = reinterpret_cast<const Vec4T<R>*>(src)[2 * lane], b = reinterpret_cast<const Vec4T<R>*>(src)[2 * lane + 1];
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+
 // ---- per-warp-tile epilogue: tile max, tile-local scan of exp(lw - m), per-tile partials ---------------
 // lwn[c] belongs to particle tile_base + 32 c + lane; callers set -inf beyond N (zero weight).
 template <class R, int W>
 __device__ __forceinline__ void warp_tile_epilogue(const R* lwn, int tile_base, int N, int lane, R* fine_out, double* sub_out,
                                                    const void* rec_new, const void* tail_new, size_t item_off,
-                                                   bool need_ws, int nws) {
+                                                   bool need_ws, int nws, R* s_tr) {
     R m = -Mth<R>::inf();
 #pragma unroll
     for (int c = 0; c < KPT; ++c) m = nan_max(m, lwn[c]);
@@ -161,15 +190,18 @@ __device__ __forceinline__ void warp_tile_epilogue(const R* lwn, int tile_base, 
     // m == -inf (every weight of the tile zero): shift by 0 instead; exp(-inf) = 0, and a NaN log-weight
     // still poisons the tile sum so that the item gets flagged
     const R msafe = (m == -Mth<R>::inf()) ? (R)0 : m;
-    R w[KPT], carry = (R)0;
+    R w[KPT], f[KPT], total;
+    __syncwarp();
 #pragma unroll
-    for (int c = 0; c < KPT; ++c) {                  // row c = 32 consecutive particles: shuffle scan + carry
+    for (int c = 0; c < KPT; ++c) {
         w[c] = Mth<R>::exp(lwn[c] - msafe);
-        const R incl = warp_incl_scan(w[c]);
-        const int i = tile_base + 32 * c + lane;
-        fine_out[i] = carry + incl;                   // `fine` is padded to whole tiles (entries >= N repeat the total)
-        carry += __shfl_sync(FULL, incl, 31);
+        s_tr[32 * c + lane] = w[c];
     }
+    __syncwarp();
+    load_lane_major<R>(s_tr, lane, f);
+    lane_major_incl_scan<R>(f, total);
+    store_lane_major<R>(fine_out + tile_base, lane, f);   // `fine` is padded to whole tiles (entries >= N repeat the total)
+    __syncwarp();
     double ws[4] = {0.0, 0.0, 0.0, 0.0};
     if (need_ws) {
 #pragma unroll
@@ -185,14 +217,14 @@ __device__ __forceinline__ void warp_tile_epilogue(const R* lwn, int tile_base, 
     }
     if (lane == 0) {
         sub_out[0] = (double)m;
-        sub_out[1] = (double)carry;
+        sub_out[1] = (double)total;
         for (int q = 0; q < 4; ++q) sub_out[2 + q] = ws[q];
     }
 }
 
 // ---- init: x0 ~ N(prior_mean, prior_var), lw = 0, stats = 0  (buffered_smoother.py:67-75) ----------
 template <class R, class Model>
-__device__ __forceinline__ void init_body(const KArgs& a, int b, int g) {
+__device__ __forceinline__ void init_body(const KArgs& a, int b, int g, R* s_tr) {
     constexpr int NX = Model::NX, NP = Model::NP, W = NX + NP;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int N = a.N;
@@ -249,10 +281,13 @@ __device__ __forceinline__ void init_body(const KArgs& a, int b, int g) {
         }
     }
     warp_tile_epilogue<R, W>(lwn, tile_base, N, lane, reinterpret_cast<R*>(a.fine[0]) + (size_t)b * a.Q * WT,
-                             a.sub[0] + ((size_t)b * a.Q + q_me) * SSTRIDE, a.rec[0], a.tail[0], item_off, false, 0);
+                             a.sub[0] + ((size_t)b * a.Q + q_me) * SSTRIDE, a.rec[0], a.tail[0], item_off, false, 0, s_tr);
 }
 template <class R, class Model>
-__global__ void __launch_bounds__(NT) pf_init_kernel(KArgs a) { init_body<R, Model>(a, blockIdx.y, blockIdx.x); }
+__global__ void __launch_bounds__(NT) pf_init_kernel(KArgs a) {
+    __shared__ __align__(32) R s_tr_all[NWARP][WT];
+    init_body<R, Model>(a, blockIdx.y, blockIdx.x, s_tr_all[threadIdx.x >> 5]);
+}
 
 // ---- per-item header: everything of a step that crosses tiles ----------------------------------------
 // One CTA per item, launched before step kernel t (final_pass = 0) and once after the last step (1):
@@ -319,14 +354,15 @@ __device__ __forceinline__ void header_body(const KArgs& a, int b, int t, int fi
         }
         double gtot;
         double grun = block_excl_scan(gl, sh_d, gtot);
+        const double kk = total / gtot;                  // stored in target units: gam[q] = total * G_q / G_total
         for (int k = 0; k < perg; ++k) {
             const int q = g0 + k;
             if (q <= Q) {
-                gam[q] = grun;
+                gam[q] = grun * kk;
                 grun += rng_gamma(key, (uint32_t)q, (uint32_t)t, (q == Q) ? 1.0 : (double)min(WT, N - q * WT));
             }
         }
-        if (tid == 0) gam[Q + 1] = gtot;
+        if (tid == 0) gam[Q + 1] = total;
     }
     if (tid == 0) {
         off[Q] = total;
@@ -377,16 +413,18 @@ __device__ __forceinline__ void propagate_store(const KArgs& a, int b, int t, in
     const R keep = carries ? (shrink ? lam : (R)1) : (R)0;
     const R hs = (carries || a.pf == SGM_PF_FILTER) ? wt : (R)0;
     const int stat_kind = (in_sub && hs != (R)0) ? a.stat_kind : SGM_STAT_NONE;
-    const void* rec_old = a.rec[par];
-    const void* tail_old = a.tail[par];
-    void* rec_new = a.rec[par ^ 1];
-    void* tail_new = a.tail[par ^ 1];
+    // per-item base pointers: the particle index stays a 32-bit register (one IMAD.WIDE per address)
+    const void* rec_old = reinterpret_cast<const Vec4T<R>*>(a.rec[par]) + item_off;
+    const void* tail_old = reinterpret_cast<const R*>(a.tail[par]) + item_off * (W - 4);
+    void* rec_new = reinterpret_cast<Vec4T<R>*>(a.rec[par ^ 1]) + item_off;
+    void* tail_new = reinterpret_cast<R*>(a.tail[par ^ 1]) + item_off * (W - 4);
+    R* lw_new = reinterpret_cast<R*>(a.lw[par ^ 1]) + item_off;
 #pragma unroll
     for (int h0 = 0; h0 < KPT; h0 += 4) {
         R ra[4][W];
 #pragma unroll
         for (int c = 0; c < 4; ++c)                       // four independent parent gathers in flight
-            if (tile_base + 32 * (h0 + c) + lane < N) load_rec<R, W>(rec_old, tail_old, item_off + anc[h0 + c], ra[c]);
+            if (tile_base + 32 * (h0 + c) + lane < N) load_rec<R, W>(rec_old, tail_old, anc[h0 + c], ra[c]);
 #pragma unroll
         for (int c4 = 0; c4 < 4; ++c4) {
             const int c = h0 + c4, i = tile_base + 32 * c + lane;
@@ -400,9 +438,9 @@ __device__ __forceinline__ void propagate_store(const KArgs& a, int b, int t, in
                 else if (stat_kind == SGM_STAT_SUFF) Model::suff(ra[c4] + NP, rn + NP, h);
 #pragma unroll
                 for (int q = 0; q < NP; ++q) rn[q] = keep * ra[c4][q] + (sbar[q] + h[q] * hs);
-                store_rec<R, W>(rec_new, tail_new, item_off + i, rn);
+                store_rec<R, W>(rec_new, tail_new, i, rn);
                 if (tracing) {
-                    if (a.need_lw) reinterpret_cast<R*>(a.lw[par ^ 1])[item_off + i] = lwn[c];
+                    if (a.need_lw) lw_new[i] = lwn[c];
                     if (a.trace_anc) a.trace_anc[((size_t)b * a.max_T + t) * N + i] = anc[c];
                     if (a.trace_x) {
                         R* tx = reinterpret_cast<R*>(a.trace_x) + (((size_t)b * (a.max_T + 1) + t + 1) * N + i) * NX;
@@ -434,6 +472,23 @@ __device__ __forceinline__ void draw_uniforms(const RngKey& key, int t, int q_me
     rng_uniform4(key, (uint32_t)(q_me * 64 + lane * 2 + 1), (uint32_t)t, STREAM_UNIFORM, u + 4);
 }
 
+// Shared-memory load at [byte address + compile-time offset] (the offset lands in the LDS immediate field).
+template <int OFF> __device__ __forceinline__ float lds_at(uint32_t addr, float) {
+    float v; asm volatile("ld.shared.f32 %0, [%1+%2];" : "=f"(v) : "r"(addr), "n"(OFF)); return v;
+}
+template <int OFF> __device__ __forceinline__ double lds_at(uint32_t addr, double) {
+    double v; asm volatile("ld.shared.f64 %0, [%1+%2];" : "=d"(v) : "r"(addr), "n"(OFF)); return v;
+}
+template <class R, int STEP>
+__device__ __forceinline__ void search_levels(uint32_t* ad, const R* rt) {
+    if constexpr (STEP > 0) {
+#pragma unroll
+        for (int c = 0; c < KPT; ++c)
+            if (lds_at<(STEP - 1) * (int)sizeof(R)>(ad[c], (R)0) <= rt[c]) ad[c] += STEP * (int)sizeof(R);
+        search_levels<R, STEP / 2>(ad, rt);
+    }
+}
+
 // ---- one resample -> propagate -> reweight -> statistic-update step (pf.py:7-38, 138-181, 40-82) ---
 // SORTED = false: iid resampling uniforms (exact reference semantics, pf.py:27-29): per child a binary
 //   search over the tile offsets and inside one tile, the 8 children of a lane interleaved.
@@ -444,6 +499,7 @@ __device__ __forceinline__ void draw_uniforms(const RngKey& key, int t, int q_me
 //   lane, neighbouring lanes read neighbouring words), and parent records are gathered as a stream.
 template <class R, class Model, bool SORTED>
 __device__ __forceinline__ void step_body(const KArgs& a, int b, int t, int q_me, int lane, R* s_cdf) {
+    R* const s_tr = s_cdf;                 // the warp's shared-memory slice doubles as the scan transposition buffer
     constexpr int NP = Model::NP, W = Model::NX + NP;
     const int N = a.N, par = t & 1;
     if (q_me >= a.Q) return;
@@ -459,7 +515,6 @@ __device__ __forceinline__ void step_body(const KArgs& a, int b, int t, int q_me
     const bool spacings = SORTED && uses_spacings(a);
     const double gam_lo = spacings ? hdr.gam[q_me] : 0.0;
     const double gam_hi = spacings ? hdr.gam[q_me + 1] : 0.0;
-    const double gam_tot = spacings ? hdr.gam[a.Q + 1] : 1.0;
     if (t >= Tb) return;
     const size_t item_off = (size_t)b * N;
     const int nws = stat_width<Model>(a.stat_kind);
@@ -522,20 +577,22 @@ __device__ __forceinline__ void step_body(const KArgs& a, int b, int t, int q_me
             // Order statistics of N iid uniforms via exponential spacings.  Within a tile the normalised
             // partial sums of P Exp(1) draws are independent of their total, which is Gamma(P, 1); the tile
             // totals are drawn directly (pf_header_kernel), so no cross-tile scan is needed.
+            // Lane l draws the spacings of ranks 8 l .. 8 l + 7 (lane-major scan), then the positions are
+            // transposed to row-major (child slot 32 c + lane has rank 32 c + lane) for coalesced gathers.
             draw_uniforms<R>(key, t, q_me, lane, u);
-            R carry = (R)0;
 #pragma unroll
-            for (int c = 0; c < KPT; ++c) {
-                const R e = (tile_base + 32 * c + lane < N) ? -Mth<R>::log(u[c]) : (R)0;
-                const R incl = warp_incl_scan(e);
-                u[c] = carry + incl;
-                carry += __shfl_sync(FULL, incl, 31);
-            }
-            const R inv = Mth<R>::rcp(carry);
+            for (int k = 0; k < KPT; ++k) u[k] = (8 * lane + k < n_valid) ? -Mth<R>::log(u[k]) : (R)0;
+            R etot;
+            lane_major_incl_scan<R>(u, etot);
+            const R inv = Mth<R>::rcp(etot);
 #pragma unroll
-            for (int c = 0; c < KPT; ++c) u[c] *= inv;
-            const double k = total / gam_tot;
-            tA = gam_lo * k; tB = (gam_hi - gam_lo) * k;
+            for (int k = 0; k < KPT; ++k) u[k] *= inv;
+            __syncwarp();
+            store_lane_major<R>(s_tr, lane, u);
+            __syncwarp();
+#pragma unroll
+            for (int c = 0; c < KPT; ++c) u[c] = s_tr[32 * c + lane];
+            tA = gam_lo; tB = gam_hi - gam_lo;
         } else {
             if (a.rng_mode == SGM_RNG_INJECTED) {
 #pragma unroll
@@ -621,31 +678,28 @@ __device__ __forceinline__ void step_body(const KArgs& a, int b, int t, int q_me
 #pragma unroll
                 for (int c = 0; c < KPT; ++c) rt[c] = spacings ? (rA + rB * u[c]) : (rA + rB * ((R)(32 * c + lane) + u[c]));
             }
-            // 8 independent branch-free binary searches per lane, interleaved; pos = #{k : s_cdf[k] <= rt}:
-            // LDS [pos + immediate], compare, predicated add
-            int pos[KPT];
+            // 8 independent branch-free binary searches per lane, interleaved; #{k : s_cdf[k] <= rt} is kept as a
+            // shared-memory byte address: LDS [addr + immediate], compare, predicated add -- 3 instructions / level
+            uint32_t ad[KPT];
+            const uint32_t ad0 = (uint32_t)__cvta_generic_to_shared(s_cdf);
 #pragma unroll
-            for (int c = 0; c < KPT; ++c) pos[c] = 0;
+            for (int c = 0; c < KPT; ++c) ad[c] = ad0;
+            constexpr int ES = (int)sizeof(R);
             if (MAXT >= 4 && wt == 4) {
 #pragma unroll
-                for (int c = 0; c < KPT; ++c) if (s_cdf[2 * WT - 1] <= rt[c]) pos[c] = 2 * WT;
+                for (int c = 0; c < KPT; ++c) if (lds_at<(2 * WT - 1) * ES>(ad0, (R)0) <= rt[c]) ad[c] += 2 * WT * ES;
             }
             if (wt >= 2) {
 #pragma unroll
-                for (int c = 0; c < KPT; ++c) if (s_cdf[pos[c] + WT - 1] <= rt[c]) pos[c] += WT;
+                for (int c = 0; c < KPT; ++c) if (lds_at<(WT - 1) * ES>(ad[c], (R)0) <= rt[c]) ad[c] += WT * ES;
             }
+            search_levels<R, WT / 2>(ad, rt);
 #pragma unroll
-            for (int step = WT / 2; step > 0; step >>= 1) {
-#pragma unroll
-                for (int c = 0; c < KPT; ++c)
-                    if (s_cdf[pos[c] + step - 1] <= rt[c]) pos[c] += step;
-            }
-#pragma unroll
-            for (int c = 0; c < KPT; ++c) anc[c] = min(q_lo * WT + pos[c], N - 1);
+            for (int c = 0; c < KPT; ++c) anc[c] = min(q_lo * WT + (int)((ad[c] - ad0) / ES), N - 1);
             __syncwarp();                   // the window is reused by this warp's next tile (fused kernel)
         } else {
             // very uneven weights: the tile spans more parent tiles than the staging window holds
-#pragma unroll 1
+#pragma unroll
             for (int c = 0; c < KPT; ++c) anc[c] = search_hdr<R>(target_of(c), hdr, fine_old, N);
         }
     }
@@ -654,14 +708,14 @@ __device__ __forceinline__ void step_body(const KArgs& a, int b, int t, int q_me
     const bool need_ws = (nws > 0) && (a.pf == SGM_PF_FILTER || shrink || (carries && t == Tb - 1));
     warp_tile_epilogue<R, W>(lwn, tile_base, N, lane, reinterpret_cast<R*>(a.fine[par ^ 1]) + (size_t)b * a.Q * WT,
                              a.sub[par ^ 1] + ((size_t)b * a.Q + q_me) * SSTRIDE, a.rec[par ^ 1], a.tail[par ^ 1],
-                             item_off, need_ws, nws);
+                             item_off, need_ws, nws, s_tr);
 }
 
 template <class R, class Model, bool SORTED>
 __global__ void __launch_bounds__(NT, (sizeof(R) == 4 ? 4 : 2)) pf_step_kernel(KArgs a, int t) {
-    __shared__ __align__(32) R s_cdf_all[SORTED ? NWARP : 1][SORTED ? WIN_BYTES / sizeof(R) : 4];
+    __shared__ __align__(32) R s_cdf_all[NWARP][SORTED ? WIN_BYTES / sizeof(R) : WT];
     const int warp = threadIdx.x >> 5;
-    step_body<R, Model, SORTED>(a, blockIdx.y, t, blockIdx.x * NWARP + warp, threadIdx.x & 31, s_cdf_all[SORTED ? warp : 0]);
+    step_body<R, Model, SORTED>(a, blockIdx.y, t, blockIdx.x * NWARP + warp, threadIdx.x & 31, s_cdf_all[warp]);
 }
 
 // ---- fused kernel for small particle counts (N <= 2048: the item fits one CTA) -----------------------------
@@ -670,16 +724,16 @@ __global__ void __launch_bounds__(NT, (sizeof(R) == 4 ? 4 : 2)) pf_step_kernel(K
 // coherent for its own writes).  This is the SGLD-with-N~1000 regime, where launch latency dominated.
 template <class R, class Model, bool SORTED>
 __global__ void __launch_bounds__(NT, (sizeof(R) == 4 ? 4 : 2)) pf_fused_kernel(KArgs a) {
-    __shared__ __align__(32) R s_cdf_all[SORTED ? NWARP : 1][SORTED ? WIN_BYTES / sizeof(R) : 4];
+    __shared__ __align__(32) R s_cdf_all[NWARP][SORTED ? WIN_BYTES / sizeof(R) : WT];
     __shared__ double sh_d[NWARP];
     const int b = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    init_body<R, Model>(a, b, 0);
+    init_body<R, Model>(a, b, 0, s_cdf_all[warp]);
     __syncthreads();
     const int Tb = a.T_buf[b];
     for (int t = 0; t < Tb; ++t) {
         header_body<R, Model>(a, b, t, 0, sh_d);
         __syncthreads();
-        step_body<R, Model, SORTED>(a, b, t, warp, lane, s_cdf_all[SORTED ? warp : 0]);
+        step_body<R, Model, SORTED>(a, b, t, warp, lane, s_cdf_all[warp]);
         __syncthreads();
     }
     header_body<R, Model>(a, b, Tb, 1, sh_d);
