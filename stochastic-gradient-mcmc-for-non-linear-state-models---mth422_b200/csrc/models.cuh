@@ -60,15 +60,15 @@ struct SvmPrior {
     }
     // svm/kernels.py:57-62
     template <class R> static __device__ __forceinline__ R log_weight(const Theta<R>& t, const R* xa, const R* xn, R y) {
-        return (R)(-0.5 * LOG_2PI_D) + (R)-0.5 * (y * y) * Mth<R>::exp(-xn[0]) * t.Rinv + t.logLRinv + (R)-0.5 * xn[0];
+        // terms that do not depend on the particle first, so that they are shared by the 8 particles of a lane
+        return (((R)-0.5 * t.Rinv) * (y * y)) * Mth<R>::exp(-xn[0]) + ((R)-0.5 * xn[0] + ((R)(-0.5 * LOG_2PI_D) + t.logLRinv));
     }
     // svm/helper.py:342-348 ; order [dLRinv, dLQinv, dA]
     template <class R> static __device__ __forceinline__ void score(const Theta<R>& t, const R* xa, const R* xn, R y, R* h) {
         const R d = xn[0] - t.A * xa[0];
         h[2] = t.Qinv * d * xa[0];
         h[1] = t.invLQ - (d * d) * t.LQinv;
-        const R dy2 = (y * y) * Mth<R>::exp(-xn[0]);       // y^2 / exp(x')
-        h[0] = t.invLR - dy2 * t.LRinv;
+        h[0] = t.invLR - ((y * y) * t.LRinv) * Mth<R>::exp(-xn[0]);       // 1/LRinv - (y^2 / exp(x')) LRinv
     }
     // particle_filters/kernels.py:121-126
     template <class R> static __device__ __forceinline__ R log_trans(const Theta<R>& t, const R* xa, const R* xn) {

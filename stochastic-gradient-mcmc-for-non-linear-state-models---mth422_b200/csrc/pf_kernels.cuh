@@ -30,6 +30,13 @@
 
 namespace sgm {
 
+#ifndef SGM_STEP_CTAS
+#define SGM_STEP_CTAS 4
+#endif
+#ifndef SGM_GATHER_BATCH
+#define SGM_GATHER_BATCH 4
+#endif
+constexpr int GB = SGM_GATHER_BATCH;   // parent gathers a lane keeps in flight
 constexpr int KPT = 8;                 // consecutive particles per lane
 constexpr int WT = 32 * KPT;           // 256 particles per warp tile
 constexpr int TILE = NT * KPT;         // 2048 particles per CTA (8 warp tiles)
@@ -413,20 +420,23 @@ __device__ __forceinline__ void propagate_store(const KArgs& a, int b, int t, in
     const R keep = carries ? (shrink ? lam : (R)1) : (R)0;
     const R hs = (carries || a.pf == SGM_PF_FILTER) ? wt : (R)0;
     const int stat_kind = (in_sub && hs != (R)0) ? a.stat_kind : SGM_STAT_NONE;
+    const bool plain = carries && !shrink;
     // per-item base pointers: the particle index stays a 32-bit register (one IMAD.WIDE per address)
     const void* rec_old = reinterpret_cast<const Vec4T<R>*>(a.rec[par]) + item_off;
     const void* tail_old = reinterpret_cast<const R*>(a.tail[par]) + item_off * (W - 4);
     void* rec_new = reinterpret_cast<Vec4T<R>*>(a.rec[par ^ 1]) + item_off;
     void* tail_new = reinterpret_cast<R*>(a.tail[par ^ 1]) + item_off * (W - 4);
     R* lw_new = reinterpret_cast<R*>(a.lw[par ^ 1]) + item_off;
+    // keep the compiler from folding the item offset back into every 64-bit address computation
+    asm volatile("" : "+l"(rec_old), "+l"(tail_old), "+l"(rec_new), "+l"(tail_new), "+l"(lw_new));
 #pragma unroll
-    for (int h0 = 0; h0 < KPT; h0 += 4) {
-        R ra[4][W];
+    for (int h0 = 0; h0 < KPT; h0 += GB) {
+        R ra[GB][W];
 #pragma unroll
-        for (int c = 0; c < 4; ++c)                       // four independent parent gathers in flight
+        for (int c = 0; c < GB; ++c)                      // GB independent parent gathers in flight
             if (tile_base + 32 * (h0 + c) + lane < N) load_rec<R, W>(rec_old, tail_old, anc[h0 + c], ra[c]);
 #pragma unroll
-        for (int c4 = 0; c4 < 4; ++c4) {
+        for (int c4 = 0; c4 < GB; ++c4) {
             const int c = h0 + c4, i = tile_base + 32 * c + lane;
             lwn[c] = -Mth<R>::inf();
             if (i < N) {
@@ -436,8 +446,13 @@ __device__ __forceinline__ void propagate_store(const KArgs& a, int b, int t, in
                 R h[4] = {(R)0, (R)0, (R)0, (R)0};
                 if (stat_kind == SGM_STAT_SCORE) Model::score(th, ra[c4] + NP, rn + NP, y, h);
                 else if (stat_kind == SGM_STAT_SUFF) Model::suff(ra[c4] + NP, rn + NP, h);
+                if (plain) {
 #pragma unroll
-                for (int q = 0; q < NP; ++q) rn[q] = keep * ra[c4][q] + (sbar[q] + h[q] * hs);
+                    for (int q = 0; q < NP; ++q) rn[q] = ra[c4][q] + h[q] * hs;           // Poyiadjis O(N): one FMA
+                } else {
+#pragma unroll
+                    for (int q = 0; q < NP; ++q) rn[q] = keep * ra[c4][q] + (sbar[q] + h[q] * hs);
+                }
                 store_rec<R, W>(rec_new, tail_new, i, rn);
                 if (tracing) {
                     if (a.need_lw) lw_new[i] = lwn[c];
@@ -618,11 +633,23 @@ __device__ __forceinline__ void step_body(const KArgs& a, int b, int t, int q_me
         };
         // ---- parent tiles of this warp tile: first child = (row 0, lane 0), last = particle n_valid - 1 ----
         const int last = n_valid - 1, l_last = last & 31, c_last = last >> 5;
-        double tl = target_of(0);
-        const double tf = __shfl_sync(FULL, tl, 0);
+        double tf, tl;
+        if (a.rng_mode == SGM_RNG_INJECTED) {
+            const double* iu = a.inj_u + ((size_t)b * a.max_T + t) * N + tile_base;
+            tf = iu[0] * total; tl = iu[last] * total;
+        } else {
+            R ul = u[KPT - 1];
+            if (n_valid != WT) {
 #pragma unroll
-        for (int c = 1; c < KPT; ++c) if (c == c_last) tl = target_of(c);
-        tl = __shfl_sync(FULL, tl, l_last);
+                for (int c = 0; c < KPT - 1; ++c) if (c == c_last) ul = u[c];
+            }
+            ul = __shfl_sync(FULL, ul, l_last);
+            const R uf = __shfl_sync(FULL, u[0], 0);
+            tf = spacings ? tA + tB * (double)uf : tA + tB * (double)uf;
+            tl = spacings ? tA + tB * (double)ul : tA + tB * ((double)last + (double)ul);
+        }
+        tf = (tf < total) ? tf : tmax;
+        tl = (tl < total) ? tl : tmax;
         int q_lo, q_hi;
         warp_search_tiles(tf, tl, c1, s1c, hdr, lane, q_lo, q_hi);
         constexpr int MAXT = WIN_BYTES / (int)(WT * sizeof(R));         // tiles the window holds: f32 4, f64 2
@@ -712,7 +739,7 @@ __device__ __forceinline__ void step_body(const KArgs& a, int b, int t, int q_me
 }
 
 template <class R, class Model, bool SORTED>
-__global__ void __launch_bounds__(NT, (sizeof(R) == 4 ? 4 : 2)) pf_step_kernel(KArgs a, int t) {
+__global__ void __launch_bounds__(NT, (sizeof(R) == 4 ? SGM_STEP_CTAS : 2)) pf_step_kernel(KArgs a, int t) {
     __shared__ __align__(32) R s_cdf_all[NWARP][SORTED ? WIN_BYTES / sizeof(R) : WT];
     const int warp = threadIdx.x >> 5;
     step_body<R, Model, SORTED>(a, blockIdx.y, t, blockIdx.x * NWARP + warp, threadIdx.x & 31, s_cdf_all[warp]);

@@ -30,8 +30,8 @@ __device__ __forceinline__ uint4 philox4x32(uint4 c, uint32_t k0, uint32_t k1) {
 __device__ __forceinline__ uint4 rng_raw(const RngKey& k, uint32_t index, uint32_t step, uint32_t stream, uint32_t sub) {
     return philox4x32(make_uint4(index, (step & 0xffffu) | (stream << 16) | (sub << 20), k.item, k.offset), k.k0, k.k1);
 }
-// open-interval uniforms
-__device__ __forceinline__ float u01f(uint32_t x) { return ((float)(x >> 9) + 0.5f) * (1.0f / 8388608.0f); }             // (0,1), 23 bits
+// uniforms: f32 in (0, 1] (x * 2^-32 + 2^-33, rounds to 1 with probability 2^-25; every consumer tolerates 1), f64 in (0, 1)
+__device__ __forceinline__ float u01f(uint32_t x) { return fmaf((float)x, 2.3283064365386963e-10f, 1.1641532182693481e-10f); }  // (0,1]: I2FP + FFMA
 __device__ __forceinline__ double u01d(uint32_t a, uint32_t b) {                                                         // (0,1), 52 bits
     return ((double)(((uint64_t)(a >> 6) << 26) | (uint64_t)(b >> 6)) + 0.5) * (1.0 / 4503599627370496.0);
 }

@@ -7,7 +7,8 @@ import sys
 
 PKG_DIR = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CSRC = os.path.join(PKG_DIR, "csrc")
-LIB_PATH = os.path.join(PKG_DIR, "libsgmpf.so")
+# SGM_LIB_PATH: developer override for A/B-testing an experimental build of the same library
+LIB_PATH = os.environ.get("SGM_LIB_PATH") or os.path.join(PKG_DIR, "libsgmpf.so")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
 
@@ -25,7 +26,7 @@ def is_stale():
 
 
 def build(force=False, verbose=False):
-    if not force and not is_stale():
+    if os.environ.get("SGM_LIB_PATH") or (not force and not is_stale()):
         return LIB_PATH
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH, os.path.join(CSRC, "sgmpf.cu")]
