@@ -26,82 +26,185 @@ __device__ __forceinline__ void stat_of(const KArgs& a, const typename Model::te
 }
 
 // ---- Poyiadjis O(N^2) ------------------------------------------------------------------------------
+// For every new particle i:  tau'_i = sum_j bw_ij (tau_j + w_t h(x_j, x'_i)),  bw_i. = softmax_j(lw_j + log q(x'_i | x_j))
+// (pf.py:115-135).  Flash-attention-style restatement, the (N, N) matrix never exists:
+//   * score: for all three models log q(x'_i | x_j) - log_trans_max = b_i u_j + gq_j + a_i (models.cuh pair_child /
+//     pair_parent), so one FMA per pair gives the exponent:  p_ij = 2^(b'_i u_j + g_j + c_i),
+//     g_j = (lw_j - M + gq_j) log2 e  (M = max_j lw_j from the item header).
+//   * bounded reference instead of a running max: lw_j <= M and log q <= log_trans_max, so every exponent is <= 0
+//     -- no overflow, no rescaling, and partial sums over disjoint parent ranges simply ADD (split-J grid).
+//     Children whose total underflows (exponents below ~-87 nats everywhere: never seen) are redone exactly.
+//   * value: h is a polynomial in x_j, so sum_j p_ij h needs only the moments of m_j (2 columns):
+//     P V with V_j = [tau_j (p columns) | m_j (2) | 1], then an O(1) epilogue per child (score_moments).
+// Work split: a thread owns N2_CPT children (accumulators in registers), a CTA streams tiles of N2_JT parents
+// through shared memory as two float4 per parent (broadcast LDS.128), grid = (child blocks, items, parent splits).
+constexpr int N2_CPT = 4;
+constexpr int N2_JT = 512;
+
+struct N2Plan { int child_blocks, splits, chunk; };
+inline N2Plan n2_plan(int B, int N) {
+    N2Plan p;
+    p.child_blocks = (N + NT * N2_CPT - 1) / (NT * N2_CPT);
+    const int tiles = (N + N2_JT - 1) / N2_JT;
+    int want = (592 + B * p.child_blocks - 1) / (B * p.child_blocks);       // ~4 CTAs on each of 148 SMs
+    if (want > 32) want = 32;
+    if (want > tiles) want = tiles;
+    if (want < 1) want = 1;
+    const int tiles_per = (tiles + want - 1) / want;
+    p.chunk = tiles_per * N2_JT;
+    p.splits = (tiles + tiles_per - 1) / tiles_per;
+    return p;
+}
+
+// exact (running-max free, two-pass) evaluation of one child, thread-serial over all parents: the fallback of
+// the bounded-reference kernel and the direct transcription of pf.py:115-135
 template <class R, class Model>
-__global__ void __launch_bounds__(NT) poyiadjis_n2_kernel(KArgs a, int t) {
+__device__ void n2_exact_child(const KArgs& a, const typename Model::template Theta<R>& th, int par, size_t item_off,
+                               const R* xi, R y, R wt, bool in_sub, R* out) {
     constexpr int NX = Model::NX, NP = Model::NP, W = NX + NP;
-    __shared__ R s_x[NX][JT];
-    __shared__ R s_S[NP][JT];
-    __shared__ R s_lw[JT];
-    __shared__ R s_k[2][JT];
-    const int b = blockIdx.y, tid = threadIdx.x;
+    const R* lw_old = reinterpret_cast<const R*>(a.lw[par]) + item_off;
+    R m = -Mth<R>::inf();
+    for (int j = 0; j < a.N; ++j) {
+        R rj[W];
+        load_rec<R, W>(a.rec[par], a.tail[par], item_off + j, rj);
+        m = nan_max(m, lw_old[j] + Model::log_trans(th, rj + NP, xi));
+    }
+    R l = (R)0, acc[4] = {(R)0, (R)0, (R)0, (R)0};
+    for (int j = 0; j < a.N; ++j) {
+        R rj[W], h[4];
+        load_rec<R, W>(a.rec[par], a.tail[par], item_off + j, rj);
+        const R p = Mth<R>::exp(lw_old[j] + Model::log_trans(th, rj + NP, xi) - m);
+        stat_of<R, Model>(a, th, rj + NP, xi, y, in_sub, h);
+        l += p;
+#pragma unroll
+        for (int q = 0; q < NP; ++q) acc[q] += p * (rj[q] + h[q] * wt);
+    }
+    for (int q = 0; q < NP; ++q) out[q] = acc[q] / l;
+}
+
+// normalise, rebuild E_j[h] from the moments, write the child's statistic (state part of the record is kept)
+template <class R, class Model>
+__device__ __forceinline__ void n2_finalize(const KArgs& a, const typename Model::template Theta<R>& th, int par, size_t item_off,
+                                            int i, R l, const R* acc, R y, R wt, bool in_sub) {
+    constexpr int NX = Model::NX, NP = Model::NP, W = NX + NP;
+    const int nws = stat_width<Model>(a.stat_kind);
+    R rn[W];
+    load_rec<R, W>(a.rec[par ^ 1], a.tail[par ^ 1], item_off + i, rn);
+    R st[4] = {(R)0, (R)0, (R)0, (R)0};
+    if (l > (R)0 && l < Mth<R>::inf()) {
+        const R il = (R)1 / l;
+        const R Em[2] = {acc[NP] * il, acc[NP + 1] * il};
+        R h[4] = {(R)0, (R)0, (R)0, (R)0};
+        if (in_sub) {
+            if (a.stat_kind == SGM_STAT_SCORE) Model::score_moments(th, Em, rn + NP, y, h);
+            else if (a.stat_kind == SGM_STAT_SUFF) Model::suff_moments(Em, rn + NP, h);
+        }
+#pragma unroll
+        for (int q = 0; q < NP; ++q) st[q] = acc[q] * il + h[q] * wt;
+    } else {
+        n2_exact_child<R, Model>(a, th, par, item_off, rn + NP, y, wt, in_sub, st);
+    }
+#pragma unroll
+    for (int q = 0; q < NP; ++q) rn[q] = (q < nws) ? st[q] : (R)0;
+    store_rec<R, W>(a.rec[par ^ 1], a.tail[par ^ 1], item_off + i, rn);
+}
+
+template <class R, class Model>
+__global__ void __launch_bounds__(NT) poyiadjis_n2_kernel(KArgs a, int t, int splits, int chunk, R* part) {
+    constexpr int NX = Model::NX, NP = Model::NP, W = NX + NP, NV = NP + 2;
+    __shared__ Vec4T<R> sA[N2_JT];          // (u_j, g_j, tau_j0, tau_j1)
+    __shared__ Vec4T<R> sB[N2_JT];          // NP = 3: (tau_j2, m_j0, m_j1, -)   NP = 4: (tau_j2, tau_j3, m_j0, m_j1)
+    const int b = blockIdx.y, z = blockIdx.z, tid = threadIdx.x;
     if (t >= a.T_buf[b]) return;
     const int N = a.N, par = t & 1;
     const size_t item_off = (size_t)b * N;
-    const int i = blockIdx.x * NT + tid;
-    const bool valid = i < N;
     const typename Model::template Theta<R> th = load_thc<R, Model>(a, b);
+    const R M = (R)a.hdr[(size_t)b * hdr_stride(a.Q) + H_M];          // max of the OLD log-weights (header of step t)
+    const R L2E = (R)1.4426950408889634;
+    const R* lw_old = reinterpret_cast<const R*>(a.lw[par]) + item_off;
+
+    R bc[N2_CPT], cc[N2_CPT], l[N2_CPT], acc[N2_CPT][NV];
+#pragma unroll
+    for (int c = 0; c < N2_CPT; ++c) {
+        const int i = (blockIdx.x * N2_CPT + c) * NT + tid;
+        R rn[W];
+#pragma unroll
+        for (int q = 0; q < W; ++q) rn[q] = (R)0;
+        if (i < N) load_rec<R, W>(a.rec[par ^ 1], a.tail[par ^ 1], item_off + i, rn);
+        R bb, aa;
+        Model::pair_child(th, rn + NP, bb, aa);
+        bc[c] = bb * L2E; cc[c] = aa * L2E; l[c] = (R)0;
+#pragma unroll
+        for (int q = 0; q < NV; ++q) acc[c][q] = (R)0;
+    }
+    const int j_begin = z * chunk, j_end = min(N, j_begin + chunk);
+    for (int j0 = j_begin; j0 < j_end; j0 += N2_JT) {
+        __syncthreads();
+        for (int j = tid; j < N2_JT; j += NT) {
+            Vec4T<R> A, Bv;
+            A.x = (R)0; A.y = -Mth<R>::inf(); A.z = A.w = (R)0; Bv.x = Bv.y = Bv.z = Bv.w = (R)0;
+            if (j0 + j < j_end) {
+                R rj[W], u, gq, m[2];
+                load_rec<R, W>(a.rec[par], a.tail[par], item_off + j0 + j, rj);
+                Model::pair_parent(th, rj + NP, u, gq, m);
+                A.x = u; A.y = (lw_old[j0 + j] - M + gq) * L2E; A.z = rj[0]; A.w = rj[1];
+                if (NP == 3) { Bv.x = rj[2]; Bv.y = m[0]; Bv.z = m[1]; }
+                else { Bv.x = rj[2]; Bv.y = rj[NP - 1]; Bv.z = m[0]; Bv.w = m[1]; }
+            }
+            sA[j] = A; sB[j] = Bv;
+        }
+        __syncthreads();
+#pragma unroll 4
+        for (int j = 0; j < N2_JT; ++j) {
+            const Vec4T<R> A = sA[j], Bv = sB[j];
+#pragma unroll
+            for (int c = 0; c < N2_CPT; ++c) {
+                const R p = Mth<R>::exp2(bc[c] * A.x + A.y + cc[c]);
+                l[c] += p;
+                acc[c][0] += p * A.z; acc[c][1] += p * A.w; acc[c][2] += p * Bv.x; acc[c][3] += p * Bv.y; acc[c][4] += p * Bv.z;
+                if (NV == 6) acc[c][NV - 1] += p * Bv.w;
+            }
+        }
+    }
     const R y = (R)a.obs[a.obs_off[b] + t];
     const bool in_sub = (t >= a.t1[b]) && (t < a.tL[b]);
     const R wt = in_sub ? ((a.wts_off && a.wts_off[b] >= 0) ? (R)a.step_weights[a.wts_off[b] + (t - a.t1[b])] : (R)1) : (R)0;
-    const int nws = stat_width<Model>(a.stat_kind);
-
-    R rn[W];
 #pragma unroll
-    for (int q = 0; q < W; ++q) rn[q] = (R)0;
-    if (valid) load_rec<R, W>(a.rec[par ^ 1], a.tail[par ^ 1], item_off + i, rn);
-    const R* xi = rn + NP;
-    const R* lw_old = reinterpret_cast<const R*>(a.lw[par]) + item_off;
-
-    R m = -Mth<R>::inf(), l = (R)0, acc[4] = {(R)0, (R)0, (R)0, (R)0};
-    for (int j0 = 0; j0 < N; j0 += JT) {
-        const int jn = min(JT, N - j0);
-        __syncthreads();
-        for (int j = tid; j < jn; j += NT) {
-            R rj[W];
-            load_rec<R, W>(a.rec[par], a.tail[par], item_off + j0 + j, rj);
-#pragma unroll
-            for (int q = 0; q < NP; ++q) s_S[q][j] = rj[q];
-#pragma unroll
-            for (int q = 0; q < NX; ++q) s_x[q][j] = rj[NP + q];
-            s_lw[j] = lw_old[j0 + j];
-            R k[2];
-            Model::jkey(th, rj + NP, k);
-            s_k[0][j] = k[0]; s_k[1][j] = k[1];
-        }
-        __syncthreads();
-        // pass 1: tile max of the backward log-weights  lw_j + log q(x'_i | x_j)   (pf.py:115-121)
-        R tm = -Mth<R>::inf();
-        for (int j = 0; j < jn; ++j) {
-            const R k[2] = {s_k[0][j], s_k[1][j]};
-            tm = fmax(tm, s_lw[j] + Model::log_trans_key(th, k, xi));
-        }
-        if (tm == -Mth<R>::inf()) continue;          // whole tile has zero weight (warp-divergent skip is fine)
-        if (tm > m) {
-            const R sc = (m == -Mth<R>::inf()) ? (R)0 : Mth<R>::exp(m - tm);
-            l *= sc;
-#pragma unroll
-            for (int q = 0; q < 4; ++q) acc[q] *= sc;
-            m = tm;
-        }
-        // pass 2: accumulate exp-weights times (statistics_j + h(x_j, x'_i) * scale)   (pf.py:123-135)
-        for (int j = 0; j < jn; ++j) {
-            const R k[2] = {s_k[0][j], s_k[1][j]};
-            const R p = Mth<R>::exp(s_lw[j] + Model::log_trans_key(th, k, xi) - m);
-            R xj[NX];
-#pragma unroll
-            for (int q = 0; q < NX; ++q) xj[q] = s_x[q][j];
-            R h[4];
-            stat_of<R, Model>(a, th, xj, xi, y, in_sub, h);
-            l += p;
-#pragma unroll
-            for (int q = 0; q < NP; ++q) acc[q] += p * (s_S[q][j] + h[q] * wt);
+    for (int c = 0; c < N2_CPT; ++c) {
+        const int i = (blockIdx.x * N2_CPT + c) * NT + tid;
+        if (i >= N) continue;
+        if (splits == 1) {
+            n2_finalize<R, Model>(a, th, par, item_off, i, l[c], acc[c], y, wt, in_sub);
+        } else {
+            Vec4T<R> p0, p1;
+            p0.x = acc[c][0]; p0.y = acc[c][1]; p0.z = acc[c][2]; p0.w = acc[c][3];
+            p1.x = acc[c][4]; p1.y = (NV == 6) ? acc[c][NV - 1] : (R)0; p1.z = (R)0; p1.w = l[c];
+            Vec4T<R>* dst = reinterpret_cast<Vec4T<R>*>(part) + (((size_t)z * a.B + b) * N + i) * 2;
+            dst[0] = p0; dst[1] = p1;
         }
     }
-    if (valid) {
-        const R il = (R)1 / l;
-        for (int q = 0; q < NP; ++q) rn[q] = (q < nws) ? acc[q] * il : (R)0;
-        store_rec<R, W>(a.rec[par ^ 1], a.tail[par ^ 1], item_off + i, rn);
+}
+
+// split-J: deterministic sum of the per-split partials (fixed order), then the same finalisation
+template <class R, class Model>
+__global__ void __launch_bounds__(NT) poyiadjis_n2_finish_kernel(KArgs a, int t, int splits, const R* part) {
+    constexpr int NP = Model::NP, NV = NP + 2;
+    const int b = blockIdx.y, i = blockIdx.x * NT + threadIdx.x;
+    if (t >= a.T_buf[b] || i >= a.N) return;
+    const int N = a.N, par = t & 1;
+    const size_t item_off = (size_t)b * N;
+    const typename Model::template Theta<R> th = load_thc<R, Model>(a, b);
+    R acc[6] = {(R)0, (R)0, (R)0, (R)0, (R)0, (R)0}, l = (R)0;
+    for (int z = 0; z < splits; ++z) {
+        const Vec4T<R>* src = reinterpret_cast<const Vec4T<R>*>(part) + (((size_t)z * a.B + b) * N + i) * 2;
+        const Vec4T<R> p0 = src[0], p1 = src[1];
+        acc[0] += p0.x; acc[1] += p0.y; acc[2] += p0.z; acc[3] += p0.w; acc[4] += p1.x; acc[5] += p1.y; l += p1.w;
     }
+    const R y = (R)a.obs[a.obs_off[b] + t];
+    const bool in_sub = (t >= a.t1[b]) && (t < a.tL[b]);
+    const R wt = in_sub ? ((a.wts_off && a.wts_off[b] >= 0) ? (R)a.step_weights[a.wts_off[b] + (t - a.t1[b])] : (R)1) : (R)0;
+    (void)NV;
+    n2_finalize<R, Model>(a, th, par, item_off, i, l, acc, y, wt, in_sub);
 }
 
 // Per-warp-tile weighted statistic sums for the final average (only on an item's last step).
@@ -136,9 +239,16 @@ __global__ void __launch_bounds__(NT) stat_ws_kernel(KArgs a, int t) {
 
 template <class R, class Model>
 int launch_poyiadjis_n2(const KArgs& a, int t, cudaStream_t stream) {
-    poyiadjis_n2_kernel<R, Model><<<dim3((a.N + NT - 1) / NT, a.B), NT, 0, stream>>>(a, t);
+    const N2Plan p = n2_plan(a.B, a.N);
+    R* part = reinterpret_cast<R*>(a.n2part);
+    poyiadjis_n2_kernel<R, Model><<<dim3(p.child_blocks, a.B, p.splits), NT, 0, stream>>>(a, t, p.splits, p.chunk, part);
+    int n = 1;
+    if (p.splits > 1) {
+        poyiadjis_n2_finish_kernel<R, Model><<<dim3((a.N + NT - 1) / NT, a.B), NT, 0, stream>>>(a, t, p.splits, part);
+        ++n;
+    }
     stat_ws_kernel<R, Model><<<dim3(a.G, a.B), NT, 0, stream>>>(a, t);
-    return 2;
+    return n + 1;
 }
 
 // ---- PaRIS ------------------------------------------------------------------------------------------

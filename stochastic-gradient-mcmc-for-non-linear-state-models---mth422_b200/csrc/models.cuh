@@ -14,6 +14,9 @@ template <> struct Mth<float> {
     static __device__ __forceinline__ float exp(float x) {
         float r; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x * 1.4426950408889634f)); return r;
     }
+    static __device__ __forceinline__ float exp2(float x) {
+        float r; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r;
+    }
     static __device__ __forceinline__ float log(float x) {
         float r; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r * 0.6931471805599453f;
     }
@@ -27,6 +30,7 @@ template <> struct Mth<float> {
 };
 template <> struct Mth<double> {
     static __device__ __forceinline__ double exp(double x) { return ::exp(x); }
+    static __device__ __forceinline__ double exp2(double x) { return ::exp2(x); }
     static __device__ __forceinline__ double log(double x) { return ::log(x); }
     static __device__ __forceinline__ double sqrt(double x) { return ::sqrt(x); }
     static __device__ __forceinline__ double rcp(double x) { return 1.0 / x; }
@@ -92,6 +96,27 @@ struct SvmPrior {
         h[0] = xn[0]; h[1] = xn[0] * xn[0]; h[2] = xa[0] * xn[0];
     }
     template <class R> static __device__ __forceinline__ void init(R mean, R sd, R z, R* x) { x[0] = mean + sd * z; }
+
+    // ---- O(N^2) backward weights as a rank-1 score (pf.py:115-135) --------------------
+    // log q(x'_i | x_j) - log_trans_max = b_i u_j + gq_j + a_i :  -0.5 Qinv (x' - A x)^2 expanded.  The statistic
+    // h(x_j, x'_i) is a polynomial in x_j, so sum_j p_ij h needs only the p-weighted moments of m_j = (x_j, x_j^2).
+    template <class R> static __device__ __forceinline__ void pair_child(const Theta<R>& t, const R* xn, R& b, R& a) {
+        b = t.Qinv * xn[0]; a = (R)-0.5 * t.Qinv * (xn[0] * xn[0]);
+    }
+    template <class R> static __device__ __forceinline__ void pair_parent(const Theta<R>& t, const R* xa, R& u, R& gq, R* m) {
+        u = t.A * xa[0]; gq = (R)-0.5 * t.Qinv * (u * u);
+        m[0] = xa[0]; m[1] = xa[0] * xa[0];
+    }
+    // E_j[h(x_j, x'_i)] from E[m]   (svm/helper.py:342-348 with x_j -> its moments)
+    template <class R> static __device__ __forceinline__ void score_moments(const Theta<R>& t, const R* Em, const R* xn, R y, R* h) {
+        h[2] = t.Qinv * (xn[0] * Em[0] - t.A * Em[1]);
+        h[1] = t.invLQ - t.LQinv * (xn[0] * xn[0] - (R)2 * t.A * xn[0] * Em[0] + t.A * t.A * Em[1]);
+        h[0] = t.invLR - ((y * y) * t.LRinv) * Mth<R>::exp(-xn[0]);
+        h[3] = (R)0;
+    }
+    template <class R> static __device__ __forceinline__ void suff_moments(const R* Em, const R* xn, R* h) {
+        h[0] = xn[0]; h[1] = xn[0] * xn[0]; h[2] = Em[0] * xn[0]; h[3] = (R)0;
+    }
 };
 
 struct LgssmPrior {
@@ -134,6 +159,17 @@ struct LgssmPrior {
     }
     template <class R> static __device__ __forceinline__ void suff(const R* xa, const R* xn, R* h) { SvmPrior::suff(xa, xn, h); }
     template <class R> static __device__ __forceinline__ void init(R mean, R sd, R z, R* x) { x[0] = mean + sd * z; }
+    template <class R> static __device__ __forceinline__ void pair_child(const Theta<R>& t, const R* xn, R& b, R& a) { SvmPrior::pair_child(t, xn, b, a); }
+    template <class R> static __device__ __forceinline__ void pair_parent(const Theta<R>& t, const R* xa, R& u, R& gq, R* m) { SvmPrior::pair_parent(t, xa, u, gq, m); }
+    // lgssm/helper.py:1270-1277 with x_j -> its moments
+    template <class R> static __device__ __forceinline__ void score_moments(const Theta<R>& t, const R* Em, const R* xn, R y, R* h) {
+        h[3] = t.Qinv * (xn[0] * Em[0] - t.A * Em[1]);
+        h[1] = t.invLQ - t.LQinv * (xn[0] * xn[0] - (R)2 * t.A * xn[0] * Em[0] + t.A * t.A * Em[1]);
+        const R dy = y - t.C * xn[0];
+        h[2] = t.Rinv * dy * xn[0];
+        h[0] = t.invLR - (dy * dy) * t.LRinv;
+    }
+    template <class R> static __device__ __forceinline__ void suff_moments(const R* Em, const R* xn, R* h) { SvmPrior::suff_moments(Em, xn, h); }
 };
 
 struct LgssmOptimal : LgssmPrior {
@@ -213,6 +249,33 @@ struct GarchPrior {
     }
     // garch/kernels.py:99-104 : sigma2_0 = 0
     template <class R> static __device__ __forceinline__ void init(R mean, R sd, R z, R* x) { x[0] = mean + sd * z; x[1] = (R)0; }
+
+    // O(N^2) backward weights: log q(x'_i | x_j) - log_trans_max = (-0.5 x'^2) (1 / s2_j) + (-0.5 log s2_j + 0.5 log alpha)
+    template <class R> static __device__ __forceinline__ void pair_child(const Theta<R>& t, const R* xn, R& b, R& a) {
+        b = (R)-0.5 * (xn[0] * xn[0]); a = (R)0;
+    }
+    template <class R> static __device__ __forceinline__ void pair_parent(const Theta<R>& t, const R* xa, R& u, R& gq, R* m) {
+        const R s2 = sigma2_next(t, xa);
+        u = Mth<R>::rcp(s2);
+        gq = (R)-0.5 * Mth<R>::log(s2) - (R)(0.5 * LOG_2PI_D) - t.ltmax;
+        const R xa2 = xa[0] * xa[0];
+        m[0] = -t.mu + t.lam * xa2 + ((R)1 - t.lam) * xa[1]; m[1] = xa2 - xa[1];
+    }
+    // garch/helper.py:350-372 with the candidate parent's terms replaced by their moments
+    template <class R> static __device__ __forceinline__ void score_moments(const Theta<R>& t, const R* Em, const R* xn, R y, R* h) {
+        const R v = xn[1];
+        const R iv = Mth<R>::rcp(v);
+        const R gv = (R)-0.5 * (v - xn[0] * xn[0]) * (iv * iv);
+        h[1] = gv * ((R)1 - t.phi) * t.mu;
+        h[2] = gv * Em[0] * ((R)1 - t.phi) * t.phi;
+        h[3] = gv * t.phi * Em[1] * ((R)1 - t.lam) * t.lam;
+        const R dy = y - xn[0];
+        h[0] = t.invLR - (dy * dy) * t.LRinv;
+    }
+    template <class R> static __device__ __forceinline__ void suff_moments(const R* Em, const R* xn, R* h) {
+        const R x2 = xn[0] * xn[0];
+        h[0] = xn[0]; h[1] = x2; h[2] = x2 * x2; h[3] = (R)0;
+    }
 };
 
 struct GarchOptimal : GarchPrior {

@@ -25,7 +25,7 @@ int fail(int code, const char* fmt, const char* extra = "") {
 size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
 
 struct Layout {
-    size_t rec[2], tail[2], fine[2], lw[2], sub[2], hdr, acc, thc, yw, Jidx, Llist[2], counters, total;
+    size_t rec[2], tail[2], fine[2], lw[2], sub[2], hdr, acc, thc, yw, Jidx, Llist[2], counters, n2part, total;
 };
 
 bool backward_pf(int pf) { return pf == SGM_PF_POY_N2 || pf == SGM_PF_PARIS; }
@@ -84,6 +84,10 @@ Layout make_layout(const sgm_pf_desc* d) {
         L.Llist[1] = off; off = align_up(off + B * N * 4);
         L.counters = off; off = align_up(off + B * 16 * 4);
     }
+    if (d->pf == SGM_PF_POY_N2) {
+        const N2Plan p = n2_plan((int)B, (int)N);
+        L.n2part = off; off = align_up(off + (p.splits > 1 ? (size_t)p.splits * B * N * 8 * es : 0));
+    }
     L.total = off;
     return L;
 }
@@ -127,6 +131,7 @@ int run_impl(const sgm_pf_desc* d, cudaStream_t stream) {
         a.Jidx = reinterpret_cast<int32_t*>(ws + L.Jidx);
         a.counters = reinterpret_cast<int32_t*>(ws + L.counters);
     }
+    if (d->pf == SGM_PF_POY_N2) a.n2part = ws + L.n2part;
     a.grad = d->grad; a.loglik = d->loglik; a.status = d->status;
     a.out_x = d->out_x; a.out_lw = d->out_lw; a.out_stats = d->out_stats;
     a.trace_anc = d->trace_anc; a.trace_x = d->trace_x; a.trace_lw = d->trace_lw; a.trace_J = d->trace_J;
