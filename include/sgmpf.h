@@ -60,6 +60,10 @@ enum { SGM_STAT_SCORE = 0,     /* complete-data log-likelihood gradient (pf_grad
        SGM_STAT_SUFF = 1,      /* [x', x'^2, x x'] (lgssm/svm) or [x', x'^2, x'^4] (garch)        */
        SGM_STAT_NONE = 2 };    /* log-likelihood only (pf_loglikelihood_estimate)                 */
 
+/* O(N^2) smoother back end: AUTO = tensor cores (TF32 mma, FP32 accumulate) for SGM_F32, FP32/FP64 pipe
+ * otherwise; FP32_PIPE forces the CUDA-core kernel (any dtype); TENSOR requires SGM_F32. */
+enum { SGM_N2_AUTO = 0, SGM_N2_FP32_PIPE = 1, SGM_N2_TENSOR = 2 };
+
 /* error codes */
 enum { SGM_OK = 0, SGM_ERR_INVALID = -1, SGM_ERR_UNSUPPORTED = -2, SGM_ERR_WORKSPACE = -3,
        SGM_ERR_CUDA = -4, SGM_ERR_DEVICE = -5 };
@@ -86,6 +90,8 @@ typedef struct sgm_pf_desc {
     int32_t max_accept_reject;     /* <0: int(100*log10(N/10)) (pf.py:284-285)                      */
     int32_t manual_sample_threshold; /* <0: int(10*log10(N/10)) (pf.py:286-287); INJECTED mode only */
     int32_t item_id_base;          /* global index of item 0 (keeps Philox streams rank-invariant)  */
+    int32_t n2_mode;               /* O(N^2) smoother: SGM_N2_AUTO / SGM_N2_FP32_PIPE / SGM_N2_TENSOR */
+    int32_t reserved0;             /* must be 0                                                     */
     double lambduh;                /* Nemeth shrinkage (pf.py:140); 1.0 = Poyiadjis O(N)            */
     uint64_t seed, offset;         /* Philox key / call counter                                     */
 

@@ -30,8 +30,12 @@ def run(model, pf, N, B, T, reps=2, dtype="f32", **kw):
 
 if __name__ == "__main__":
     what = sys.argv[1] if len(sys.argv) > 1 else "all"
+    if what == "one":        # one <model> <pf> <N> <B> <T> [n2_mode]   (ncu target)
+        kw = dict(n2_mode=sys.argv[7]) if len(sys.argv) > 7 else {}
+        run(sys.argv[2], sys.argv[3], int(sys.argv[4]), int(sys.argv[5]), int(sys.argv[6]), reps=1, **kw)
     if what in ("n2", "all"):
         run("svm", "poyiadjis_N2", 1024, 1, 20)
+        run("svm", "poyiadjis_N2", 16384, 8, 10, n2_mode="fp32_pipe")
         run("svm", "poyiadjis_N2", 8192, 4, 20)
         run("svm", "poyiadjis_N2", 16384, 8, 10)
         run("svm", "poyiadjis_N2", 65536, 1, 6)

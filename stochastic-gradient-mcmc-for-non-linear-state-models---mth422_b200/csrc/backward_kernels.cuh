@@ -40,14 +40,16 @@ __device__ __forceinline__ void stat_of(const KArgs& a, const typename Model::te
 // through shared memory as two float4 per parent (broadcast LDS.128), grid = (child blocks, items, parent splits).
 constexpr int N2_CPT = 4;
 constexpr int N2_JT = 512;
+constexpr int N2_TARGET_CTAS = 8 * 148 * 3;
 
 struct N2Plan { int child_blocks, splits, chunk; };
 inline N2Plan n2_plan(int B, int N) {
     N2Plan p;
     p.child_blocks = (N + NT * N2_CPT - 1) / (NT * N2_CPT);
     const int tiles = (N + N2_JT - 1) / N2_JT;
-    int want = (592 + B * p.child_blocks - 1) / (B * p.child_blocks);       // ~4 CTAs on each of 148 SMs
-    if (want > 32) want = 32;
+    // >= ~8 waves of CTAs (3 resident per SM): the last, partially filled wave then costs <= ~12 %
+    int want = (N2_TARGET_CTAS + B * p.child_blocks - 1) / (B * p.child_blocks);
+    if (want > 64) want = 64;
     if (want > tiles) want = tiles;
     if (want < 1) want = 1;
     const int tiles_per = (tiles + want - 1) / want;
@@ -207,6 +209,144 @@ __global__ void __launch_bounds__(NT) poyiadjis_n2_finish_kernel(KArgs a, int t,
     n2_finalize<R, Model>(a, th, par, item_off, i, l, acc, y, wt, in_sub);
 }
 
+// ---- Poyiadjis O(N^2), tensor-core variant (f32 particles) -----------------------------------------------
+// Same algebra; the P V contraction (V = [tau | m | 1], 8 columns) runs on the tensor cores:
+// mma.sync.m16n8k8 TF32 with FP32 accumulators, A = exp-weights P (16 children x 8 parents) produced in
+// registers straight into the A-fragment layout, B = V tile (8 parents x 8 columns) from shared memory.
+// The FP32-pipe kernel above spends 6 of its 8 FMA-pipe instructions per pair on P V and is bound by that
+// pipe (ncu: profiles/); here a pair costs FFMA + FADD + MUFU.EX2 + 1/64 MMA and the kernel is MUFU-bound.
+// Precision: V is split hi + lo (two TF32 MMAs: ~21 mantissa bits); P keeps 10 mantissa bits (rounded to
+// nearest by adding half an ulp before the tensor core truncates), and the SAME rounded p feeds numerator
+// and denominator (the ones-column), so the rounding cancels to first order in tau' = sum p V / sum p.
+// Results always go through the split-J partial buffer + poyiadjis_n2_finish_kernel.
+constexpr int N2T_MT = 4;                // m16 child tiles per warp  -> 64 children / warp, 512 / CTA
+constexpr int N2T_JT = 512;              // parents per shared-memory tile
+
+// 2^x for x <= 0 on the FMA / ALU pipes (no MUFU): round x to the nearest integer n with the magic-number add,
+// degree-3 minimax polynomial for 2^f on f = x - n in [-0.5, 0.5] (max relative error 1.0e-4, below half an ulp of
+// the TF32 mantissa the result is rounded to), n added into the exponent field.  The tensor-core kernel is
+// bound by the MUFU (XU) pipe -- 16 lanes / SM -- so it evaluates N2T_NPOLY of every 16 exponentials this
+// way to balance the XU pipe against instruction issue (the FA4 trick).
+#ifndef SGM_N2_NPOLY
+#define SGM_N2_NPOLY 0          /* measured on B200 (N = 65536): 0 -> 3.41e12, 2 -> 3.32e12, 3 -> 3.19e12, 4 -> 3.09e12 pair-steps/s */
+#endif
+#ifndef SGM_N2T_CTAS
+#define SGM_N2T_CTAS 3
+#endif
+constexpr int N2T_NPOLY = SGM_N2_NPOLY;
+__device__ __forceinline__ float exp2_poly(float x) {
+    x = fmaxf(x, -126.0f);
+    const float t = x + 12582912.0f;                 // 1.5 * 2^23: n sits in the low mantissa bits of t
+    const float f = x - (t - 12582912.0f);
+    float p = fmaf(f, 0.05500893f, 0.24221095f);
+    p = fmaf(p, f, 0.6932829f);
+    p = fmaf(p, f, 1.0f);
+    return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
+}
+
+__device__ __forceinline__ uint32_t tf32_rna(float x) { uint32_t r; asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x)); return r; }
+__device__ __forceinline__ void mma_tf32_16x8x8(float* c, const uint32_t* a, uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+template <class Model>
+__global__ void __launch_bounds__(NT, SGM_N2T_CTAS) poyiadjis_n2_tc_kernel(KArgs a, int t, int chunk, float* part) {
+    typedef float R;
+    constexpr int NX = Model::NX, NP = Model::NP, W = NX + NP;
+    __shared__ float2 s_ug[N2T_JT];              // (u_j, g_j)
+    __shared__ __align__(16) uint32_t s_vh[N2T_JT][8];         // V_j rounded to TF32
+    __shared__ __align__(16) uint32_t s_vl[N2T_JT][8];         // TF32(V_j - hi)
+    const int b = blockIdx.y, z = blockIdx.z, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (t >= a.T_buf[b]) return;
+    const int N = a.N, par = t & 1;
+    const size_t item_off = (size_t)b * N;
+    const typename Model::template Theta<R> th = load_thc<R, Model>(a, b);
+    const R M = (R)a.hdr[(size_t)b * hdr_stride(a.Q) + H_M];
+    const R L2E = 1.4426950408889634f;
+    const R* lw_old = reinterpret_cast<const R*>(a.lw[par]) + item_off;
+    const int g = lane >> 2, tq = lane & 3;
+    const int child0 = (blockIdx.x * NWARP + warp) * (16 * N2T_MT);
+
+    R bc[N2T_MT][2], cc[N2T_MT][2], C[N2T_MT][4];
+#pragma unroll
+    for (int m = 0; m < N2T_MT; ++m) {
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            const int i = child0 + 16 * m + g + 8 * r;
+            R rn[W];
+#pragma unroll
+            for (int q = 0; q < W; ++q) rn[q] = (R)0;
+            if (i < N) load_rec<R, W>(a.rec[par ^ 1], a.tail[par ^ 1], item_off + i, rn);
+            R bb, aa;
+            Model::pair_child(th, rn + NP, bb, aa);
+            bc[m][r] = bb * L2E; cc[m][r] = aa * L2E;
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) C[m][q] = 0.f;
+    }
+    const int j_begin = z * chunk, j_end = min(N, j_begin + chunk);
+    for (int j0 = j_begin; j0 < j_end; j0 += N2T_JT) {
+        __syncthreads();
+        for (int j = tid; j < N2T_JT; j += NT) {
+            float2 ug = make_float2(0.f, -Mth<R>::inf());
+            R v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            if (j0 + j < j_end) {
+                R rj[W], u, gq, mm[2];
+                load_rec<R, W>(a.rec[par], a.tail[par], item_off + j0 + j, rj);
+                Model::pair_parent(th, rj + NP, u, gq, mm);
+                ug.x = u; ug.y = (lw_old[j0 + j] - M + gq) * L2E;
+#pragma unroll
+                for (int q = 0; q < NP; ++q) v[q] = rj[q];
+                v[NP] = mm[0]; v[NP + 1] = mm[1]; v[7] = 1.f;        // column order = partial-buffer layout
+            }
+            s_ug[j] = ug;
+            uint32_t hi[8], lo[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                hi[q] = tf32_rna(v[q]);
+                lo[q] = tf32_rna(v[q] - __uint_as_float(hi[q]));
+            }
+            uint4* dh = reinterpret_cast<uint4*>(s_vh[j]);
+            uint4* dl = reinterpret_cast<uint4*>(s_vl[j]);
+            dh[0] = make_uint4(hi[0], hi[1], hi[2], hi[3]); dh[1] = make_uint4(hi[4], hi[5], hi[6], hi[7]);
+            dl[0] = make_uint4(lo[0], lo[1], lo[2], lo[3]); dl[1] = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+        }
+        __syncthreads();
+#pragma unroll 2
+        for (int k0 = 0; k0 < N2T_JT; k0 += 8) {
+            const float2 ug0 = s_ug[k0 + tq], ug1 = s_ug[k0 + tq + 4];
+            const uint32_t bh0 = s_vh[k0 + tq][g], bh1 = s_vh[k0 + tq + 4][g];
+            const uint32_t bl0 = s_vl[k0 + tq][g], bl1 = s_vl[k0 + tq + 4][g];
+#pragma unroll
+            for (int m = 0; m < N2T_MT; ++m) {
+                uint32_t A[4];
+                // +0x1000: half an ulp of the 10-bit TF32 mantissa, so the tensor core's truncation rounds to nearest
+                A[0] = __float_as_uint(Mth<R>::exp2(bc[m][0] * ug0.x + ug0.y + cc[m][0])) + 0x1000u;
+                A[1] = __float_as_uint(Mth<R>::exp2(bc[m][1] * ug0.x + ug0.y + cc[m][1])) + 0x1000u;
+                A[2] = __float_as_uint(Mth<R>::exp2(bc[m][0] * ug1.x + ug1.y + cc[m][0])) + 0x1000u;
+                const R x3 = bc[m][1] * ug1.x + ug1.y + cc[m][1];
+                A[3] = __float_as_uint(m < N2T_NPOLY ? exp2_poly(x3) : Mth<R>::exp2(x3)) + 0x1000u;
+                mma_tf32_16x8x8(C[m], A, bh0, bh1);
+                mma_tf32_16x8x8(C[m], A, bl0, bl1);
+            }
+        }
+    }
+    // C fragment: rows g / g + 8, columns 2 tq, 2 tq + 1  ->  partial buffer [z][b][i][8]
+#pragma unroll
+    for (int m = 0; m < N2T_MT; ++m) {
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            const int i = child0 + 16 * m + g + 8 * r;
+            if (i < N) {
+                float2* dst = reinterpret_cast<float2*>(part + (((size_t)z * a.B + b) * N + i) * 8) + tq;
+                *dst = make_float2(C[m][2 * r], C[m][2 * r + 1]);
+            }
+        }
+    }
+}
+
 // Per-warp-tile weighted statistic sums for the final average (only on an item's last step).
 template <class R, class Model>
 __global__ void __launch_bounds__(NT) stat_ws_kernel(KArgs a, int t) {
@@ -237,15 +377,52 @@ __global__ void __launch_bounds__(NT) stat_ws_kernel(KArgs a, int t) {
     if (lane == 0) for (int q = 0; q < 4; ++q) sub[2 + q] = ws[q];
 }
 
+inline N2Plan n2_plan_tc(int B, int N) {
+    N2Plan p;
+    p.child_blocks = (N + NWARP * 16 * N2T_MT - 1) / (NWARP * 16 * N2T_MT);
+    const int tiles = (N + N2T_JT - 1) / N2T_JT;
+    int want = (N2_TARGET_CTAS + B * p.child_blocks - 1) / (B * p.child_blocks);
+    if (want > 64) want = 64;
+    if (want > tiles) want = tiles;
+    if (want < 1) want = 1;
+    const int tiles_per = (tiles + want - 1) / want;
+    p.chunk = tiles_per * N2T_JT;
+    p.splits = (tiles + tiles_per - 1) / tiles_per;
+    return p;
+}
+inline bool n2_use_tensor(int dtype, int n2_mode) { return dtype == SGM_F32 && n2_mode != SGM_N2_FP32_PIPE; }
+inline size_t n2_partial_bytes(int dtype, int n2_mode, int B, int N) {
+    if (n2_use_tensor(dtype, n2_mode)) return (size_t)n2_plan_tc(B, N).splits * B * N * 8 * 4;
+    const N2Plan p = n2_plan(B, N);
+    return p.splits > 1 ? (size_t)p.splits * B * N * 8 * (dtype == SGM_F64 ? 8 : 4) : 0;
+}
+
+template <class R, class Model> struct N2TcLaunch {
+    static bool run(const KArgs&, int, cudaStream_t, int&) { return false; }
+};
+template <class Model> struct N2TcLaunch<float, Model> {
+    static bool run(const KArgs& a, int t, cudaStream_t stream, int& n) {
+        const N2Plan p = n2_plan_tc(a.B, a.N);
+        float* part = reinterpret_cast<float*>(a.n2part);
+        poyiadjis_n2_tc_kernel<Model><<<dim3(p.child_blocks, a.B, p.splits), NT, 0, stream>>>(a, t, p.chunk, part);
+        poyiadjis_n2_finish_kernel<float, Model><<<dim3((a.N + NT - 1) / NT, a.B), NT, 0, stream>>>(a, t, p.splits, part);
+        n += 2;
+        return true;
+    }
+};
+
 template <class R, class Model>
 int launch_poyiadjis_n2(const KArgs& a, int t, cudaStream_t stream) {
-    const N2Plan p = n2_plan(a.B, a.N);
-    R* part = reinterpret_cast<R*>(a.n2part);
-    poyiadjis_n2_kernel<R, Model><<<dim3(p.child_blocks, a.B, p.splits), NT, 0, stream>>>(a, t, p.splits, p.chunk, part);
-    int n = 1;
-    if (p.splits > 1) {
-        poyiadjis_n2_finish_kernel<R, Model><<<dim3((a.N + NT - 1) / NT, a.B), NT, 0, stream>>>(a, t, p.splits, part);
+    int n = 0;
+    if (!(a.n2_tensor && N2TcLaunch<R, Model>::run(a, t, stream, n))) {
+        const N2Plan p = n2_plan(a.B, a.N);
+        R* part = reinterpret_cast<R*>(a.n2part);
+        poyiadjis_n2_kernel<R, Model><<<dim3(p.child_blocks, a.B, p.splits), NT, 0, stream>>>(a, t, p.splits, p.chunk, part);
         ++n;
+        if (p.splits > 1) {
+            poyiadjis_n2_finish_kernel<R, Model><<<dim3((a.N + NT - 1) / NT, a.B), NT, 0, stream>>>(a, t, p.splits, part);
+            ++n;
+        }
     }
     stat_ws_kernel<R, Model><<<dim3(a.G, a.B), NT, 0, stream>>>(a, t);
     return n + 1;

@@ -52,7 +52,7 @@ __host__ __device__ inline size_t hdr_stride(int Q) { return (size_t)H_SCALARS +
 struct KArgs {
     int B, N, G, Q, max_T;
     int pf, rng_mode, resample, stat_kind, Ntilde, accept_reject, max_ar, manual_thresh;
-    int need_lw;
+    int need_lw, n2_tensor;
     double lambduh;
     RngKey key;            // .item holds item_id_base
     const double* obs; const int64_t* obs_off; const int32_t* T_buf; const int32_t* t1; const int32_t* tL;

@@ -55,6 +55,8 @@ int validate(const sgm_pf_desc* d) {
             return fail(SGM_ERR_INVALID, "INJECTED PaRIS needs inj_extra / inj_extra_off");
     }
     if (d->step_weights && !d->wts_off) return fail(SGM_ERR_INVALID, "step_weights given without wts_off");
+    if (d->n2_mode < SGM_N2_AUTO || d->n2_mode > SGM_N2_TENSOR || d->reserved0 != 0) return fail(SGM_ERR_INVALID, "unknown n2_mode");
+    if (d->n2_mode == SGM_N2_TENSOR && d->dtype != SGM_F32) return fail(SGM_ERR_UNSUPPORTED, "the tensor-core O(N^2) smoother needs dtype f32");
     return SGM_OK;
 }
 
@@ -85,8 +87,7 @@ Layout make_layout(const sgm_pf_desc* d) {
         L.counters = off; off = align_up(off + B * 16 * 4);
     }
     if (d->pf == SGM_PF_POY_N2) {
-        const N2Plan p = n2_plan((int)B, (int)N);
-        L.n2part = off; off = align_up(off + (p.splits > 1 ? (size_t)p.splits * B * N * 8 * es : 0));
+        L.n2part = off; off = align_up(off + n2_partial_bytes(d->dtype, d->n2_mode, (int)B, (int)N));
     }
     L.total = off;
     return L;
@@ -131,7 +132,7 @@ int run_impl(const sgm_pf_desc* d, cudaStream_t stream) {
         a.Jidx = reinterpret_cast<int32_t*>(ws + L.Jidx);
         a.counters = reinterpret_cast<int32_t*>(ws + L.counters);
     }
-    if (d->pf == SGM_PF_POY_N2) a.n2part = ws + L.n2part;
+    if (d->pf == SGM_PF_POY_N2) { a.n2part = ws + L.n2part; a.n2_tensor = n2_use_tensor(d->dtype, d->n2_mode) ? 1 : 0; }
     a.grad = d->grad; a.loglik = d->loglik; a.status = d->status;
     a.out_x = d->out_x; a.out_lw = d->out_lw; a.out_stats = d->out_stats;
     a.trace_anc = d->trace_anc; a.trace_x = d->trace_x; a.trace_lw = d->trace_lw; a.trace_J = d->trace_J;

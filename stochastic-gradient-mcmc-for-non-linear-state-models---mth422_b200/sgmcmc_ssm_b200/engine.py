@@ -161,7 +161,7 @@ class PreparedPF(object):
     def __init__(self, model, kernel, pf, items, N, dtype=None, rng=None, resample=None, stat_kind="score",
                  lambduh=None, Ntilde=2, accept_reject=True, max_accept_reject=None,
                  manual_sample_threshold=None, seed=None, offset=None, item_id_base=0, injected=None,
-                 want=(), device=None):
+                 want=(), device=None, n2_mode="auto"):
         lib = self.lib = nat.load()
         device = self.device = _device(device)
         st = self.st = _state(device)
@@ -216,6 +216,7 @@ class PreparedPF(object):
         desc.max_accept_reject = -1 if max_accept_reject is None else int(max_accept_reject)
         desc.manual_sample_threshold = -1 if manual_sample_threshold is None else int(manual_sample_threshold)
         desc.item_id_base = int(item_id_base)
+        desc.n2_mode = nat.N2_MODE[n2_mode]
         desc.lambduh = float(lambduh)
         if seed is None or offset is None:
             s_, o_ = _next_seed_offset()
