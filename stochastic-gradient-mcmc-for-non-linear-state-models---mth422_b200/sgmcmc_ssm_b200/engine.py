@@ -122,6 +122,74 @@ class PFItems(object):
     def __len__(self):
         return len(self.obs)
 
+    def pack(self):
+        """Flatten to the arrays the C-ABI descriptor points at."""
+        B = len(self.obs)
+        T_buf = np.array([o.shape[0] for o in self.obs], dtype=np.int32)
+        has_w = any(w is not None for w in self.weights)
+        wts_off = np.full(B, -1, dtype=np.int64)
+        wlen = 0
+        if has_w:
+            for b, w in enumerate(self.weights):
+                if w is not None:
+                    wts_off[b] = wlen
+                    wlen += w.shape[0]
+        return PackedItems(
+            obs_flat=np.concatenate(self.obs) if B else np.zeros(0), T_buf=T_buf,
+            t1=np.array(self.t1, dtype=np.int32), tL=np.array(self.tL, dtype=np.int32),
+            wts_flat=np.concatenate([w for w in self.weights if w is not None]) if has_w else None, wts_off=wts_off,
+            theta=np.stack(self.theta) if B else np.zeros((0, nat.THETA_STRIDE)),
+            prior_mean=np.array(self.prior_mean, dtype=np.float64), prior_var=np.array(self.prior_var, dtype=np.float64))
+
+
+class PackedItems(object):
+    """The same batch as flat arrays (what a vectorised caller builds directly, skipping the per-item
+    Python work of PFItems.add): obs_flat (sum T_buf,), T_buf / t1 / tL (B,), wts_flat + wts_off (-1 = all
+    ones) or wts_flat None, theta (B, 12) or (12,) shared by all items, prior_mean / prior_var (B,) or scalars."""
+
+    def __init__(self, obs_flat, T_buf, t1, tL, wts_flat, wts_off, theta, prior_mean, prior_var):
+        self.T_buf = np.ascontiguousarray(T_buf, dtype=np.int32)
+        B = self.T_buf.shape[0]
+        self.obs_flat = np.ascontiguousarray(obs_flat, dtype=np.float64).reshape(-1)
+        self.t1 = np.ascontiguousarray(t1, dtype=np.int32)
+        self.tL = np.ascontiguousarray(tL, dtype=np.int32)
+        self.wts_flat = None if wts_flat is None else np.ascontiguousarray(wts_flat, dtype=np.float64).reshape(-1)
+        self.wts_off = (np.full(B, -1, dtype=np.int64) if wts_off is None else np.ascontiguousarray(wts_off, dtype=np.int64))
+        theta = np.asarray(theta, dtype=np.float64)
+        if theta.ndim == 1:
+            row = np.zeros(nat.THETA_STRIDE)
+            row[:theta.shape[0]] = theta
+            theta = np.broadcast_to(row, (B, nat.THETA_STRIDE))
+        self.theta = theta
+        self.prior_mean = np.broadcast_to(np.asarray(prior_mean, dtype=np.float64), (B,))
+        self.prior_var = np.broadcast_to(np.asarray(prior_var, dtype=np.float64), (B,))
+        if self.obs_flat.shape[0] != int(self.T_buf.sum()):
+            raise ValueError("obs_flat does not match T_buf")
+
+    def __len__(self):
+        return self.T_buf.shape[0]
+
+    def pack(self):
+        return self
+
+    def slice(self, lo, hi):
+        """Items [lo, hi) (the shard of one rank)."""
+        obs_off = np.concatenate([[0], np.cumsum(self.T_buf)])
+        wts_flat, wts_off = self.wts_flat, self.wts_off[lo:hi]
+        if wts_flat is not None and hi > lo:
+            # a weighted item's slice ends where the next weighted item's begins (or at the end)
+            used = wts_off[wts_off >= 0]
+            if used.size:
+                nxt = self.wts_off[hi:]
+                nxt = nxt[nxt >= 0]
+                w_lo, w_hi = int(used.min()), int(nxt.min()) if nxt.size else wts_flat.shape[0]
+                wts_flat = wts_flat[w_lo:w_hi]
+                wts_off = np.where(wts_off >= 0, wts_off - w_lo, -1)
+            else:
+                wts_flat = None
+        return PackedItems(self.obs_flat[obs_off[lo]:obs_off[hi]], self.T_buf[lo:hi], self.t1[lo:hi], self.tL[lo:hi],
+                           wts_flat, wts_off, self.theta[lo:hi], self.prior_mean[lo:hi], self.prior_var[lo:hi])
+
 
 class PFResult(object):
     """Handle of an asynchronous sgm_pf_run; `.wait()` synchronises and parses the packed result."""
@@ -182,22 +250,18 @@ class PreparedPF(object):
         self.p = lib.sgm_stat_dim(model_id, nat.STAT[stat_kind])
         self.n = n = lib.sgm_state_dim(model_id)
         NPrec = lib.sgm_stat_dim(model_id, 0)
-        T_buf = self.T_buf = np.array([o.shape[0] for o in items.obs], dtype=np.int32)
+        pk = items.pack()
+        T_buf = self.T_buf = pk.T_buf
         max_T = self.max_T = int(T_buf.max())
         t_real = torch.float64 if dtype == "f64" else torch.float32
 
         # ---- layout of the packed host buffer ----------------------------------------------------
         obs_off = np.zeros(B, dtype=np.int64)
         obs_off[1:] = np.cumsum(T_buf[:-1])
-        n_obs = int(T_buf.sum())
-        has_w = any(w is not None for w in items.weights)
-        wts_off = np.full(B, -1, dtype=np.int64)
-        wlen = 0
-        if has_w:
-            for b, w in enumerate(items.weights):
-                if w is not None:
-                    wts_off[b] = wlen
-                    wlen += w.shape[0]
+        n_obs = int(pk.obs_flat.shape[0])
+        has_w = pk.wts_flat is not None
+        wts_off = pk.wts_off
+        wlen = pk.wts_flat.shape[0] if has_w else 0
         sections = [("obs", n_obs * 8), ("wts", max(wlen, 1) * 8), ("theta", B * nat.THETA_STRIDE * 8),
                     ("prior_mean", B * 8), ("prior_var", B * 8), ("obs_off", B * 8), ("wts_off", B * 8),
                     ("T_buf", B * 4), ("t1", B * 4), ("tL", B * 4)]
@@ -278,17 +342,17 @@ class PreparedPF(object):
             def view(name, dt, count):
                 return host[offs[name]:offs[name] + count * np.dtype(dt).itemsize].view(dt)
 
-            view("obs", np.float64, n_obs)[:] = np.concatenate(items.obs)
+            view("obs", np.float64, n_obs)[:] = pk.obs_flat
             if has_w:
-                view("wts", np.float64, wlen)[:] = np.concatenate([w for w in items.weights if w is not None])
-            view("theta", np.float64, B * nat.THETA_STRIDE)[:] = np.concatenate(items.theta)
-            view("prior_mean", np.float64, B)[:] = items.prior_mean
-            view("prior_var", np.float64, B)[:] = items.prior_var
+                view("wts", np.float64, wlen)[:] = pk.wts_flat
+            view("theta", np.float64, B * nat.THETA_STRIDE).reshape(B, nat.THETA_STRIDE)[:] = pk.theta
+            view("prior_mean", np.float64, B)[:] = pk.prior_mean
+            view("prior_var", np.float64, B)[:] = pk.prior_var
             view("obs_off", np.int64, B)[:] = obs_off
             view("wts_off", np.int64, B)[:] = wts_off
             view("T_buf", np.int32, B)[:] = T_buf
-            view("t1", np.int32, B)[:] = items.t1
-            view("tL", np.int32, B)[:] = items.tL
+            view("t1", np.int32, B)[:] = pk.t1
+            view("tL", np.int32, B)[:] = pk.tL
 
             base_in = self.base_in = _aligned_ptr(st.dev_in)
             for name in ("obs", "theta", "prior_mean", "prior_var", "obs_off", "wts_off", "T_buf", "t1", "tL"):

@@ -52,6 +52,23 @@ class SGMCMCHelper(object):
         keys = S.MODEL_SPECS[self._model]["grad_keys"]
         return [{k: g[i] for i, k in enumerate(keys)} for g in res.grad], res
 
+    def pf_gradient_sum_packed(self, packed, parameters, pf="poyiadjis_N", N=1000, kernel=None, **kwargs):
+        """Sum over the items of an engine.PackedItems batch of their gradient estimates (dict keyed like
+        pf_gradient_estimate) -- the vectorised path of the samplers: no per-item Python work."""
+        K = self._get_kernel(kernel)
+        K.set_parameters(parameters)
+        if N is None:
+            raise TypeError("N (number of particles) must be given for kind='pf'")
+        res = batched_pf(pf, K.model, K.kernel, packed, N, stat_kind="score", **kwargs)
+        keys = S.MODEL_SPECS[self._model]["grad_keys"]
+        total = res.grad.sum(axis=0)
+        return {k: float(total[i]) for i, k in enumerate(keys)}, res
+
+    def packed_items(self, parameters, forward_message=None, **arrays):
+        prior_mean, prior_var = self._prior_moments(forward_message, parameters)
+        theta = S.MODEL_SPECS[self._model]["theta"](parameters)
+        return engine.PackedItems(theta=theta, prior_mean=prior_mean, prior_var=prior_var, **arrays)
+
     def pf_loglikelihood_estimate_batch(self, windows, parameters, pf="poyiadjis_N", N=1000, kernel=None,
                                         forward_message=None, **kwargs):
         K = self._get_kernel(kernel)

@@ -19,7 +19,7 @@ from . import statistics as S
 
 _PF_NAMES = ("nemeth", "poyiadjis_N", "poyiadjis_N2", "paris", "filter")
 _ENGINE_KW = ("dtype", "rng", "resample", "lambduh", "Ntilde", "accept_reject", "max_accept_reject",
-              "manual_sample_threshold", "seed", "offset", "device", "item_id_base")
+              "manual_sample_threshold", "seed", "offset", "device", "item_id_base", "n2_mode")
 
 
 def _theta(model, parameters):
@@ -52,7 +52,7 @@ def batched_pf(pf, model, kernel, items, N, stat_kind="score", want=(), sync=Tru
         if pf == "paris":
             raise NotImplementedError("rng='injected' with pf='paris' needs a recorded stream "
                                       "(data-dependent number of draws); pass injected=dict(...)")
-        kw["injected"] = _draw_injected(int(N), [o.shape[0] for o in items.obs])
+        kw["injected"] = _draw_injected(int(N), [int(T) for T in items.pack().T_buf])
         kw.setdefault("resample", "multinomial")
     elif "injected" in kwargs:
         kw["injected"] = kwargs["injected"]

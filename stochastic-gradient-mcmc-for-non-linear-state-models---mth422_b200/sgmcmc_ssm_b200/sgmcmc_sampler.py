@@ -49,6 +49,41 @@ def random_subsequence_and_weights(S, T, partition_style=None):
     return int(start), int(end), weights
 
 
+def random_subsequences_packed(observations, S, M, buffer_length, partition_style=None):
+    """Vectorised form of M calls of random_subsequence_and_weights + the buffer / window slicing of
+    sgmcmc_sampler.py:259-288, 364-374 for the 'uniform' and 'naive' partition styles.  Consumes the numpy
+    stream exactly like the M sequential `np.random.randint(0, T - S + 1)` calls of the reference (legacy
+    RandomState draws bounded integers element by element: checked in tests/test_host_logic.py).
+    Returns the keyword arrays of engine.PackedItems (without theta / prior)."""
+    T = observations.shape[0]
+    if buffer_length == -1:
+        buffer_length = T
+    start = np.random.randint(0, T - S + 1, size=M).astype(np.int64)
+    end = start + S
+    if partition_style in (None, "uniform"):
+        t = start[:, None] + np.arange(S)[None, :]
+        cap = min(S, T - S + 1)
+        num = np.full((M, S), float(S))
+        head = end <= 2 * S
+        tail = (~head) & (start >= T - 2 * S - 1)
+        num[head] = np.minimum(t[head] + 1, cap)
+        num[tail] = np.minimum(T - t[tail], cap)
+        weights = (T - S + 1) / num
+    elif partition_style == "naive":
+        weights = np.full((M, S), float(T) / S)
+    else:
+        raise ValueError("Unrecognized partition_style = '{0}'".format(partition_style))
+    left = np.maximum(0, start - buffer_length)
+    right = np.minimum(T, end + buffer_length)
+    lens = right - left
+    off = np.concatenate([[0], np.cumsum(lens)[:-1]])
+    idx = np.arange(int(lens.sum())) - np.repeat(off, lens) + np.repeat(left, lens)
+    obs = np.asarray(observations, dtype=np.float64).reshape(T, -1)
+    return dict(obs_flat=obs[idx, 0], T_buf=lens.astype(np.int32), t1=(start - left).astype(np.int32),
+                tL=(end - left).astype(np.int32), wts_flat=weights.reshape(-1),
+                wts_off=np.arange(M, dtype=np.int64) * S)
+
+
 def _window(observations, bd):
     """Buffered window + relative subsequence of one buffer_dict (sgmcmc_sampler.py:364-374)."""
     return dict(observations=observations[bd["left_buffer_start"]:bd["right_buffer_end"]],
@@ -179,10 +214,36 @@ class SGMCMCSampler(object):
             if kind in ("marginal", "complete"):
                 raise NotImplementedError(_NOT_PF.format(kind))
             raise ValueError("Unrecognized kind = {0}".format(kind))
-        windows = self._pf_windows(subsequence_length, minibatch_size, buffer_length, observations, buffer_dicts)
         if kwargs.get("N", None) is None:
             kwargs["N"] = num_samples
         noisy_grad = {var: np.zeros_like(value) for var, value in self.parameters.as_dict().items()}
+        obs_all = self._get_observations(observations, check_shape=False)
+        T_all = obs_all.shape[0]
+        style = self.options.get("partition_style")
+        if (buffer_dicts is None and minibatch_size > 1 and subsequence_length != -1 and T_all - subsequence_length > 0
+                and style in (None, "uniform", "naive") and np.ndim(obs_all) == 2 and obs_all.shape[1] == 1):
+            # vectorised minibatch: same numpy draws as the loop below, no per-item Python work
+            from . import parallel
+            distributed = kwargs.pop("distributed", False)
+            packed = self.message_helper.packed_items(
+                self.parameters, forward_message=kwargs.pop("forward_message", None),
+                **random_subsequences_packed(obs_all, subsequence_length, minibatch_size, buffer_length, style))
+            keys = list(noisy_grad)
+            if distributed:
+                lo, hi = parallel.shard_bounds(minibatch_size)
+                local = np.zeros(len(keys))
+                if hi > lo:
+                    sums, _ = self.message_helper.pf_gradient_sum_packed(packed.slice(lo, hi), self.parameters,
+                                                                         item_id_base=lo, **kwargs)
+                    local = np.array([sums[k] for k in keys])
+                total = parallel.allreduce_sum(local)
+            else:
+                sums, _ = self.message_helper.pf_gradient_sum_packed(packed, self.parameters, **kwargs)
+                total = [sums[k] for k in keys]
+            for k, v in zip(keys, total):
+                noisy_grad[k] += v / minibatch_size
+            return self._check_noisy_grad(noisy_grad)
+        windows = self._pf_windows(subsequence_length, minibatch_size, buffer_length, observations, buffer_dicts)
         if kwargs.pop("distributed", False):
             # every rank holds the same sampler state and numpy stream, hence the same windows; rank r
             # filters its contiguous shard and ONE all-reduce sums the per-rank gradient sums
@@ -202,6 +263,10 @@ class SGMCMCSampler(object):
             for g in grads:
                 for var in noisy_grad:
                     noisy_grad[var] += g[var] * 1.0 / minibatch_size
+        return self._check_noisy_grad(noisy_grad)
+
+    @staticmethod
+    def _check_noisy_grad(noisy_grad):
         for var in noisy_grad:
             if np.any(np.isnan(noisy_grad[var])):
                 raise ValueError("NaNs in gradient of {0}".format(var))

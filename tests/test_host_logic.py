@@ -155,3 +155,40 @@ def test_sampler_errors_and_kwargs_contract():
     assert names == ["sample_sgld", "project_parameters"] * 2 and kws[0]["Ntilde"] == 3 and kws[0]["N"] == 100
     bd = s._random_subsequence_and_buffers(buffer_length=4, subsequence_length=-1)
     assert (bd["subsequence_start"], bd["subsequence_end"], bd["weights"]) == (0, 50, None)
+
+
+@pytest.mark.parametrize("style", [None, "uniform", "naive"])
+@pytest.mark.parametrize("T,S,B", [(1000, 40, 10), (100, 16, 20), (90, 40, 3), (300, 16, -1)])
+def test_vectorised_minibatch_windows_equal_the_sequential_draws(style, T, S, B):
+    """random_subsequences_packed == M sequential _random_subsequence_and_buffers + _window calls
+    (sgmcmc_sampler.py:259-288, 364-374, 1969-2017), including the numpy stream position afterwards."""
+    from sgmcmc_ssm_b200.sgmcmc_sampler import random_subsequences_packed, _window
+    from sgmcmc_ssm_b200 import engine
+    rs = np.random.RandomState(3)
+    obs = rs.normal(size=(T, 1))
+    s = SVMSampler(n=1, m=1, observations=obs, parameters=svm_params(), partition_style=style)
+    M = 37
+    np.random.seed(99)
+    windows = [_window(obs, s._random_subsequence_and_buffers(buffer_length=B, subsequence_length=S, T=T)) for _ in range(M)]
+    after_seq = np.random.random_sample()
+    np.random.seed(99)
+    arrays = random_subsequences_packed(obs, S, M, B, style)
+    after_vec = np.random.random_sample()
+    assert after_seq == after_vec
+    items = engine.PFItems()
+    for w in windows:
+        items.add(w["observations"], [1.0, 2.0], t1=w["subsequence_start"], tL=w["subsequence_end"], weights=w["weights"])
+    ref = items.pack()
+    pk = engine.PackedItems(theta=[1.0, 2.0], prior_mean=0.0, prior_var=1.0, **arrays)
+    for name in ("obs_flat", "T_buf", "t1", "tL", "wts_flat", "wts_off"):
+        np.testing.assert_array_equal(getattr(pk, name), getattr(ref, name), err_msg=name)
+    np.testing.assert_array_equal(pk.theta, ref.theta)
+    # shard slicing keeps every item intact
+    lo, hi = 5, 21
+    sl = pk.slice(lo, hi)
+    off = np.concatenate([[0], np.cumsum(pk.T_buf)])
+    np.testing.assert_array_equal(sl.obs_flat, pk.obs_flat[off[lo]:off[hi]])
+    np.testing.assert_array_equal(sl.T_buf, pk.T_buf[lo:hi])
+    for b in range(hi - lo):
+        n = int(sl.tL[b] - sl.t1[b])
+        np.testing.assert_array_equal(sl.wts_flat[sl.wts_off[b]:sl.wts_off[b] + n], windows[lo + b]["weights"][:n])
