@@ -112,7 +112,7 @@ def run_reference(args):
         os.environ.setdefault(k, "1")
     cores = os.cpu_count() or 1
     y = svm_series()
-    windows = draw_windows(256)
+    windows = draw_windows(512)
     rate, dt, done = cpu_rate(y, windows, cores, args.steps, min(args.warmup, 1))
     sample = "{0} independent subsequence gradients per step (one per core), N=2^16, T_buf<=60".format(cores)
     line = {"metric": METRIC, "value": rate, "unit": UNIT, "impl": "reference", "n_gpus": args.gpus,
@@ -283,7 +283,8 @@ def run_gpu(args):
                 "api": "SVMSampler.noisy_gradient(kind='pf', minibatch_size=M*n_gpus, ...)"},
         "gpu_launches": int(launches_per_step * args.steps),
         "clocks": clk,
-        "roofline": {"bound": "hbm", "kernel": "pf_step_kernel<float, SvmPrior, SORTED=true> (+ pf_header_kernel, <2 % of the step)", "achieved": achieved, "peak": hbm,
+        "roofline": {"bound": "hbm", "kernel": "pf_step_kernel<float, SvmPrior, SORTED=true> (+ pf_header_kernel; the batch runs as two halves "
+                                               "on two streams, avg_launch_ms = time of one time step of the whole batch)", "achieved": achieved, "peak": hbm,
                      "unit": "GB/s", "frac": achieved / hbm, "traffic": traffic,
                      "peak_source": "MEASURED_PEAKS.json (measured)" if peaks else "fallback 6650 GB/s",
                      "alg_bytes_per_particle_step": ALG_BYTES, "particles_per_launch": prep.B * N_PARTICLES,
@@ -338,6 +339,30 @@ def extras(sg, y, theta, windows, torch):
         s.sample_sgld(**kw); s.project_parameters()
     torch.cuda.synchronize()
     out["sgld_iters_per_sec_lgssm_T1000_N1000"] = 100 / (time.perf_counter() - t0)
+
+    # O(N^2) smoother (configs[1]: N up to 2^16) and PaRIS (configs[2]: GARCH N = 2^14), device-timed
+    def timed(model, kern, pf, th, N, B, T, **kw):
+        rs = np.random.RandomState(1)
+        its = sg.PFItems()
+        for _ in range(B):
+            its.add(rs.normal(size=T) * 0.7, th, t1=2, tL=T - 2, prior_mean=0.0, prior_var=1.0)
+        pp = sg.engine.PreparedPF(model, kern, pf, its, N, dtype="f32", rng="philox", resample="multinomial_sorted", **kw).upload()
+        pp.launch(offset=1)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        a.record()
+        for k in range(2):
+            pp.launch(offset=2 + k)
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / 2 * 1e-3
+    sec = timed("svm", "prior", "poyiadjis_N2", theta, N_PARTICLES, 1, 8)
+    out["n2_tensor_pair_steps_per_sec_svm_N65536"] = N_PARTICLES * float(N_PARTICLES) * 8 / sec
+    sec = timed("svm", "prior", "poyiadjis_N2", theta, N_PARTICLES, 1, 8, n2_mode="fp32_pipe")
+    out["n2_fp32pipe_pair_steps_per_sec_svm_N65536"] = N_PARTICLES * float(N_PARTICLES) * 8 / sec
+    gth = [0.1, 0.8, 0.05, 0.1 / 0.15, 0.85, 0.8 / 0.85, 1 / 0.3, 1 / 0.09, 0.09]
+    sec = timed("garch", "optimal", "paris", gth, 1 << 14, 64, 60)
+    out["paris_particle_steps_per_sec_garch_N16384_B64"] = (1 << 14) * 64 * 60 / sec
     return out
 
 
@@ -347,7 +372,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--minibatch", type=int, default=256, help="subsequences per GPU per step")
+    ap.add_argument("--minibatch", type=int, default=512, help="subsequences per GPU per step")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true")

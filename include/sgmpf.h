@@ -128,6 +128,12 @@ typedef struct sgm_pf_desc {
 
     void* workspace;               /* >= sgm_pf_workspace_bytes(desc), 256-byte aligned             */
     uint64_t workspace_bytes;
+    /* optional two-stream pipelining of the O(N) smoothers: the batch is split in two halves that alternate on
+     * `stream` and `aux_stream`, so one half's (latency-bound) per-step header and launch gaps hide behind the
+     * other half's step kernel.  All three handles are caller-owned; leave NULL to run on `stream` only. */
+    void* aux_stream;              /* cudaStream_t                                                   */
+    void* ev_aux_fork;             /* cudaEvent_t (timing disabled is fine)                          */
+    void* ev_aux_join;             /* cudaEvent_t                                                    */
     void* ev_steps_begin;          /* optional cudaEvent_t recorded on `stream` before the first ...  */
     void* ev_steps_end;            /* ... and after the last step-kernel launch (bench roofline timing) */
 } sgm_pf_desc;

@@ -53,6 +53,7 @@ struct KArgs {
     int B, N, G, Q, max_T;
     int pf, rng_mode, resample, stat_kind, Ntilde, accept_reject, max_ar, manual_thresh;
     int need_lw, n2_tensor;
+    int b0;                // first item of this launch (a batch may be split over two streams)
     double lambduh;
     RngKey key;            // .item holds item_id_base
     const double* obs; const int64_t* obs_off; const int32_t* T_buf; const int32_t* t1; const int32_t* tL;
@@ -294,7 +295,7 @@ __device__ __forceinline__ void init_body(const KArgs& a, int b, int g, R* s_tr)
 template <class R, class Model>
 __global__ void __launch_bounds__(NT) pf_init_kernel(KArgs a) {
     __shared__ __align__(32) R s_tr_all[NWARP][WT];
-    init_body<R, Model>(a, blockIdx.y, blockIdx.x, s_tr_all[threadIdx.x >> 5]);
+    init_body<R, Model>(a, a.b0 + blockIdx.y, blockIdx.x, s_tr_all[threadIdx.x >> 5]);
 }
 
 // ---- per-item header: everything of a step that crosses tiles ----------------------------------------
@@ -397,7 +398,7 @@ __device__ __forceinline__ void header_body(const KArgs& a, int b, int t, int fi
 template <class R, class Model>
 __global__ void __launch_bounds__(NT) pf_header_kernel(KArgs a, int t, int final_pass) {
     __shared__ double sh_d[NWARP];
-    header_body<R, Model>(a, blockIdx.x, t, final_pass, sh_d);
+    header_body<R, Model>(a, a.b0 + blockIdx.x, t, final_pass, sh_d);
 }
 
 // ---- gather parents -> propagate -> reweight -> statistic update -> store (pf.py:30-36, 168-179) -----
@@ -743,7 +744,7 @@ template <class R, class Model, bool SORTED>
 __global__ void __launch_bounds__(NT, (sizeof(R) == 4 ? SGM_STEP_CTAS : 2)) pf_step_kernel(KArgs a, int t) {
     __shared__ __align__(32) R s_cdf_all[NWARP][SORTED ? WIN_BYTES / sizeof(R) : WT];
     const int warp = threadIdx.x >> 5;
-    step_body<R, Model, SORTED>(a, blockIdx.y, t, blockIdx.x * NWARP + warp, threadIdx.x & 31, s_cdf_all[warp]);
+    step_body<R, Model, SORTED>(a, a.b0 + blockIdx.y, t, blockIdx.x * NWARP + warp, threadIdx.x & 31, s_cdf_all[warp]);
 }
 
 // ---- fused kernel for small particle counts (N <= 2048: the item fits one CTA) -----------------------------

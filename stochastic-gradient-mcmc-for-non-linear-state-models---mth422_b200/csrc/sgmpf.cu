@@ -148,18 +148,38 @@ int run_impl(const sgm_pf_desc* d, cudaStream_t stream) {
         ++launches;
         if (d->ev_steps_end) cudaEventRecord(reinterpret_cast<cudaEvent_t>(d->ev_steps_end), stream);
     } else {
-        pf_init_kernel<R, Model><<<grid, block, 0, stream>>>(a); ++launches;
+        // Two-stream pipelining (O(N) smoothers, big batches): the halves alternate on `stream` / `aux_stream`, so
+        // the one-CTA-per-item header kernel and the launch gap of one half overlap the step kernel of the other.
+        const bool piped = d->aux_stream && d->ev_aux_fork && d->ev_aux_join && !backward_pf(d->pf) &&
+                           (int64_t)a.B * a.G >= 2 * 148 * 4 && a.B >= 2;
+        const int nh = piped ? 2 : 1;
+        cudaStream_t sh[2] = {stream, piped ? reinterpret_cast<cudaStream_t>(d->aux_stream) : stream};
+        KArgs ah[2] = {a, a};
+        int nb[2] = {piped ? a.B / 2 : a.B, piped ? a.B - a.B / 2 : 0};
+        ah[1].b0 = nb[0];
+        if (piped) {
+            cudaEventRecord(reinterpret_cast<cudaEvent_t>(d->ev_aux_fork), stream);
+            cudaStreamWaitEvent(sh[1], reinterpret_cast<cudaEvent_t>(d->ev_aux_fork), 0);
+        }
+        for (int h = 0; h < nh; ++h) { pf_init_kernel<R, Model><<<dim3(a.G, nb[h]), block, 0, sh[h]>>>(ah[h]); ++launches; }
         if (d->ev_steps_begin) cudaEventRecord(reinterpret_cast<cudaEvent_t>(d->ev_steps_begin), stream);
         for (int t = 0; t < a.max_T; ++t) {
-            pf_header_kernel<R, Model><<<a.B, block, 0, stream>>>(a, t, 0); ++launches;
-            if (d->resample == SGM_RESAMPLE_MULTINOMIAL) pf_step_kernel<R, Model, false><<<grid, block, 0, stream>>>(a, t);
-            else pf_step_kernel<R, Model, true><<<grid, block, 0, stream>>>(a, t);
-            ++launches;
+            for (int h = 0; h < nh; ++h) {
+                const dim3 gh(a.G, nb[h]);
+                pf_header_kernel<R, Model><<<nb[h], block, 0, sh[h]>>>(ah[h], t, 0); ++launches;
+                if (d->resample == SGM_RESAMPLE_MULTINOMIAL) pf_step_kernel<R, Model, false><<<gh, block, 0, sh[h]>>>(ah[h], t);
+                else pf_step_kernel<R, Model, true><<<gh, block, 0, sh[h]>>>(ah[h], t);
+                ++launches;
+            }
             if (d->pf == SGM_PF_POY_N2) launches += launch_poyiadjis_n2<R, Model>(a, t, stream);
             else if (d->pf == SGM_PF_PARIS) launches += launch_paris<R, Model>(a, t, stream);
         }
+        for (int h = 0; h < nh; ++h) { pf_header_kernel<R, Model><<<nb[h], block, 0, sh[h]>>>(ah[h], a.max_T, 1); ++launches; }
+        if (piped) {
+            cudaEventRecord(reinterpret_cast<cudaEvent_t>(d->ev_aux_join), sh[1]);
+            cudaStreamWaitEvent(stream, reinterpret_cast<cudaEvent_t>(d->ev_aux_join), 0);
+        }
         if (d->ev_steps_end) cudaEventRecord(reinterpret_cast<cudaEvent_t>(d->ev_steps_end), stream);
-        pf_header_kernel<R, Model><<<a.B, block, 0, stream>>>(a, a.max_T, 1); ++launches;
     }
     if (d->out_x || d->out_lw || d->out_stats) {
         pf_export_kernel<R, Model><<<dim3((a.N + NT - 1) / NT, a.B), block, 0, stream>>>(a); ++launches;

@@ -37,6 +37,7 @@ class SgmPfDesc(ctypes.Structure):
         ("out_x", c_vp), ("out_lw", c_vp), ("out_stats", c_vp),
         ("trace_anc", c_vp), ("trace_x", c_vp), ("trace_lw", c_vp), ("trace_J", c_vp),
         ("workspace", c_vp), ("workspace_bytes", c_u64),
+        ("aux_stream", c_vp), ("ev_aux_fork", c_vp), ("ev_aux_join", c_vp),
         ("ev_steps_begin", c_vp), ("ev_steps_end", c_vp),
     ]
 

@@ -22,6 +22,7 @@ class Config(object):
     rng = "philox"                   # 'philox' (device) or 'injected' (numpy legacy stream, parity mode)
     resample = "multinomial_sorted"  # 'multinomial' | 'multinomial_sorted' | 'systematic' | 'stratified'
     device = None                    # torch device; default = current CUDA device
+    two_streams = True               # split big O(N) batches over two streams (hides the per-step header kernel)
 
 
 config = Config()
@@ -61,6 +62,7 @@ class _DeviceState(object):
         self.pin_out = None
         self.dev_out = None
         self.checked = False
+        self.aux = None            # (stream, fork event, join event) for the two-stream pipelining of big batches
 
     @staticmethod
     def _grow(t, nbytes, **kw):
@@ -362,6 +364,13 @@ class PreparedPF(object):
             desc.grad, desc.loglik, desc.status = base_out, base_out + B * 64, base_out + B * 72
             desc.workspace = _aligned_ptr(st.workspace)
             desc.workspace_bytes = ws_bytes
+            if config.two_streams:
+                if st.aux is None:
+                    st.aux = (torch.cuda.Stream(device), torch.cuda.Event(), torch.cuda.Event())
+                    for ev in st.aux[1:]:
+                        ev.record()                      # creates the handles
+                desc.aux_stream = st.aux[0].cuda_stream
+                desc.ev_aux_fork, desc.ev_aux_join = st.aux[1].cuda_event, st.aux[2].cuda_event
         self.launches = 0
         self.particle_steps = int(N) * int(T_buf.sum())
 

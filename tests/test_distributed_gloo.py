@@ -22,6 +22,21 @@ def _fake_batch(self, windows, parameters, item_id_base=0, **kwargs):
     return grads, None
 
 
+def _fake_packed(self, packed, parameters, item_id_base=0, **kwargs):
+    """Stand-in of Helper.pf_gradient_sum_packed (the vectorised minibatch path): same per-item values as
+    _fake_batch, summed over the shard."""
+    off = np.concatenate([[0], np.cumsum(packed.T_buf)])
+    tot = dict(LRinv_vec=0.0, LQinv_vec=0.0, A=0.0)
+    for k in range(len(packed)):
+        s = float(np.sum(packed.obs_flat[off[k]:off[k + 1]])) + 0.01 * (item_id_base + k)
+        n = int(packed.tL[k] - packed.t1[k])
+        wt = 1.0 if packed.wts_off[k] < 0 else float(np.sum(packed.wts_flat[packed.wts_off[k]:packed.wts_off[k] + n]))
+        tot["LRinv_vec"] += s
+        tot["LQinv_vec"] += 2 * s + wt
+        tot["A"] += np.sin(s)
+    return tot, None
+
+
 def _worker(rank, world, port, out):
     os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank), MASTER_ADDR="127.0.0.1",
                       MASTER_PORT=str(port))
@@ -44,6 +59,7 @@ def _worker(rank, world, port, out):
     assert parallel.allreduce_max(float(rank)) == 1.0
     # (3) sampler path
     SVMHelper.pf_gradient_estimate_batch = _fake_batch
+    SVMHelper.pf_gradient_sum_packed = _fake_packed
     rs = np.random.RandomState(0)
     y = rs.normal(size=(500, 1))
     p = SVMParameters(A=np.eye(1) * 0.9, LQinv=np.eye(1), LRinv=np.eye(1))
@@ -54,6 +70,13 @@ def _worker(rank, world, port, out):
     g_one = s.noisy_gradient(kind="pf", N=8, subsequence_length=20, buffer_length=5, minibatch_size=7)
     for k in g_one:
         np.testing.assert_allclose(g_dist[k], g_one[k], rtol=1e-13, atol=1e-13)
+    # the vectorised minibatch path and the per-window loop (explicit buffer_dicts) agree
+    np.random.seed(5)
+    bds = [s._random_subsequence_and_buffers(buffer_length=5, subsequence_length=20, T=500) for _ in range(7)]
+    g_loop = s.noisy_gradient(kind="pf", N=8, subsequence_length=20, buffer_length=5, minibatch_size=7, buffer_dicts=bds,
+                              distributed=True)
+    for k in g_one:
+        np.testing.assert_allclose(g_loop[k], g_one[k], rtol=1e-12, atol=1e-12)
     parallel.barrier()
     out.put((rank, covered, {k: float(np.ravel(v)[0]) for k, v in g_dist.items()}))
     torch.distributed.destroy_process_group()
