@@ -58,7 +58,9 @@ enum { SGM_RESAMPLE_MULTINOMIAL = 0, SGM_RESAMPLE_MULTINOMIAL_SORTED = 1,
 /* additive statistic carried by the smoother */
 enum { SGM_STAT_SCORE = 0,     /* complete-data log-likelihood gradient (pf_gradient_estimate)   */
        SGM_STAT_SUFF = 1,      /* [x', x'^2, x x'] (lgssm/svm) or [x', x'^2, x'^4] (garch)        */
-       SGM_STAT_NONE = 2 };    /* log-likelihood only (pf_loglikelihood_estimate)                 */
+       SGM_STAT_NONE = 2,      /* log-likelihood only (pf_loglikelihood_estimate)                 */
+       SGM_STAT_PRED = 3 };    /* k-step-ahead predictive log-likelihood, pf = FILTER only
+                                * (pf_predictive_loglikelihood_estimate; pf.py:73-76 `logsumexp`)   */
 
 /* O(N^2) smoother back end: AUTO = tensor cores (TF32 mma, FP32 accumulate) for SGM_F32, FP32/FP64 pipe
  * otherwise; FP32_PIPE forces the CUDA-core kernel (any dtype); TENSOR requires SGM_F32. */
@@ -75,8 +77,8 @@ enum { SGM_STATUS_NAN_WEIGHT = 1,   /* NaN / +inf log-weight: np.random.choice w
 
 #define SGM_THETA_STRIDE 12
 /* theta layout (doubles, values exactly as the reference Parameters object computes them):
- *   SVM   : A, LQinv, Qinv, LRinv, Rinv
- *   LGSSM : A, LQinv, Qinv, C, LRinv, Rinv
+ *   SVM   : A, LQinv, Qinv, LRinv, Rinv                 [10] = Q, [11] = R (SGM_STAT_PRED only)
+ *   LGSSM : A, LQinv, Qinv, C, LRinv, Rinv              [10] = Q, [11] = R (SGM_STAT_PRED only)
  *   GARCH : alpha, beta, gamma, mu, phi, lambduh, LRinv, Rinv, R                                    */
 
 typedef struct sgm_pf_desc {
@@ -91,6 +93,9 @@ typedef struct sgm_pf_desc {
     int32_t manual_sample_threshold; /* <0: int(10*log10(N/10)) (pf.py:286-287); INJECTED mode only */
     int32_t item_id_base;          /* global index of item 0 (keeps Philox streams rank-invariant)  */
     int32_t n2_mode;               /* O(N^2) smoother: SGM_N2_AUTO / SGM_N2_FP32_PIPE / SGM_N2_TENSOR */
+    int32_t pred_steps_ahead;      /* SGM_STAT_PRED: num_steps_ahead K (0..7); the statistic has K + 1 entries */
+    int32_t pred_per_horizon;      /* SGM_STAT_PRED: 0 = the reference's log-sum over ALL horizons (pf.py:73-76),
+                                    * 1 = one log-sum per horizon                                    */
     int32_t reserved0;             /* must be 0                                                     */
     double lambduh;                /* Nemeth shrinkage (pf.py:140); 1.0 = Poyiadjis O(N)            */
     uint64_t seed, offset;         /* Philox key / call counter                                     */
@@ -113,6 +118,8 @@ typedef struct sgm_pf_desc {
     const double* inj_z;           /* [B][max_T][N]   proposal normals                              */
     const double* inj_extra;       /* flat PaRIS accept-reject / exact-sampling uniforms            */
     const int64_t* inj_extra_off;  /* [B][max_T]      start of (item, step)'s slice of inj_extra    */
+    const double* inj_pred;        /* [B][max_T][8][N] SGM_STAT_PRED: normals of the predictive statistic
+                                    * (svm/helper.py:379, garch/kernels.py:66), horizon-major        */
 
     /* outputs */
     double* grad;                  /* [B][8]  final weighted-average statistic (average_statistic)  */

@@ -428,6 +428,84 @@ int launch_poyiadjis_n2(const KArgs& a, int t, cudaStream_t stream) {
     return n + 1;
 }
 
+// ---- k-step-ahead predictive log-likelihood (pf = 'filter', `logsumexp`) ----------------------------
+// After step t has produced the new particles and log-weights: per particle h_ik = log Pr(y_{t+k} | x'_i), k = 0..K
+// (models.cuh pred_*), then  stat_k += max_i h_ik + log( sum over i [and, as in the reference pf.py:73-76, over ALL k]
+// of exp(h_ik - max_k) W_i ),  W = normalised new weights.  Outside [t1, tL) the statistic function is identically 0,
+// for which the reference's all-horizon sum adds log(K + 1) to every entry.  One CTA per item, two passes over the
+// particles (h is recomputed -- counter-based / injected randoms); an evaluation metric, not a throughput path.
+template <class R, class Model>
+__device__ __forceinline__ void pred_h(const KArgs& a, const typename Model::template Theta<R>& th, const RngKey& key, int b, int t,
+                                       int i, int kmax, R wt, const double* obs, const R* xn, R* h) {
+    R ps[2];
+    Model::pred_begin(xn, ps);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) h[k] = (R)0;
+    for (int k = 0; k <= kmax; ++k) {
+        R z = (R)0;
+        if (Model::PRED_RNG) {
+            if (a.rng_mode == SGM_RNG_INJECTED) z = (R)a.inj_pred[(((size_t)b * a.max_T + t) * 8 + k) * a.N + i];
+            else rng_normal1(key, (uint32_t)i, (uint32_t)t, STREAM_PRED, (uint32_t)k, z);
+        }
+        h[k] = Model::pred_ll(th, ps, (R)obs[t + k], z) * wt;
+        Model::pred_next(th, ps, z);
+    }
+}
+
+template <class R, class Model>
+__global__ void __launch_bounds__(NT) pf_pred_kernel(KArgs a, int t) {
+    constexpr int NX = Model::NX, NP = Model::NP, W = NX + NP;
+    __shared__ R sh_r[NWARP];
+    __shared__ double sh_d[NWARP];
+    const int b = blockIdx.x, tid = threadIdx.x;
+    const int Tb = a.T_buf[b];
+    if (t >= Tb) return;
+    const int K = a.pred_K, N = a.N, par = t & 1;
+    double* acc = a.acc + (size_t)b * ACC_STRIDE;
+    const bool in_sub = (t >= a.t1[b]) && (t < a.tL[b]);
+    if (!in_sub) {
+        if (tid == 0 && !a.pred_per_horizon) for (int k = 0; k <= K; ++k) acc[1 + k] += ::log((double)(K + 1));
+        return;
+    }
+    const R wt = (a.wts_off && a.wts_off[b] >= 0) ? (R)a.step_weights[a.wts_off[b] + (t - a.t1[b])] : (R)1;
+    const size_t item_off = (size_t)b * N;
+    const R* lw_new = reinterpret_cast<const R*>(a.lw[par ^ 1]) + item_off;
+    const typename Model::template Theta<R> th = load_thc<R, Model>(a, b);
+    const double* obs = a.obs + a.obs_off[b];
+    const int kmax = min(K, Tb - 1 - t);
+    RngKey key = a.key; key.item += (uint32_t)b;
+    R mx[8], mlw = -Mth<R>::inf();
+#pragma unroll
+    for (int k = 0; k < 8; ++k) mx[k] = -Mth<R>::inf();
+    for (int i = tid; i < N; i += NT) {
+        R rn[W], h[8];
+        load_rec<R, W>(a.rec[par ^ 1], a.tail[par ^ 1], item_off + i, rn);
+        pred_h<R, Model>(a, th, key, b, t, i, kmax, wt, obs, rn + NP, h);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) mx[k] = nan_max(mx[k], h[k]);
+        mlw = nan_max(mlw, lw_new[i]);
+    }
+    for (int k = 0; k < 8; ++k) mx[k] = block_max(mx[k], sh_r);
+    mlw = block_max(mlw, sh_r);
+    double s[8] = {0, 0, 0, 0, 0, 0, 0, 0}, Wsum = 0.0;
+    for (int i = tid; i < N; i += NT) {
+        R rn[W], h[8];
+        load_rec<R, W>(a.rec[par ^ 1], a.tail[par ^ 1], item_off + i, rn);
+        pred_h<R, Model>(a, th, key, b, t, i, kmax, wt, obs, rn + NP, h);
+        const double w = (double)Mth<R>::exp(lw_new[i] - mlw);
+        Wsum += w;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) s[k] += (double)Mth<R>::exp(h[k] - mx[k]) * w;
+    }
+    for (int k = 0; k < 8; ++k) s[k] = block_sum(s[k], sh_d);
+    Wsum = block_sum(Wsum, sh_d);
+    if (tid == 0) {
+        double tot = 0.0;
+        for (int k = 0; k <= K; ++k) tot += s[k] / Wsum;
+        for (int k = 0; k <= K; ++k) acc[1 + k] += (double)mx[k] + ::log(a.pred_per_horizon ? s[k] / Wsum : tot);
+    }
+}
+
 // ---- PaRIS ------------------------------------------------------------------------------------------
 // Exact draw(s) from the backward kernel of child i:  J ~ Cat(softmax_j(lw_j + log q(x'_i | x_j)))
 // (pf.py:328-339 and the naive branch :226-237).  Block-cooperative, fixed summation order.

@@ -46,6 +46,7 @@ template <class R> struct GaussTheta {
     R A, LQinv, Qinv, C, LRinv, Rinv;
     R invLQ, invLR, logLQinv, logLRinv;     // LQinv**-1, LRinv**-1, log LQinv, log LRinv
     R opt_sd, opt_iprec, opt_ivar, opt_lvar; // LGSSM optimal kernel: prec**-0.5, 1/prec, 1/(1/Qinv+1/Rinv), log(1/Qinv+1/Rinv)
+    R Qv, Rv;                                // parameters.Q, parameters.R (predictive statistic only)
 };
 
 struct SvmPrior {
@@ -56,6 +57,7 @@ struct SvmPrior {
         t.A = (R)th[0]; t.LQinv = (R)th[1]; t.Qinv = (R)th[2]; t.LRinv = (R)th[3]; t.Rinv = (R)th[4]; t.C = (R)1;
         t.invLQ = (R)(1.0 / th[1]); t.invLR = (R)(1.0 / th[3]); t.logLQinv = (R)::log(th[1]); t.logLRinv = (R)::log(th[3]);
         t.opt_sd = t.opt_iprec = t.opt_ivar = t.opt_lvar = (R)0;
+        t.Qv = (R)th[10]; t.Rv = (R)th[11];
         return t;
     }
     // svm/kernels.py:34-37
@@ -117,6 +119,19 @@ struct SvmPrior {
     template <class R> static __device__ __forceinline__ void suff_moments(const R* Em, const R* xn, R* h) {
         h[0] = xn[0]; h[1] = xn[0] * xn[0]; h[2] = Em[0] * xn[0]; h[3] = (R)0;
     }
+    // ---- k-step-ahead predictive log-likelihood (svm/helper.py:352-395, Ntilde = 1) ----------------------------
+    // predictive state ps = (mean, cov) of x_{t+k} given the particle; one normal per horizon (also at k = 0,
+    // where it multiplies sqrt(0)); y ~ N(0, R exp(x_mc))
+    static constexpr bool PRED_RNG = true;
+    template <class R> static __device__ __forceinline__ void pred_begin(const R* xn, R* ps) { ps[0] = xn[0]; ps[1] = (R)0; }
+    template <class R> static __device__ __forceinline__ R pred_ll(const Theta<R>& t, const R* ps, R yk, R z) {
+        const R x_mc = ps[0] + Mth<R>::sqrt(ps[1]) * z;
+        const R y_cov = t.Rv * Mth<R>::exp(x_mc);
+        return (R)-0.5 * (yk * yk) / y_cov + (R)(-0.5 * LOG_2PI_D) - (R)0.5 * Mth<R>::log(y_cov);
+    }
+    template <class R> static __device__ __forceinline__ void pred_next(const Theta<R>& t, R* ps, R z) {
+        ps[0] = t.A * ps[0]; ps[1] = t.Qv + (t.A * t.A) * ps[1];
+    }
 };
 
 struct LgssmPrior {
@@ -129,6 +144,7 @@ struct LgssmPrior {
         const double prec = th[2] + th[3] * th[3] * th[5];          // lgssm/kernels.py:91-93
         const double var = 1.0 / th[2] + 1.0 / th[5];                // lgssm/kernels.py:118
         t.opt_sd = (R)(1.0 / ::sqrt(prec)); t.opt_iprec = (R)(1.0 / prec); t.opt_ivar = (R)(1.0 / var); t.opt_lvar = (R)::log(var);
+        t.Qv = (R)th[10]; t.Rv = (R)th[11];
         return t;
     }
     // lgssm/kernels.py:29-33
@@ -170,6 +186,17 @@ struct LgssmPrior {
         h[0] = t.invLR - (dy * dy) * t.LRinv;
     }
     template <class R> static __device__ __forceinline__ void suff_moments(const R* Em, const R* xn, R* h) { SvmPrior::suff_moments(Em, xn, h); }
+    // lgssm/helper.py:1281-1336 (m = n = 1): analytic, no random numbers
+    static constexpr bool PRED_RNG = false;
+    template <class R> static __device__ __forceinline__ void pred_begin(const R* xn, R* ps) { ps[0] = xn[0]; ps[1] = (R)0; }
+    template <class R> static __device__ __forceinline__ R pred_ll(const Theta<R>& t, const R* ps, R yk, R z) {
+        const R diff = yk - ps[0] * t.C;
+        const R y_cov = t.Rv + t.C * ps[1] * t.C;
+        return (R)-0.5 * (diff * diff) / y_cov + (R)(-0.5 * LOG_2PI_D) - (R)0.5 * Mth<R>::log(y_cov);
+    }
+    template <class R> static __device__ __forceinline__ void pred_next(const Theta<R>& t, R* ps, R z) {
+        ps[0] = t.A * ps[0]; ps[1] = t.Qv + (t.A * t.A) * ps[1];
+    }
 };
 
 struct LgssmOptimal : LgssmPrior {
@@ -275,6 +302,17 @@ struct GarchPrior {
     template <class R> static __device__ __forceinline__ void suff_moments(const R* Em, const R* xn, R* h) {
         const R x2 = xn[0] * xn[0];
         h[0] = xn[0]; h[1] = x2; h[2] = x2 * x2; h[3] = (R)0;
+    }
+    // garch/helper.py:374-412: y ~ N(x_pred, R); x_pred advanced with the PRIOR kernel (one normal per horizon)
+    static constexpr bool PRED_RNG = true;
+    template <class R> static __device__ __forceinline__ void pred_begin(const R* xn, R* ps) { ps[0] = xn[0]; ps[1] = xn[1]; }
+    template <class R> static __device__ __forceinline__ R pred_ll(const Theta<R>& t, const R* ps, R yk, R z) {
+        const R diff = yk - ps[0];
+        return (R)-0.5 * (diff * diff) / t.Rv + (R)(-0.5 * LOG_2PI_D) - (R)0.5 * Mth<R>::log(t.Rv);
+    }
+    template <class R> static __device__ __forceinline__ void pred_next(const Theta<R>& t, R* ps, R z) {
+        const R s2 = t.alpha + t.beta * (ps[0] * ps[0]) + t.gamma * ps[1];
+        ps[0] = Mth<R>::sqrt(s2) * z; ps[1] = s2;
     }
 };
 

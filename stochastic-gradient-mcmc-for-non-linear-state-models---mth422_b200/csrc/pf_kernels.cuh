@@ -43,7 +43,7 @@ constexpr int TILE = NT * KPT;         // 2048 particles per CTA (8 warp tiles)
 constexpr int MAX_Q = 4096;            // N <= 2^20
 constexpr int WIN_BYTES = 4096;        // per-warp shared-memory window of the staged parent CDF (sorted resampling)
 constexpr int SSTRIDE = 8;             // doubles per `sub` entry
-constexpr int ACC_STRIDE = 8;          // doubles per `acc` entry
+constexpr int ACC_STRIDE = 16;         // doubles per `acc` entry: log-likelihood, then up to 8 filter / predictive statistics
 constexpr int THC_BYTES = 128;         // per-item slot for the model's derived constants
 constexpr int H_M = 0, H_TOTAL = 1, H_SBAR = 2, H_SCALARS = 8;
 
@@ -53,6 +53,8 @@ struct KArgs {
     int B, N, G, Q, max_T;
     int pf, rng_mode, resample, stat_kind, Ntilde, accept_reject, max_ar, manual_thresh;
     int need_lw, n2_tensor;
+    int pred_K, pred_per_horizon;  // SGM_STAT_PRED: num_steps_ahead, log-sum variant
+    const double* inj_pred;
     int b0;                // first item of this launch (a batch may be split over two streams)
     double lambduh;
     RngKey key;            // .item holds item_id_base
@@ -391,6 +393,7 @@ __device__ __forceinline__ void header_body(const KArgs& a, int b, int t, int fi
             a.loglik[b] = acc[0];
             for (int j = 0; j < 8; ++j) a.grad[(size_t)b * 8 + j] = 0.0;
             for (int j = 0; j < nstat; ++j) a.grad[(size_t)b * 8 + j] = (a.pf == SGM_PF_FILTER) ? acc[1 + j] : sbar[j];
+            if (a.stat_kind == SGM_STAT_PRED) for (int j = 0; j <= a.pred_K; ++j) a.grad[(size_t)b * 8 + j] = acc[1 + j];
         }
     }
 }

@@ -11,7 +11,7 @@
 
 namespace sgm {
 
-enum : uint32_t { STREAM_NORMAL = 0, STREAM_UNIFORM = 1, STREAM_GAMMA = 2, STREAM_PARIS = 3, STREAM_EXACT = 4 };
+enum : uint32_t { STREAM_NORMAL = 0, STREAM_UNIFORM = 1, STREAM_GAMMA = 2, STREAM_PARIS = 3, STREAM_EXACT = 4, STREAM_PRED = 5 };
 
 struct RngKey { uint32_t k0, k1, item, offset; };
 
@@ -61,6 +61,19 @@ __device__ __forceinline__ void rng_normal4(const RngKey& k, uint32_t q, uint32_
     sincospi(2.0 * u01d(a.z, a.w), &s0, &c0);
     sincospi(2.0 * u01d(b.z, b.w), &s1, &c1);
     z[0] = r0 * c0; z[1] = r0 * s0; z[2] = r1 * c1; z[3] = r1 * s1;
+}
+// one standard normal for (index, step, stream, sub)
+__device__ __forceinline__ void rng_normal1(const RngKey& k, uint32_t index, uint32_t step, uint32_t stream, uint32_t sub, float& z) {
+    const uint4 r = rng_raw(k, index, step, stream, sub);
+    float s, c;
+    __sincosf(6.28318530717958647692f * u01f(r.y), &s, &c);
+    z = sqrtf(-2.0f * __logf(u01f(r.x))) * c;
+}
+__device__ __forceinline__ void rng_normal1(const RngKey& k, uint32_t index, uint32_t step, uint32_t stream, uint32_t sub, double& z) {
+    const uint4 r = rng_raw(k, index, step, stream, sub);
+    double s, c;
+    sincospi(2.0 * u01d(r.z, r.w), &s, &c);
+    z = sqrt(-2.0 * log(u01d(r.x, r.y))) * c;
 }
 // Gamma(shape, 1), shape >= 1 (Marsaglia & Tsang 2000) with their squeeze test (no logs ~98 % of the time);
 // the variate is generated in f32 (relative resolution 6e-8, far below its Monte-Carlo spread) and

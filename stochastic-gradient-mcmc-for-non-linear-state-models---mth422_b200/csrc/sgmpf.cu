@@ -40,7 +40,13 @@ int validate(const sgm_pf_desc* d) {
     if (d->dtype != SGM_F32 && d->dtype != SGM_F64) return fail(SGM_ERR_INVALID, "unknown dtype");
     if (d->rng_mode != SGM_RNG_PHILOX && d->rng_mode != SGM_RNG_INJECTED) return fail(SGM_ERR_INVALID, "unknown rng_mode");
     if (d->resample < 0 || d->resample > SGM_RESAMPLE_STRATIFIED) return fail(SGM_ERR_INVALID, "unknown resample");
-    if (d->stat_kind < 0 || d->stat_kind > SGM_STAT_NONE) return fail(SGM_ERR_INVALID, "unknown stat_kind");
+    if (d->stat_kind < 0 || d->stat_kind > SGM_STAT_PRED) return fail(SGM_ERR_INVALID, "unknown stat_kind");
+    if (d->stat_kind == SGM_STAT_PRED) {
+        if (d->pf != SGM_PF_FILTER) return fail(SGM_ERR_INVALID, "Only can use pf = 'filter' since we are filtering");
+        if (d->pred_steps_ahead < 0 || d->pred_steps_ahead > 7) return fail(SGM_ERR_UNSUPPORTED, "num_steps_ahead must be in [0, 7]");
+        if (d->rng_mode == SGM_RNG_INJECTED && d->model != SGM_MODEL_LGSSM && !d->inj_pred)
+            return fail(SGM_ERR_INVALID, "INJECTED predictive statistic needs inj_pred");
+    }
     if (d->n_items < 1 || d->n_items > 65535) return fail(SGM_ERR_INVALID, "n_items must be in [1, 65535]");
     if (d->n_particles < 1 || d->n_particles > WT * MAX_Q) return fail(SGM_ERR_INVALID, "n_particles must be in [1, 2^20]");
     if (d->max_T < 0 || d->max_T > 65000) return fail(SGM_ERR_INVALID, "max_T out of range");
@@ -69,7 +75,7 @@ Layout make_layout(const sgm_pf_desc* d) {
     const size_t es = d->dtype == SGM_F64 ? 8 : 4;
     const size_t B = d->n_items, N = d->n_particles, Q = (N + WT - 1) / WT;
     const size_t KT = state_dim(d->model) + score_dim(d->model) - 4;
-    const bool need_lw = backward_pf(d->pf) || d->out_lw || d->trace_lw;
+    const bool need_lw = backward_pf(d->pf) || d->out_lw || d->trace_lw || d->stat_kind == SGM_STAT_PRED;
     size_t off = 0;
     for (int k = 0; k < 2; ++k) { L.rec[k] = off; off = align_up(off + B * N * 4 * es); }
     for (int k = 0; k < 2; ++k) { L.tail[k] = off; off = align_up(off + B * N * KT * es); }
@@ -110,7 +116,8 @@ int run_impl(const sgm_pf_desc* d, cudaStream_t stream) {
     if (a.max_ar < 0) a.max_ar = 0;
     if (d->pf == SGM_PF_PARIS && d->rng_mode == SGM_RNG_PHILOX && (int64_t)a.max_ar * a.Ntilde >= 4096)
         return fail(SGM_ERR_INVALID, "Ntilde * max_accept_reject must be < 4096 in PHILOX mode");
-    a.need_lw = (backward_pf(d->pf) || d->out_lw || d->trace_lw) ? 1 : 0;
+    a.need_lw = (backward_pf(d->pf) || d->out_lw || d->trace_lw || d->stat_kind == SGM_STAT_PRED) ? 1 : 0;
+    a.pred_K = d->pred_steps_ahead; a.pred_per_horizon = d->pred_per_horizon; a.inj_pred = d->inj_pred;
     a.lambduh = d->lambduh;
     a.key.k0 = (uint32_t)(d->seed & 0xffffffffu); a.key.k1 = (uint32_t)(d->seed >> 32);
     a.key.item = (uint32_t)d->item_id_base; a.key.offset = (uint32_t)(d->offset & 0xffffffffu);
@@ -139,7 +146,8 @@ int run_impl(const sgm_pf_desc* d, cudaStream_t stream) {
 
     const dim3 grid(a.G, a.B), block(NT);
     int64_t launches = 0;
-    const bool fused = (a.Q <= NWARP) && !backward_pf(d->pf);
+    const bool pred = d->stat_kind == SGM_STAT_PRED;
+    const bool fused = (a.Q <= NWARP) && !backward_pf(d->pf) && !pred;
     if (fused) {
         // small N: the whole time loop of an item in one launch (one CTA per item)
         if (d->ev_steps_begin) cudaEventRecord(reinterpret_cast<cudaEvent_t>(d->ev_steps_begin), stream);
@@ -150,7 +158,7 @@ int run_impl(const sgm_pf_desc* d, cudaStream_t stream) {
     } else {
         // Two-stream pipelining (O(N) smoothers, big batches): the halves alternate on `stream` / `aux_stream`, so
         // the one-CTA-per-item header kernel and the launch gap of one half overlap the step kernel of the other.
-        const bool piped = d->aux_stream && d->ev_aux_fork && d->ev_aux_join && !backward_pf(d->pf) &&
+        const bool piped = d->aux_stream && d->ev_aux_fork && d->ev_aux_join && !backward_pf(d->pf) && !pred &&
                            (int64_t)a.B * a.G >= 2 * 148 * 4 && a.B >= 2;
         const int nh = piped ? 2 : 1;
         cudaStream_t sh[2] = {stream, piped ? reinterpret_cast<cudaStream_t>(d->aux_stream) : stream};
@@ -171,6 +179,7 @@ int run_impl(const sgm_pf_desc* d, cudaStream_t stream) {
                 else pf_step_kernel<R, Model, true><<<gh, block, 0, sh[h]>>>(ah[h], t);
                 ++launches;
             }
+            if (pred) { pf_pred_kernel<R, Model><<<a.B, block, 0, stream>>>(a, t); ++launches; }
             if (d->pf == SGM_PF_POY_N2) launches += launch_poyiadjis_n2<R, Model>(a, t, stream);
             else if (d->pf == SGM_PF_PARIS) launches += launch_paris<R, Model>(a, t, stream);
         }
@@ -230,6 +239,7 @@ int sgm_stat_dim(int32_t model, int32_t stat_kind) {
     if (stat_kind == SGM_STAT_SCORE) return score_dim(model);
     if (stat_kind == SGM_STAT_SUFF) return 3;
     if (stat_kind == SGM_STAT_NONE) return 0;
+    if (stat_kind == SGM_STAT_PRED) return 8;          /* upper bound: num_steps_ahead + 1 <= 8 */
     return SGM_ERR_INVALID;
 }
 

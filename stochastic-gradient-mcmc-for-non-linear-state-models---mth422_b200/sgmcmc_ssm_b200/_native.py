@@ -15,7 +15,7 @@ PF = dict(nemeth=0, poyiadjis_N=0, poyiadjis_N2=1, paris=2, filter=3)
 DTYPE = dict(f32=0, f64=1)
 RNG = dict(philox=0, injected=1)
 RESAMPLE = dict(multinomial=0, multinomial_sorted=1, sorted=1, systematic=2, stratified=3)
-STAT = dict(score=0, suff=1, none=2)
+STAT = dict(score=0, suff=1, none=2, pred=3)
 N2_MODE = dict(auto=0, fp32_pipe=1, tensor=2)
 STATUS_NAN_WEIGHT, STATUS_ZERO_WEIGHT, STATUS_AR_OVERFLOW = 1, 2, 4
 THETA_STRIDE = 12
@@ -28,11 +28,12 @@ class SgmPfDesc(ctypes.Structure):
         ("rng_mode", c_i32), ("resample", c_i32), ("stat_kind", c_i32),
         ("n_items", c_i32), ("n_particles", c_i32), ("max_T", c_i32), ("Ntilde", c_i32),
         ("accept_reject", c_i32), ("max_accept_reject", c_i32), ("manual_sample_threshold", c_i32),
-        ("item_id_base", c_i32), ("n2_mode", c_i32), ("reserved0", c_i32),
+        ("item_id_base", c_i32), ("n2_mode", c_i32), ("pred_steps_ahead", c_i32),
+        ("pred_per_horizon", c_i32), ("reserved0", c_i32),
         ("lambduh", c_f64), ("seed", c_u64), ("offset", c_u64),
         ("obs", c_vp), ("obs_off", c_vp), ("T_buf", c_vp), ("t1", c_vp), ("tL", c_vp),
         ("step_weights", c_vp), ("wts_off", c_vp), ("theta", c_vp), ("prior_mean", c_vp), ("prior_var", c_vp),
-        ("inj_z0", c_vp), ("inj_u", c_vp), ("inj_z", c_vp), ("inj_extra", c_vp), ("inj_extra_off", c_vp),
+        ("inj_z0", c_vp), ("inj_u", c_vp), ("inj_z", c_vp), ("inj_extra", c_vp), ("inj_extra_off", c_vp), ("inj_pred", c_vp),
         ("grad", c_vp), ("loglik", c_vp), ("status", c_vp),
         ("out_x", c_vp), ("out_lw", c_vp), ("out_stats", c_vp),
         ("trace_anc", c_vp), ("trace_x", c_vp), ("trace_lw", c_vp), ("trace_J", c_vp),

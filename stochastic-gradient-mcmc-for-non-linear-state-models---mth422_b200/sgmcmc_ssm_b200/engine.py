@@ -231,7 +231,7 @@ class PreparedPF(object):
     def __init__(self, model, kernel, pf, items, N, dtype=None, rng=None, resample=None, stat_kind="score",
                  lambduh=None, Ntilde=2, accept_reject=True, max_accept_reject=None,
                  manual_sample_threshold=None, seed=None, offset=None, item_id_base=0, injected=None,
-                 want=(), device=None, n2_mode="auto"):
+                 want=(), device=None, n2_mode="auto", num_steps_ahead=5, per_horizon=False):
         lib = self.lib = nat.load()
         device = self.device = _device(device)
         st = self.st = _state(device)
@@ -250,6 +250,10 @@ class PreparedPF(object):
         N = self.N = int(N)
         model_id, kernel_id = nat.MODEL[model], nat.KERNEL[kernel]
         self.p = lib.sgm_stat_dim(model_id, nat.STAT[stat_kind])
+        if stat_kind == "pred":
+            if not 0 <= int(num_steps_ahead) <= 7:
+                raise NotImplementedError("num_steps_ahead must be in [0, 7] on the CUDA path")
+            self.p = int(num_steps_ahead) + 1
         self.n = n = lib.sgm_state_dim(model_id)
         NPrec = lib.sgm_stat_dim(model_id, 0)
         pk = items.pack()
@@ -283,6 +287,7 @@ class PreparedPF(object):
         desc.manual_sample_threshold = -1 if manual_sample_threshold is None else int(manual_sample_threshold)
         desc.item_id_base = int(item_id_base)
         desc.n2_mode = nat.N2_MODE[n2_mode]
+        desc.pred_steps_ahead, desc.pred_per_horizon = int(num_steps_ahead), int(bool(per_horizon))
         desc.lambduh = float(lambduh)
         if seed is None or offset is None:
             s_, o_ = _next_seed_offset()
@@ -321,6 +326,8 @@ class PreparedPF(object):
                 desc.inj_z0 = dev64(injected["z0"], (B, N))
                 desc.inj_u = dev64(injected["u"], (B, max_T, N))
                 desc.inj_z = dev64(injected["z"], (B, max_T, N))
+                if injected.get("zp") is not None:       # predictive-statistic normals, (B, max_T, 8, N)
+                    desc.inj_pred = dev64(injected["zp"], (B, max_T, 8, N))
                 if injected.get("extra") is not None:
                     flat = np.concatenate([np.asarray(e, dtype=np.float64).ravel() for e in injected["extra"]] + [np.zeros(1)])
                     lens = np.array([np.asarray(e).size for e in injected["extra"]], dtype=np.int64)

@@ -125,9 +125,27 @@ class SGMCMCHelper(object):
     def pf_predictive_loglikelihood_estimate(self, observations, parameters, num_steps_ahead=5,
                                              subsequence_start=0, subsequence_end=None, pf="filter",
                                              N=1000, kernel=None, forward_message=None, **kwargs):
+        """k-step-ahead predictive log-likelihood for k = 0..num_steps_ahead (svm/helper.py:187-247,
+        lgssm/helper.py:1048-1087, garch/helper.py pf_predictive_loglikelihood_estimate): particle FILTER with
+        the `logsumexp` statistic; element 0 is the log-likelihood estimate.  per_horizon=False (default)
+        reproduces the reference's log-sum over ALL horizons (pf.py:73-76); True gives one log-sum per horizon."""
+        return self.pf_predictive_loglikelihood_estimate_batch(
+            [dict(observations=observations, subsequence_start=subsequence_start, subsequence_end=subsequence_end)],
+            parameters, num_steps_ahead=num_steps_ahead, pf=pf, N=N, kernel=kernel, forward_message=forward_message,
+            **kwargs)[0]
+
+    def pf_predictive_loglikelihood_estimate_batch(self, windows, parameters, num_steps_ahead=5, pf="filter", N=1000,
+                                                   kernel=None, forward_message=None, **kwargs):
         if pf != "filter":
             raise ValueError("Only can use pf = 'filter' since we are filtering")
-        raise NotImplementedError("k-step-ahead predictive log-likelihood (SURVEY 8(f2)) is not on the CUDA path yet")
+        K = self._get_kernel(kernel)
+        K.set_parameters(parameters)
+        kwargs.pop("weights", None)                     # the reference passes no weights here
+        items = self.make_items([dict(w, weights=None) for w in windows], parameters, forward_message)
+        res = batched_pf(pf, K.model, K.kernel, items, N, stat_kind="pred", num_steps_ahead=num_steps_ahead, **kwargs)
+        out = res.grad[:, :int(num_steps_ahead) + 1].copy()
+        out[:, 0] = res.loglik
+        return out
 
     def _forward_messages(self, *args, **kwargs):
         raise NotImplementedError("analytic message passing is outside the particle-filter hot path")

@@ -19,27 +19,38 @@ from . import statistics as S
 
 _PF_NAMES = ("nemeth", "poyiadjis_N", "poyiadjis_N2", "paris", "filter")
 _ENGINE_KW = ("dtype", "rng", "resample", "lambduh", "Ntilde", "accept_reject", "max_accept_reject",
-              "manual_sample_threshold", "seed", "offset", "device", "item_id_base", "n2_mode")
+              "manual_sample_threshold", "seed", "offset", "device", "item_id_base", "n2_mode", "num_steps_ahead", "per_horizon")
 
 
 def _theta(model, parameters):
     return S.MODEL_SPECS[model]["theta"](parameters)
 
 
-def _draw_injected(N, T_list):
+def _draw_injected(N, T_list, pred=None):
     """Consume the GLOBAL numpy legacy stream exactly as the reference would for these items
     (SURVEY Appendix B): per item: N normals (sample_x0), then per step N uniforms (np.random.choice)
-    and N normals (kernel.rv)."""
+    and N normals (kernel.rv).  pred = (K, t1s, tLs): additionally the normal blocks of the predictive
+    statistic, one per horizon k <= K with t + k < T, for steps in [t1, tL) (svm/helper.py:379,
+    garch/helper.py:410 -> garch/kernels.py:66)."""
     B, max_T = len(T_list), max(T_list)
     z0 = np.zeros((B, N))
     u = np.zeros((B, max_T, N))
     z = np.zeros((B, max_T, N))
+    zp = np.zeros((B, max_T, 8, N)) if pred is not None else None
     for b, T in enumerate(T_list):
         z0[b] = np.random.normal(size=N)
         for t in range(T):
             u[b, t] = np.random.random_sample(N)
             z[b, t] = np.random.normal(size=N)
-    return dict(z0=z0, u=u, z=z)
+            if pred is not None and pred[1][b] <= t < pred[2][b]:
+                for k in range(pred[0] + 1):
+                    if t + k >= T:
+                        break
+                    zp[b, t, k] = np.random.normal(size=N)
+    out = dict(z0=z0, u=u, z=z)
+    if zp is not None:
+        out["zp"] = zp
+    return out
 
 
 def batched_pf(pf, model, kernel, items, N, stat_kind="score", want=(), sync=True, **kwargs):
@@ -52,7 +63,11 @@ def batched_pf(pf, model, kernel, items, N, stat_kind="score", want=(), sync=Tru
         if pf == "paris":
             raise NotImplementedError("rng='injected' with pf='paris' needs a recorded stream "
                                       "(data-dependent number of draws); pass injected=dict(...)")
-        kw["injected"] = _draw_injected(int(N), [int(T) for T in items.pack().T_buf])
+        pk = items.pack()
+        pred = None
+        if stat_kind == "pred" and model != "lgssm":      # the LGSSM predictive statistic is analytic (no draws)
+            pred = (int(kw.get("num_steps_ahead", 5)), [int(v) for v in pk.t1], [int(v) for v in pk.tL])
+        kw["injected"] = _draw_injected(int(N), [int(T) for T in pk.T_buf], pred=pred)
         kw.setdefault("resample", "multinomial")
     elif "injected" in kwargs:
         kw["injected"] = kwargs["injected"]

@@ -14,12 +14,13 @@ def _gauss_dims_ok(p):
 
 def svm_theta(p):
     _gauss_dims_ok(p)
-    return [_f(p.A), _f(p.LQinv), _f(p.Qinv), _f(p.LRinv), _f(p.Rinv)]
+    # slots 10, 11: Q, R as the Parameters object computes them (predictive statistic, svm/helper.py:374)
+    return [_f(p.A), _f(p.LQinv), _f(p.Qinv), _f(p.LRinv), _f(p.Rinv), 0.0, 0.0, 0.0, 0.0, 0.0, _f(p.Q), _f(p.R)]
 
 
 def lgssm_theta(p):
     _gauss_dims_ok(p)
-    return [_f(p.A), _f(p.LQinv), _f(p.Qinv), _f(p.C), _f(p.LRinv), _f(p.Rinv)]
+    return [_f(p.A), _f(p.LQinv), _f(p.Qinv), _f(p.C), _f(p.LRinv), _f(p.Rinv), 0.0, 0.0, 0.0, 0.0, _f(p.Q), _f(p.R)]
 
 
 def garch_theta(p):

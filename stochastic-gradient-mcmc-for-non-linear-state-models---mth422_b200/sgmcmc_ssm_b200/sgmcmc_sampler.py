@@ -155,10 +155,49 @@ class SGMCMCSampler(object):
             return dict(logjoint=loglikelihood + logprior, loglikelihood=loglikelihood)
         return loglikelihood + logprior
 
-    def predictive_loglikelihood(self, kind="marginal", **kwargs):
-        if kind == "pf":
-            raise NotImplementedError("pf predictive log-likelihood (SURVEY 8(f2)) is not on the CUDA path yet")
-        raise NotImplementedError(_NOT_PF.format(kind))
+    def predictive_loglikelihood(self, kind="marginal", num_steps_ahead=10, subsequence_length=-1, minibatch_size=1,
+                                 buffer_length=10, num_samples=1000, parameters=None, observations=None, **kwargs):
+        """Subsequence estimate of the k-step-ahead predictive log-likelihood, k = 0..num_steps_ahead
+        (sgmcmc_sampler.py:61-128, pf branch :94-126): every minibatch item's estimate is rescaled by
+        (T - k) / (S - k); all items run in one batched launch."""
+        observations = self._get_observations(observations)
+        T = observations.shape[0]
+        if kind != "pf":
+            if kind in ("marginal", "complete"):
+                raise NotImplementedError(_NOT_PF.format(kind))
+            raise ValueError("Unrecognized kind = {0}".format(kind))
+        if kwargs.get("N", None) is None:
+            kwargs["N"] = num_samples
+        from . import engine
+        from .particle_filters.buffered_smoother import _draw_injected
+        replay = kwargs.get("rng", engine.config.rng) == "injected" and "injected" not in kwargs
+        windows, scales, drawn = [], [], []
+        for _ in range(minibatch_size):
+            bd = self._random_subsequence_and_buffers(buffer_length=buffer_length,
+                                                      subsequence_length=subsequence_length, T=T)
+            windows.append(_window(observations, bd))
+            S = bd["subsequence_end"] - bd["subsequence_start"]
+            with np.errstate(divide="ignore"):
+                scales.append((T - np.arange(num_steps_ahead + 1)) / (S - np.arange(num_steps_ahead + 1.0)))
+            if replay:                                  # the reference filters each window before drawing the next
+                w = windows[-1]
+                pred = None if self.message_helper._model == "lgssm" else (
+                    num_steps_ahead, [w["subsequence_start"]], [w["subsequence_end"]])
+                drawn.append(_draw_injected(int(kwargs["N"]), [w["observations"].shape[0]], pred=pred))
+        if replay:
+            merged = _merge_injected(drawn)
+            if "zp" in drawn[0]:
+                max_T = merged["u"].shape[1]
+                merged["zp"] = np.concatenate([np.pad(d["zp"], ((0, 0), (0, max_T - d["zp"].shape[1]), (0, 0), (0, 0)))
+                                               for d in drawn])
+            kwargs["injected"] = merged
+            kwargs.setdefault("resample", "multinomial")
+        est = self.message_helper.pf_predictive_loglikelihood_estimate_batch(
+            windows, self.parameters, num_steps_ahead=num_steps_ahead, **kwargs)
+        pred_loglikelihood = np.zeros(num_steps_ahead + 1)
+        for add, sc in zip(est, scales):
+            pred_loglikelihood += add * sc
+        return pred_loglikelihood * 1.0 / minibatch_size
 
     # ---- gradients ------------------------------------------------------------------------------
     def _random_subsequence_and_buffers(self, buffer_length, subsequence_length, T=None):
