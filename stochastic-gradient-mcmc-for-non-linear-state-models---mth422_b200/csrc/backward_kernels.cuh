@@ -557,65 +557,173 @@ __device__ __forceinline__ void exact_backward_sample(const KArgs& a, const type
     __syncthreads();
 }
 
-// PHILOX mode: independent accept-reject loop per (child, replicate)  (pf.py:292-325 in law).
+// ---- PHILOX mode (pf.py:260-341 in law) -------------------------------------------------------------------
+// The accept-reject sampler proposes I ~ Cat(softmax(lw)) and accepts with probability q(x'_i | x_I) / q_max; the
+// exact sampler draws from softmax_j(lw_j + log q(x'_i | x_j)) directly.  Both return exact draws of the backward
+// kernel, so the cap on the number of proposals only moves cost between them (it is not part of the law): entries
+// still unresolved after PARIS_CAP rounds go to the exact sampler.
+//   paris_guide_kernel : flat f64 CDF of the OLD weights + a guide table (bucket k -> first particle whose
+//                        cumulative mass exceeds k / N of the total), so a proposal is ~4 dependent loads
+//                        instead of a 16-probe binary search over the hierarchical CDF.
+//   paris_ar_kernel    : one CTA owns PARIS_CH children x Ntilde replicates; the unresolved entries live in a
+//                        shared-memory work queue that is compacted every round (the reference's shrinking list
+//                        L, pf.py:292-325), so threads never idle behind one unlucky child.
+//   paris_exact_kernel : one WARP per leftover entry, two passes over the parents (total, then the crossing).
+constexpr int PARIS_CH = 1024;         // children per CTA of the accept-reject kernel
+constexpr int PARIS_CAP = 128;         // proposal rounds before an entry falls back to the exact sampler
+constexpr int PARIS_MAXQ = 4096;       // queue capacity >= children per CTA * Ntilde (Ntilde > 4: fewer children per CTA)
+
 template <class R, class Model>
-__global__ void __launch_bounds__(NT) paris_ar_kernel(KArgs a, int t) {
+__global__ void __launch_bounds__(NT) paris_guide_kernel(KArgs a, int t) {
     constexpr int NX = Model::NX, NP = Model::NP, W = NX + NP;
-    const int b = blockIdx.y, g = blockIdx.x, tid = threadIdx.x;
-    if (t >= a.T_buf[b]) return;
+    const int b = blockIdx.y, i = blockIdx.x * NT + threadIdx.x;
+    if (t >= a.T_buf[b] || i > a.N) return;
     const int N = a.N, par = t & 1;
     const size_t item_off = (size_t)b * N;
-    const ItemHdr hdr = load_hdr(a, b);            // header of the OLD weights (built before step t)
-    const typename Model::template Theta<R> th = load_thc<R, Model>(a, b);
-    const R ltmax = Model::log_trans_max(th);
+    const ItemHdr hdr = load_hdr(a, b);
     const R* fine_old = reinterpret_cast<const R*>(a.fine[par]) + (size_t)b * a.Q * WT;
-    RngKey key = a.key; key.item += (uint32_t)b;
-    const int tries = a.accept_reject ? a.max_ar : 0;
-    for (int c = 0; c < KPT; ++c) {
-        const int i = g * TILE + c * NT + tid;      // strided: neighbouring lanes, neighbouring children
-        if (i >= N) continue;
-        R rn[W];
-        load_rec<R, W>(a.rec[par ^ 1], a.tail[par ^ 1], item_off + i, rn);
-        for (int jt = 0; jt < a.Ntilde; ++jt) {
-            int J = -1;
-            for (int r = 0; r < tries; ++r) {
-                const uint4 raw = rng_raw(key, (uint32_t)i, (uint32_t)t, STREAM_PARIS, (uint32_t)(jt * a.max_ar + r));
-                const int I = search_hdr<R>(u01d(raw.x, raw.y) * hdr.total, hdr, fine_old, N);
-                R ra[W];
-                load_rec<R, W>(a.rec[par], a.tail[par], item_off + I, ra);
-                const R thr = Mth<R>::exp(Model::log_trans(th, ra + NP, rn + NP) - ltmax);
-                if ((R)u01d(raw.z, raw.w) <= thr) { J = I; break; }
-            }
-            a.Jidx[(item_off + i) * a.Ntilde + jt] = J;
-            if (J < 0) {
-                const int slot = atomicAdd(a.counters + b * 16, 1);
-                a.Llist[0][item_off * a.Ntilde + slot] = i * a.Ntilde + jt;
-            }
-        }
+    double* cdf = a.pcdf + item_off;
+    int32_t* guide = a.pguide + (size_t)b * (N + 1);
+    if (i < N) {
+        const int q = i / WT;
+        cdf[i] = hdr.off[q] + (double)fine_old[i] * hdr.sc[q];
+        guide[i] = search_hdr<R>((double)i * (hdr.total / (double)N), hdr, fine_old, N);
+        // per-parent key of the rank-1 score (models.cuh pair_parent): log q(x'|x_j) - log_trans_max = b u_j + gq_j + a
+        const typename Model::template Theta<R> th = load_thc<R, Model>(a, b);
+        R rj[W], u, gq, mm[2];
+        load_rec<R, W>(a.rec[par], a.tail[par], item_off + i, rj);
+        Model::pair_parent(th, rj + NP, u, gq, mm);
+        Vec4T<R> k;
+        k.x = u; k.y = gq; k.z = reinterpret_cast<const R*>(a.lw[par])[item_off + i] - (R)hdr.M; k.w = (R)0;
+        reinterpret_cast<Vec4T<R>*>(a.pkey)[item_off + i] = k;
+    } else {
+        guide[N] = N - 1;
     }
 }
 
 template <class R, class Model>
+__global__ void __launch_bounds__(NT) paris_ar_kernel(KArgs a, int t, int ch) {
+    constexpr int NX = Model::NX, NP = Model::NP, W = NX + NP;
+    __shared__ R s_x[2][PARIS_CH];                 // per child (b_i, a_i) of the rank-1 score
+    __shared__ uint16_t s_q[2][PARIS_MAXQ];
+    __shared__ int s_n[2];
+    const int b = blockIdx.y, tid = threadIdx.x;
+    if (t >= a.T_buf[b]) return;
+    const int N = a.N, par = t & 1, Nt = a.Ntilde;
+    const size_t item_off = (size_t)b * N;
+    const int c0 = blockIdx.x * ch, nch = min(ch, N - c0);
+    if (nch <= 0) return;
+    const typename Model::template Theta<R> th = load_thc<R, Model>(a, b);
+    const double total = a.hdr[(size_t)b * hdr_stride(a.Q) + H_TOTAL];
+    const Vec4T<R>* pkey = reinterpret_cast<const Vec4T<R>*>(a.pkey) + item_off;
+    const double* cdf = a.pcdf + item_off;
+    const int32_t* guide = a.pguide + (size_t)b * (N + 1);
+    RngKey key = a.key; key.item += (uint32_t)b;
+    for (int k = tid; k < nch; k += NT) {
+        R rn[W], bb, aa;
+        load_rec<R, W>(a.rec[par ^ 1], a.tail[par ^ 1], item_off + c0 + k, rn);
+        Model::pair_child(th, rn + NP, bb, aa);
+        s_x[0][k] = bb; s_x[1][k] = aa;
+    }
+    int qlen = nch * Nt;
+    for (int e = tid; e < qlen; e += NT) s_q[0][e] = (uint16_t)e;
+    if (tid == 0) { s_n[0] = qlen; s_n[1] = 0; }
+    __syncthreads();
+    const int cap = a.accept_reject ? min(a.max_ar, PARIS_CAP) : 0;
+    int cur = 0;
+    for (int round = 0; round < cap && qlen > 0; ++round) {
+        for (int e = tid; e < qlen; e += NT) {
+            const int entry = s_q[cur][e], k = entry / Nt, jt = entry - k * Nt, i = c0 + k;
+            const uint4 raw = rng_raw(key, (uint32_t)i, (uint32_t)t, STREAM_PARIS, (uint32_t)(jt * PARIS_CAP + round));
+            const double u = u01d(raw.x, raw.y);
+            double target = u * total;
+            if (!(target < total)) target = total * (1.0 - 1.2e-16);
+            const int kb = min((int)(u * (double)N), N - 1);
+            int I = guide[kb];
+            const int hi = guide[kb + 1];
+            while (I < hi && cdf[I] <= target) ++I;               // first particle whose cumulative mass exceeds the target
+            const Vec4T<R> pk = pkey[I];
+            const R thr = Mth<R>::exp(s_x[0][k] * pk.x + pk.y + s_x[1][k]);        // q(x'_i | x_I) / q_max
+            if ((R)u01d(raw.z, raw.w) <= thr) a.Jidx[(item_off + i) * Nt + jt] = I;
+            else s_q[cur ^ 1][atomicAdd(&s_n[cur ^ 1], 1)] = (uint16_t)entry;
+        }
+        __syncthreads();
+        qlen = s_n[cur ^ 1];
+        __syncthreads();
+        if (tid == 0) s_n[cur] = 0;
+        cur ^= 1;
+        __syncthreads();
+    }
+    if (qlen > 0) {                                                  // leftovers -> exact sampler
+        __shared__ int s_base;
+        if (tid == 0) s_base = atomicAdd(a.counters + b * 16, qlen);
+        __syncthreads();
+        for (int e = tid; e < qlen; e += NT) {
+            const int entry = s_q[cur][e], k = entry / Nt, jt = entry - k * Nt;
+            a.Llist[0][item_off * Nt + s_base + e] = (c0 + k) * Nt + jt;
+        }
+    }
+}
+
+// one warp per leftover (child, replicate): J ~ Cat(softmax_j(lw_j + log q(x'_i | x_j)))   (pf.py:328-339).
+// Weights relative to the bounded reference M + log_trans_max (every exponent <= 0: no max pass), evaluated from
+// the per-parent keys with one FMA + one exp.  Pass 1 streams all parents (coalesced), keeping the total of every
+// 2048-parent segment; the segment holding the target is then re-scanned with warp prefix sums.
+constexpr int PSEG = 2048;
+template <class R, class Model>
 __global__ void __launch_bounds__(NT) paris_exact_kernel(KArgs a, int t) {
     constexpr int NX = Model::NX, NP = Model::NP, W = NX + NP;
-    __shared__ R sh_r[NWARP];
-    __shared__ double sh_d[NWARP];
-    const int b = blockIdx.y;
+    __shared__ double s_seg[NWARP][MAX_Q * WT / PSEG];
+    const int b = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (t >= a.T_buf[b]) return;
-    const int N = a.N, par = t & 1;
+    const int N = a.N, par = t & 1, Nt = a.Ntilde;
     const size_t item_off = (size_t)b * N;
     const int count = a.counters[b * 16];
-    if (count > 0 && blockIdx.x == 0 && threadIdx.x == 0 && a.accept_reject) a.status[b] |= SGM_STATUS_AR_OVERFLOW;
     const typename Model::template Theta<R> th = load_thc<R, Model>(a, b);
+    const Vec4T<R>* pkey = reinterpret_cast<const Vec4T<R>*>(a.pkey) + item_off;
     RngKey key = a.key; key.item += (uint32_t)b;
-    for (int e = blockIdx.x; e < count; e += gridDim.x) {
-        const int entry = a.Llist[0][item_off * a.Ntilde + e];
-        const int i = entry / a.Ntilde, jt = entry % a.Ntilde;
-        R rn[W];
+    const int nwarps = gridDim.x * NWARP, nseg = (N + PSEG - 1) / PSEG;
+    double* seg = s_seg[warp];
+    for (int e = blockIdx.x * NWARP + warp; e < count; e += nwarps) {
+        const int entry = a.Llist[0][item_off * Nt + e];
+        const int i = entry / Nt, jt = entry - i * Nt;
+        R rn[W], bb, aa;
         load_rec<R, W>(a.rec[par ^ 1], a.tail[par ^ 1], item_off + i, rn);
+        Model::pair_child(th, rn + NP, bb, aa);
+        double tot = 0.0;
+        for (int sg = 0; sg < nseg; ++sg) {
+            R loc = (R)0;
+            const int jend = min(N, (sg + 1) * PSEG);
+            for (int j = sg * PSEG + lane; j < jend; j += 32) {
+                const Vec4T<R> pk = pkey[j];
+                loc += Mth<R>::exp(bb * pk.x + pk.y + pk.z + aa);
+            }
+            const double st = warp_sum((double)loc);
+            if (lane == 0) seg[sg] = st;
+            tot += st;
+        }
+        __syncwarp();
         const uint4 raw = rng_raw(key, (uint32_t)i, (uint32_t)t, STREAM_EXACT, (uint32_t)jt);
-        const double u = u01d(raw.x, raw.y);
-        exact_backward_sample<R, Model>(a, th, par, item_off, rn + NP, 1, &u, a.Jidx + (item_off + i) * a.Ntilde + jt, 1, sh_r, sh_d);
+        double target = u01d(raw.x, raw.y) * tot;
+        if (!(target < tot)) target = tot * (1.0 - 1.2e-16);
+        // segment of the crossing (sequential over <= 512 segment totals, warp-uniform)
+        int sg = 0;
+        double run = 0.0;
+        while (sg < nseg - 1 && run + seg[sg] <= target) { run += seg[sg]; ++sg; }
+        int J = min(N, (sg + 1) * PSEG) - 1;                         // rounding guard: last parent of the segment
+        bool done = false;
+        const int jend = min(N, (sg + 1) * PSEG);
+        for (int j0 = sg * PSEG; j0 < jend && !done; j0 += 32) {
+            const int j = j0 + lane;
+            double w = 0.0;
+            if (j < jend) { const Vec4T<R> pk = pkey[j]; w = (double)Mth<R>::exp(bb * pk.x + pk.y + pk.z + aa); }
+            const double incl = warp_incl_scan(w);
+            const unsigned hit = __ballot_sync(FULL, (j < jend) && (run + incl > target));
+            if (hit) { J = j0 + __ffs(hit) - 1; done = true; }
+            run += __shfl_sync(FULL, incl, 31);
+        }
+        if (lane == 0) a.Jidx[(item_off + i) * Nt + jt] = J;
+        __syncwarp();
     }
 }
 
@@ -731,7 +839,9 @@ int launch_paris(const KArgs& a, int t, cudaStream_t stream) {
     if (a.rng_mode == SGM_RNG_INJECTED) {
         paris_injected_kernel<R, Model><<<a.B, NT, 0, stream>>>(a, t); ++n;
     } else {
-        paris_ar_kernel<R, Model><<<dim3(a.G, a.B), NT, 0, stream>>>(a, t); ++n;
+        const int ch = (PARIS_CH * a.Ntilde <= PARIS_MAXQ) ? PARIS_CH : PARIS_MAXQ / a.Ntilde;
+        paris_guide_kernel<R, Model><<<dim3(a.N / NT + 1, a.B), NT, 0, stream>>>(a, t); ++n;
+        paris_ar_kernel<R, Model><<<dim3((a.N + ch - 1) / ch, a.B), NT, 0, stream>>>(a, t, ch); ++n;
         paris_exact_kernel<R, Model><<<dim3(EXACT_CTAS, a.B), NT, 0, stream>>>(a, t); ++n;
     }
     paris_update_kernel<R, Model><<<dim3((a.N + NT - 1) / NT, a.B), NT, 0, stream>>>(a, t); ++n;

@@ -64,6 +64,8 @@ struct KArgs {
     const double* inj_z0; const double* inj_u; const double* inj_z; const double* inj_extra; const int64_t* inj_extra_off;
     void* rec[2]; void* tail[2]; void* fine[2]; void* lw[2]; double* sub[2]; double* hdr; double* acc;
     int32_t* Jidx; int32_t* Llist[2]; int32_t* counters;
+    double* pcdf; int32_t* pguide;   // PaRIS (PHILOX): flat f64 CDF [B][N] and guide table [B][N+1] of the old weights
+    void* pkey;                      // PaRIS (PHILOX): [B][N][4] R per-parent score keys (u, gq, lw - M, -)
     void* n2part;          // [splits][B][N][8] R  split-J partial sums of the O(N^2) smoother
     char* thc;             // [B][THC_BYTES]   Model::Theta<R> (derived constants) written by the init kernel
     void* yw;              // [B][max_T][2] R  (y_t, statistic weight of step t: w_t inside [t1, tL), else 0)

@@ -25,7 +25,7 @@ int fail(int code, const char* fmt, const char* extra = "") {
 size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
 
 struct Layout {
-    size_t rec[2], tail[2], fine[2], lw[2], sub[2], hdr, acc, thc, yw, Jidx, Llist[2], counters, n2part, total;
+    size_t rec[2], tail[2], fine[2], lw[2], sub[2], hdr, acc, thc, yw, Jidx, Llist[2], counters, pcdf, pguide, pkey, n2part, total;
 };
 
 bool backward_pf(int pf) { return pf == SGM_PF_POY_N2 || pf == SGM_PF_PARIS; }
@@ -91,6 +91,9 @@ Layout make_layout(const sgm_pf_desc* d) {
         L.Llist[0] = off; off = align_up(off + B * N * (size_t)d->Ntilde * 4);
         L.Llist[1] = off; off = align_up(off + B * N * 4);
         L.counters = off; off = align_up(off + B * 16 * 4);
+        L.pcdf = off; off = align_up(off + B * N * 8);
+        L.pguide = off; off = align_up(off + B * (N + 1) * 4);
+        L.pkey = off; off = align_up(off + B * N * 4 * es);
     }
     if (d->pf == SGM_PF_POY_N2) {
         L.n2part = off; off = align_up(off + n2_partial_bytes(d->dtype, d->n2_mode, (int)B, (int)N));
@@ -114,8 +117,6 @@ int run_impl(const sgm_pf_desc* d, cudaStream_t stream) {
     a.max_ar = d->max_accept_reject >= 0 ? d->max_accept_reject : (int)(100.0 * l10);        // pf.py:284-285
     a.manual_thresh = d->manual_sample_threshold >= 0 ? d->manual_sample_threshold : (int)(10.0 * l10);  // pf.py:286-287
     if (a.max_ar < 0) a.max_ar = 0;
-    if (d->pf == SGM_PF_PARIS && d->rng_mode == SGM_RNG_PHILOX && (int64_t)a.max_ar * a.Ntilde >= 4096)
-        return fail(SGM_ERR_INVALID, "Ntilde * max_accept_reject must be < 4096 in PHILOX mode");
     a.need_lw = (backward_pf(d->pf) || d->out_lw || d->trace_lw || d->stat_kind == SGM_STAT_PRED) ? 1 : 0;
     a.pred_K = d->pred_steps_ahead; a.pred_per_horizon = d->pred_per_horizon; a.inj_pred = d->inj_pred;
     a.lambduh = d->lambduh;
@@ -138,6 +139,9 @@ int run_impl(const sgm_pf_desc* d, cudaStream_t stream) {
     if (d->pf == SGM_PF_PARIS) {
         a.Jidx = reinterpret_cast<int32_t*>(ws + L.Jidx);
         a.counters = reinterpret_cast<int32_t*>(ws + L.counters);
+        a.pcdf = reinterpret_cast<double*>(ws + L.pcdf);
+        a.pguide = reinterpret_cast<int32_t*>(ws + L.pguide);
+        a.pkey = ws + L.pkey;
     }
     if (d->pf == SGM_PF_POY_N2) { a.n2part = ws + L.n2part; a.n2_tensor = n2_use_tensor(d->dtype, d->n2_mode) ? 1 : 0; }
     a.grad = d->grad; a.loglik = d->loglik; a.status = d->status;

@@ -70,3 +70,21 @@ def test_n2_matches_on_of_n_estimator_statistically(model):
     err = np.abs(g2 - g1).mean(axis=0)
     spread = np.abs(g1).mean(axis=0) + 1.0
     assert np.all(err <= 0.5 * spread), (err, spread)
+
+
+@pytest.mark.parametrize("model,Ntilde", [("svm", 2), ("garch", 2), ("garch", 5), ("lgssm", 3)])
+def test_paris_philox_matches_n2_statistically(model, Ntilde):
+    """PaRIS with device randoms (guide-table proposals, shared-memory work queue, exact fallback; pf.py:183-341
+    in law) estimates what the O(N^2) smoother computes exactly: batch means over 24 items at N = 4096 must agree
+    within Monte-Carlo error, every backward index must be valid, and the fallback must be exercised somewhere."""
+    import sgmcmc_ssm_b200 as sg
+    kern = "prior" if model == "svm" else "optimal"
+    it = _items(model, 24, 14, 9)
+    rp = sg.run_pf(model, kern, "paris", it, 4096, dtype="f32", seed=21, offset=1, Ntilde=Ntilde, want=("J",))
+    J = rp.tensor("J").cpu().numpy()
+    assert J.min() >= 0 and J.max() < 4096
+    r2 = sg.run_pf(model, kern, "poyiadjis_N2", it, 4096, dtype="f32", seed=22, offset=1)
+    gp, g2 = rp.grad.mean(axis=0), r2.grad.mean(axis=0)
+    spread = np.abs(r2.grad - g2).mean(axis=0) + 0.05 * np.abs(g2) + 1e-3
+    assert np.all(np.abs(gp - g2) <= 1.0 * spread), (gp, g2, spread)
+    np.testing.assert_allclose(rp.loglik.mean(), r2.loglik.mean(), rtol=0.02, atol=0.2)
