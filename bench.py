@@ -271,7 +271,8 @@ def run_gpu(args):
     achieved = ALG_BYTES * prep.B * N_PARTICLES / (step_kernel_ms * 1e-3) / 1e9
     traffic = None
     try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "step_kernel_traffic.json")))["dram_bytes_per_launch"]
+        # measured DRAM bytes per particle-step (ncu --set full of the bench command) x particles of one time step
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "step_kernel_traffic.json")))["dram_bytes_per_particle_step"] * prep.B * N_PARTICLES
     except Exception:
         pass
     line = {

@@ -192,3 +192,17 @@ def test_vectorised_minibatch_windows_equal_the_sequential_draws(style, T, S, B)
     for b in range(hi - lo):
         n = int(sl.tL[b] - sl.t1[b])
         np.testing.assert_array_equal(sl.wts_flat[sl.wts_off[b]:sl.wts_off[b] + n], windows[lo + b]["weights"][:n])
+
+
+def test_python_descriptor_mirror_has_the_size_the_library_expects():
+    """sgm_pf_run checks struct_bytes against its own sizeof(sgm_pf_desc): with the mirror's size filled in the
+    validation must get past the size check (and then reject the empty descriptor for another reason)."""
+    from sgmcmc_ssm_b200 import _native as nat
+    lib = nat.load()
+    d = nat.SgmPfDesc()
+    d.struct_bytes = ctypes.sizeof(nat.SgmPfDesc)
+    assert lib.sgm_pf_run(ctypes.byref(d), None) == -1
+    assert b"size mismatch" not in lib.sgm_last_error()
+    d.model, d.kernel = nat.MODEL["svm"], nat.KERNEL["optimal"]
+    d.n_items = d.n_particles = 1
+    assert lib.sgm_pf_run(ctypes.byref(d), None) == -2 and b"optimal" in lib.sgm_last_error()   # NotImplementedError
