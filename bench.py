@@ -128,8 +128,8 @@ def run_reference(args):
 
 def workload_config(world, M):
     return {"workload": "SVM synthetic T=10000 (A,Q,R)=(0.95,0.5,0.5), buffered PF gradient, pf=poyiadjis_N, "
-                        "N=65536 particles/subsequence, subsequence 40 + buffer 10 (T_buf<=60), "
-                        "minibatch {0} subsequences/GPU x {1} GPU".format(M, world),
+                        "N={2} particles/subsequence, subsequence 40 + buffer 10 (T_buf<=60), "
+                        "minibatch {0} subsequences/GPU x {1} GPU".format(M, world, N_PARTICLES),
             "minibatch_per_gpu": M, "n_particles": N_PARTICLES, "subsequence_length": SUBSEQ,
             "buffer_length": BUFFER, "pf": "poyiadjis_N", "resample": "multinomial_sorted", "rng": "philox",
             "parallelism": "items sharded over {0} GPU, one NCCL all-reduce of gradient sums per step".format(world),
@@ -374,10 +374,15 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--minibatch", type=int, default=512, help="subsequences per GPU per step")
+    ap.add_argument("--particles", type=int, default=N_PARTICLES,
+                    help="particles per subsequence (default 2^16 = the metric's configuration; 2^20 with --minibatch 128 "
+                         "is one GPU's share of BASELINE configs[4])")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true")
     args = ap.parse_args()
+    global N_PARTICLES
+    N_PARTICLES = int(args.particles)
     if args.impl == "reference":
         return run_reference(args)
     return run_gpu(args)

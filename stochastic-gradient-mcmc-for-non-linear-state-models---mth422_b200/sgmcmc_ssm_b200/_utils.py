@@ -1,7 +1,14 @@
 """Small linear-algebra helpers used by the parameter containers (host side, numpy).
 Behavioural reference: sgmcmc_ssm/_utils.py:17-183."""
+import functools
+
 import numpy as np
 import scipy.stats
+
+
+@functools.lru_cache(maxsize=None)
+def _tril_indices(n):
+    return np.tril_indices(n)
 
 
 def tril_vector_to_mat(vec):
@@ -9,7 +16,7 @@ def tril_vector_to_mat(vec):
     vec = np.atleast_1d(vec)
     n = int(np.sqrt(len(vec) * 2))
     mat = np.zeros((n, n), dtype=float)
-    mat[np.tril_indices(n)] = vec
+    mat[_tril_indices(n)] = vec
     return mat
 
 

@@ -174,6 +174,25 @@ class PackedItems(object):
     def pack(self):
         return self
 
+    @staticmethod
+    def concat(parts):
+        """One batch from several (e.g. one per chain); items keep their order."""
+        parts = [p.pack() for p in parts]
+        any_w = any(p.wts_flat is not None for p in parts)
+        wts_flat, wts_off, base = [], [], 0
+        for p in parts:
+            if p.wts_flat is None:
+                wts_off.append(np.full(len(p), -1, dtype=np.int64))
+            else:
+                wts_off.append(np.where(p.wts_off >= 0, p.wts_off + base, -1))
+                wts_flat.append(p.wts_flat)
+                base += p.wts_flat.shape[0]
+        return PackedItems(np.concatenate([p.obs_flat for p in parts]), np.concatenate([p.T_buf for p in parts]),
+                           np.concatenate([p.t1 for p in parts]), np.concatenate([p.tL for p in parts]),
+                           np.concatenate(wts_flat) if any_w else None, np.concatenate(wts_off),
+                           np.concatenate([p.theta for p in parts]), np.concatenate([p.prior_mean for p in parts]),
+                           np.concatenate([p.prior_var for p in parts]))
+
     def slice(self, lo, hi):
         """Items [lo, hi) (the shard of one rank)."""
         obs_off = np.concatenate([[0], np.cumsum(self.T_buf)])

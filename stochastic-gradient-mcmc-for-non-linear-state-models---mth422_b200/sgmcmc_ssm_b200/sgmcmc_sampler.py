@@ -244,6 +244,21 @@ class SGMCMCSampler(object):
             raise ValueError("len(buffer_dicts != minibatch_size")
         return [_window(observations, bd) for bd in buffer_dicts]
 
+    def _pf_plan(self, subsequence_length=-1, minibatch_size=1, buffer_length=0, observations=None, buffer_dicts=None,
+                 **unused):
+        """The work items of one gradient evaluation and how to combine their gradients: (windows, finish) with
+        finish(list of per-window gradient dicts) -> noisy_grad dict (sgmcmc_sampler.py:390-425).  Lets
+        ensemble.ChainEnsemble pack the items of many chains into one launch."""
+        windows = self._pf_windows(subsequence_length, minibatch_size, buffer_length, observations, buffer_dicts)
+
+        def finish(grads):
+            noisy_grad = {var: np.zeros_like(value) for var, value in self.parameters.as_dict().items()}
+            for g in grads:
+                for var in noisy_grad:
+                    noisy_grad[var] += g[var] * 1.0 / minibatch_size
+            return self._check_noisy_grad(noisy_grad)
+        return windows, finish
+
     def _noisy_grad_loglikelihood(self, subsequence_length=-1, minibatch_size=1, buffer_length=0,
                                   observations=None, buffer_dicts=None, kind="marginal", num_samples=None,
                                   parameters=None, **kwargs):
@@ -315,7 +330,9 @@ class SGMCMCSampler(object):
 
     def noisy_gradient(self, preconditioner=None, is_scaled=True, **kwargs):
         """grad log-likelihood estimate + grad log-prior, scaled by 1/T (sgmcmc_sampler.py:427-464)."""
-        noisy_grad_loglike = self._noisy_grad_loglikelihood(**kwargs)
+        noisy_grad_loglike = kwargs.pop("noisy_grad_loglike", None)       # precomputed by ensemble.ChainEnsemble
+        if noisy_grad_loglike is None:
+            noisy_grad_loglike = self._noisy_grad_loglikelihood(**kwargs)
         noisy_grad_prior = self.prior.grad_logprior(parameters=kwargs.get("parameters", self.parameters))
         noisy_gradient = {var: noisy_grad_prior[var] + noisy_grad_loglike[var] for var in noisy_grad_prior}
         if preconditioner is None:
@@ -364,8 +381,10 @@ class SGMCMCSampler(object):
         """theta += eps * grad + sqrt(2 eps) * N(0, 1/T)   (sgmcmc_sampler.py:549-567)."""
         if "preconditioner" in kwargs:
             raise ValueError("Use SGRLD instead")
+        white_noise = kwargs.pop("white_noise", None)          # pre-drawn by ensemble.ChainEnsemble (same stream order)
         delta = self.noisy_gradient(**kwargs)
-        white_noise = self._get_sgmcmc_noise(**kwargs)
+        if white_noise is None:
+            white_noise = self._get_sgmcmc_noise(**kwargs)
         for var in self.parameters.var_dict:
             self.parameters.var_dict[var] += epsilon * delta[var] + np.sqrt(2.0 * epsilon) * white_noise[var]
         return self.parameters
@@ -538,7 +557,11 @@ class SeqSGMCMCSampler(object):
         T = kwargs.get("T")
         if T is None:
             observations = self._get_observations(kwargs.get("observations"))
+            cache = getattr(self, "_T_cache", None)
+            if cache is not None and cache[0] is observations and cache[1] == len(observations):
+                return cache[2]
             T = int(np.sum([np.shape(o)[0] for o in observations]))
+            self._T_cache = (observations, len(observations), T)
         return T
 
     def _check_observation_shape(self, observations):
@@ -603,6 +626,31 @@ class SeqSGMCMCSampler(object):
             scale = self._get_T() / S
             noisy_grad = {var: noisy_grad[var] * scale for var in noisy_grad}
         return noisy_grad
+
+    def _pf_plan(self, num_sequences=-1, subsequence_length=-1, minibatch_size=1, buffer_length=0, buffer_dicts=None,
+                 **unused):
+        """Seq form of SGMCMCSampler._pf_plan (sgmcmc_sampler.py:1249-1283): same numpy draws as
+        _noisy_grad_loglikelihood (sequence choice, then the windows of each chosen sequence)."""
+        seqs = self.observations
+        idx = self._pick_sequences(seqs, num_sequences)
+        windows, S = [], 0.0
+        for k in idx:
+            windows += SGMCMCSampler._pf_windows(self, subsequence_length, minibatch_size, buffer_length, seqs[k], buffer_dicts)
+            S += seqs[k].shape[0]
+
+        def finish(grads):
+            noisy_grad = {var: np.zeros_like(value) for var, value in self.parameters.as_dict().items()}
+            for g in grads:
+                for var in noisy_grad:
+                    noisy_grad[var] += g[var] * 1.0 / minibatch_size
+            for var in noisy_grad:
+                if np.any(np.isnan(noisy_grad[var])):
+                    raise ValueError("NaNs in gradient of {0}".format(var))
+            if num_sequences != -1:
+                scale = self._get_T() / S
+                noisy_grad = {var: noisy_grad[var] * scale for var in noisy_grad}
+            return noisy_grad
+        return windows, finish
 
     def predict(self, *args, **kwargs):
         raise NotImplementedError()
