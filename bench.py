@@ -368,6 +368,7 @@ def extras(sg, y, theta, windows, torch):
 
 
 def main():
+    global N_PARTICLES
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
@@ -381,7 +382,6 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true")
     args = ap.parse_args()
-    global N_PARTICLES
     N_PARTICLES = int(args.particles)
     if args.impl == "reference":
         return run_reference(args)
