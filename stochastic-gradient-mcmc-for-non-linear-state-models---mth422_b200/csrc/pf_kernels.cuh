@@ -310,11 +310,80 @@ __global__ void __launch_bounds__(NT) pf_init_kernel(KArgs a) {
 //     with the max shift: M + log(total / N)), degenerate-weight flags
 //   * exclusive prefix of the per-tile Gamma(P_q, 1) draws (+ one Exp(1)) of the order-statistics sampler
 //   * final: grad = average_statistic (buffered_smoother.py:151-154) or the filter statistic (pf.py:77-80)
+// scalar tail of the header (one thread): totals, status flags, log-likelihood increment, final outputs
+template <class Model>
+__device__ __forceinline__ void header_finish(const KArgs& a, int b, int t_done, int final_pass, int nstat, double M, double total,
+                                              const double* sbar, double* base, double* off) {
+    const int Q = a.Q, N = a.N;
+    const double NEG_INF = -Mth<double>::inf();
+    off[Q] = total;
+    base[H_M] = M; base[H_TOTAL] = total;
+    for (int j = 0; j < 4; ++j) base[H_SBAR + j] = sbar[j];
+    if (!(total > 0.0) || !(total < Mth<double>::inf()) || !(M == M) || !(fabs(M) < Mth<double>::inf()))
+        a.status[b] |= (total == 0.0 || M == NEG_INF) ? SGM_STATUS_ZERO_WEIGHT : SGM_STATUS_NAN_WEIGHT;
+    double* acc = a.acc + (size_t)b * ACC_STRIDE;
+    if (t_done >= 0) {
+        if (t_done >= a.t1[b] && t_done < a.tL[b]) {
+            const double wt = (a.wts_off && a.wts_off[b] >= 0) ? a.step_weights[a.wts_off[b] + (t_done - a.t1[b])] : 1.0;
+            acc[0] += wt * (M + ::log(total / (double)N));
+        }
+        if (a.pf == SGM_PF_FILTER) for (int j = 0; j < nstat; ++j) acc[1 + j] += sbar[j];     // pf.py:77-80
+    }
+    if (final_pass) {
+        a.loglik[b] = acc[0];
+        for (int j = 0; j < 8; ++j) a.grad[(size_t)b * 8 + j] = 0.0;
+        for (int j = 0; j < nstat; ++j) a.grad[(size_t)b * 8 + j] = (a.pf == SGM_PF_FILTER) ? acc[1 + j] : sbar[j];
+        if (a.stat_kind == SGM_STAT_PRED) for (int j = 0; j <= a.pred_K; ++j) a.grad[(size_t)b * 8 + j] = acc[1 + j];
+    }
+}
+
+// Header of an item with fewer than 32 warp tiles (N < 8192): ONE warp, shuffles only -- no block barrier.
+// This is the per-step latency of the single-launch kernel for small N (the SGLD-with-N~1000 regime).
+template <class R, class Model>
+__device__ __forceinline__ void header_warp(const KArgs& a, int b, int t, int final_pass) {
+    if (threadIdx.x >= 32) return;
+    const int lane = threadIdx.x;
+    const int Tb = a.T_buf[b];
+    const int par = final_pass ? (Tb & 1) : (t & 1);
+    const int t_done = final_pass ? Tb - 1 : t - 1;
+    const int Q = a.Q, N = a.N;
+    const int nstat = stat_width<Model>(a.stat_kind);
+    const bool shrink = (a.pf == SGM_PF_NEMETH) && (a.lambduh != 1.0);
+    const int nws = (final_pass || shrink || a.pf == SGM_PF_FILTER) ? nstat : 0;
+    const double* sub = a.sub[par] + (size_t)b * Q * SSTRIDE;
+    double* base = a.hdr + (size_t)b * hdr_stride(Q);
+    double* off = base + H_SCALARS;
+    double* sc = off + (Q + 2);
+    double* gam = sc + (Q + 2);
+    const double NEG_INF = -Mth<double>::inf();
+    const bool has = lane < Q;
+    const double* p = sub + (size_t)lane * SSTRIDE;
+    const double mq = has ? p[0] : NEG_INF;
+    const double M = warp_max(mq);
+    const double e = (has && mq != NEG_INF) ? ::exp(mq - M) : 0.0;
+    const double loc = has ? e * p[1] : 0.0;
+    const double incl = warp_incl_scan(loc);
+    const double total = __shfl_sync(FULL, incl, 31);
+    if (has) { off[lane] = incl - loc; sc[lane] = e; }
+    double sbar[4] = {0.0, 0.0, 0.0, 0.0};
+    for (int j = 0; j < nws; ++j) sbar[j] = warp_sum(has ? e * p[2 + j] : 0.0) / total;
+    if (!final_pass && uses_spacings(a)) {
+        RngKey key = a.key; key.item += (uint32_t)b;
+        const double g = (lane <= Q) ? rng_gamma(key, (uint32_t)lane, (uint32_t)t, (lane == Q) ? 1.0 : (double)min(WT, N - lane * WT)) : 0.0;
+        const double gincl = warp_incl_scan(g);
+        const double kk = total / __shfl_sync(FULL, gincl, 31);
+        if (lane <= Q) gam[lane] = (gincl - g) * kk;
+        if (lane == 0) gam[Q + 1] = total;
+    }
+    if (lane == 0) header_finish<Model>(a, b, t_done, final_pass, nstat, M, total, sbar, base, off);
+}
+
 template <class R, class Model>
 __device__ __forceinline__ void header_body(const KArgs& a, int b, int t, int final_pass, double* sh_d) {
     const int tid = threadIdx.x;
     const int Tb = a.T_buf[b];
     if (!final_pass && t >= Tb) return;
+    if (a.Q < 32) { header_warp<R, Model>(a, b, t, final_pass); return; }
     const int par = final_pass ? (Tb & 1) : (t & 1);
     const int t_done = final_pass ? Tb - 1 : t - 1;
     const int Q = a.Q, N = a.N;
@@ -377,27 +446,7 @@ __device__ __forceinline__ void header_body(const KArgs& a, int b, int t, int fi
         }
         if (tid == 0) gam[Q + 1] = total;
     }
-    if (tid == 0) {
-        off[Q] = total;
-        base[H_M] = M; base[H_TOTAL] = total;
-        for (int j = 0; j < 4; ++j) base[H_SBAR + j] = sbar[j];
-        if (!(total > 0.0) || !(total < Mth<double>::inf()) || !(M == M) || !(fabs(M) < Mth<double>::inf()))
-            a.status[b] |= (total == 0.0 || M == NEG_INF) ? SGM_STATUS_ZERO_WEIGHT : SGM_STATUS_NAN_WEIGHT;
-        double* acc = a.acc + (size_t)b * ACC_STRIDE;
-        if (t_done >= 0) {
-            if (t_done >= a.t1[b] && t_done < a.tL[b]) {
-                const double wt = (a.wts_off && a.wts_off[b] >= 0) ? a.step_weights[a.wts_off[b] + (t_done - a.t1[b])] : 1.0;
-                acc[0] += wt * (M + ::log(total / (double)N));
-            }
-            if (a.pf == SGM_PF_FILTER) for (int j = 0; j < nstat; ++j) acc[1 + j] += sbar[j];     // pf.py:77-80
-        }
-        if (final_pass) {
-            a.loglik[b] = acc[0];
-            for (int j = 0; j < 8; ++j) a.grad[(size_t)b * 8 + j] = 0.0;
-            for (int j = 0; j < nstat; ++j) a.grad[(size_t)b * 8 + j] = (a.pf == SGM_PF_FILTER) ? acc[1 + j] : sbar[j];
-            if (a.stat_kind == SGM_STAT_PRED) for (int j = 0; j <= a.pred_K; ++j) a.grad[(size_t)b * 8 + j] = acc[1 + j];
-        }
-    }
+    if (tid == 0) header_finish<Model>(a, b, t_done, final_pass, nstat, M, total, sbar, base, off);
 }
 
 template <class R, class Model>

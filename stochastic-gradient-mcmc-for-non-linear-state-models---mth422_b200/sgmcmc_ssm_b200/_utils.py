@@ -11,6 +11,12 @@ def _tril_indices(n):
     return np.tril_indices(n)
 
 
+def tril_indices_from(mat):
+    """np.tril_indices_from with the index arrays cached per size (the parameter containers call it on every
+    gradient / projection; for the 1 x 1 matrices of this path the index construction dominated)."""
+    return _tril_indices(np.shape(mat)[0])
+
+
 def tril_vector_to_mat(vec):
     """Lower-triangular matrix from its row-major packed vector (_utils.py:134-139)."""
     vec = np.atleast_1d(vec)

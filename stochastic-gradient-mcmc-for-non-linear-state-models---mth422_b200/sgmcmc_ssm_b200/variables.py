@@ -11,7 +11,7 @@ import numpy as np
 import scipy.stats
 from scipy.special import expit, logit
 
-from ._utils import (array_wishart_rvs, matrix_normal_logpdf, pos_def_mat_inv, tril_vector_to_mat,
+from ._utils import (array_wishart_rvs, matrix_normal_logpdf, pos_def_mat_inv, tril_indices_from, tril_vector_to_mat,
                      varp_stability_projection)
 
 logger = logging.getLogger(name=__name__)
@@ -48,7 +48,7 @@ class CovarianceVar(object):
             n, n2 = np.shape(L)
             if n != n2:
                 raise ValueError("{0} must be square matrix".format(self.chol))
-            vec = L[np.tril_indices_from(L)]
+            vec = L[tril_indices_from(L)]
         else:
             raise ValueError("{0} not provided".format(self.chol))
         param.var_dict[self.vec] = vec
@@ -61,7 +61,7 @@ class CovarianceVar(object):
             return tril_vector_to_mat(p.var_dict[vec])
 
         def set_chol(p, value):
-            p.var_dict[vec] = value[np.tril_indices_from(value)]
+            p.var_dict[vec] = value[tril_indices_from(value)]
 
         def get_inv(p):                       # covariance.py:141-146: L L^T + 1e-16 I
             L = get_chol(p)
@@ -83,7 +83,7 @@ class CovarianceVar(object):
             if np.any(np.diag(L) < 0.0):      # reflect: covariance.py:67-79
                 logger.info("Reflecting {0}: {1} < 0.0".format(self.chol, L))
                 L = np.linalg.cholesky(np.dot(L, L.T) + np.eye(L.shape[0]) * 1e-16)
-            param.var_dict[self.vec] = L[np.tril_indices_from(L)]
+            param.var_dict[self.vec] = L[tril_indices_from(L)]
 
     def flatten(self, var_dict):
         return [np.atleast_1d(var_dict[self.vec])]
@@ -110,7 +110,7 @@ class CovarianceVar(object):
     def sample_prior(self, prior, var_dict):
         Qinv = array_wishart_rvs(df=prior.hyperparams[self.df], scale=prior.hyperparams[self.scale])
         L = np.linalg.cholesky(Qinv)
-        var_dict[self.vec] = L[np.tril_indices_from(L)]
+        var_dict[self.vec] = L[tril_indices_from(L)]
 
     def logprior(self, prior, parameters):
         return scipy.stats.wishart.logpdf(getattr(parameters, self.inv), df=prior.hyperparams[self.df],
@@ -120,7 +120,7 @@ class CovarianceVar(object):
         L = getattr(parameters, self.chol)
         g = ((prior.hyperparams[self.df] - L.shape[0] - 1) * np.linalg.inv(L.T)
              - np.linalg.solve(prior.hyperparams[self.scale], L))
-        grad[self.vec] = g[np.tril_indices_from(g)]
+        grad[self.vec] = g[tril_indices_from(g)]
 
     def _hyper(self, kw, Qinv, var):
         df = np.shape(Qinv)[-1] + 1.0 + var ** -1
@@ -138,14 +138,14 @@ class CovarianceVar(object):
     def precondition(self, out, grad, parameters):
         Qinv = getattr(parameters, self.inv)
         G = np.zeros(Qinv.shape)
-        G[np.tril_indices_from(G)] = grad[self.vec]
+        G[tril_indices_from(G)] = grad[self.vec]
         P = np.dot(0.5 * Qinv, G)
-        out[self.vec] = P[np.tril_indices_from(P)]
+        out[self.vec] = P[tril_indices_from(P)]
 
     def precondition_noise(self, out, parameters):
         L = tril_vector_to_mat(parameters.var_dict[self.vec])
         Z = np.dot(np.sqrt(0.5) * L, np.random.normal(loc=0, size=L.shape))
-        out[self.vec] = Z[np.tril_indices_from(Z)]
+        out[self.vec] = Z[tril_indices_from(Z)]
 
     def correction_term(self, out, parameters):
         vec = parameters.var_dict[self.vec]
