@@ -33,6 +33,9 @@ namespace sgm {
 #ifndef SGM_STEP_CTAS
 #define SGM_STEP_CTAS 4
 #endif
+#ifndef SGM_FUSED_CTAS
+#define SGM_FUSED_CTAS 3          /* measured: 4 -> 0.425 ms, 3 -> 0.362 ms, 2 -> 0.350 ms per 60-step item at N = 1024; 3 is also best at 1024 items */
+#endif
 #ifndef SGM_GATHER_BATCH
 #define SGM_GATHER_BATCH 4
 #endif
@@ -806,7 +809,7 @@ __global__ void __launch_bounds__(NT, (sizeof(R) == 4 ? SGM_STEP_CTAS : 2)) pf_s
 // barrier replaces the kernel boundary (all global-memory traffic of an item stays on one SM, whose L1 is
 // coherent for its own writes).  This is the SGLD-with-N~1000 regime, where launch latency dominated.
 template <class R, class Model, bool SORTED>
-__global__ void __launch_bounds__(NT, (sizeof(R) == 4 ? 4 : 2)) pf_fused_kernel(KArgs a) {
+__global__ void __launch_bounds__(NT, (sizeof(R) == 4 ? SGM_FUSED_CTAS : 2)) pf_fused_kernel(KArgs a) {
     __shared__ __align__(32) R s_cdf_all[NWARP][SORTED ? WIN_BYTES / sizeof(R) : WT];
     __shared__ double sh_d[NWARP];
     const int b = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
