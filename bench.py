@@ -313,18 +313,20 @@ def extras(sg, y, theta, windows, torch):
                           weights=w["weights"], prior_mean=0.0, prior_var=10.0)
     prep = sg.engine.PreparedPF("svm", "prior", "poyiadjis_N", it, N_PARTICLES, dtype="f32", rng="philox",
                                 resample="multinomial_sorted").upload()
+    go = prep.launch_graph if prep.graph_eligible() else prep.launch     # what run_pf / the samplers do for a small batch
     for k in range(3):
-        prep.launch(offset=k)
+        go(offset=k)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
     e0.record()
     for k in range(20):
-        prep.launch(offset=10 + k)
+        go(offset=10 + k)
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / 20
     out["minibatch1_ms_per_gradient"] = ms
     out["minibatch1_particle_steps_per_sec"] = prep.particle_steps / (ms * 1e-3)
+    out["minibatch1_cuda_graph"] = bool(prep.graph_eligible())
     # SGLD iterations / s, BASELINE configs[0]: LGSSM T=1000, N=1000, S=40, B=10, minibatch 1
     from sgmcmc_ssm_b200.models.lgssm import LGSSMSampler, LGSSMParameters, generate_lgssm_data
     np.random.seed(12345)

@@ -99,6 +99,9 @@ typedef struct sgm_pf_desc {
     int32_t reserved0;             /* must be 0                                                     */
     double lambduh;                /* Nemeth shrinkage (pf.py:140); 1.0 = Poyiadjis O(N)            */
     uint64_t seed, offset;         /* Philox key / call counter                                     */
+    const uint64_t* offset_dev;    /* optional DEVICE pointer: when set the call counter is read from there by the
+                                    * kernels and `offset` is ignored -- lets a captured CUDA graph of this call be
+                                    * replayed with fresh random numbers                              */
 
     /* per-item inputs */
     const double* obs;             /* flat observations                                             */

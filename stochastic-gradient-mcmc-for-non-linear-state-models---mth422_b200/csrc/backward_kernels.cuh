@@ -473,7 +473,7 @@ __global__ void __launch_bounds__(NT) pf_pred_kernel(KArgs a, int t) {
     const typename Model::template Theta<R> th = load_thc<R, Model>(a, b);
     const double* obs = a.obs + a.obs_off[b];
     const int kmax = min(K, Tb - 1 - t);
-    RngKey key = a.key; key.item += (uint32_t)b;
+    const RngKey key = item_key(a, b);
     R mx[8], mlw = -Mth<R>::inf();
 #pragma unroll
     for (int k = 0; k < 8; ++k) mx[k] = -Mth<R>::inf();
@@ -618,7 +618,7 @@ __global__ void __launch_bounds__(NT) paris_ar_kernel(KArgs a, int t, int ch) {
     const Vec4T<R>* pkey = reinterpret_cast<const Vec4T<R>*>(a.pkey) + item_off;
     const double* cdf = a.pcdf + item_off;
     const int32_t* guide = a.pguide + (size_t)b * (N + 1);
-    RngKey key = a.key; key.item += (uint32_t)b;
+    const RngKey key = item_key(a, b);
     for (int k = tid; k < nch; k += NT) {
         R rn[W], bb, aa;
         load_rec<R, W>(a.rec[par ^ 1], a.tail[par ^ 1], item_off + c0 + k, rn);
@@ -681,7 +681,7 @@ __global__ void __launch_bounds__(NT) paris_exact_kernel(KArgs a, int t) {
     const int count = a.counters[b * 16];
     const typename Model::template Theta<R> th = load_thc<R, Model>(a, b);
     const Vec4T<R>* pkey = reinterpret_cast<const Vec4T<R>*>(a.pkey) + item_off;
-    RngKey key = a.key; key.item += (uint32_t)b;
+    const RngKey key = item_key(a, b);
     const int nwarps = gridDim.x * NWARP, nseg = (N + PSEG - 1) / PSEG;
     double* seg = s_seg[warp];
     for (int e = blockIdx.x * NWARP + warp; e < count; e += nwarps) {

@@ -59,6 +59,7 @@ struct KArgs {
     int pred_K, pred_per_horizon;  // SGM_STAT_PRED: num_steps_ahead, log-sum variant
     const double* inj_pred;
     int b0;                // first item of this launch (a batch may be split over two streams)
+    const uint64_t* offset_dev;   // optional: Philox call offset read from device memory (CUDA-graph replays)
     double lambduh;
     RngKey key;            // .item holds item_id_base
     const double* obs; const int64_t* obs_off; const int32_t* T_buf; const int32_t* t1; const int32_t* tL;
@@ -75,6 +76,19 @@ struct KArgs {
     double* grad; double* loglik; int32_t* status;
     void* out_x; void* out_lw; void* out_stats; int32_t* trace_anc; void* trace_x; void* trace_lw; int32_t* trace_J;
 };
+
+// Philox key of item b.  The call offset normally travels in the kernel arguments; a captured CUDA graph replays
+// the same arguments, so there it is read from device memory instead.
+__device__ __forceinline__ RngKey item_key(const KArgs& a, int b) {
+    RngKey key = a.key;
+    if (a.offset_dev) {
+        const uint64_t o = *a.offset_dev;
+        key.offset = (uint32_t)(o & 0xffffffffu);
+        key.k1 ^= (uint32_t)(o >> 32);
+    }
+    key.item += (uint32_t)b;
+    return key;
+}
 
 // ---- record access ---------------------------------------------------------------------------
 template <class R> struct alignas(4 * sizeof(R)) Vec4T { R x, y, z, w; };
@@ -267,7 +281,7 @@ __device__ __forceinline__ void init_body(const KArgs& a, int b, int g, R* s_tr)
     const int q_me = g * NWARP + warp;
     if (q_me >= a.Q) return;
     const int tile_base = q_me * WT;
-    RngKey key = a.key; key.item += (uint32_t)b;
+    const RngKey key = item_key(a, b);
     const R mean = (R)a.prior_mean[b], sd = (R)::sqrt(a.prior_var[b]);
     R lwn[KPT];
     R z[KPT];
@@ -371,7 +385,7 @@ __device__ __forceinline__ void header_warp(const KArgs& a, int b, int t, int fi
     double sbar[4] = {0.0, 0.0, 0.0, 0.0};
     for (int j = 0; j < nws; ++j) sbar[j] = warp_sum(has ? e * p[2 + j] : 0.0) / total;
     if (!final_pass && uses_spacings(a)) {
-        RngKey key = a.key; key.item += (uint32_t)b;
+        const RngKey key = item_key(a, b);
         const double g = (lane <= Q) ? rng_gamma(key, (uint32_t)lane, (uint32_t)t, (lane == Q) ? 1.0 : (double)min(WT, N - lane * WT)) : 0.0;
         const double gincl = warp_incl_scan(g);
         const double kk = total / __shfl_sync(FULL, gincl, 31);
@@ -430,7 +444,7 @@ __device__ __forceinline__ void header_body(const KArgs& a, int b, int t, int fi
     for (int j = 0; j < nws; ++j) sbar[j] = block_sum(ws[j], sh_d) / total;
 
     if (!final_pass && uses_spacings(a)) {
-        RngKey key = a.key; key.item += (uint32_t)b;
+        const RngKey key = item_key(a, b);
         const int perg = (Q + 1 + NT - 1) / NT, g0 = tid * perg;
         double gl = 0.0;
         for (int k = 0; k < perg; ++k) {
@@ -597,7 +611,7 @@ __device__ __forceinline__ void step_body(const KArgs& a, int b, int t, int q_me
     const R* fine_old = reinterpret_cast<const R*>(a.fine[par]) + (size_t)b * a.Q * WT;      // padded to whole tiles
     const int tile_base = q_me * WT;
     const int n_valid = min(WT, N - tile_base);
-    RngKey key = a.key; key.item += (uint32_t)b;
+    const RngKey key = item_key(a, b);
     const double total = hdr.total;
     const double tmax = total * (1.0 - 1.2e-16);
     int anc[KPT];

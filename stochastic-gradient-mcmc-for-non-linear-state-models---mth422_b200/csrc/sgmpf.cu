@@ -121,8 +121,9 @@ int run_impl(const sgm_pf_desc* d, cudaStream_t stream) {
     a.pred_K = d->pred_steps_ahead; a.pred_per_horizon = d->pred_per_horizon; a.inj_pred = d->inj_pred;
     a.lambduh = d->lambduh;
     a.key.k0 = (uint32_t)(d->seed & 0xffffffffu); a.key.k1 = (uint32_t)(d->seed >> 32);
-    a.key.item = (uint32_t)d->item_id_base; a.key.offset = (uint32_t)(d->offset & 0xffffffffu);
-    a.key.k1 ^= (uint32_t)(d->offset >> 32);
+    a.key.item = (uint32_t)d->item_id_base;
+    a.offset_dev = d->offset_dev;
+    if (!d->offset_dev) { a.key.offset = (uint32_t)(d->offset & 0xffffffffu); a.key.k1 ^= (uint32_t)(d->offset >> 32); }
     a.obs = d->obs; a.obs_off = d->obs_off; a.T_buf = d->T_buf; a.t1 = d->t1; a.tL = d->tL;
     a.step_weights = d->step_weights; a.wts_off = d->step_weights ? d->wts_off : nullptr; a.theta = d->theta;
     a.prior_mean = d->prior_mean; a.prior_var = d->prior_var;

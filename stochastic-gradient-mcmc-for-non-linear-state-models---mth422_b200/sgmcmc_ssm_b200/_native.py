@@ -30,7 +30,7 @@ class SgmPfDesc(ctypes.Structure):
         ("accept_reject", c_i32), ("max_accept_reject", c_i32), ("manual_sample_threshold", c_i32),
         ("item_id_base", c_i32), ("n2_mode", c_i32), ("pred_steps_ahead", c_i32),
         ("pred_per_horizon", c_i32), ("reserved0", c_i32),
-        ("lambduh", c_f64), ("seed", c_u64), ("offset", c_u64),
+        ("lambduh", c_f64), ("seed", c_u64), ("offset", c_u64), ("offset_dev", c_vp),
         ("obs", c_vp), ("obs_off", c_vp), ("T_buf", c_vp), ("t1", c_vp), ("tL", c_vp),
         ("step_weights", c_vp), ("wts_off", c_vp), ("theta", c_vp), ("prior_mean", c_vp), ("prior_var", c_vp),
         ("inj_z0", c_vp), ("inj_u", c_vp), ("inj_z", c_vp), ("inj_extra", c_vp), ("inj_extra_off", c_vp), ("inj_pred", c_vp),

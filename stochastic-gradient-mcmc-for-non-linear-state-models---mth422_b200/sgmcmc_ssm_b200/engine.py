@@ -23,6 +23,7 @@ class Config(object):
     resample = "multinomial_sorted"  # 'multinomial' | 'multinomial_sorted' | 'systematic' | 'stratified'
     device = None                    # torch device; default = current CUDA device
     two_streams = True               # split big O(N) batches over two streams (hides the per-step header kernel)
+    cuda_graphs = True               # replay a captured CUDA graph for small launch-bound batches (one wave of CTAs)
 
 
 config = Config()
@@ -79,6 +80,7 @@ class _DeviceState(object):
 
 
 _STATES = {}
+_GRAPHS = {}        # graph key -> (torch.cuda.CUDAGraph, device offset tensor, launches per replay)
 
 
 def _state(device):
@@ -422,6 +424,45 @@ class PreparedPF(object):
         self.launches = int(self.lib.sgm_last_launch_count())
         return self
 
+    # ---- CUDA-graph replay for launch-bound batches ----------------------------------------------------------
+    def graph_eligible(self):
+        """2 * max_T + 2 tiny launches per call: worth a graph when the whole batch is at most one wave of CTAs and the
+        item does not already run in the single-launch kernel (N <= 2048).  Device randoms only (a graph bakes the
+        kernel arguments in; the Philox call offset is then read from device memory, sgm_pf_desc.offset_dev)."""
+        d = self.desc
+        if not config.cuda_graphs or d.rng_mode != nat.RNG["philox"] or self.extra or self.N <= 2048:
+            return False
+        return self.B * ((self.N + 2047) // 2048) <= 148
+
+    def _graph_key(self):
+        d = self.desc
+        skip = ("offset", "offset_dev", "ev_steps_begin", "ev_steps_end", "aux_stream", "ev_aux_fork", "ev_aux_join")
+        return (self.device.index,) + tuple(getattr(d, name) for name, _ in d._fields_ if name not in skip)
+
+    def launch_graph(self, offset=None):
+        """Same work as launch(), replayed from a cached CUDA graph (captured on first use of this exact shape)."""
+        if offset is not None:
+            self.desc.offset = int(offset)
+        key = self._graph_key()
+        with torch.cuda.device(self.device):
+            entry = _GRAPHS.get(key)
+            if entry is None:
+                off_t = torch.zeros(1, dtype=torch.int64, device=self.device)
+                self.desc.offset_dev = off_t.data_ptr()
+                self.desc.aux_stream = self.desc.ev_aux_fork = self.desc.ev_aux_join = None
+                self.desc.ev_steps_begin = self.desc.ev_steps_end = None
+                self.launch()                                   # warm-up outside the capture (module load, checks)
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph):
+                    self.launch()
+                if len(_GRAPHS) >= 32:
+                    _GRAPHS.pop(next(iter(_GRAPHS)))
+                entry = _GRAPHS[key] = (graph, off_t, self.launches)
+            graph, off_t, self.launches = entry
+            off_t.fill_(int(self.desc.offset) & (2 ** 63 - 1))
+            graph.replay()
+        return self
+
     def download(self):
         st = self.st
         with torch.cuda.device(self.device):
@@ -443,7 +484,8 @@ def run_pf(model, kernel, pf, items, N, sync=True, check=True, **kwargs):
     Mirrors particle_filters/buffered_smoother.py:156-199 (`pf` dispatch) for a whole batch.
     Returns a PFResult with .grad (B, p), .loglik (B,), .status (B,).  One call may be outstanding per
     device (staging buffers are shared)."""
-    res = PreparedPF(model, kernel, pf, items, N, **kwargs).upload().launch().download()
+    prep = PreparedPF(model, kernel, pf, items, N, **kwargs).upload()
+    res = (prep.launch_graph() if prep.graph_eligible() else prep.launch()).download()
     if sync:
         res.wait(check=check)
     return res

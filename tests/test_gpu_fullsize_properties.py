@@ -97,3 +97,23 @@ def test_largest_particle_count_runs_and_agrees():
     np.testing.assert_allclose(big.loglik, ref.loglik, rtol=0, atol=0.3)
     with pytest.raises(ValueError):
         sg.run_pf("svm", "prior", "poyiadjis_N", it, (1 << 20) + 1)
+
+
+def test_cuda_graph_replay_is_bit_identical_to_direct_launches():
+    """Launch-bound batches replay a captured CUDA graph (Philox call offset read from device memory): the results of
+    two calls with different offsets must equal the direct-launch results, and differ from each other."""
+    import sgmcmc_ssm_b200 as sg
+    from sgmcmc_ssm_b200 import engine
+    it = _items(3, seed=17)
+    outs = {}
+    for graphs in (True, False):
+        engine.config.cuda_graphs = graphs
+        try:
+            outs[graphs] = [sg.run_pf("svm", "prior", "poyiadjis_N", it, N16, dtype="f32", seed=21, offset=o) for o in (5, 6, 5)]
+        finally:
+            engine.config.cuda_graphs = True
+    for a, b in zip(outs[True], outs[False]):
+        np.testing.assert_array_equal(a.grad, b.grad)
+        np.testing.assert_array_equal(a.loglik, b.loglik)
+    np.testing.assert_array_equal(outs[True][0].grad, outs[True][2].grad)
+    assert np.any(outs[True][0].grad != outs[True][1].grad)
