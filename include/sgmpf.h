@@ -161,6 +161,11 @@ int sgm_state_dim(int32_t model);
 uint64_t sgm_pf_workspace_bytes(const sgm_pf_desc* d);
 /* run the whole buffered t-loop for the batch on `stream` (a cudaStream_t passed as void*) */
 int sgm_pf_run(const sgm_pf_desc* d, void* stream);
+/* IMQ kernel Stein discrepancy of a trace (sgmcmc_ssm/trace_metric_functions.py:20-81): x, gradlogp are DEVICE
+ * [num_points][dim] float64 (dim <= 8); writes ceil(num_points / 256) partial sums of sum_{i,j} k0(x_i, x_j) to the
+ * DEVICE array `partial`; KSD = sqrt(sum(partial)) / num_points. */
+int sgm_ksd_imq(const double* x, const double* gradlogp, int32_t num_points, int32_t dim, double c, double beta,
+                double* partial, void* stream);
 /* number of kernel launches the last sgm_pf_run on this thread issued (for bench accounting) */
 int64_t sgm_last_launch_count(void);
 

@@ -9,6 +9,7 @@
 #include "../../include/sgmpf.h"
 #include "pf_kernels.cuh"
 #include "backward_kernels.cuh"
+#include "ksd_kernel.cuh"
 
 using namespace sgm;
 
@@ -246,6 +247,18 @@ int sgm_stat_dim(int32_t model, int32_t stat_kind) {
     if (stat_kind == SGM_STAT_NONE) return 0;
     if (stat_kind == SGM_STAT_PRED) return 8;          /* upper bound: num_steps_ahead + 1 <= 8 */
     return SGM_ERR_INVALID;
+}
+
+int sgm_ksd_imq(const double* x, const double* gradlogp, int32_t num_points, int32_t dim, double c, double beta,
+                double* partial, void* stream) {
+    if (!x || !gradlogp || !partial) return fail(SGM_ERR_INVALID, "sgm_ksd_imq: null pointer");
+    if (num_points < 1 || dim < 1 || dim > KSD_MAXD) return fail(SGM_ERR_UNSUPPORTED, "sgm_ksd_imq: dim must be in [1, 8]");
+    g_err[0] = 0;
+    const int blocks = (num_points + NT - 1) / NT;
+    ksd_imq_kernel<<<blocks, NT, 0, reinterpret_cast<cudaStream_t>(stream)>>>(x, gradlogp, num_points, dim, c * c, beta, partial);
+    const cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(SGM_ERR_CUDA, "CUDA launch failed: %s", cudaGetErrorString(e));
+    return SGM_OK;
 }
 
 uint64_t sgm_pf_workspace_bytes(const sgm_pf_desc* d) {

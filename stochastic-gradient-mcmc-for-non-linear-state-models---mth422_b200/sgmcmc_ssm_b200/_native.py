@@ -44,7 +44,7 @@ class SgmPfDesc(ctypes.Structure):
 
 
 EXPORTS = ["sgm_version", "sgm_device_check", "sgm_last_error", "sgm_stat_dim", "sgm_state_dim",
-           "sgm_pf_workspace_bytes", "sgm_pf_run", "sgm_last_launch_count"]
+           "sgm_pf_workspace_bytes", "sgm_pf_run", "sgm_last_launch_count", "sgm_ksd_imq"]
 _lib = None
 
 
@@ -70,6 +70,8 @@ def load():
     lib.sgm_pf_run.restype = c_i32
     lib.sgm_pf_run.argtypes = [ctypes.POINTER(SgmPfDesc), c_vp]
     lib.sgm_last_launch_count.restype = c_i64
+    lib.sgm_ksd_imq.restype = c_i32
+    lib.sgm_ksd_imq.argtypes = [c_vp, c_vp, c_i32, c_i32, c_f64, c_f64, c_vp, c_vp]
     _lib = lib
     return lib
 
