@@ -49,16 +49,18 @@ def random_subsequence_and_weights(S, T, partition_style=None):
     return int(start), int(end), weights
 
 
-def random_subsequences_packed(observations, S, M, buffer_length, partition_style=None):
+def random_subsequences_packed(observations, S, M, buffer_length, partition_style=None, lo=0, hi=None):
     """Vectorised form of M calls of random_subsequence_and_weights + the buffer / window slicing of
     sgmcmc_sampler.py:259-288, 364-374 for the 'uniform' and 'naive' partition styles.  Consumes the numpy
     stream exactly like the M sequential `np.random.randint(0, T - S + 1)` calls of the reference (legacy
     RandomState draws bounded integers element by element: checked in tests/test_host_logic.py).
-    Returns the keyword arrays of engine.PackedItems (without theta / prior)."""
+    Returns the keyword arrays of engine.PackedItems (without theta / prior) for the items [lo, hi) of the minibatch."""
     T = observations.shape[0]
     if buffer_length == -1:
         buffer_length = T
-    start = np.random.randint(0, T - S + 1, size=M).astype(np.int64)
+    start = np.random.randint(0, T - S + 1, size=M).astype(np.int64)     # all M draws: every rank keeps the same stream
+    start = start[lo:hi]                                                  # ... and packs only its own shard
+    M = start.shape[0]
     end = start + S
     if partition_style in (None, "uniform"):
         t = start[:, None] + np.arange(S)[None, :]
@@ -279,21 +281,16 @@ class SGMCMCSampler(object):
             # vectorised minibatch: same numpy draws as the loop below, no per-item Python work
             from . import parallel
             distributed = kwargs.pop("distributed", False)
-            packed = self.message_helper.packed_items(
-                self.parameters, forward_message=kwargs.pop("forward_message", None),
-                **random_subsequences_packed(obs_all, subsequence_length, minibatch_size, buffer_length, style))
+            lo, hi = parallel.shard_bounds(minibatch_size) if distributed else (0, minibatch_size)
+            fm = kwargs.pop("forward_message", None)
+            arrays = random_subsequences_packed(obs_all, subsequence_length, minibatch_size, buffer_length, style, lo, hi)
             keys = list(noisy_grad)
-            if distributed:
-                lo, hi = parallel.shard_bounds(minibatch_size)
-                local = np.zeros(len(keys))
-                if hi > lo:
-                    sums, _ = self.message_helper.pf_gradient_sum_packed(packed.slice(lo, hi), self.parameters,
-                                                                         item_id_base=lo, **kwargs)
-                    local = np.array([sums[k] for k in keys])
-                total = parallel.allreduce_sum(local)
-            else:
-                sums, _ = self.message_helper.pf_gradient_sum_packed(packed, self.parameters, **kwargs)
-                total = [sums[k] for k in keys]
+            local = np.zeros(len(keys))
+            if hi > lo:
+                packed = self.message_helper.packed_items(self.parameters, forward_message=fm, **arrays)
+                sums, _ = self.message_helper.pf_gradient_sum_packed(packed, self.parameters, item_id_base=lo, **kwargs)
+                local = np.array([sums[k] for k in keys])
+            total = parallel.allreduce_sum(local) if distributed else local
             for k, v in zip(keys, total):
                 noisy_grad[k] += v / minibatch_size
             return self._check_noisy_grad(noisy_grad)

@@ -183,6 +183,13 @@ def test_vectorised_minibatch_windows_equal_the_sequential_draws(style, T, S, B)
     for name in ("obs_flat", "T_buf", "t1", "tL", "wts_flat", "wts_off"):
         np.testing.assert_array_equal(getattr(pk, name), getattr(ref, name), err_msg=name)
     np.testing.assert_array_equal(pk.theta, ref.theta)
+    # packing only a rank's shard == slicing the full batch (and the numpy stream advances identically)
+    np.random.seed(99)
+    shard = engine.PackedItems(theta=[1.0, 2.0], prior_mean=0.0, prior_var=1.0, **random_subsequences_packed(obs, S, M, B, style, 5, 21))
+    assert np.random.random_sample() == after_seq
+    full_slice = pk.slice(5, 21)
+    for name in ("obs_flat", "T_buf", "t1", "tL", "wts_flat", "wts_off"):
+        np.testing.assert_array_equal(getattr(shard, name), getattr(full_slice, name), err_msg=name)
     # shard slicing keeps every item intact
     lo, hi = 5, 21
     sl = pk.slice(lo, hi)
