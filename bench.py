@@ -6,14 +6,21 @@
 
 Workload (BASELINE.json configs[1]): SVM synthetic T=10000 (A, Q, R) = (0.95, 0.5, 0.5), Poyiadjis O(N)
 smoother, N = 2^16 particles per subsequence, subsequence 40 + buffers 10 (T_buf = 60 steps), a minibatch
-of M subsequences per GPU (weak scaling), f32 particle arithmetic with f64 CDF offsets, device Philox
-randoms, order-statistics multinomial resampling (same law as the reference's multinomial).
+of M = 512 subsequences per GPU (weak scaling), f32 particle arithmetic with f64 CDF offsets, device Philox
+randoms, order-statistics multinomial resampling (same law as the reference's multinomial).  The batch runs
+as two halves on two CUDA streams (sgm_pf_desc.aux_stream).  `--particles 1048576 --minibatch 128` is one
+GPU's share of configs[4].
 
 A "step" = one noisy-gradient evaluation of the minibatch = one pass of the hot path over one batch.
   value : device-timed (CUDA events, max over ranks), inputs resident in HBM; includes the per-step
           NCCL all-reduce of the gradient sums when N > 1.
   e2e   : the same metric through the public API `sampler.noisy_gradient(kind='pf', ...)` with HOST
-          observation buffers: packing, H2D, all kernels, D2H and the all-reduce inside the timed region.
+          observation buffers: window draws, packing, H2D, all kernels, D2H and the all-reduce inside the
+          timed region.
+  roofline : algorithmic 40 B / particle-step x particles of one time step / time of one time step
+          (CUDA events on the launch stream around the step loop / T_buf), against MEASURED_PEAKS.json.
+  extra : single-subsequence latency (CUDA-graph replay), SGLD iterations/s (configs[0]), O(N^2) pair-steps/s on
+          the tensor cores and on the FP32 pipe, PaRIS particle-steps/s (configs[2] shape).
 """
 import argparse
 import json
