@@ -811,11 +811,17 @@ __device__ __forceinline__ void step_body(const KArgs& a, int b, int t, int q_me
                              item_off, need_ws, nws, s_tr);
 }
 
+// CTA shape of the step kernel: its warps are independent (no block barrier), so the CTA size only sets the
+// register-allocation granularity.  SGM_STEP_WARPS warps per CTA, SGM_STEP_CTAS CTAs per SM (f32).
+#ifndef SGM_STEP_WARPS
+#define SGM_STEP_WARPS 8
+#endif
+constexpr int STEP_WARPS = SGM_STEP_WARPS;
 template <class R, class Model, bool SORTED>
-__global__ void __launch_bounds__(NT, (sizeof(R) == 4 ? SGM_STEP_CTAS : 2)) pf_step_kernel(KArgs a, int t) {
-    __shared__ __align__(32) R s_cdf_all[NWARP][SORTED ? WIN_BYTES / sizeof(R) : WT];
+__global__ void __launch_bounds__(32 * STEP_WARPS, (sizeof(R) == 4 ? SGM_STEP_CTAS : 2 * 8 / STEP_WARPS)) pf_step_kernel(KArgs a, int t) {
+    __shared__ __align__(32) R s_cdf_all[STEP_WARPS][SORTED ? WIN_BYTES / sizeof(R) : WT];
     const int warp = threadIdx.x >> 5;
-    step_body<R, Model, SORTED>(a, a.b0 + blockIdx.y, t, blockIdx.x * NWARP + warp, threadIdx.x & 31, s_cdf_all[warp]);
+    step_body<R, Model, SORTED>(a, a.b0 + blockIdx.y, t, blockIdx.x * STEP_WARPS + warp, threadIdx.x & 31, s_cdf_all[warp]);
 }
 
 // ---- fused kernel for small particle counts (N <= 2048: the item fits one CTA) -----------------------------

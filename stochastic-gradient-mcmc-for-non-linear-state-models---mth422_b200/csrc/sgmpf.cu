@@ -179,10 +179,10 @@ int run_impl(const sgm_pf_desc* d, cudaStream_t stream) {
         if (d->ev_steps_begin) cudaEventRecord(reinterpret_cast<cudaEvent_t>(d->ev_steps_begin), stream);
         for (int t = 0; t < a.max_T; ++t) {
             for (int h = 0; h < nh; ++h) {
-                const dim3 gh(a.G, nb[h]);
+                const dim3 gh((a.Q + STEP_WARPS - 1) / STEP_WARPS, nb[h]), bs(32 * STEP_WARPS);
                 pf_header_kernel<R, Model><<<nb[h], block, 0, sh[h]>>>(ah[h], t, 0); ++launches;
-                if (d->resample == SGM_RESAMPLE_MULTINOMIAL) pf_step_kernel<R, Model, false><<<gh, block, 0, sh[h]>>>(ah[h], t);
-                else pf_step_kernel<R, Model, true><<<gh, block, 0, sh[h]>>>(ah[h], t);
+                if (d->resample == SGM_RESAMPLE_MULTINOMIAL) pf_step_kernel<R, Model, false><<<gh, bs, 0, sh[h]>>>(ah[h], t);
+                else pf_step_kernel<R, Model, true><<<gh, bs, 0, sh[h]>>>(ah[h], t);
                 ++launches;
             }
             if (pred) { pf_pred_kernel<R, Model><<<a.B, block, 0, stream>>>(a, t); ++launches; }
