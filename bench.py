@@ -63,15 +63,29 @@ def svm_theta():
     return dict(A=0.95, LQinv=LQinv, Qinv=LQinv * LQinv + 1e-16, LRinv=LRinv, Rinv=LRinv * LRinv + 1e-16)
 
 
+def uniform_partition_weights(S, T, start):
+    """Per-step importance weights of a 'uniform'-partition subsequence [start, start + S)
+    (sgmcmc_sampler.py:1994-2008: (T - S + 1) / number of subsequences covering t).  Workload construction only --
+    the GPU arm imports nothing from oracle/."""
+    t = np.arange(start, start + S)
+    cap = min(S, T - S + 1)
+    if start + S <= 2 * S:
+        num = np.minimum(t + 1, cap)
+    elif start >= T - 2 * S - 1:
+        num = np.minimum(T - t, cap)
+    else:
+        num = np.full(S, S)
+    return np.ones(S, dtype=float) * (T - S + 1) / num
+
+
 def draw_windows(n, T=T_SERIES, seed=777):
     """n subsequence starts + 'uniform' partition weights (sgmcmc_sampler.py:1969-2017)."""
-    from oracle import pf_oracle as po
     rs = np.random.RandomState(seed)
     out = []
     for _ in range(n):
         start = int(rs.randint(0, T - SUBSEQ + 1))
         lo, hi = max(0, start - BUFFER), min(T, start + SUBSEQ + BUFFER)
-        out.append(dict(start=start, lo=lo, hi=hi, weights=po.subsequence_weights(SUBSEQ, T, start)))
+        out.append(dict(start=start, lo=lo, hi=hi, weights=uniform_partition_weights(SUBSEQ, T, start)))
     return out
 
 
