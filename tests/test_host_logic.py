@@ -213,3 +213,18 @@ def test_python_descriptor_mirror_has_the_size_the_library_expects():
     d.model, d.kernel = nat.MODEL["svm"], nat.KERNEL["optimal"]
     d.n_items = d.n_particles = 1
     assert lib.sgm_pf_run(ctypes.byref(d), None) == -2 and b"optimal" in lib.sgm_last_error()   # NotImplementedError
+
+
+def test_product_path_never_touches_the_oracle():
+    """oracle/ is test infrastructure: nothing under the package, the drop-in alias or scripts/ may import it, and in
+    bench.py only the CPU legs (cpu_baseline / --impl reference) do."""
+    pkg = os.path.join(ROOT, "stochastic-gradient-mcmc-for-non-linear-state-models---mth422_b200")
+    for base in (pkg, os.path.join(ROOT, "scripts")):
+        for dirpath, _, files in os.walk(base):
+            for f in files:
+                if f.endswith((".py", ".cu", ".cuh", ".h")):
+                    assert "oracle" not in open(os.path.join(dirpath, f)).read(), os.path.join(dirpath, f)
+    src = open(os.path.join(ROOT, "bench.py")).read()
+    gpu_arm = src[src.index("def run_gpu("):src.index("def extras(")]
+    assert "import pf_oracle" not in gpu_arm and "po." not in gpu_arm.replace("cpu_rate", "")
+    assert src.count("from oracle import pf_oracle") == 1 and "def _cpu_one_gradient" in src
