@@ -9,10 +9,12 @@ TH = {"svm": [0.95, np.sqrt(2.0), 2.0, np.sqrt(2.0), 2.0],
       "lgssm": [0.9, np.sqrt(10.0), 10.0, 1.0, 1.0, 1.0],
       "garch": [0.1, 0.8, 0.05, 0.1 / 0.15, 0.85, 0.8 / 0.85, 1 / 0.3, 1 / 0.09, 0.09]}
 
-def run(model, pf, N, B, T, reps=2, dtype="f32", **kw):
+def run(model, pf, N, B, T, reps=2, dtype="f32", hetero=False, **kw):
     y = rs.normal(size=T) * 0.7
     it = sg.PFItems()
     for b in range(B):
+        if hetero:                       # every item its own series (what a minibatch of subsequences looks like)
+            y = rs.normal(size=T) * 0.7
         it.add(y, TH[model], t1=2, tL=T - 2, weights=np.ones(T - 4) * 250.0, prior_mean=0.0, prior_var=1.0 if model == "garch" else 10.0)
     kern = "prior" if model == "svm" else "optimal"
     r = sg.run_pf(model, kern, pf, it, N, dtype=dtype, **kw)
@@ -31,7 +33,9 @@ def run(model, pf, N, B, T, reps=2, dtype="f32", **kw):
 if __name__ == "__main__":
     what = sys.argv[1] if len(sys.argv) > 1 else "all"
     if what == "one":        # one <model> <pf> <N> <B> <T> [n2_mode]   (ncu target)
-        kw = dict(n2_mode=sys.argv[7]) if len(sys.argv) > 7 else {}
+        kw = dict(n2_mode=sys.argv[7]) if len(sys.argv) > 7 and sys.argv[7] != "hetero" else {}
+        if "hetero" in sys.argv:
+            kw["hetero"] = True
         run(sys.argv[2], sys.argv[3], int(sys.argv[4]), int(sys.argv[5]), int(sys.argv[6]), reps=1, **kw)
     if what in ("n2", "all"):
         run("svm", "poyiadjis_N2", 1024, 1, 20)

@@ -570,7 +570,7 @@ __device__ __forceinline__ void exact_backward_sample(const KArgs& a, const type
 //                        L, pf.py:292-325), so threads never idle behind one unlucky child.
 //   paris_exact_kernel : one WARP per leftover entry, two passes over the parents (total, then the crossing).
 constexpr int PARIS_CH = 1024;         // children per CTA of the accept-reject kernel
-constexpr int PARIS_CAP = 128;         // proposal rounds before an entry falls back to the exact sampler
+constexpr int PARIS_CAP = 512;         // proposals per entry before it falls back to the exact sampler (x Ntilde <= 8 fits the 12-bit Philox sub-counter)
 constexpr int PARIS_MAXQ = 4096;       // queue capacity >= children per CTA * Ntilde (Ntilde > 4: fewer children per CTA)
 
 template <class R, class Model>
@@ -623,30 +623,51 @@ __global__ void __launch_bounds__(NT) paris_ar_kernel(KArgs a, int t, int ch) {
         R rn[W], bb, aa;
         load_rec<R, W>(a.rec[par ^ 1], a.tail[par ^ 1], item_off + c0 + k, rn);
         Model::pair_child(th, rn + NP, bb, aa);
-        s_x[0][k] = bb; s_x[1][k] = aa;
+        s_x[0][k] = bb; s_x[1][k] = aa - Model::pair_bound(th, rn + NP);       // accept w.p. q(x'|x_I) / sup_j q(x'|x_j)
     }
     int qlen = nch * Nt;
     for (int e = tid; e < qlen; e += NT) s_q[0][e] = (uint16_t)e;
     if (tid == 0) { s_n[0] = qlen; s_n[1] = 0; }
     __syncthreads();
+    // Proposal budget per entry (PARIS_CAP; the reference's max_accept_reject only lowers it).  While the queue is
+    // long every thread tries one proposal of one entry per round; once it is shorter than the CTA, groups of
+    // tpr = 2 .. 32 lanes try tpr consecutive proposals of the SAME entry at once and the first accepted one in
+    // proposal order wins -- the same draw sequential accept-reject would have taken, in 1 / tpr of the rounds.
     const int cap = a.accept_reject ? min(a.max_ar, PARIS_CAP) : 0;
-    int cur = 0;
-    for (int round = 0; round < cap && qlen > 0; ++round) {
-        for (int e = tid; e < qlen; e += NT) {
-            const int entry = s_q[cur][e], k = entry / Nt, jt = entry - k * Nt, i = c0 + k;
-            const uint4 raw = rng_raw(key, (uint32_t)i, (uint32_t)t, STREAM_PARIS, (uint32_t)(jt * PARIS_CAP + round));
-            const double u = u01d(raw.x, raw.y);
-            double target = u * total;
-            if (!(target < total)) target = total * (1.0 - 1.2e-16);
-            const int kb = min((int)(u * (double)N), N - 1);
-            int I = guide[kb];
-            const int hi = guide[kb + 1];
-            while (I < hi && cdf[I] <= target) ++I;               // first particle whose cumulative mass exceeds the target
-            const Vec4T<R> pk = pkey[I];
-            const R thr = Mth<R>::exp(s_x[0][k] * pk.x + pk.y + s_x[1][k]);        // q(x'_i | x_I) / q_max
-            if ((R)u01d(raw.z, raw.w) <= thr) a.Jidx[(item_off + i) * Nt + jt] = I;
-            else s_q[cur ^ 1][atomicAdd(&s_n[cur ^ 1], 1)] = (uint16_t)entry;
+    int cur = 0, tries_done = 0;
+    while (tries_done < cap && qlen > 0) {
+        int tpr = 1;
+        while (tpr < 32 && qlen * tpr * 2 <= NT && tries_done + tpr * 2 <= cap) tpr *= 2;
+        const int r = tid & (tpr - 1), gshift = (tid & 31) & ~(tpr - 1), per_round = NT / tpr;
+        for (int base = 0; base < qlen; base += per_round) {          // warp-uniform trip count: full-warp ballots
+            const int e = base + tid / tpr;
+            const bool live = e < qlen;
+            bool ok = false;
+            int entry = 0, I = 0, i = 0, jt = 0;
+            if (live) {
+                entry = s_q[cur][e];
+                const int k = entry / Nt;
+                jt = entry - k * Nt; i = c0 + k;
+                const uint4 raw = rng_raw(key, (uint32_t)i, (uint32_t)t, STREAM_PARIS, (uint32_t)(jt * PARIS_CAP + tries_done + r));
+                const double u = u01d(raw.x, raw.y);
+                double target = u * total;
+                if (!(target < total)) target = total * (1.0 - 1.2e-16);
+                const int kb = min((int)(u * (double)N), N - 1);
+                I = guide[kb];
+                const int hi = guide[kb + 1];
+                while (I < hi && cdf[I] <= target) ++I;           // first particle whose cumulative mass exceeds the target
+                const Vec4T<R> pk = pkey[I];
+                const R thr = Mth<R>::exp(s_x[0][k] * pk.x + pk.y + s_x[1][k]);        // q(x'_i | x_I) / (per-child bound)
+                ok = (R)u01d(raw.z, raw.w) <= thr;
+            }
+            // first accepted proposal of the group, in proposal order
+            const unsigned grp = (__ballot_sync(FULL, ok) >> gshift) & (tpr == 32 ? 0xffffffffu : ((1u << tpr) - 1u));
+            if (live) {
+                if (grp) { if (r == __ffs(grp) - 1) a.Jidx[(item_off + i) * Nt + jt] = I; }
+                else if (r == 0) s_q[cur ^ 1][atomicAdd(&s_n[cur ^ 1], 1)] = (uint16_t)entry;
+            }
         }
+        tries_done += tpr;
         __syncthreads();
         qlen = s_n[cur ^ 1];
         __syncthreads();

@@ -109,6 +109,10 @@ struct SvmPrior {
         u = t.A * xa[0]; gq = (R)-0.5 * t.Qinv * (u * u);
         m[0] = xa[0]; m[1] = xa[0] * xa[0];
     }
+    // Per-child upper bound of log q(x'_i | x_j) - log_trans_max over ALL admissible parents (PaRIS accept-reject,
+    // device-random mode): the tighter the bound, the higher the acceptance rate; the sampler stays exact for any
+    // bound that dominates.  Gaussian AR(1): parents can sit anywhere, the global maximum is the bound.
+    template <class R> static __device__ __forceinline__ R pair_bound(const Theta<R>& t, const R* xn) { return (R)0; }
     // E_j[h(x_j, x'_i)] from E[m]   (svm/helper.py:342-348 with x_j -> its moments)
     template <class R> static __device__ __forceinline__ void score_moments(const Theta<R>& t, const R* Em, const R* xn, R y, R* h) {
         h[2] = t.Qinv * (xn[0] * Em[0] - t.A * Em[1]);
@@ -177,6 +181,7 @@ struct LgssmPrior {
     template <class R> static __device__ __forceinline__ void init(R mean, R sd, R z, R* x) { x[0] = mean + sd * z; }
     template <class R> static __device__ __forceinline__ void pair_child(const Theta<R>& t, const R* xn, R& b, R& a) { SvmPrior::pair_child(t, xn, b, a); }
     template <class R> static __device__ __forceinline__ void pair_parent(const Theta<R>& t, const R* xa, R& u, R& gq, R* m) { SvmPrior::pair_parent(t, xa, u, gq, m); }
+    template <class R> static __device__ __forceinline__ R pair_bound(const Theta<R>& t, const R* xn) { return (R)0; }
     // lgssm/helper.py:1270-1277 with x_j -> its moments
     template <class R> static __device__ __forceinline__ void score_moments(const Theta<R>& t, const R* Em, const R* xn, R y, R* h) {
         h[3] = t.Qinv * (xn[0] * Em[0] - t.A * Em[1]);
@@ -287,6 +292,14 @@ struct GarchPrior {
         gq = (R)-0.5 * Mth<R>::log(s2) - (R)(0.5 * LOG_2PI_D) - t.ltmax;
         const R xa2 = xa[0] * xa[0];
         m[0] = -t.mu + t.lam * xa2 + ((R)1 - t.lam) * xa[1]; m[1] = xa2 - xa[1];
+    }
+    // sup over s2 >= alpha of  -0.5 x'^2 / s2 - 0.5 log(s2 / alpha)  is attained at s2 = max(x'^2, alpha): for a child
+    // in the tails the global maximum (s2 = alpha, x' = 0; garch/kernels.py:131-133) under-estimates the acceptance
+    // probability by a factor exp(x'^2 / (2 alpha))-ish, which is what makes plain accept-reject stall there.
+    template <class R> static __device__ __forceinline__ R pair_bound(const Theta<R>& t, const R* xn) {
+        const R x2 = xn[0] * xn[0];
+        const R s2 = x2 > t.alpha ? x2 : t.alpha;
+        return (R)-0.5 * x2 * Mth<R>::rcp(s2) - (R)0.5 * Mth<R>::log(s2 * Mth<R>::rcp(t.alpha));
     }
     // garch/helper.py:350-372 with the candidate parent's terms replaced by their moments
     template <class R> static __device__ __forceinline__ void score_moments(const Theta<R>& t, const R* Em, const R* xn, R y, R* h) {

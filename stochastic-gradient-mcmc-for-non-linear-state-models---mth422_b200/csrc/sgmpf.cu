@@ -115,7 +115,10 @@ int run_impl(const sgm_pf_desc* d, cudaStream_t stream) {
     a.pf = d->pf; a.rng_mode = d->rng_mode; a.resample = d->resample; a.stat_kind = d->stat_kind;
     a.Ntilde = d->Ntilde; a.accept_reject = d->accept_reject;
     const double l10 = log10((double)a.N / 10.0);
-    a.max_ar = d->max_accept_reject >= 0 ? d->max_accept_reject : (int)(100.0 * l10);        // pf.py:284-285
+    // pf.py:284-285.  With device randoms the cap is only a cost knob (both the accept-reject and the exact sampler
+    // draw from the backward kernel exactly), so the default is the kernel's own budget (PARIS_CAP proposals).
+    a.max_ar = d->max_accept_reject >= 0 ? d->max_accept_reject
+                                         : (d->rng_mode == SGM_RNG_PHILOX ? PARIS_CAP : (int)(100.0 * l10));
     a.manual_thresh = d->manual_sample_threshold >= 0 ? d->manual_sample_threshold : (int)(10.0 * l10);  // pf.py:286-287
     if (a.max_ar < 0) a.max_ar = 0;
     a.need_lw = (backward_pf(d->pf) || d->out_lw || d->trace_lw || d->stat_kind == SGM_STAT_PRED) ? 1 : 0;
