@@ -234,16 +234,20 @@ __device__ __forceinline__ void warp_tile_epilogue(const R* lwn, int tile_base, 
     __syncwarp();
     double ws[4] = {0.0, 0.0, 0.0, 0.0};
     if (need_ws) {
+        // weighted statistic sums of the tile (Nemeth shrinkage, filter statistic, final average): summed in R within
+        // the tile (256 terms with weights <= 1), in f64 across tiles (header kernel)
+        R wl[4] = {(R)0, (R)0, (R)0, (R)0};
 #pragma unroll
         for (int c = 0; c < KPT; ++c) {
             const int i = tile_base + 32 * c + lane;
             if (i < N) {
                 R r[W];
                 load_rec<R, W>(rec_new, tail_new, item_off + i, r);
-                for (int q = 0; q < nws; ++q) ws[q] += (double)(r[q] * w[c]);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) if (q < nws) wl[q] += r[q] * w[c];
             }
         }
-        for (int q = 0; q < nws; ++q) ws[q] = warp_sum(ws[q]);
+        for (int q = 0; q < nws; ++q) ws[q] = (double)warp_sum(wl[q]);
     }
     if (lane == 0) {
         sub_out[0] = (double)m;
