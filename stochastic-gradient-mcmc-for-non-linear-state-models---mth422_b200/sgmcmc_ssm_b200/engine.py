@@ -453,7 +453,8 @@ class PreparedPF(object):
                 self.desc.ev_steps_begin = self.desc.ev_steps_end = None
                 self.launch()                                   # warm-up outside the capture (module load, checks)
                 graph = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(graph):
+                # thread_local: other threads of the process (e.g. the NCCL watchdog under torchrun) may touch CUDA
+                with torch.cuda.graph(graph, capture_error_mode="thread_local"):
                     self.launch()
                 if len(_GRAPHS) >= 32:
                     _GRAPHS.pop(next(iter(_GRAPHS)))
