@@ -45,7 +45,7 @@ enum { SGM_KERNEL_PRIOR = 0, SGM_KERNEL_OPTIMAL = 1 };
 enum { SGM_PF_NEMETH = 0, SGM_PF_POY_N2 = 1, SGM_PF_PARIS = 2, SGM_PF_FILTER = 3 };
 /* arithmetic / storage type of the particle arrays */
 enum { SGM_F32 = 0, SGM_F64 = 1 };
-/* random numbers: device Philox4x32-10, or arrays recorded from the reference's numpy stream */
+/* random numbers: device Philox4x32-7, or arrays recorded from the reference's numpy stream */
 enum { SGM_RNG_PHILOX = 0, SGM_RNG_INJECTED = 1 };
 /* resampling scheme.  MULTINOMIAL = reference semantics (pf.py:27-29; iid uniforms, child i gets
  * searchsorted(cdf, u_i, 'right')).  MULTINOMIAL_SORTED draws the *order statistics* of N iid
@@ -73,7 +73,9 @@ enum { SGM_OK = 0, SGM_ERR_INVALID = -1, SGM_ERR_UNSUPPORTED = -2, SGM_ERR_WORKS
 /* per-item status bits (device int32) */
 enum { SGM_STATUS_NAN_WEIGHT = 1,   /* NaN / +inf log-weight: np.random.choice would raise ValueError */
        SGM_STATUS_ZERO_WEIGHT = 2,  /* all weights underflowed                                         */
-       SGM_STATUS_AR_OVERFLOW = 4 };/* PaRIS accept-reject hit max_accept_reject (exact fallback used) */
+       SGM_STATUS_AR_OVERFLOW = 4 };/* PaRIS, INJECTED mode: accept-reject hit max_accept_reject with more than
+                                     * manual_sample_threshold entries left (the reference's warning, pf.py:326-327).
+                                     * With device randoms the exact fallback is part of normal operation: no flag. */
 
 #define SGM_THETA_STRIDE 12
 /* theta layout (doubles, values exactly as the reference Parameters object computes them):
@@ -89,7 +91,8 @@ typedef struct sgm_pf_desc {
     int32_t max_T;                 /* max over items of T_buf                                       */
     int32_t Ntilde;                /* PaRIS backward samples per particle (pf.py:185)               */
     int32_t accept_reject;         /* PaRIS: 1 = accept-reject (default), 0 = naive O(N^2)          */
-    int32_t max_accept_reject;     /* <0: int(100*log10(N/10)) (pf.py:284-285)                      */
+    int32_t max_accept_reject;     /* <0: int(100*log10(N/10)) (pf.py:284-285) in INJECTED mode, the kernel's own
+                                    * proposal budget (512) with device randoms (a cost knob, not part of the law) */
     int32_t manual_sample_threshold; /* <0: int(10*log10(N/10)) (pf.py:286-287); INJECTED mode only */
     int32_t item_id_base;          /* global index of item 0 (keeps Philox streams rank-invariant)  */
     int32_t n2_mode;               /* O(N^2) smoother: SGM_N2_AUTO / SGM_N2_FP32_PIPE / SGM_N2_TENSOR */
