@@ -74,7 +74,7 @@ enum { SGM_OK = 0, SGM_ERR_INVALID = -1, SGM_ERR_UNSUPPORTED = -2, SGM_ERR_WORKS
 enum { SGM_STATUS_NAN_WEIGHT = 1,   /* NaN / +inf log-weight: np.random.choice would raise ValueError */
        SGM_STATUS_ZERO_WEIGHT = 2,  /* all weights underflowed                                         */
        SGM_STATUS_AR_OVERFLOW = 4 };/* PaRIS, INJECTED mode: accept-reject hit max_accept_reject with more than
-                                     * manual_sample_threshold entries left (the reference's warning, pf.py:326-327).
+                                     * manual_sample_threshold entries left (pf.py:326: a commented-out diagnostic in the reference).
                                      * With device randoms the exact fallback is part of normal operation: no flag. */
 
 #define SGM_THETA_STRIDE 12
