@@ -570,7 +570,10 @@ __device__ __forceinline__ void exact_backward_sample(const KArgs& a, const type
 //                        L, pf.py:292-325), so threads never idle behind one unlucky child.
 //   paris_exact_kernel : one WARP per leftover entry, two passes over the parents (total, then the crossing).
 constexpr int PARIS_CH = 1024;         // children per CTA of the accept-reject kernel
-constexpr int PARIS_CAP = 512;         // proposals per entry before it falls back to the exact sampler (x Ntilde <= 8 fits the 12-bit Philox sub-counter)
+#ifndef SGM_PARIS_CAP
+#define SGM_PARIS_CAP 512
+#endif
+constexpr int PARIS_CAP = SGM_PARIS_CAP;   // proposals per entry before it falls back to the exact sampler (x Ntilde <= 8 fits the 12-bit Philox sub-counter)
 constexpr int PARIS_MAXQ = 4096;       // queue capacity >= children per CTA * Ntilde (Ntilde > 4: fewer children per CTA)
 
 template <class R, class Model>
@@ -654,8 +657,13 @@ __global__ void __launch_bounds__(NT) paris_ar_kernel(KArgs a, int t, int ch) {
                 if (!(target < total)) target = total * (1.0 - 1.2e-16);
                 const int kb = min((int)(u * (double)N), N - 1);
                 I = guide[kb];
-                const int hi = guide[kb + 1];
-                while (I < hi && cdf[I] <= target) ++I;           // first particle whose cumulative mass exceeds the target
+                int hi = guide[kb + 1];
+                // first particle in [guide[kb], guide[kb + 1]] whose cumulative mass exceeds the target: usually 0-2
+                // bisections; a bucket holds many particles only where the weights are tiny (degenerate steps)
+                while (I < hi) {
+                    const int mid = (I + hi) >> 1;
+                    if (cdf[mid] <= target) I = mid + 1; else hi = mid;
+                }
                 const Vec4T<R> pk = pkey[I];
                 const R thr = Mth<R>::exp(s_x[0][k] * pk.x + pk.y + s_x[1][k]);        // q(x'_i | x_I) / (per-child bound)
                 ok = (R)u01d(raw.z, raw.w) <= thr;
@@ -715,9 +723,18 @@ __global__ void __launch_bounds__(NT) paris_exact_kernel(KArgs a, int t) {
         for (int sg = 0; sg < nseg; ++sg) {
             R loc = (R)0;
             const int jend = min(N, (sg + 1) * PSEG);
-            for (int j = sg * PSEG + lane; j < jend; j += 32) {
-                const Vec4T<R> pk = pkey[j];
-                loc += Mth<R>::exp(bb * pk.x + pk.y + pk.z + aa);
+            if (jend - sg * PSEG == PSEG) {
+                // full segment: 8 independent key loads in flight per lane (one entry alone is latency-bound otherwise)
+#pragma unroll 8
+                for (int j = sg * PSEG + lane; j < (sg + 1) * PSEG; j += 32) {
+                    const Vec4T<R> pk = pkey[j];
+                    loc += Mth<R>::exp(bb * pk.x + pk.y + pk.z + aa);
+                }
+            } else {
+                for (int j = sg * PSEG + lane; j < jend; j += 32) {
+                    const Vec4T<R> pk = pkey[j];
+                    loc += Mth<R>::exp(bb * pk.x + pk.y + pk.z + aa);
+                }
             }
             const double st = warp_sum((double)loc);
             if (lane == 0) seg[sg] = st;
