@@ -12,13 +12,13 @@ template <> struct Mth<float> {
     // single MUFU instructions (flush-to-zero, ~2 ulp): the f32 path is the throughput path; the f64
     // instantiation below is the parity path
     static __device__ __forceinline__ float exp(float x) {
-        float r; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x * 1.4426950408889634f)); return r;
+        float r; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(__fmul_rn(x, 1.4426950408889634f))); return r;
     }
     static __device__ __forceinline__ float exp2(float x) {
         float r; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r;
     }
     static __device__ __forceinline__ float log(float x) {
-        float r; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r * 0.6931471805599453f;
+        float r; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return __fmul_rn(r, 0.6931471805599453f);
     }
     static __device__ __forceinline__ float sqrt(float x) {
         float r; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r;
@@ -27,6 +27,11 @@ template <> struct Mth<float> {
         float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r;
     }
     static __device__ __forceinline__ float inf() { return __int_as_float(0x7f800000); }
+    // explicitly rounded primitives: never contracted or re-associated by the compiler, so the particle system
+    // (and with it the genealogy) is bit-identical across the instantiations of a kernel
+    static __device__ __forceinline__ float fma(float a, float b, float c) { return __fmaf_rn(a, b, c); }
+    static __device__ __forceinline__ float mul(float a, float b) { return __fmul_rn(a, b); }
+    static __device__ __forceinline__ float add(float a, float b) { return __fadd_rn(a, b); }
 };
 template <> struct Mth<double> {
     static __device__ __forceinline__ double exp(double x) { return ::exp(x); }
@@ -35,6 +40,9 @@ template <> struct Mth<double> {
     static __device__ __forceinline__ double sqrt(double x) { return ::sqrt(x); }
     static __device__ __forceinline__ double rcp(double x) { return 1.0 / x; }
     static __device__ __forceinline__ double inf() { return __longlong_as_double(0x7ff0000000000000LL); }
+    static __device__ __forceinline__ double fma(double a, double b, double c) { return __fma_rn(a, b, c); }
+    static __device__ __forceinline__ double mul(double a, double b) { return __dmul_rn(a, b); }
+    static __device__ __forceinline__ double add(double a, double b) { return __dadd_rn(a, b); }
 };
 
 constexpr double LOG_2PI_D = 1.8378770664093453;
@@ -62,12 +70,14 @@ struct SvmPrior {
     }
     // svm/kernels.py:34-37
     template <class R> static __device__ __forceinline__ void propagate(const Theta<R>& t, const R* xa, R y, R z, R* xn) {
-        xn[0] = t.invLQ * z + xa[0] * t.A;
+        xn[0] = Mth<R>::fma(t.invLQ, z, Mth<R>::mul(xa[0], t.A));
     }
     // svm/kernels.py:57-62
     template <class R> static __device__ __forceinline__ R log_weight(const Theta<R>& t, const R* xa, const R* xn, R y) {
         // terms that do not depend on the particle first, so that they are shared by the 8 particles of a lane
-        return (((R)-0.5 * t.Rinv) * (y * y)) * Mth<R>::exp(-xn[0]) + ((R)-0.5 * xn[0] + ((R)(-0.5 * LOG_2PI_D) + t.logLRinv));
+        const R k = Mth<R>::mul(Mth<R>::mul((R)-0.5, t.Rinv), Mth<R>::mul(y, y));
+        const R c0 = Mth<R>::add((R)(-0.5 * LOG_2PI_D), t.logLRinv);
+        return Mth<R>::fma(k, Mth<R>::exp(-xn[0]), Mth<R>::fma((R)-0.5, xn[0], c0));
     }
     // svm/helper.py:342-348 ; order [dLRinv, dLQinv, dA]
     template <class R> static __device__ __forceinline__ void score(const Theta<R>& t, const R* xa, const R* xn, R y, R* h) {
@@ -153,12 +163,12 @@ struct LgssmPrior {
     }
     // lgssm/kernels.py:29-33
     template <class R> static __device__ __forceinline__ void propagate(const Theta<R>& t, const R* xa, R y, R z, R* xn) {
-        xn[0] = t.invLQ * z + xa[0] * t.A;
+        xn[0] = Mth<R>::fma(t.invLQ, z, Mth<R>::mul(xa[0], t.A));
     }
     // lgssm/kernels.py:58-62
     template <class R> static __device__ __forceinline__ R log_weight(const Theta<R>& t, const R* xa, const R* xn, R y) {
-        const R d = y - t.C * xn[0];
-        return (R)(-0.5 * LOG_2PI_D) + (R)-0.5 * (d * d) * t.Rinv + t.logLRinv;
+        const R d = Mth<R>::fma(-t.C, xn[0], y);
+        return Mth<R>::add(Mth<R>::fma(Mth<R>::mul((R)-0.5, Mth<R>::mul(d, d)), t.Rinv, (R)(-0.5 * LOG_2PI_D)), t.logLRinv);
     }
     // lgssm/helper.py:1270-1277 ; order [dLRinv, dLQinv, dC, dA]
     template <class R> static __device__ __forceinline__ void score(const Theta<R>& t, const R* xa, const R* xn, R y, R* h) {
@@ -207,13 +217,14 @@ struct LgssmPrior {
 struct LgssmOptimal : LgssmPrior {
     // lgssm/kernels.py:87-97
     template <class R> static __device__ __forceinline__ void propagate(const Theta<R>& t, const R* xa, R y, R z, R* xn) {
-        const R mp = xa[0] * t.A * t.Qinv + y * t.C * t.Rinv;
-        xn[0] = t.opt_sd * z + mp * t.opt_iprec;
+        const R mp = Mth<R>::fma(Mth<R>::mul(xa[0], t.A), t.Qinv, Mth<R>::mul(Mth<R>::mul(y, t.C), t.Rinv));
+        xn[0] = Mth<R>::fma(t.opt_sd, z, Mth<R>::mul(mp, t.opt_iprec));
     }
     // lgssm/kernels.py:117-120 (ignores C, as the reference does)
     template <class R> static __device__ __forceinline__ R log_weight(const Theta<R>& t, const R* xa, const R* xn, R y) {
-        const R d = y - t.A * xa[0];
-        return (R)-0.5 * (d * d) * t.opt_ivar - (R)(0.5 * LOG_2PI_D) - (R)0.5 * t.opt_lvar;
+        const R d = Mth<R>::fma(-t.A, xa[0], y);
+        const R c0 = Mth<R>::fma((R)-0.5, t.opt_lvar, (R)(-0.5 * LOG_2PI_D));
+        return Mth<R>::fma(Mth<R>::mul((R)-0.5, Mth<R>::mul(d, d)), t.opt_ivar, c0);
     }
 };
 
@@ -236,18 +247,18 @@ struct GarchPrior {
         return t;
     }
     template <class R> static __device__ __forceinline__ R sigma2_next(const Theta<R>& t, const R* xa) {
-        return t.alpha + t.beta * (xa[0] * xa[0]) + t.gamma * xa[1];
+        return Mth<R>::fma(t.gamma, xa[1], Mth<R>::fma(t.beta, Mth<R>::mul(xa[0], xa[0]), t.alpha));
     }
     // garch/kernels.py:60-68
     template <class R> static __device__ __forceinline__ void propagate(const Theta<R>& t, const R* xa, R y, R z, R* xn) {
         const R s2 = sigma2_next(t, xa);
-        xn[0] = Mth<R>::sqrt(s2) * z;
+        xn[0] = Mth<R>::mul(Mth<R>::sqrt(s2), z);
         xn[1] = s2;
     }
     // garch/kernels.py:82-89
     template <class R> static __device__ __forceinline__ R log_weight(const Theta<R>& t, const R* xa, const R* xn, R y) {
-        const R d = y - xn[0];
-        return (R)(-0.5 * LOG_2PI_D) + (R)-0.5 * (d * d) * t.Rinv + t.logLRinv;
+        const R d = Mth<R>::add(y, -xn[0]);
+        return Mth<R>::add(Mth<R>::fma(Mth<R>::mul((R)-0.5, Mth<R>::mul(d, d)), t.Rinv, (R)(-0.5 * LOG_2PI_D)), t.logLRinv);
     }
     // garch/helper.py:350-372 ; order [dLRinv, dlog_mu, dlogit_phi, dlogit_lambduh]
     template <class R> static __device__ __forceinline__ void score(const Theta<R>& t, const R* xa, const R* xn, R y, R* h) {
@@ -333,15 +344,16 @@ struct GarchOptimal : GarchPrior {
     // garch/kernels.py:147-158
     template <class R> static __device__ __forceinline__ void propagate(const Theta<R>& t, const R* xa, R y, R z, R* xn) {
         const R s2 = sigma2_next(t, xa);
-        const R var = Mth<R>::rcp(t.Rinv + Mth<R>::rcp(s2));
-        const R mean = var * (y * t.Rinv);
-        xn[0] = mean + Mth<R>::sqrt(var) * z;
+        const R var = Mth<R>::rcp(Mth<R>::add(t.Rinv, Mth<R>::rcp(s2)));
+        const R mean = Mth<R>::mul(var, Mth<R>::mul(y, t.Rinv));
+        xn[0] = Mth<R>::fma(Mth<R>::sqrt(var), z, mean);
         xn[1] = s2;
     }
     // garch/kernels.py:172-180
     template <class R> static __device__ __forceinline__ R log_weight(const Theta<R>& t, const R* xa, const R* xn, R y) {
-        const R var = xn[1] + t.Rv;
-        return (R)(-0.5 * LOG_2PI_D) + (R)-0.5 * (y * y) * Mth<R>::rcp(var) + (R)-0.5 * Mth<R>::log(var);
+        const R var = Mth<R>::add(xn[1], t.Rv);
+        const R q = Mth<R>::fma(Mth<R>::mul((R)-0.5, Mth<R>::mul(y, y)), Mth<R>::rcp(var), (R)(-0.5 * LOG_2PI_D));
+        return Mth<R>::fma((R)-0.5, Mth<R>::log(var), q);
     }
 };
 

@@ -479,7 +479,7 @@ __global__ void __launch_bounds__(NT) pf_header_kernel(KArgs a, int t, int final
 // ---- gather parents -> propagate -> reweight -> statistic update -> store (pf.py:30-36, 168-179) -----
 // Row c of the warp tile = particles tile_base + 32 c + lane: coalesced stores, and with ascending
 // ancestors the parent gathers of a row are (nearly) contiguous too.
-template <class R, class Model>
+template <class R, class Model, bool FAST = false>
 __device__ __forceinline__ void propagate_store(const KArgs& a, int b, int t, int par, int tile_base, int lane, size_t item_off,
                                                 const int* anc, const R* z, const ItemHdr& hdr, int nws,
                                                 bool carries, bool shrink, R* lwn,
@@ -490,14 +490,14 @@ __device__ __forceinline__ void propagate_store(const KArgs& a, int b, int t, in
     const R lam = (R)a.lambduh;
     R sbar[4] = {(R)0, (R)0, (R)0, (R)0};
     if (shrink) for (int q = 0; q < nws; ++q) sbar[q] = (R)((1.0 - a.lambduh) * hdr.base[H_SBAR + q]);
-    const bool tracing = a.need_lw || a.trace_anc || a.trace_x || a.trace_lw;
+    const bool tracing = !FAST && (a.need_lw || a.trace_anc || a.trace_x || a.trace_lw);
     // new statistic = keep * parent statistic + sbar + h * hs   (one FMA chain for every smoother):
     //   Poyiadjis O(N)/Nemeth: keep = lambduh, hs = w_t (pf.py:175-179); filter: keep = 0, hs = w_t
     //   (pf.py:70-71); O(N^2)/PaRIS: keep = hs = 0 (the backward kernel writes the statistic)
     const R keep = carries ? (shrink ? lam : (R)1) : (R)0;
-    const R hs = (carries || a.pf == SGM_PF_FILTER) ? wt : (R)0;
-    const int stat_kind = (in_sub && hs != (R)0) ? a.stat_kind : SGM_STAT_NONE;
-    const bool plain = carries && !shrink;
+    const R hs = (FAST || carries || a.pf == SGM_PF_FILTER) ? wt : (R)0;
+    const int stat_kind = (in_sub && hs != (R)0) ? (FAST ? (int)SGM_STAT_SCORE : a.stat_kind) : (int)SGM_STAT_NONE;
+    const bool plain = FAST || (carries && !shrink);
     // per-item base pointers: the particle index stays a 32-bit register (one IMAD.WIDE per address)
     const void* rec_old = reinterpret_cast<const Vec4T<R>*>(a.rec[par]) + item_off;
     const void* tail_old = reinterpret_cast<const R*>(a.tail[par]) + item_off * (W - 4);
@@ -511,12 +511,12 @@ __device__ __forceinline__ void propagate_store(const KArgs& a, int b, int t, in
         R ra[GB][W];
 #pragma unroll
         for (int c = 0; c < GB; ++c)                      // GB independent parent gathers in flight
-            if (tile_base + 32 * (h0 + c) + lane < N) load_rec<R, W>(rec_old, tail_old, anc[h0 + c], ra[c]);
+            if (FAST || tile_base + 32 * (h0 + c) + lane < N) load_rec<R, W>(rec_old, tail_old, anc[h0 + c], ra[c]);
 #pragma unroll
         for (int c4 = 0; c4 < GB; ++c4) {
             const int c = h0 + c4, i = tile_base + 32 * c + lane;
             lwn[c] = -Mth<R>::inf();
-            if (i < N) {
+            if (FAST || i < N) {
                 R rn[W];
                 Model::propagate(th, ra[c4] + NP, y, z[c], rn + NP);
                 lwn[c] = Model::log_weight(th, ra[c4] + NP, rn + NP, y);
@@ -589,8 +589,13 @@ __device__ __forceinline__ void search_levels(uint32_t* ad, const R* rt) {
 //   [lo, hi]: a paired warp-cooperative search finds it, the CDF of the range is staged in the warp's slice
 //   of shared memory in global units, each child binary-searches that slice (8 interleaved searches per
 //   lane, neighbouring lanes read neighbouring words), and parent records are gathered as a stream.
-template <class R, class Model, bool SORTED>
+// FAST = the production configuration, checked by the host before it picks this instantiation: device randoms,
+// order-statistics resampling, Poyiadjis O(N) (lambduh = 1) with the model score, N a multiple of 256, no traces /
+// exported log-weights.  It only turns the run-time flags below into constants (fewer uniform branches, constant
+// loads and bound checks: ~9 % of the generic kernel's instructions); the arithmetic is identical.
+template <class R, class Model, bool SORTED, bool FAST = false>
 __device__ __forceinline__ void step_body(const KArgs& a, int b, int t, int q_me, int lane, R* s_cdf) {
+    static_assert(!FAST || SORTED, "FAST implies sorted resampling");
     R* const s_tr = s_cdf;                 // the warp's shared-memory slice doubles as the scan transposition buffer
     constexpr int NP = Model::NP, W = Model::NX + NP;
     const int N = a.N, par = t & 1;
@@ -604,17 +609,18 @@ __device__ __forceinline__ void step_body(const KArgs& a, int b, int t, int q_me
     const R* ywp = reinterpret_cast<const R*>(a.yw) + ((size_t)b * a.max_T + min(t, a.max_T - 1)) * 2;
     const R y_t = ywp[0], w_t = ywp[1];
     const typename Model::template Theta<R> th = load_thc<R, Model>(a, b);
-    const bool spacings = SORTED && uses_spacings(a);
+    const bool spacings = FAST || (SORTED && uses_spacings(a));
+    const bool injected = !FAST && a.rng_mode == SGM_RNG_INJECTED;
     const double gam_lo = spacings ? hdr.gam[q_me] : 0.0;
     const double gam_hi = spacings ? hdr.gam[q_me + 1] : 0.0;
     if (t >= Tb) return;
     const size_t item_off = (size_t)b * N;
-    const int nws = stat_width<Model>(a.stat_kind);
-    const bool carries = (a.pf == SGM_PF_NEMETH);            // stats follow the resampled genealogy here
-    const bool shrink = carries && (a.lambduh != 1.0);
+    const int nws = FAST ? NP : stat_width<Model>(a.stat_kind);
+    const bool carries = FAST || (a.pf == SGM_PF_NEMETH);    // stats follow the resampled genealogy here
+    const bool shrink = !FAST && carries && (a.lambduh != 1.0);
     const R* fine_old = reinterpret_cast<const R*>(a.fine[par]) + (size_t)b * a.Q * WT;      // padded to whole tiles
     const int tile_base = q_me * WT;
-    const int n_valid = min(WT, N - tile_base);
+    const int n_valid = FAST ? WT : min(WT, N - tile_base);
     const RngKey key = item_key(a, b);
     const double total = hdr.total;
     const double tmax = total * (1.0 - 1.2e-16);
@@ -678,7 +684,7 @@ __device__ __forceinline__ void step_body(const KArgs& a, int b, int t, int q_me
             lane_major_incl_scan<R>(u, etot);
             const R inv = Mth<R>::rcp(etot);
 #pragma unroll
-            for (int k = 0; k < KPT; ++k) u[k] *= inv;
+            for (int k = 0; k < KPT; ++k) u[k] = Mth<R>::mul(u[k], inv);
             __syncwarp();
             store_lane_major<R>(s_tr, lane, u);
             __syncwarp();
@@ -686,7 +692,7 @@ __device__ __forceinline__ void step_body(const KArgs& a, int b, int t, int q_me
             for (int c = 0; c < KPT; ++c) u[c] = s_tr[32 * c + lane];
             tA = gam_lo; tB = gam_hi - gam_lo;
         } else {
-            if (a.rng_mode == SGM_RNG_INJECTED) {
+            if (injected) {
 #pragma unroll
                 for (int c = 0; c < KPT; ++c) u[c] = (R)0;            // targets come from inj_u (target_of)
             } else if (a.resample == SGM_RESAMPLE_SYSTEMATIC) {
@@ -703,7 +709,7 @@ __device__ __forceinline__ void step_body(const KArgs& a, int b, int t, int q_me
         auto target_of = [&](int c) -> double {
             double tg;
             const int i = tile_base + 32 * c + lane;
-            if (a.rng_mode == SGM_RNG_INJECTED) tg = (i < N) ? a.inj_u[((size_t)b * a.max_T + t) * N + i] * total : 0.0;
+            if (injected) tg = (i < N) ? a.inj_u[((size_t)b * a.max_T + t) * N + i] * total : 0.0;
             else if (spacings) tg = tA + tB * (double)u[c];
             else tg = tA + tB * ((double)(32 * c + lane) + (double)u[c]);
             return (tg < total) ? tg : tmax;
@@ -711,7 +717,7 @@ __device__ __forceinline__ void step_body(const KArgs& a, int b, int t, int q_me
         // ---- parent tiles of this warp tile: first child = (row 0, lane 0), last = particle n_valid - 1 ----
         const int last = n_valid - 1, l_last = last & 31, c_last = last >> 5;
         double tf, tl;
-        if (a.rng_mode == SGM_RNG_INJECTED) {
+        if (injected) {
             const double* iu = a.inj_u + ((size_t)b * a.max_T + t) * N + tile_base;
             tf = iu[0] * total; tl = iu[last] * total;
         } else {
@@ -764,8 +770,8 @@ __device__ __forceinline__ void step_body(const KArgs& a, int b, int t, int q_me
 #pragma unroll
                             for (int h = 0; h < 2; ++h) {
                                 Vec4T<R> v;
-                                v.x = o[j] + f[j][h].x * sc[j]; v.y = o[j] + f[j][h].y * sc[j];
-                                v.z = o[j] + f[j][h].z * sc[j]; v.w = o[j] + f[j][h].w * sc[j];
+                                v.x = Mth<R>::fma(f[j][h].x, sc[j], o[j]); v.y = Mth<R>::fma(f[j][h].y, sc[j], o[j]);
+                                v.z = Mth<R>::fma(f[j][h].z, sc[j], o[j]); v.w = Mth<R>::fma(f[j][h].w, sc[j], o[j]);
                                 dst[(j0 + j) * (WT / 4) + 32 * h + lane] = v;
                             }
                         }
@@ -774,13 +780,14 @@ __device__ __forceinline__ void step_body(const KArgs& a, int b, int t, int q_me
             }
             __syncwarp();
             R rt[KPT];
-            if (a.rng_mode == SGM_RNG_INJECTED) {
+            if (injected) {
 #pragma unroll
                 for (int c = 0; c < KPT; ++c) rt[c] = (R)(target_of(c) - cbase);
             } else {
                 const R rA = (R)(tA - cbase), rB = (R)tB;
 #pragma unroll
-                for (int c = 0; c < KPT; ++c) rt[c] = spacings ? (rA + rB * u[c]) : (rA + rB * ((R)(32 * c + lane) + u[c]));
+                for (int c = 0; c < KPT; ++c)
+                    rt[c] = spacings ? Mth<R>::fma(rB, u[c], rA) : Mth<R>::fma(rB, Mth<R>::add((R)(32 * c + lane), u[c]), rA);
             }
             // 8 independent branch-free binary searches per lane, interleaved; #{k : s_cdf[k] <= rt} is kept as a
             // shared-memory byte address: LDS [addr + immediate], compare, predicated add -- 3 instructions / level
@@ -808,8 +815,8 @@ __device__ __forceinline__ void step_body(const KArgs& a, int b, int t, int q_me
         }
     }
     R lwn[KPT];
-    propagate_store<R, Model>(a, b, t, par, tile_base, lane, item_off, anc, z, hdr, nws, carries, shrink, lwn, th, y_t, w_t);
-    const bool need_ws = (nws > 0) && (a.pf == SGM_PF_FILTER || shrink || (carries && t == Tb - 1));
+    propagate_store<R, Model, FAST>(a, b, t, par, tile_base, lane, item_off, anc, z, hdr, nws, carries, shrink, lwn, th, y_t, w_t);
+    const bool need_ws = (nws > 0) && ((!FAST && a.pf == SGM_PF_FILTER) || shrink || (carries && t == Tb - 1));
     warp_tile_epilogue<R, W>(lwn, tile_base, N, lane, reinterpret_cast<R*>(a.fine[par ^ 1]) + (size_t)b * a.Q * WT,
                              a.sub[par ^ 1] + ((size_t)b * a.Q + q_me) * SSTRIDE, a.rec[par ^ 1], a.tail[par ^ 1],
                              item_off, need_ws, nws, s_tr);
@@ -821,11 +828,11 @@ __device__ __forceinline__ void step_body(const KArgs& a, int b, int t, int q_me
 #define SGM_STEP_WARPS 8
 #endif
 constexpr int STEP_WARPS = SGM_STEP_WARPS;
-template <class R, class Model, bool SORTED>
+template <class R, class Model, bool SORTED, bool FAST = false>
 __global__ void __launch_bounds__(32 * STEP_WARPS, (sizeof(R) == 4 ? SGM_STEP_CTAS : 2 * 8 / STEP_WARPS)) pf_step_kernel(KArgs a, int t) {
     __shared__ __align__(32) R s_cdf_all[STEP_WARPS][SORTED ? WIN_BYTES / sizeof(R) : WT];
     const int warp = threadIdx.x >> 5;
-    step_body<R, Model, SORTED>(a, a.b0 + blockIdx.y, t, blockIdx.x * STEP_WARPS + warp, threadIdx.x & 31, s_cdf_all[warp]);
+    step_body<R, Model, SORTED, FAST>(a, a.b0 + blockIdx.y, t, blockIdx.x * STEP_WARPS + warp, threadIdx.x & 31, s_cdf_all[warp]);
 }
 
 // ---- fused kernel for small particle counts (N <= 2048: the item fits one CTA) -----------------------------

@@ -170,6 +170,10 @@ int run_impl(const sgm_pf_desc* d, cudaStream_t stream) {
         const bool piped = d->aux_stream && d->ev_aux_fork && d->ev_aux_join && !backward_pf(d->pf) && !pred &&
                            (int64_t)a.B * a.G >= 2 * 148 * 4 && a.B >= 2;
         const int nh = piped ? 2 : 1;
+        // the production configuration runs the step kernel with its run-time flags folded to constants
+        const bool fast_path = sizeof(R) == 4 && d->rng_mode == SGM_RNG_PHILOX && d->resample == SGM_RESAMPLE_MULTINOMIAL_SORTED &&
+                               d->pf == SGM_PF_NEMETH && d->lambduh == 1.0 && d->stat_kind == SGM_STAT_SCORE &&
+                               a.N % WT == 0 && !a.need_lw && !d->trace_anc && !d->trace_x && !d->trace_lw;
         cudaStream_t sh[2] = {stream, piped ? reinterpret_cast<cudaStream_t>(d->aux_stream) : stream};
         KArgs ah[2] = {a, a};
         int nb[2] = {piped ? a.B / 2 : a.B, piped ? a.B - a.B / 2 : 0};
@@ -185,6 +189,7 @@ int run_impl(const sgm_pf_desc* d, cudaStream_t stream) {
                 const dim3 gh((a.Q + STEP_WARPS - 1) / STEP_WARPS, nb[h]), bs(32 * STEP_WARPS);
                 pf_header_kernel<R, Model><<<nb[h], block, 0, sh[h]>>>(ah[h], t, 0); ++launches;
                 if (d->resample == SGM_RESAMPLE_MULTINOMIAL) pf_step_kernel<R, Model, false><<<gh, bs, 0, sh[h]>>>(ah[h], t);
+                else if (fast_path) pf_step_kernel<R, Model, true, true><<<gh, bs, 0, sh[h]>>>(ah[h], t);
                 else pf_step_kernel<R, Model, true><<<gh, bs, 0, sh[h]>>>(ah[h], t);
                 ++launches;
             }
