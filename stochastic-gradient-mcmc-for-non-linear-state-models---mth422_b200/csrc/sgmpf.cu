@@ -1,35 +1,31 @@
-// C-ABI entry points (include/sgmpf.h) and launch orchestration of the batched buffered particle
-// filter.  One sgm_pf_run() = init kernel + max_T step launches (+ backward kernels for the
-// O(N^2) / PaRIS smoothers) + final reduce, all asynchronous on the caller's stream.
-#include <cuda_runtime.h>
-#include <math.h>
-#include <stdio.h>
-#include <string.h>
-
-#include "../../include/sgmpf.h"
-#include "pf_kernels.cuh"
-#include "backward_kernels.cuh"
+// C-ABI entry points (include/sgmpf.h): descriptor validation, workspace layout, dtype dispatch.  The launch
+// orchestration (one sgm_pf_run() = init kernel + max_T step launches (+ backward kernels for the O(N^2) / PaRIS
+// smoothers) + final reduce, all asynchronous on the caller's stream) lives in run_impl.cuh and is instantiated per
+// arithmetic type in sgmpf_f32.cu / sgmpf_f64.cu.
+#include "host_common.cuh"
 #include "ksd_kernel.cuh"
 
 using namespace sgm;
 
 namespace {
 
+
 thread_local char g_err[512] = "";
 thread_local int64_t g_launches = 0;
 
-int fail(int code, const char* fmt, const char* extra = "") {
+}  // namespace
+
+namespace sgmhost {
+int fail(int code, const char* fmt, const char* extra) {
     snprintf(g_err, sizeof(g_err), fmt, extra);
     return code;
 }
+void set_launch_count(int64_t n) { g_launches = n; }
+}  // namespace sgmhost
 
-size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
+using namespace sgmhost;
 
-struct Layout {
-    size_t rec[2], tail[2], fine[2], lw[2], sub[2], hdr, acc, thc, yw, Jidx, Llist[2], counters, pcdf, pguide, pkey, n2part, total;
-};
-
-bool backward_pf(int pf) { return pf == SGM_PF_POY_N2 || pf == SGM_PF_PARIS; }
+namespace {
 
 int validate(const sgm_pf_desc* d) {
     if (!d) return fail(SGM_ERR_INVALID, "null descriptor");
@@ -67,10 +63,10 @@ int validate(const sgm_pf_desc* d) {
     return SGM_OK;
 }
 
-int state_dim(int model) { return model == SGM_MODEL_GARCH ? 2 : 1; }
-int score_dim(int model) { return model == SGM_MODEL_SVM ? 3 : 4; }
 
-Layout make_layout(const sgm_pf_desc* d) {
+}  // namespace
+
+Layout sgmhost::make_layout(const sgm_pf_desc* d) {
     Layout L;
     memset(&L, 0, sizeof(L));
     const size_t es = d->dtype == SGM_F64 ? 8 : 4;
@@ -102,127 +98,6 @@ Layout make_layout(const sgm_pf_desc* d) {
     L.total = off;
     return L;
 }
-
-template <class R, class Model>
-int run_impl(const sgm_pf_desc* d, cudaStream_t stream) {
-    const Layout L = make_layout(d);
-    if (!d->workspace || d->workspace_bytes < L.total) return fail(SGM_ERR_WORKSPACE, "workspace too small");
-    if (((uintptr_t)d->workspace & 255) != 0) return fail(SGM_ERR_WORKSPACE, "workspace must be 256-byte aligned");
-    char* ws = reinterpret_cast<char*>(d->workspace);
-    KArgs a;
-    memset(&a, 0, sizeof(a));
-    a.B = d->n_items; a.N = d->n_particles; a.G = (a.N + TILE - 1) / TILE; a.Q = (a.N + WT - 1) / WT; a.max_T = d->max_T;
-    a.pf = d->pf; a.rng_mode = d->rng_mode; a.resample = d->resample; a.stat_kind = d->stat_kind;
-    a.Ntilde = d->Ntilde; a.accept_reject = d->accept_reject;
-    const double l10 = log10((double)a.N / 10.0);
-    // pf.py:284-285.  With device randoms the cap is only a cost knob (both the accept-reject and the exact sampler
-    // draw from the backward kernel exactly), so the default is the kernel's own budget (PARIS_CAP proposals).
-    a.max_ar = d->max_accept_reject >= 0 ? d->max_accept_reject
-                                         : (d->rng_mode == SGM_RNG_PHILOX ? PARIS_CAP : (int)(100.0 * l10));
-    a.manual_thresh = d->manual_sample_threshold >= 0 ? d->manual_sample_threshold : (int)(10.0 * l10);  // pf.py:286-287
-    if (a.max_ar < 0) a.max_ar = 0;
-    a.need_lw = (backward_pf(d->pf) || d->out_lw || d->trace_lw || d->stat_kind == SGM_STAT_PRED) ? 1 : 0;
-    a.pred_K = d->pred_steps_ahead; a.pred_per_horizon = d->pred_per_horizon; a.inj_pred = d->inj_pred;
-    a.lambduh = d->lambduh;
-    a.key.k0 = (uint32_t)(d->seed & 0xffffffffu); a.key.k1 = (uint32_t)(d->seed >> 32);
-    a.key.item = (uint32_t)d->item_id_base;
-    a.offset_dev = d->offset_dev;
-    if (!d->offset_dev) { a.key.offset = (uint32_t)(d->offset & 0xffffffffu); a.key.k1 ^= (uint32_t)(d->offset >> 32); }
-    a.obs = d->obs; a.obs_off = d->obs_off; a.T_buf = d->T_buf; a.t1 = d->t1; a.tL = d->tL;
-    a.step_weights = d->step_weights; a.wts_off = d->step_weights ? d->wts_off : nullptr; a.theta = d->theta;
-    a.prior_mean = d->prior_mean; a.prior_var = d->prior_var;
-    a.inj_z0 = d->inj_z0; a.inj_u = d->inj_u; a.inj_z = d->inj_z; a.inj_extra = d->inj_extra; a.inj_extra_off = d->inj_extra_off;
-    for (int k = 0; k < 2; ++k) {
-        a.rec[k] = ws + L.rec[k]; a.tail[k] = ws + L.tail[k]; a.fine[k] = ws + L.fine[k]; a.lw[k] = ws + L.lw[k];
-        a.sub[k] = reinterpret_cast<double*>(ws + L.sub[k]);
-        if (d->pf == SGM_PF_PARIS) a.Llist[k] = reinterpret_cast<int32_t*>(ws + L.Llist[k]);
-    }
-    a.acc = reinterpret_cast<double*>(ws + L.acc);
-    a.hdr = reinterpret_cast<double*>(ws + L.hdr);
-    a.thc = ws + L.thc;
-    a.yw = ws + L.yw;
-    if (d->pf == SGM_PF_PARIS) {
-        a.Jidx = reinterpret_cast<int32_t*>(ws + L.Jidx);
-        a.counters = reinterpret_cast<int32_t*>(ws + L.counters);
-        a.pcdf = reinterpret_cast<double*>(ws + L.pcdf);
-        a.pguide = reinterpret_cast<int32_t*>(ws + L.pguide);
-        a.pkey = ws + L.pkey;
-    }
-    if (d->pf == SGM_PF_POY_N2) { a.n2part = ws + L.n2part; a.n2_tensor = n2_use_tensor(d->dtype, d->n2_mode) ? 1 : 0; }
-    a.grad = d->grad; a.loglik = d->loglik; a.status = d->status;
-    a.out_x = d->out_x; a.out_lw = d->out_lw; a.out_stats = d->out_stats;
-    a.trace_anc = d->trace_anc; a.trace_x = d->trace_x; a.trace_lw = d->trace_lw; a.trace_J = d->trace_J;
-
-    const dim3 grid(a.G, a.B), block(NT);
-    int64_t launches = 0;
-    const bool pred = d->stat_kind == SGM_STAT_PRED;
-    const bool fused = (a.Q <= NWARP) && !backward_pf(d->pf) && !pred;
-    if (fused) {
-        // small N: the whole time loop of an item in one launch (one CTA per item)
-        if (d->ev_steps_begin) cudaEventRecord(reinterpret_cast<cudaEvent_t>(d->ev_steps_begin), stream);
-        if (d->resample == SGM_RESAMPLE_MULTINOMIAL) pf_fused_kernel<R, Model, false><<<a.B, block, 0, stream>>>(a);
-        else pf_fused_kernel<R, Model, true><<<a.B, block, 0, stream>>>(a);
-        ++launches;
-        if (d->ev_steps_end) cudaEventRecord(reinterpret_cast<cudaEvent_t>(d->ev_steps_end), stream);
-    } else {
-        // Two-stream pipelining (O(N) smoothers, big batches): the halves alternate on `stream` / `aux_stream`, so
-        // the one-CTA-per-item header kernel and the launch gap of one half overlap the step kernel of the other.
-        const bool piped = d->aux_stream && d->ev_aux_fork && d->ev_aux_join && !backward_pf(d->pf) && !pred &&
-                           (int64_t)a.B * a.G >= 2 * 148 * 4 && a.B >= 2;
-        const int nh = piped ? 2 : 1;
-        // the production configuration runs the step kernel with its run-time flags folded to constants
-        const bool fast_path = sizeof(R) == 4 && d->rng_mode == SGM_RNG_PHILOX && d->resample == SGM_RESAMPLE_MULTINOMIAL_SORTED &&
-                               d->pf == SGM_PF_NEMETH && d->lambduh == 1.0 && d->stat_kind == SGM_STAT_SCORE &&
-                               a.N % WT == 0 && !a.need_lw && !d->trace_anc && !d->trace_x && !d->trace_lw;
-        cudaStream_t sh[2] = {stream, piped ? reinterpret_cast<cudaStream_t>(d->aux_stream) : stream};
-        KArgs ah[2] = {a, a};
-        int nb[2] = {piped ? a.B / 2 : a.B, piped ? a.B - a.B / 2 : 0};
-        ah[1].b0 = nb[0];
-        if (piped) {
-            cudaEventRecord(reinterpret_cast<cudaEvent_t>(d->ev_aux_fork), stream);
-            cudaStreamWaitEvent(sh[1], reinterpret_cast<cudaEvent_t>(d->ev_aux_fork), 0);
-        }
-        for (int h = 0; h < nh; ++h) { pf_init_kernel<R, Model><<<dim3(a.G, nb[h]), block, 0, sh[h]>>>(ah[h]); ++launches; }
-        if (d->ev_steps_begin) cudaEventRecord(reinterpret_cast<cudaEvent_t>(d->ev_steps_begin), stream);
-        for (int t = 0; t < a.max_T; ++t) {
-            for (int h = 0; h < nh; ++h) {
-                const dim3 gh((a.Q + STEP_WARPS - 1) / STEP_WARPS, nb[h]), bs(32 * STEP_WARPS);
-                pf_header_kernel<R, Model><<<nb[h], block, 0, sh[h]>>>(ah[h], t, 0); ++launches;
-                if (d->resample == SGM_RESAMPLE_MULTINOMIAL) pf_step_kernel<R, Model, false><<<gh, bs, 0, sh[h]>>>(ah[h], t);
-                else if (fast_path) pf_step_kernel<R, Model, true, true><<<gh, bs, 0, sh[h]>>>(ah[h], t);
-                else pf_step_kernel<R, Model, true><<<gh, bs, 0, sh[h]>>>(ah[h], t);
-                ++launches;
-            }
-            if (pred) { pf_pred_kernel<R, Model><<<a.B, block, 0, stream>>>(a, t); ++launches; }
-            if (d->pf == SGM_PF_POY_N2) launches += launch_poyiadjis_n2<R, Model>(a, t, stream);
-            else if (d->pf == SGM_PF_PARIS) launches += launch_paris<R, Model>(a, t, stream);
-        }
-        for (int h = 0; h < nh; ++h) { pf_header_kernel<R, Model><<<nb[h], block, 0, sh[h]>>>(ah[h], a.max_T, 1); ++launches; }
-        if (piped) {
-            cudaEventRecord(reinterpret_cast<cudaEvent_t>(d->ev_aux_join), sh[1]);
-            cudaStreamWaitEvent(stream, reinterpret_cast<cudaEvent_t>(d->ev_aux_join), 0);
-        }
-        if (d->ev_steps_end) cudaEventRecord(reinterpret_cast<cudaEvent_t>(d->ev_steps_end), stream);
-    }
-    if (d->out_x || d->out_lw || d->out_stats) {
-        pf_export_kernel<R, Model><<<dim3((a.N + NT - 1) / NT, a.B), block, 0, stream>>>(a); ++launches;
-    }
-    g_launches = launches;
-    const cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) return fail(SGM_ERR_CUDA, "CUDA launch failed: %s", cudaGetErrorString(e));
-    return SGM_OK;
-}
-
-template <class R>
-int run_model(const sgm_pf_desc* d, cudaStream_t s) {
-    switch (d->model) {
-        case SGM_MODEL_SVM: return run_impl<R, SvmPrior>(d, s);
-        case SGM_MODEL_LGSSM: return d->kernel == SGM_KERNEL_PRIOR ? run_impl<R, LgssmPrior>(d, s) : run_impl<R, LgssmOptimal>(d, s);
-        default: return d->kernel == SGM_KERNEL_PRIOR ? run_impl<R, GarchPrior>(d, s) : run_impl<R, GarchOptimal>(d, s);
-    }
-}
-
-}  // namespace
 
 extern "C" {
 
@@ -279,7 +154,7 @@ int sgm_pf_run(const sgm_pf_desc* d, void* stream) {
     if (v != SGM_OK) return v;
     g_err[0] = 0;
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-    return d->dtype == SGM_F64 ? run_model<double>(d, s) : run_model<float>(d, s);
+    return d->dtype == SGM_F64 ? sgmhost::run_model<double>(d, s) : sgmhost::run_model<float>(d, s);
 }
 
 }  // extern "C"

@@ -1,0 +1,3 @@
+// f32 instantiations of the launch orchestration (see run_impl.cuh)
+#include "run_impl.cuh"
+namespace sgmhost { template int run_model<float>(const sgm_pf_desc* d, cudaStream_t s); }
