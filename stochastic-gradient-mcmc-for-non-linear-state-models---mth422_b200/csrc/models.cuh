@@ -20,6 +20,9 @@ template <> struct Mth<float> {
     static __device__ __forceinline__ float log(float x) {
         float r; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return __fmul_rn(r, 0.6931471805599453f);
     }
+    static __device__ __forceinline__ float log2(float x) {
+        float r; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r;
+    }
     static __device__ __forceinline__ float sqrt(float x) {
         float r; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r;
     }
@@ -36,6 +39,7 @@ template <> struct Mth<float> {
 template <> struct Mth<double> {
     static __device__ __forceinline__ double exp(double x) { return ::exp(x); }
     static __device__ __forceinline__ double exp2(double x) { return ::exp2(x); }
+    static __device__ __forceinline__ double log2(double x) { return ::log2(x); }
     static __device__ __forceinline__ double log(double x) { return ::log(x); }
     static __device__ __forceinline__ double sqrt(double x) { return ::sqrt(x); }
     static __device__ __forceinline__ double rcp(double x) { return 1.0 / x; }

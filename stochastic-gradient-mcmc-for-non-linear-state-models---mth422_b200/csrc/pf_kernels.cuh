@@ -679,7 +679,9 @@ __device__ __forceinline__ void step_body(const KArgs& a, int b, int t, int q_me
             // transposed to row-major (child slot 32 c + lane has rank 32 c + lane) for coalesced gathers.
             draw_uniforms<R>(key, t, q_me, lane, u);
 #pragma unroll
-            for (int k = 0; k < KPT; ++k) u[k] = (8 * lane + k < n_valid) ? -Mth<R>::log(u[k]) : (R)0;
+            // Exp(1) spacings up to a common factor: the positions are normalised by the tile's total below, so
+            // -ln u and log2 u (same sign throughout, no scaling multiply, no negation) give identical positions
+            for (int k = 0; k < KPT; ++k) u[k] = (8 * lane + k < n_valid) ? Mth<R>::log2(u[k]) : (R)0;
             R etot;
             lane_major_incl_scan<R>(u, etot);
             const R inv = Mth<R>::rcp(etot);

@@ -45,10 +45,12 @@ __device__ __forceinline__ void rng_uniform4(const RngKey& k, uint32_t q, uint32
     const uint4 r0 = rng_raw(k, q, step, stream, 0), r1 = rng_raw(k, q, step, stream, 1);
     u[0] = u01d(r0.x, r0.y); u[1] = u01d(r0.z, r0.w); u[2] = u01d(r1.x, r1.y); u[3] = u01d(r1.z, r1.w);
 }
+__device__ __forceinline__ float sqrt_approx(float x) { float r; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 // 4 standard normals for particle quad q (Box-Muller)
 __device__ __forceinline__ void rng_normal4(const RngKey& k, uint32_t q, uint32_t step, float* z) {
     const uint4 r = rng_raw(k, q, step, STREAM_NORMAL, 0);
-    const float r0 = sqrtf(-2.0f * __logf(u01f(r.x))), r1 = sqrtf(-2.0f * __logf(u01f(r.z)));
+    // sqrt(-2 ln u) = sqrt(log2(u) * (-2 ln 2)): one multiply between the two MUFU ops
+    const float r0 = sqrt_approx(__log2f(u01f(r.x)) * -1.3862943611198906f), r1 = sqrt_approx(__log2f(u01f(r.z)) * -1.3862943611198906f);
     float s0, c0, s1, c1;
     __sincosf(6.28318530717958647692f * u01f(r.y), &s0, &c0);
     __sincosf(6.28318530717958647692f * u01f(r.w), &s1, &c1);
