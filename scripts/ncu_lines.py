@@ -10,9 +10,15 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 PKG = os.path.join(ROOT, "stochastic-gradient-mcmc-for-non-linear-state-models---mth422_b200")
 tmp = tempfile.mkdtemp()
 subprocess.run(["cuobjdump", "-xelf", "all", os.path.join(PKG, "libsgmpf.so")], cwd=tmp, capture_output=True)
-cubin = [f for f in os.listdir(tmp) if f.endswith(".cubin")][0]
-sass = subprocess.run(["nvdisasm", "-g", os.path.join(tmp, cubin)], capture_output=True, text=True).stdout.split("\n")
-start = [i for i, l in enumerate(sass) if l.startswith(".text." + kern + ":")][0]
+sass, start = None, None
+for cubin in sorted(f for f in os.listdir(tmp) if f.endswith(".cubin")):          # one cubin per translation unit
+    lines = subprocess.run(["nvdisasm", "-g", os.path.join(tmp, cubin)], capture_output=True, text=True).stdout.split("\n")
+    hit = [i for i, l in enumerate(lines) if l.startswith(".text." + kern + ":")]
+    if hit:
+        sass, start = lines, hit[0]
+        break
+if sass is None:
+    sys.exit("kernel %s not found in libsgmpf.so" % kern)
 cur, seq = None, []
 for l in sass[start + 1:]:
     if l.startswith("//-----"):
