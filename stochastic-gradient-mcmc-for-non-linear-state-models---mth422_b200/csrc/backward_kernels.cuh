@@ -1,13 +1,15 @@
-// Backward-weight smoothers that run after pf_step_kernel has produced the new particles:
-//   * Poyiadjis O(N^2)  (pf.py:84-136)   -- flash-attention-style: tiles of old particles staged in
-//     shared memory, per-child online max / sum, exp-weights times (statistics + score) accumulated
-//     in registers; the (N, N) backward-weight matrix is never materialised.
+// Kernels that run after pf_step_kernel has produced the new particles of a step:
+//   * Poyiadjis O(N^2)  (pf.py:84-136)   -- flash-attention-style restatement: rank-1 scores (one FMA per pair),
+//     bounded-reference softmax (no running max, partial sums over parent ranges add), statistics through the moments
+//     of two per-parent features; the P V contraction on the tensor cores (TF32 mma.sync, f32) or on the FP32 / FP64
+//     pipe; split-J grid + deterministic finish kernel.  The (N, N) backward-weight matrix is never materialised.
 //   * PaRIS            (pf.py:183-341)   -- accept-reject backward sampling with exact fallback.
-//       PHILOX mode : every child runs its own accept-reject loop (counter-based draws);
-//                     children that exhaust max_accept_reject go to an exact O(N) sampler.
+//       PHILOX mode : guide-table proposals, shared-memory work queue compacted every round, multi-proposal
+//                     rounds for short queues, per-child acceptance bound, warp-per-entry exact sampler.
 //       INJECTED mode: one CTA per item replays the reference's round structure (stable compaction
 //                     of the unresolved list L, uniforms consumed at a running offset) so that the
 //                     recorded numpy stream lines up draw for draw.
+//   * predictive log-likelihood statistic of the particle filter (pf.py:40-82 `logsumexp`), pf_pred_kernel.
 #pragma once
 #include "pf_kernels.cuh"
 

@@ -7,7 +7,8 @@
 // update statistics, tile-local scan of the new weights -- with shuffles and __syncwarp only: the step
 // kernel contains NO block barrier, so the 32+ resident warps of an SM hide each other's memory latency.
 // All cross-tile work of a step (global max, tile offsets, log-likelihood, Gamma prefix) is done by a
-// tiny per-item header kernel between two step kernels.
+// tiny per-item header kernel between two step kernels (a single warp for items with < 32 tiles); items with
+// N <= 2048 run the whole time loop in one launch (pf_fused_kernel).
 //
 // Data layout in HBM (caller workspace; B items, N particles, Q = ceil(N / 256) warp tiles per item):
 //   rec [2][B][N][4]   R   first four components of the particle record  (stats..., then state)
@@ -18,7 +19,7 @@
 //   hdr [B][8+3(Q+2)]  f64 per item, rebuilt every step: M, total, sbar[4]; off[Q+1] exclusive prefix of
 //                          tile masses in units of exp(-M); sc[Q] = exp(m_tile - M); gam[Q+2] Gamma prefix
 //                          (order-statistics sampler: first target of every child tile, in units of exp(-M))
-//   acc [B][8]         f64 running log-likelihood (+ filter statistic)
+//   acc [B][16]        f64 running log-likelihood (+ filter / predictive statistic)
 // rec / tail / fine / lw / sub are double-buffered on step parity: step t reads [t & 1], writes [(t+1) & 1].
 //
 // The global CDF of an item is never materialised: c_i = off[q] + fine_i * sc[q]  (flash-attention style
