@@ -826,16 +826,28 @@ __device__ __forceinline__ void step_body(const KArgs& a, int b, int t, int q_me
 }
 
 // CTA shape of the step kernel: its warps are independent (no block barrier), so the CTA size only sets the
-// register-allocation granularity.  SGM_STEP_WARPS warps per CTA, SGM_STEP_CTAS CTAs per SM (f32).
+// register-allocation granularity.  Generic instantiations: 8 warps x SGM_STEP_CTAS (4) CTAs / SM at 64 registers.
+// FAST instantiation: 4 warps x 9 CTAs / SM at 56 registers = 36 resident warps (measured: 1.31e11 -> 1.36e11
+// particle-steps/s; 10 CTAs at 48 registers and the 8-warp shape at 64 registers are both slower).
 #ifndef SGM_STEP_WARPS
 #define SGM_STEP_WARPS 8
 #endif
-constexpr int STEP_WARPS = SGM_STEP_WARPS;
+#ifndef SGM_FAST_WARPS
+#define SGM_FAST_WARPS 4
+#endif
+#ifndef SGM_FAST_CTAS
+#define SGM_FAST_CTAS 9
+#endif
+template <bool FAST> struct StepShape {
+    static constexpr int WARPS = FAST ? SGM_FAST_WARPS : SGM_STEP_WARPS;
+    template <class R> static constexpr int ctas() { return FAST ? SGM_FAST_CTAS : (sizeof(R) == 4 ? SGM_STEP_CTAS : 2 * 8 / SGM_STEP_WARPS); }
+};
 template <class R, class Model, bool SORTED, bool FAST = false>
-__global__ void __launch_bounds__(32 * STEP_WARPS, (sizeof(R) == 4 ? SGM_STEP_CTAS : 2 * 8 / STEP_WARPS)) pf_step_kernel(KArgs a, int t) {
-    __shared__ __align__(32) R s_cdf_all[STEP_WARPS][SORTED ? WIN_BYTES / sizeof(R) : WT];
+__global__ void __launch_bounds__(32 * StepShape<FAST>::WARPS, StepShape<FAST>::template ctas<R>()) pf_step_kernel(KArgs a, int t) {
+    constexpr int SW = StepShape<FAST>::WARPS;
+    __shared__ __align__(32) R s_cdf_all[SW][SORTED ? WIN_BYTES / sizeof(R) : WT];
     const int warp = threadIdx.x >> 5;
-    step_body<R, Model, SORTED, FAST>(a, a.b0 + blockIdx.y, t, blockIdx.x * STEP_WARPS + warp, threadIdx.x & 31, s_cdf_all[warp]);
+    step_body<R, Model, SORTED, FAST>(a, a.b0 + blockIdx.y, t, blockIdx.x * SW + warp, threadIdx.x & 31, s_cdf_all[warp]);
 }
 
 // ---- fused kernel for small particle counts (N <= 2048: the item fits one CTA) -----------------------------

@@ -88,11 +88,15 @@ int run_impl(const sgm_pf_desc* d, cudaStream_t stream) {
         if (d->ev_steps_begin) cudaEventRecord(reinterpret_cast<cudaEvent_t>(d->ev_steps_begin), stream);
         for (int t = 0; t < a.max_T; ++t) {
             for (int h = 0; h < nh; ++h) {
-                const dim3 gh((a.Q + STEP_WARPS - 1) / STEP_WARPS, nb[h]), bs(32 * STEP_WARPS);
+                constexpr int SW = StepShape<false>::WARPS, FW = StepShape<true>::WARPS;
+                const dim3 gh((a.Q + SW - 1) / SW, nb[h]), bs(32 * SW);
                 pf_header_kernel<R, Model><<<nb[h], block, 0, sh[h]>>>(ah[h], t, 0); ++launches;
                 bool done = false;
                 if constexpr (sizeof(R) == 4) {                    // the FAST instantiation exists for f32 only
-                    if (fast_path) { pf_step_kernel<R, Model, true, true><<<gh, bs, 0, sh[h]>>>(ah[h], t); done = true; }
+                    if (fast_path) {
+                        pf_step_kernel<R, Model, true, true><<<dim3((a.Q + FW - 1) / FW, nb[h]), 32 * FW, 0, sh[h]>>>(ah[h], t);
+                        done = true;
+                    }
                 }
                 if (done) {}
                 else if (d->resample == SGM_RESAMPLE_MULTINOMIAL) pf_step_kernel<R, Model, false><<<gh, bs, 0, sh[h]>>>(ah[h], t);
