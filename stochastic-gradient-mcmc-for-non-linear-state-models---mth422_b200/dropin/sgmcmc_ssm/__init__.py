@@ -14,7 +14,8 @@ if _here not in sys.path:
 import sgmcmc_ssm_b200 as _impl  # noqa: E402
 
 _SUBMODULES = [
-    "_utils", "base_parameters", "variables", "sgmcmc_sampler", "helper", "engine", "trace_metric_functions", "ensemble",
+    "_utils", "base_parameters", "variables", "sgmcmc_sampler", "helper", "engine", "trace_metric_functions", "metric_functions",
+    "ensemble",
     "particle_filters", "particle_filters.buffered_smoother", "particle_filters.pf", "particle_filters.kernels",
     "models", "models.svm", "models.svm.parameters", "models.svm.helper", "models.svm.kernels", "models.svm.sampler",
     "models.lgssm", "models.lgssm.parameters", "models.lgssm.helper", "models.lgssm.kernels", "models.lgssm.sampler",
