@@ -56,6 +56,11 @@ enum { SGM_RNG_PHILOX = 0, SGM_RNG_INJECTED = 1 };
 enum { SGM_RESAMPLE_MULTINOMIAL = 0, SGM_RESAMPLE_MULTINOMIAL_SORTED = 1,
        SGM_RESAMPLE_SYSTEMATIC = 2, SGM_RESAMPLE_STRATIFIED = 3 };
 /* additive statistic carried by the smoother */
+/* SGM_STAT_PRED: row width of `grad` / horizon slots of `inj_pred`, and the largest num_steps_ahead (the reference's
+ * default is 10, sgmcmc_sampler.py:61; its drivers use 5). */
+#define SGM_PRED_SLOTS 16
+#define SGM_PRED_MAX_STEPS 14
+
 enum { SGM_STAT_SCORE = 0,     /* complete-data log-likelihood gradient (pf_gradient_estimate)   */
        SGM_STAT_SUFF = 1,      /* [x', x'^2, x x'] (lgssm/svm) or [x', x'^2, x'^4] (garch)        */
        SGM_STAT_NONE = 2,      /* log-likelihood only (pf_loglikelihood_estimate)                 */
@@ -96,7 +101,7 @@ typedef struct sgm_pf_desc {
     int32_t manual_sample_threshold; /* <0: int(10*log10(N/10)) (pf.py:286-287); INJECTED mode only */
     int32_t item_id_base;          /* global index of item 0 (keeps Philox streams rank-invariant)  */
     int32_t n2_mode;               /* O(N^2) smoother: SGM_N2_AUTO / SGM_N2_FP32_PIPE / SGM_N2_TENSOR */
-    int32_t pred_steps_ahead;      /* SGM_STAT_PRED: num_steps_ahead K (0..7); the statistic has K + 1 entries */
+    int32_t pred_steps_ahead;      /* SGM_STAT_PRED: num_steps_ahead K (0..SGM_PRED_MAX_STEPS); K + 1 entries */
     int32_t pred_per_horizon;      /* SGM_STAT_PRED: 0 = the reference's log-sum over ALL horizons (pf.py:73-76),
                                     * 1 = one log-sum per horizon                                    */
     int32_t reserved0;             /* must be 0                                                     */
@@ -124,11 +129,12 @@ typedef struct sgm_pf_desc {
     const double* inj_z;           /* [B][max_T][N]   proposal normals                              */
     const double* inj_extra;       /* flat PaRIS accept-reject / exact-sampling uniforms            */
     const int64_t* inj_extra_off;  /* [B][max_T]      start of (item, step)'s slice of inj_extra    */
-    const double* inj_pred;        /* [B][max_T][8][N] SGM_STAT_PRED: normals of the predictive statistic
+    const double* inj_pred;        /* [B][max_T][SGM_PRED_SLOTS][N] SGM_STAT_PRED: normals of the predictive statistic
                                     * (svm/helper.py:379, garch/kernels.py:66), horizon-major        */
 
     /* outputs */
-    double* grad;                  /* [B][8]  final weighted-average statistic (average_statistic)  */
+    double* grad;                  /* [B][8]  final weighted-average statistic (average_statistic);
+                                    * SGM_STAT_PRED: [B][SGM_PRED_SLOTS], entries 0..K               */
     double* loglik;                /* [B]     log-likelihood estimate over [t1, tL)                 */
     int32_t* status;               /* [B]                                                           */
     void* out_x;                   /* optional [B][N][n]  final particles (dtype)                   */

@@ -439,14 +439,15 @@ int launch_poyiadjis_n2(const KArgs& a, int t, cudaStream_t stream) {
 template <class R, class Model>
 __device__ __forceinline__ void pred_h(const KArgs& a, const typename Model::template Theta<R>& th, const RngKey& key, int b, int t,
                                        int i, int kmax, R wt, const double* obs, const R* xn, R* h) {
+    constexpr int PS = SGM_PRED_SLOTS;
     R ps[2];
     Model::pred_begin(xn, ps);
 #pragma unroll
-    for (int k = 0; k < 8; ++k) h[k] = (R)0;
+    for (int k = 0; k < PS; ++k) h[k] = (R)0;
     for (int k = 0; k <= kmax; ++k) {
         R z = (R)0;
         if (Model::PRED_RNG) {
-            if (a.rng_mode == SGM_RNG_INJECTED) z = (R)a.inj_pred[(((size_t)b * a.max_T + t) * 8 + k) * a.N + i];
+            if (a.rng_mode == SGM_RNG_INJECTED) z = (R)a.inj_pred[(((size_t)b * a.max_T + t) * PS + k) * a.N + i];
             else rng_normal1(key, (uint32_t)i, (uint32_t)t, STREAM_PRED, (uint32_t)k, z);
         }
         h[k] = Model::pred_ll(th, ps, (R)obs[t + k], z) * wt;
@@ -456,7 +457,7 @@ __device__ __forceinline__ void pred_h(const KArgs& a, const typename Model::tem
 
 template <class R, class Model>
 __global__ void __launch_bounds__(NT) pf_pred_kernel(KArgs a, int t) {
-    constexpr int NX = Model::NX, NP = Model::NP, W = NX + NP;
+    constexpr int NX = Model::NX, NP = Model::NP, W = NX + NP, PS = SGM_PRED_SLOTS;
     __shared__ R sh_r[NWARP];
     __shared__ double sh_d[NWARP];
     const int b = blockIdx.x, tid = threadIdx.x;
@@ -476,35 +477,41 @@ __global__ void __launch_bounds__(NT) pf_pred_kernel(KArgs a, int t) {
     const double* obs = a.obs + a.obs_off[b];
     const int kmax = min(K, Tb - 1 - t);
     const RngKey key = item_key(a, b);
-    R mx[8], mlw = -Mth<R>::inf();
+    R mx[PS], mlw = -Mth<R>::inf();
 #pragma unroll
-    for (int k = 0; k < 8; ++k) mx[k] = -Mth<R>::inf();
+    for (int k = 0; k < PS; ++k) mx[k] = -Mth<R>::inf();
     for (int i = tid; i < N; i += NT) {
-        R rn[W], h[8];
+        R rn[W], h[PS];
         load_rec<R, W>(a.rec[par ^ 1], a.tail[par ^ 1], item_off + i, rn);
         pred_h<R, Model>(a, th, key, b, t, i, kmax, wt, obs, rn + NP, h);
 #pragma unroll
-        for (int k = 0; k < 8; ++k) mx[k] = nan_max(mx[k], h[k]);
+        for (int k = 0; k < PS; ++k) mx[k] = nan_max(mx[k], h[k]);
         mlw = nan_max(mlw, lw_new[i]);
     }
-    for (int k = 0; k < 8; ++k) mx[k] = block_max(mx[k], sh_r);
+#pragma unroll
+    for (int k = 0; k < PS; ++k) if (k <= K) mx[k] = block_max(mx[k], sh_r);      // K is uniform over the CTA
     mlw = block_max(mlw, sh_r);
-    double s[8] = {0, 0, 0, 0, 0, 0, 0, 0}, Wsum = 0.0;
+    double s[PS], Wsum = 0.0;
+#pragma unroll
+    for (int k = 0; k < PS; ++k) s[k] = 0.0;
     for (int i = tid; i < N; i += NT) {
-        R rn[W], h[8];
+        R rn[W], h[PS];
         load_rec<R, W>(a.rec[par ^ 1], a.tail[par ^ 1], item_off + i, rn);
         pred_h<R, Model>(a, th, key, b, t, i, kmax, wt, obs, rn + NP, h);
         const double w = (double)Mth<R>::exp(lw_new[i] - mlw);
         Wsum += w;
 #pragma unroll
-        for (int k = 0; k < 8; ++k) s[k] += (double)Mth<R>::exp(h[k] - mx[k]) * w;
+        for (int k = 0; k < PS; ++k) if (k <= K) s[k] += (double)Mth<R>::exp(h[k] - mx[k]) * w;
     }
-    for (int k = 0; k < 8; ++k) s[k] = block_sum(s[k], sh_d);
+#pragma unroll
+    for (int k = 0; k < PS; ++k) if (k <= K) s[k] = block_sum(s[k], sh_d);
     Wsum = block_sum(Wsum, sh_d);
     if (tid == 0) {
         double tot = 0.0;
-        for (int k = 0; k <= K; ++k) tot += s[k] / Wsum;
-        for (int k = 0; k <= K; ++k) acc[1 + k] += (double)mx[k] + ::log(a.pred_per_horizon ? s[k] / Wsum : tot);
+#pragma unroll
+        for (int k = 0; k < PS; ++k) if (k <= K) tot += s[k] / Wsum;
+#pragma unroll
+        for (int k = 0; k < PS; ++k) if (k <= K) acc[1 + k] += (double)mx[k] + ::log(a.pred_per_horizon ? s[k] / Wsum : tot);
     }
 }
 

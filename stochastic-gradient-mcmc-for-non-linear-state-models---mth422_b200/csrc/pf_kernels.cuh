@@ -47,7 +47,8 @@ constexpr int TILE = NT * KPT;         // 2048 particles per CTA (8 warp tiles)
 constexpr int MAX_Q = 4096;            // N <= 2^20
 constexpr int WIN_BYTES = 4096;        // per-warp shared-memory window of the staged parent CDF (sorted resampling)
 constexpr int SSTRIDE = 8;             // doubles per `sub` entry
-constexpr int ACC_STRIDE = 16;         // doubles per `acc` entry: log-likelihood, then up to 8 filter / predictive statistics
+constexpr int ACC_STRIDE = 16;         // doubles per `acc` entry: log-likelihood, then up to 15 filter / predictive statistics
+static_assert(SGM_PRED_MAX_STEPS + 2 <= ACC_STRIDE && SGM_PRED_MAX_STEPS < SGM_PRED_SLOTS, "predictive horizons must fit acc / grad rows");
 constexpr int THC_BYTES = 128;         // per-item slot for the model's derived constants
 constexpr int H_M = 0, H_TOTAL = 1, H_SBAR = 2, H_SCALARS = 8;
 
@@ -353,9 +354,12 @@ __device__ __forceinline__ void header_finish(const KArgs& a, int b, int t_done,
     }
     if (final_pass) {
         a.loglik[b] = acc[0];
-        for (int j = 0; j < 8; ++j) a.grad[(size_t)b * 8 + j] = 0.0;
-        for (int j = 0; j < nstat; ++j) a.grad[(size_t)b * 8 + j] = (a.pf == SGM_PF_FILTER) ? acc[1 + j] : sbar[j];
-        if (a.stat_kind == SGM_STAT_PRED) for (int j = 0; j <= a.pred_K; ++j) a.grad[(size_t)b * 8 + j] = acc[1 + j];
+        if (a.stat_kind == SGM_STAT_PRED) {                 // K + 1 horizons in a row of SGM_PRED_SLOTS
+            for (int j = 0; j < SGM_PRED_SLOTS; ++j) a.grad[(size_t)b * SGM_PRED_SLOTS + j] = (j <= a.pred_K) ? acc[1 + j] : 0.0;
+        } else {
+            for (int j = 0; j < 8; ++j) a.grad[(size_t)b * 8 + j] = 0.0;
+            for (int j = 0; j < nstat; ++j) a.grad[(size_t)b * 8 + j] = (a.pf == SGM_PF_FILTER) ? acc[1 + j] : sbar[j];
+        }
     }
 }
 

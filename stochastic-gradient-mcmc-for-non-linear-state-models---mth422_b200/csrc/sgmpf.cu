@@ -40,7 +40,8 @@ int validate(const sgm_pf_desc* d) {
     if (d->stat_kind < 0 || d->stat_kind > SGM_STAT_PRED) return fail(SGM_ERR_INVALID, "unknown stat_kind");
     if (d->stat_kind == SGM_STAT_PRED) {
         if (d->pf != SGM_PF_FILTER) return fail(SGM_ERR_INVALID, "Only can use pf = 'filter' since we are filtering");
-        if (d->pred_steps_ahead < 0 || d->pred_steps_ahead > 7) return fail(SGM_ERR_UNSUPPORTED, "num_steps_ahead must be in [0, 7]");
+        if (d->pred_steps_ahead < 0 || d->pred_steps_ahead > SGM_PRED_MAX_STEPS)
+            return fail(SGM_ERR_UNSUPPORTED, "num_steps_ahead must be in [0, 14]");
         if (d->rng_mode == SGM_RNG_INJECTED && d->model != SGM_MODEL_LGSSM && !d->inj_pred)
             return fail(SGM_ERR_INVALID, "INJECTED predictive statistic needs inj_pred");
     }
@@ -128,7 +129,7 @@ int sgm_stat_dim(int32_t model, int32_t stat_kind) {
     if (stat_kind == SGM_STAT_SCORE) return score_dim(model);
     if (stat_kind == SGM_STAT_SUFF) return 3;
     if (stat_kind == SGM_STAT_NONE) return 0;
-    if (stat_kind == SGM_STAT_PRED) return 8;          /* upper bound: num_steps_ahead + 1 <= 8 */
+    if (stat_kind == SGM_STAT_PRED) return SGM_PRED_MAX_STEPS + 1;          /* upper bound: num_steps_ahead + 1 */
     return SGM_ERR_INVALID;
 }
 

@@ -19,6 +19,7 @@ STAT = dict(score=0, suff=1, none=2, pred=3)
 N2_MODE = dict(auto=0, fp32_pipe=1, tensor=2)
 STATUS_NAN_WEIGHT, STATUS_ZERO_WEIGHT, STATUS_AR_OVERFLOW = 1, 2, 4
 THETA_STRIDE = 12
+PRED_SLOTS, PRED_MAX_STEPS = 16, 14           # SGM_PRED_SLOTS, SGM_PRED_MAX_STEPS (include/sgmpf.h)
 ERR = {-1: ValueError, -2: NotImplementedError, -3: MemoryError, -4: RuntimeError, -5: RuntimeError}
 
 

@@ -227,9 +227,10 @@ class PFResult(object):
         self._event.synchronize()
         B = self.B
         out = self._pin_out.numpy()
-        self.grad = out[:B * 64].view(np.float64).reshape(B, 8)[:, :max(self.p, 0)].copy()
-        self.loglik = out[B * 64:B * 72].view(np.float64).copy()
-        self.status = out[B * 72:B * 76].view(np.int32).copy()
+        gb = 8 * self.grad_slots                         # bytes of one row of `grad`
+        self.grad = out[:B * gb].view(np.float64).reshape(B, self.grad_slots)[:, :max(self.p, 0)].copy()
+        self.loglik = out[B * gb:B * (gb + 8)].view(np.float64).copy()
+        self.status = out[B * (gb + 8):B * (gb + 12)].view(np.int32).copy()
         self._done = True
         if check:
             bad = self.status & (nat.STATUS_NAN_WEIGHT | nat.STATUS_ZERO_WEIGHT)
@@ -272,8 +273,8 @@ class PreparedPF(object):
         model_id, kernel_id = nat.MODEL[model], nat.KERNEL[kernel]
         self.p = lib.sgm_stat_dim(model_id, nat.STAT[stat_kind])
         if stat_kind == "pred":
-            if not 0 <= int(num_steps_ahead) <= 7:
-                raise NotImplementedError("num_steps_ahead must be in [0, 7] on the CUDA path")
+            if not 0 <= int(num_steps_ahead) <= nat.PRED_MAX_STEPS:
+                raise NotImplementedError("num_steps_ahead must be in [0, %d] on the CUDA path" % nat.PRED_MAX_STEPS)
             self.p = int(num_steps_ahead) + 1
         self.n = n = lib.sgm_state_dim(model_id)
         NPrec = lib.sgm_stat_dim(model_id, 0)
@@ -296,7 +297,8 @@ class PreparedPF(object):
         for name, nb in sections:
             offs[name] = tot
             tot = _align(tot + nb, 16)
-        self.in_bytes, self.out_bytes = tot, B * 76 + 64
+        gs = self.grad_slots = nat.PRED_SLOTS if stat_kind == "pred" else 8
+        self.in_bytes, self.out_bytes = tot, B * (8 * gs + 12) + 64
 
         desc = self.desc = nat.SgmPfDesc()
         desc.struct_bytes = ctypes.sizeof(nat.SgmPfDesc)
@@ -347,8 +349,8 @@ class PreparedPF(object):
                 desc.inj_z0 = dev64(injected["z0"], (B, N))
                 desc.inj_u = dev64(injected["u"], (B, max_T, N))
                 desc.inj_z = dev64(injected["z"], (B, max_T, N))
-                if injected.get("zp") is not None:       # predictive-statistic normals, (B, max_T, 8, N)
-                    desc.inj_pred = dev64(injected["zp"], (B, max_T, 8, N))
+                if injected.get("zp") is not None:       # predictive-statistic normals, (B, max_T, PRED_SLOTS, N)
+                    desc.inj_pred = dev64(injected["zp"], (B, max_T, nat.PRED_SLOTS, N))
                 if injected.get("extra") is not None:
                     flat = np.concatenate([np.asarray(e, dtype=np.float64).ravel() for e in injected["extra"]] + [np.zeros(1)])
                     lens = np.array([np.asarray(e).size for e in injected["extra"]], dtype=np.int64)
@@ -389,7 +391,7 @@ class PreparedPF(object):
                 setattr(desc, name, base_in + offs[name])
             desc.step_weights = (base_in + offs["wts"]) if has_w else None
             base_out = self.base_out = _aligned_ptr(st.dev_out)
-            desc.grad, desc.loglik, desc.status = base_out, base_out + B * 64, base_out + B * 72
+            desc.grad, desc.loglik, desc.status = base_out, base_out + B * 8 * gs, base_out + B * (8 * gs + 8)
             desc.workspace = _aligned_ptr(st.workspace)
             desc.workspace_bytes = ws_bytes
             if config.two_streams:
@@ -475,7 +477,7 @@ class PreparedPF(object):
         return PFResult(B=self.B, N=self.N, p=self.p, n=self.n, max_T=self.max_T, T_buf=self.T_buf, _event=ev,
                         _pin_out=st.pin_out, _extra=self.extra, _keep=self.keep, launches=self.launches,
                         h2d_bytes=self.in_bytes, d2h_bytes=self.out_bytes, particle_steps=self.particle_steps,
-                        ws_bytes=self.ws_bytes)
+                        ws_bytes=self.ws_bytes, grad_slots=self.grad_slots)
 
 
 def run_pf(model, kernel, pf, items, N, sync=True, check=True, **kwargs):

@@ -15,6 +15,7 @@ sufficient statistics); arbitrary Python callables cannot run on the device.
 import numpy as np
 
 from .. import engine
+from .. import _native as nat
 from . import statistics as S
 
 _PF_NAMES = ("nemeth", "poyiadjis_N", "poyiadjis_N2", "paris", "filter")
@@ -36,7 +37,7 @@ def _draw_injected(N, T_list, pred=None):
     z0 = np.zeros((B, N))
     u = np.zeros((B, max_T, N))
     z = np.zeros((B, max_T, N))
-    zp = np.zeros((B, max_T, 8, N)) if pred is not None else None
+    zp = np.zeros((B, max_T, nat.PRED_SLOTS, N)) if pred is not None else None
     for b, T in enumerate(T_list):
         z0[b] = np.random.normal(size=N)
         for t in range(T):

@@ -20,7 +20,8 @@ OUT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "pred_cases.npz")
 store = {}
 SAMPLERS = {"svm": M.SVMSampler, "lgssm": M.LGSSMSampler, "garch": M.GARCHSampler}
 for model, spec in M.MODELS.items():
-    for tag, (T, t1, tL, K, N, seed) in {"a": (30, 5, 25, 3, 300, 11), "b": (12, 0, 12, 5, 64, 12), "c": (20, 4, 20, 5, 1000, 13)}.items():
+    for tag, (T, t1, tL, K, N, seed) in {"a": (30, 5, 25, 3, 300, 11), "b": (12, 0, 12, 5, 64, 12), "c": (20, 4, 20, 5, 1000, 13),
+                                            "d": (40, 5, 35, 10, 200, 14)}.items():   # d: the default horizon (10)
         np.random.seed(1000 + seed)
         p = spec["params"]()
         data = spec["gen"](T=T + 5, parameters=p)
@@ -45,5 +46,8 @@ for model, spec in M.MODELS.items():
     pre = "ps/{0}".format(model)
     for k, v in dict(obs=data["observations"], theta=M.theta_of(model, p), out=out).items():
         store[pre + "/" + k] = np.asarray(v)
+    np.random.seed(6)                         # default num_steps_ahead (10), as the drivers' metric gets it (lag= is ignored)
+    out = s.predictive_loglikelihood(kind="pf", subsequence_length=30, minibatch_size=2, buffer_length=4, N=100)
+    store["ps10/{0}/out".format(model)] = np.asarray(out)
 np.savez_compressed(OUT, **store)
 print("wrote", OUT, len(store), "arrays")

@@ -35,20 +35,52 @@ def _theta_vec(model, c):
 @pytest.mark.parametrize("per_horizon", [False, True])
 @pytest.mark.parametrize("name", _names("p"))
 def test_predictive_kernel_level_f64(name, per_horizon):
+    _kernel_level(name, per_horizon)
+
+
+@pytest.mark.parametrize("K", [8, 10, 14])
+@pytest.mark.parametrize("name", ["p/svm_prior_c", "p/lgssm_optimal_c", "p/garch_optimal_c", "p/garch_prior_a"])
+def test_predictive_kernel_level_long_horizons(name, K):
+    """The reference's default horizon (num_steps_ahead = 10, sgmcmc_sampler.py:61) and the largest supported one
+    (SGM_PRED_MAX_STEPS = 14) against the oracle; includes horizons that run past the end of the buffer."""
+    if name not in _names("p"):
+        pytest.skip("no such stored case")
+    _kernel_level(name, False, K=K)
+    _kernel_level(name, True, K=K)
+
+
+@pytest.mark.parametrize("model", ["svm", "lgssm", "garch"])
+def test_predictive_default_horizon_and_limit(model):
+    """num_steps_ahead left at the reference's default (10) -- what the drivers' predictive metric ends up running --
+    against the unmodified reference under the same seed; horizons above SGM_PRED_MAX_STEPS are refused."""
+    make_params, _, Sampler = MODELS[model]
+    s = Sampler(n=1, m=1, observations=_case("ps/" + model)["obs"], parameters=make_params())
+    np.random.seed(6)
+    out = s.predictive_loglikelihood(kind="pf", subsequence_length=30, minibatch_size=2, buffer_length=4, N=100,
+                                     dtype="f64", rng="injected")
+    assert out.shape == (11,)
+    np.testing.assert_allclose(out, C.load("pred_cases.npz")["ps10/{0}/out".format(model)], rtol=1e-8, atol=1e-7)
+    with pytest.raises(NotImplementedError):
+        s.predictive_loglikelihood(kind="pf", num_steps_ahead=15, subsequence_length=30, N=128)
+
+
+def _kernel_level(name, per_horizon, K=None):
     import sgmcmc_ssm_b200 as sg
     c = _case(name)
     model, kernel = name.split("/")[1].split("_")[:2]
     theta = C.theta_dict(model, c["theta"])
-    N, K, t1, tL = int(c["N"]), int(c["K"]), int(c["t1"]), int(c["tL"])
+    N, t1, tL = int(c["N"]), int(c["t1"]), int(c["tL"])
+    stored = K is None
+    K = int(c["K"]) if stored else K
     rec = po.LegacyStream(int(c["seed"]), record=True)
     ref = po.pf_predictive_loglikelihood_estimate(model, c["obs"], theta, float(c["Q"]), float(c["R"]), rec, num_steps_ahead=K,
                                                   subsequence_start=t1, subsequence_end=tL, N=N, kernel=kernel,
                                                   per_horizon=per_horizon)
-    if not per_horizon:
+    if stored and not per_horizon:
         np.testing.assert_allclose(ref, c["out"], rtol=1e-11, atol=1e-11)
     parts = po.split_events_pred(rec.events, N)
     T = c["obs"].shape[0]
-    zp = np.zeros((1, T, 8, N))
+    zp = np.zeros((1, T, 16, N))            # SGM_PRED_SLOTS horizon slots
     for t, blk in enumerate(parts["zp"]):
         zp[0, t, :blk.shape[0]] = blk
     pm, pv = po.prior_moments(model, theta, None)
