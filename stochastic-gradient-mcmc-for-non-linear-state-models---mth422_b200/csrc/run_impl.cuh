@@ -5,6 +5,13 @@
 
 namespace sgmhost {
 
+// N <= 2048: the single-launch kernel (one CTA per item, whole time loop) wins while launch latency dominates; from
+// ~1000 items on the per-step kernels fill the machine better (measured, SVM f32, N = 1024: 512 items 0.70 vs 0.87 ms,
+// 2048 items 1.96 vs 1.47 ms, 8192 items 7.45 vs 4.58 ms; same crossover at N = 256 and 2048).
+#ifndef SGM_FUSED_MAX_ITEMS
+#define SGM_FUSED_MAX_ITEMS 1024
+#endif
+
 template <class R, class Model>
 int run_impl(const sgm_pf_desc* d, cudaStream_t stream) {
     const Layout L = make_layout(d);
@@ -58,7 +65,7 @@ int run_impl(const sgm_pf_desc* d, cudaStream_t stream) {
     const dim3 grid(a.G, a.B), block(NT);
     int64_t launches = 0;
     const bool pred = d->stat_kind == SGM_STAT_PRED;
-    const bool fused = (a.Q <= NWARP) && !backward_pf(d->pf) && !pred;
+    const bool fused = (a.Q <= NWARP) && !backward_pf(d->pf) && !pred && a.B <= SGM_FUSED_MAX_ITEMS;
     if (fused) {
         // small N: the whole time loop of an item in one launch (one CTA per item)
         if (d->ev_steps_begin) cudaEventRecord(reinterpret_cast<cudaEvent_t>(d->ev_steps_begin), stream);
