@@ -29,7 +29,8 @@ for N in (1000, 1024, 2048, 4096, 8192, 10000, 16384, 32768, 65536, 100000, 2621
     e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / reps
     ps = B * N * T / (ms * 1e-3)
-    path = "fused (one CTA per item)" if N <= 2048 else ("FAST step kernel" if N % 256 == 0 else "generic step kernel")
+    path = "single-launch kernel (one CTA per item)" if (N <= 2048 and B <= 1024) else (
+        "FAST step kernel" if N % 256 == 0 else "FAST step kernel, ragged last tile")
     rows.append(dict(N=N, items=B, ms_per_gradient_batch=ms, particle_steps_per_s=ps, hbm_roofline_frac=ps * BYTES / PEAK,
                      state_bytes=B * N * 20, kernel=path))
     print("N=%-8d items=%-5d %8.3f ms  %.3e p-s/s  %.1f %%  %s" % (N, B, ms, ps, 100 * ps * BYTES / PEAK, path), flush=True)

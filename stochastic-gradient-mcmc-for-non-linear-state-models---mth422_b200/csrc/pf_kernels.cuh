@@ -484,12 +484,13 @@ __global__ void __launch_bounds__(NT) pf_header_kernel(KArgs a, int t, int final
 // ---- gather parents -> propagate -> reweight -> statistic update -> store (pf.py:30-36, 168-179) -----
 // Row c of the warp tile = particles tile_base + 32 c + lane: coalesced stores, and with ascending
 // ancestors the parent gathers of a row are (nearly) contiguous too.
-template <class R, class Model, bool FAST = false>
+template <class R, class Model, bool FAST = false, bool RAGGED = false>
 __device__ __forceinline__ void propagate_store(const KArgs& a, int b, int t, int par, int tile_base, int lane, size_t item_off,
                                                 const int* anc, const R* z, const ItemHdr& hdr, int nws,
                                                 bool carries, bool shrink, R* lwn,
                                                 const typename Model::template Theta<R>& th, R y, R wt) {
     constexpr int NX = Model::NX, NP = Model::NP, W = NX + NP;
+    constexpr bool FULLT = FAST && !RAGGED;        // every tile of the item is complete: no bound checks
     const int N = a.N;
     const bool in_sub = wt != (R)0;               // yw[1] is zero outside [t1, tL)
     const R lam = (R)a.lambduh;
@@ -516,12 +517,12 @@ __device__ __forceinline__ void propagate_store(const KArgs& a, int b, int t, in
         R ra[GB][W];
 #pragma unroll
         for (int c = 0; c < GB; ++c)                      // GB independent parent gathers in flight
-            if (FAST || tile_base + 32 * (h0 + c) + lane < N) load_rec<R, W>(rec_old, tail_old, anc[h0 + c], ra[c]);
+            if (FULLT || tile_base + 32 * (h0 + c) + lane < N) load_rec<R, W>(rec_old, tail_old, anc[h0 + c], ra[c]);
 #pragma unroll
         for (int c4 = 0; c4 < GB; ++c4) {
             const int c = h0 + c4, i = tile_base + 32 * c + lane;
             lwn[c] = -Mth<R>::inf();
-            if (FAST || i < N) {
+            if (FULLT || i < N) {
                 R rn[W];
                 Model::propagate(th, ra[c4] + NP, y, z[c], rn + NP);
                 lwn[c] = Model::log_weight(th, ra[c4] + NP, rn + NP, y);
@@ -595,10 +596,11 @@ __device__ __forceinline__ void search_levels(uint32_t* ad, const R* rt) {
 //   of shared memory in global units, each child binary-searches that slice (8 interleaved searches per
 //   lane, neighbouring lanes read neighbouring words), and parent records are gathered as a stream.
 // FAST = the production configuration, checked by the host before it picks this instantiation: device randoms,
-// order-statistics resampling, Poyiadjis O(N) (lambduh = 1) with the model score, N a multiple of 256, no traces /
-// exported log-weights.  It only turns the run-time flags below into constants (fewer uniform branches, constant
-// loads and bound checks: ~9 % of the generic kernel's instructions); the arithmetic is identical.
-template <class R, class Model, bool SORTED, bool FAST = false>
+// order-statistics resampling, Poyiadjis O(N) (lambduh = 1) with the model score, no traces / exported log-weights.
+// It only turns the run-time flags below into constants (fewer uniform branches, constant loads and -- unless RAGGED,
+// i.e. N is not a multiple of 256 -- bound checks: ~9 % of the generic kernel's instructions); the arithmetic is
+// identical.
+template <class R, class Model, bool SORTED, bool FAST = false, bool RAGGED = false>
 __device__ __forceinline__ void step_body(const KArgs& a, int b, int t, int q_me, int lane, R* s_cdf) {
     static_assert(!FAST || SORTED, "FAST implies sorted resampling");
     R* const s_tr = s_cdf;                 // the warp's shared-memory slice doubles as the scan transposition buffer
@@ -625,7 +627,7 @@ __device__ __forceinline__ void step_body(const KArgs& a, int b, int t, int q_me
     const bool shrink = !FAST && carries && (a.lambduh != 1.0);
     const R* fine_old = reinterpret_cast<const R*>(a.fine[par]) + (size_t)b * a.Q * WT;      // padded to whole tiles
     const int tile_base = q_me * WT;
-    const int n_valid = FAST ? WT : min(WT, N - tile_base);
+    const int n_valid = (FAST && !RAGGED) ? WT : min(WT, N - tile_base);
     const RngKey key = item_key(a, b);
     const double total = hdr.total;
     const double tmax = total * (1.0 - 1.2e-16);
@@ -822,7 +824,7 @@ __device__ __forceinline__ void step_body(const KArgs& a, int b, int t, int q_me
         }
     }
     R lwn[KPT];
-    propagate_store<R, Model, FAST>(a, b, t, par, tile_base, lane, item_off, anc, z, hdr, nws, carries, shrink, lwn, th, y_t, w_t);
+    propagate_store<R, Model, FAST, RAGGED>(a, b, t, par, tile_base, lane, item_off, anc, z, hdr, nws, carries, shrink, lwn, th, y_t, w_t);
     const bool need_ws = (nws > 0) && ((!FAST && a.pf == SGM_PF_FILTER) || shrink || (carries && t == Tb - 1));
     warp_tile_epilogue<R, W>(lwn, tile_base, N, lane, reinterpret_cast<R*>(a.fine[par ^ 1]) + (size_t)b * a.Q * WT,
                              a.sub[par ^ 1] + ((size_t)b * a.Q + q_me) * SSTRIDE, a.rec[par ^ 1], a.tail[par ^ 1],
@@ -846,12 +848,12 @@ template <bool FAST> struct StepShape {
     static constexpr int WARPS = FAST ? SGM_FAST_WARPS : SGM_STEP_WARPS;
     template <class R> static constexpr int ctas() { return FAST ? SGM_FAST_CTAS : (sizeof(R) == 4 ? SGM_STEP_CTAS : 2 * 8 / SGM_STEP_WARPS); }
 };
-template <class R, class Model, bool SORTED, bool FAST = false>
+template <class R, class Model, bool SORTED, bool FAST = false, bool RAGGED = false>
 __global__ void __launch_bounds__(32 * StepShape<FAST>::WARPS, StepShape<FAST>::template ctas<R>()) pf_step_kernel(KArgs a, int t) {
     constexpr int SW = StepShape<FAST>::WARPS;
     __shared__ __align__(32) R s_cdf_all[SW][SORTED ? WIN_BYTES / sizeof(R) : WT];
     const int warp = threadIdx.x >> 5;
-    step_body<R, Model, SORTED, FAST>(a, a.b0 + blockIdx.y, t, blockIdx.x * SW + warp, threadIdx.x & 31, s_cdf_all[warp]);
+    step_body<R, Model, SORTED, FAST, RAGGED>(a, a.b0 + blockIdx.y, t, blockIdx.x * SW + warp, threadIdx.x & 31, s_cdf_all[warp]);
 }
 
 // ---- fused kernel for small particle counts (N <= 2048: the item fits one CTA) -----------------------------

@@ -82,7 +82,7 @@ int run_impl(const sgm_pf_desc* d, cudaStream_t stream) {
         // the production configuration runs the step kernel with its run-time flags folded to constants
         const bool fast_path = sizeof(R) == 4 && d->rng_mode == SGM_RNG_PHILOX && d->resample == SGM_RESAMPLE_MULTINOMIAL_SORTED &&
                                d->pf == SGM_PF_NEMETH && d->lambduh == 1.0 && d->stat_kind == SGM_STAT_SCORE &&
-                               a.N % WT == 0 && !a.need_lw && !d->trace_anc && !d->trace_x && !d->trace_lw;
+                               !a.need_lw && !d->trace_anc && !d->trace_x && !d->trace_lw;
         cudaStream_t sh[2] = {stream, piped ? reinterpret_cast<cudaStream_t>(d->aux_stream) : stream};
         KArgs ah[2] = {a, a};
         int nb[2] = {piped ? a.B / 2 : a.B, piped ? a.B - a.B / 2 : 0};
@@ -101,7 +101,9 @@ int run_impl(const sgm_pf_desc* d, cudaStream_t stream) {
                 bool done = false;
                 if constexpr (sizeof(R) == 4) {                    // the FAST instantiation exists for f32 only
                     if (fast_path) {
-                        pf_step_kernel<R, Model, true, true><<<dim3((a.Q + FW - 1) / FW, nb[h]), 32 * FW, 0, sh[h]>>>(ah[h], t);
+                        const dim3 gf((a.Q + FW - 1) / FW, nb[h]);
+                        if (a.N % WT == 0) pf_step_kernel<R, Model, true, true, false><<<gf, 32 * FW, 0, sh[h]>>>(ah[h], t);
+                        else pf_step_kernel<R, Model, true, true, true><<<gf, 32 * FW, 0, sh[h]>>>(ah[h], t);   // ragged last tile
                         done = true;
                     }
                 }
