@@ -1,5 +1,5 @@
 // Warp-shuffle / block-level reductions and scans with a FIXED combination tree (deterministic).
-// All block primitives assume blockDim.x == NT (256) and are called by every thread of the block.
+// All block primitives assume blockDim.x == 32 * NW (default NT = 256) and are called by every thread of the block.
 #pragma once
 #include <cuda_runtime.h>
 
@@ -33,30 +33,30 @@ template <class T> __device__ __forceinline__ T warp_max(T v) {
     return v;
 }
 
-// Block max.  `sh` needs NWARP elements.  Result valid in all threads.
-template <class T> __device__ __forceinline__ T block_max(T v, T* sh) {
+// Block max.  `sh` needs NW elements.  Result valid in all threads.
+template <int NW = NWARP, class T> __device__ __forceinline__ T block_max(T v, T* sh) {
     v = warp_max(v);
     __syncthreads();                      // protect sh from a previous use
     if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
     __syncthreads();
     T r = sh[0];
 #pragma unroll
-    for (int w = 1; w < NWARP; ++w) r = nan_max(r, sh[w]);
+    for (int w = 1; w < NW; ++w) r = nan_max(r, sh[w]);
     return r;
 }
 // Block sum, fixed order (warp tree, then warps 0..7 left to right).
-template <class T> __device__ __forceinline__ T block_sum(T v, T* sh) {
+template <int NW = NWARP, class T> __device__ __forceinline__ T block_sum(T v, T* sh) {
     v = warp_sum(v);
     __syncthreads();
     if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
     __syncthreads();
     T r = sh[0];
 #pragma unroll
-    for (int w = 1; w < NWARP; ++w) r += sh[w];
+    for (int w = 1; w < NW; ++w) r += sh[w];
     return r;
 }
 // Block exclusive scan of one value per thread (thread order); returns exclusive prefix, sets total.
-template <class T> __device__ __forceinline__ T block_excl_scan(T v, T* sh, T& total) {
+template <int NW = NWARP, class T> __device__ __forceinline__ T block_excl_scan(T v, T* sh, T& total) {
     T incl = warp_incl_scan(v);
     __syncthreads();
     if ((threadIdx.x & 31) == 31) sh[threadIdx.x >> 5] = incl;
@@ -64,7 +64,7 @@ template <class T> __device__ __forceinline__ T block_excl_scan(T v, T* sh, T& t
     T base = T(0), tot = T(0);
     const int w = threadIdx.x >> 5;
 #pragma unroll
-    for (int k = 0; k < NWARP; ++k) {
+    for (int k = 0; k < NW; ++k) {
         T s = sh[k];
         if (k < w) base += s;
         tot += s;

@@ -404,7 +404,9 @@ __device__ __forceinline__ void header_warp(const KArgs& a, int b, int t, int fi
     if (lane == 0) header_finish<Model>(a, b, t_done, final_pass, nstat, M, total, sbar, base, off);
 }
 
-template <class R, class Model>
+// NTH = threads of the CTA: 256, or 1024 for items with more than 256 tiles (N > 65536), where the per-thread chunk of
+// tiles (and with it the serial part of the scans) shrinks 4x.
+template <class R, class Model, int NTH = NT>
 __device__ __forceinline__ void header_body(const KArgs& a, int b, int t, int final_pass, double* sh_d) {
     const int tid = threadIdx.x;
     const int Tb = a.T_buf[b];
@@ -423,10 +425,10 @@ __device__ __forceinline__ void header_body(const KArgs& a, int b, int t, int fi
     double* gam = sc + (Q + 2);
     const double NEG_INF = -Mth<double>::inf();
 
-    const int per = (Q + NT - 1) / NT, q0 = tid * per;
+    const int per = (Q + NTH - 1) / NTH, q0 = tid * per;
     double m = NEG_INF;
     for (int k = 0; k < per; ++k) if (q0 + k < Q) m = fmax(m, sub[(size_t)(q0 + k) * SSTRIDE]);
-    const double M = block_max(m, sh_d);
+    const double M = block_max<NTH / 32>(m, sh_d);
     double loc = 0.0, ws[4] = {0.0, 0.0, 0.0, 0.0};
     for (int k = 0; k < per; ++k) {
         const int q = q0 + k;
@@ -438,7 +440,7 @@ __device__ __forceinline__ void header_body(const KArgs& a, int b, int t, int fi
         }
     }
     double total;
-    double run = block_excl_scan(loc, sh_d, total);
+    double run = block_excl_scan<NTH / 32>(loc, sh_d, total);
     for (int k = 0; k < per; ++k) {
         const int q = q0 + k;
         if (q < Q) {
@@ -450,18 +452,18 @@ __device__ __forceinline__ void header_body(const KArgs& a, int b, int t, int fi
         }
     }
     double sbar[4] = {0.0, 0.0, 0.0, 0.0};
-    for (int j = 0; j < nws; ++j) sbar[j] = block_sum(ws[j], sh_d) / total;
+    for (int j = 0; j < nws; ++j) sbar[j] = block_sum<NTH / 32>(ws[j], sh_d) / total;
 
     if (!final_pass && uses_spacings(a)) {
         const RngKey key = item_key(a, b);
-        const int perg = (Q + 1 + NT - 1) / NT, g0 = tid * perg;
+        const int perg = (Q + 1 + NTH - 1) / NTH, g0 = tid * perg;
         double gl = 0.0;
         for (int k = 0; k < perg; ++k) {
             const int q = g0 + k;
             if (q <= Q) gl += rng_gamma(key, (uint32_t)q, (uint32_t)t, (q == Q) ? 1.0 : (double)min(WT, N - q * WT));
         }
         double gtot;
-        double grun = block_excl_scan(gl, sh_d, gtot);
+        double grun = block_excl_scan<NTH / 32>(gl, sh_d, gtot);
         const double kk = total / gtot;                  // stored in target units: gam[q] = total * G_q / G_total
         for (int k = 0; k < perg; ++k) {
             const int q = g0 + k;
@@ -475,10 +477,10 @@ __device__ __forceinline__ void header_body(const KArgs& a, int b, int t, int fi
     if (tid == 0) header_finish<Model>(a, b, t_done, final_pass, nstat, M, total, sbar, base, off);
 }
 
-template <class R, class Model>
-__global__ void __launch_bounds__(NT) pf_header_kernel(KArgs a, int t, int final_pass) {
-    __shared__ double sh_d[NWARP];
-    header_body<R, Model>(a, a.b0 + blockIdx.x, t, final_pass, sh_d);
+template <class R, class Model, int NTH = NT>
+__global__ void __launch_bounds__(NTH) pf_header_kernel(KArgs a, int t, int final_pass) {
+    __shared__ double sh_d[NTH / 32];
+    header_body<R, Model, NTH>(a, a.b0 + blockIdx.x, t, final_pass, sh_d);
 }
 
 // ---- gather parents -> propagate -> reweight -> statistic update -> store (pf.py:30-36, 168-179) -----

@@ -79,6 +79,7 @@ int run_impl(const sgm_pf_desc* d, cudaStream_t stream) {
         const bool piped = d->aux_stream && d->ev_aux_fork && d->ev_aux_join && !backward_pf(d->pf) && !pred &&
                            (int64_t)a.B * a.G >= 2 * 148 * 4 && a.B >= 2;
         const int nh = piped ? 2 : 1;
+        const bool big_hdr = a.Q > NT;                 // more than one tile per header thread: use the 1024-thread header
         // the production configuration runs the step kernel with its run-time flags folded to constants
         const bool fast_path = sizeof(R) == 4 && d->rng_mode == SGM_RNG_PHILOX && d->resample == SGM_RESAMPLE_MULTINOMIAL_SORTED &&
                                d->pf == SGM_PF_NEMETH && d->lambduh == 1.0 && d->stat_kind == SGM_STAT_SCORE &&
@@ -97,7 +98,9 @@ int run_impl(const sgm_pf_desc* d, cudaStream_t stream) {
             for (int h = 0; h < nh; ++h) {
                 constexpr int SW = StepShape<false>::WARPS, FW = StepShape<true>::WARPS;
                 const dim3 gh((a.Q + SW - 1) / SW, nb[h]), bs(32 * SW);
-                pf_header_kernel<R, Model><<<nb[h], block, 0, sh[h]>>>(ah[h], t, 0); ++launches;
+                if (big_hdr) pf_header_kernel<R, Model, 1024><<<nb[h], 1024, 0, sh[h]>>>(ah[h], t, 0);
+                else pf_header_kernel<R, Model><<<nb[h], block, 0, sh[h]>>>(ah[h], t, 0);
+                ++launches;
                 bool done = false;
                 if constexpr (sizeof(R) == 4) {                    // the FAST instantiation exists for f32 only
                     if (fast_path) {
@@ -116,7 +119,11 @@ int run_impl(const sgm_pf_desc* d, cudaStream_t stream) {
             if (d->pf == SGM_PF_POY_N2) launches += launch_poyiadjis_n2<R, Model>(a, t, stream);
             else if (d->pf == SGM_PF_PARIS) launches += launch_paris<R, Model>(a, t, stream);
         }
-        for (int h = 0; h < nh; ++h) { pf_header_kernel<R, Model><<<nb[h], block, 0, sh[h]>>>(ah[h], a.max_T, 1); ++launches; }
+        for (int h = 0; h < nh; ++h) {
+            if (big_hdr) pf_header_kernel<R, Model, 1024><<<nb[h], 1024, 0, sh[h]>>>(ah[h], a.max_T, 1);
+            else pf_header_kernel<R, Model><<<nb[h], block, 0, sh[h]>>>(ah[h], a.max_T, 1);
+            ++launches;
+        }
         if (piped) {
             cudaEventRecord(reinterpret_cast<cudaEvent_t>(d->ev_aux_join), sh[1]);
             cudaStreamWaitEvent(stream, reinterpret_cast<cudaEvent_t>(d->ev_aux_join), 0);

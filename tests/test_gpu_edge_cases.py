@@ -34,7 +34,7 @@ def _run(N, obs, t1, tL, pf="poyiadjis_N", resample="multinomial", seed=3, weigh
 
 
 @pytest.mark.parametrize("resample", ["multinomial", "multinomial_sorted"])
-@pytest.mark.parametrize("N", [1, 2, 31, 255, 256, 257, 511, 513, 2047, 2049])
+@pytest.mark.parametrize("N", [1, 2, 31, 255, 256, 257, 511, 513, 2047, 2049, 8191, 65537, 70000])   # 65537+: 1024-thread header
 def test_tiny_and_tile_boundary_particle_counts(N, resample):
     obs = np.array([0.3, -1.2, 0.8, 2.0, -0.1, 0.4])
     res, expect, ref = _run(N, obs, 1, 5, resample=resample, weights=np.array([1.0, 2.0, 0.5, 3.0]))
