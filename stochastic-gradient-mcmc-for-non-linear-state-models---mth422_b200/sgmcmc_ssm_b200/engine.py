@@ -480,15 +480,18 @@ class PreparedPF(object):
                         ws_bytes=self.ws_bytes, grad_slots=self.grad_slots)
 
 
-def run_pf(model, kernel, pf, items, N, sync=True, check=True, **kwargs):
+def run_pf(model, kernel, pf, items, N, sync=True, check=True, while_running=None, **kwargs):
     """Run the buffered particle filter / smoother for a batch of work items on the GPU: pack, one H2D
     copy, the whole t-loop through the C-ABI, one D2H copy.
 
     Mirrors particle_filters/buffered_smoother.py:156-199 (`pf` dispatch) for a whole batch.
     Returns a PFResult with .grad (B, p), .loglik (B,), .status (B,).  One call may be outstanding per
-    device (staging buffers are shared)."""
+    device (staging buffers are shared).  `while_running`: host work to do between the launch and the wait
+    (the samplers evaluate the prior gradient there)."""
     prep = PreparedPF(model, kernel, pf, items, N, **kwargs).upload()
     res = (prep.launch_graph() if prep.graph_eligible() else prep.launch()).download()
+    if while_running is not None:
+        while_running()
     if sync:
         res.wait(check=check)
     return res

@@ -72,7 +72,8 @@ def batched_pf(pf, model, kernel, items, N, stat_kind="score", want=(), sync=Tru
         kw.setdefault("resample", "multinomial")
     elif "injected" in kwargs:
         kw["injected"] = kwargs["injected"]
-    return engine.run_pf(model, kernel, pf, items, N, stat_kind=stat_kind, want=want, sync=sync, **kw)
+    return engine.run_pf(model, kernel, pf, items, N, stat_kind=stat_kind, want=want, sync=sync,
+                         while_running=kwargs.get("while_running"), **kw)
 
 
 def buffered_pf_wrapper(pf, observations=None, parameters=None, N=1000, kernel=None,

@@ -328,9 +328,18 @@ class SGMCMCSampler(object):
     def noisy_gradient(self, preconditioner=None, is_scaled=True, **kwargs):
         """grad log-likelihood estimate + grad log-prior, scaled by 1/T (sgmcmc_sampler.py:427-464)."""
         noisy_grad_loglike = kwargs.pop("noisy_grad_loglike", None)       # precomputed by ensemble.ChainEnsemble
-        if noisy_grad_loglike is None:
-            noisy_grad_loglike = self._noisy_grad_loglikelihood(**kwargs)
-        noisy_grad_prior = self.prior.grad_logprior(parameters=kwargs.get("parameters", self.parameters))
+        if noisy_grad_loglike is None and kwargs.get("kind") == "pf" and not kwargs.get("distributed", False):
+            # the prior gradient (host numpy, no random numbers) is evaluated while the particle filters run
+            box = []
+            noisy_grad_loglike = self._noisy_grad_loglikelihood(
+                while_running=lambda: box or box.append(
+                    self.prior.grad_logprior(parameters=kwargs.get("parameters", self.parameters))),
+                **kwargs)
+            noisy_grad_prior = box[0] if box else self.prior.grad_logprior(parameters=kwargs.get("parameters", self.parameters))
+        else:
+            if noisy_grad_loglike is None:
+                noisy_grad_loglike = self._noisy_grad_loglikelihood(**kwargs)
+            noisy_grad_prior = self.prior.grad_logprior(parameters=kwargs.get("parameters", self.parameters))
         noisy_gradient = {var: noisy_grad_prior[var] + noisy_grad_loglike[var] for var in noisy_grad_prior}
         if preconditioner is None:
             if is_scaled:
