@@ -314,7 +314,9 @@ def run_gpu(args):
     }
     if world == 1 and not args.no_cpu_baseline:
         windows = draw_windows(8, seed=99)
-        n_grad = max(1, int(args.cpu_seconds // 3))
+        # size the sample from one timed gradient (about 1 s on the box's cores) so it fills ~cpu_seconds
+        _, dt1, _ = cpu_rate(y, windows, 1, 1, 0)
+        n_grad = int(min(64, max(2, args.cpu_seconds / max(dt1, 1e-3))))
         rate, dt, done = cpu_rate(y, windows, 1, n_grad, 0)
         line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": 1, "kind": "port",
                                 "sample": "{0} subsequence gradient(s) of the same workload (N=2^16, T_buf<=60), "
