@@ -79,7 +79,6 @@ int run_impl(const sgm_pf_desc* d, cudaStream_t stream) {
         const bool piped = d->aux_stream && d->ev_aux_fork && d->ev_aux_join && !backward_pf(d->pf) && !pred &&
                            (int64_t)a.B * a.G >= 2 * 148 * 4 && a.B >= 2;
         const int nh = piped ? 2 : 1;
-        const bool big_hdr = a.Q > NT;                 // more than one tile per header thread: use the 1024-thread header
         // the production configuration runs the step kernel with its run-time flags folded to constants
         const bool fast_path = sizeof(R) == 4 && d->rng_mode == SGM_RNG_PHILOX && d->resample == SGM_RESAMPLE_MULTINOMIAL_SORTED &&
                                d->pf == SGM_PF_NEMETH && d->lambduh == 1.0 && d->stat_kind == SGM_STAT_SCORE &&
@@ -92,38 +91,39 @@ int run_impl(const sgm_pf_desc* d, cudaStream_t stream) {
             cudaEventRecord(reinterpret_cast<cudaEvent_t>(d->ev_aux_fork), stream);
             cudaStreamWaitEvent(sh[1], reinterpret_cast<cudaEvent_t>(d->ev_aux_fork), 0);
         }
+        // one CTA per item; 1024 threads once an item has more than one tile per header thread
+        auto launch_header = [&](int h, int t, int final_pass) {
+            if (a.Q > NT) pf_header_kernel<R, Model, 1024><<<nb[h], 1024, 0, sh[h]>>>(ah[h], t, final_pass);
+            else pf_header_kernel<R, Model><<<nb[h], block, 0, sh[h]>>>(ah[h], t, final_pass);
+            ++launches;
+        };
+        auto launch_step = [&](int h, int t) {
+            constexpr int SW = StepShape<false>::WARPS, FW = StepShape<true>::WARPS;
+            ++launches;
+            if constexpr (sizeof(R) == 4) {                    // the FAST instantiations exist for f32 only
+                if (fast_path) {
+                    const dim3 gf((a.Q + FW - 1) / FW, nb[h]);
+                    if (a.N % WT == 0) pf_step_kernel<R, Model, true, true, false><<<gf, 32 * FW, 0, sh[h]>>>(ah[h], t);
+                    else pf_step_kernel<R, Model, true, true, true><<<gf, 32 * FW, 0, sh[h]>>>(ah[h], t);   // ragged last tile
+                    return;
+                }
+            }
+            const dim3 gh((a.Q + SW - 1) / SW, nb[h]), bs(32 * SW);
+            if (d->resample == SGM_RESAMPLE_MULTINOMIAL) pf_step_kernel<R, Model, false><<<gh, bs, 0, sh[h]>>>(ah[h], t);
+            else pf_step_kernel<R, Model, true><<<gh, bs, 0, sh[h]>>>(ah[h], t);
+        };
         for (int h = 0; h < nh; ++h) { pf_init_kernel<R, Model><<<dim3(a.G, nb[h]), block, 0, sh[h]>>>(ah[h]); ++launches; }
         if (d->ev_steps_begin) cudaEventRecord(reinterpret_cast<cudaEvent_t>(d->ev_steps_begin), stream);
         for (int t = 0; t < a.max_T; ++t) {
             for (int h = 0; h < nh; ++h) {
-                constexpr int SW = StepShape<false>::WARPS, FW = StepShape<true>::WARPS;
-                const dim3 gh((a.Q + SW - 1) / SW, nb[h]), bs(32 * SW);
-                if (big_hdr) pf_header_kernel<R, Model, 1024><<<nb[h], 1024, 0, sh[h]>>>(ah[h], t, 0);
-                else pf_header_kernel<R, Model><<<nb[h], block, 0, sh[h]>>>(ah[h], t, 0);
-                ++launches;
-                bool done = false;
-                if constexpr (sizeof(R) == 4) {                    // the FAST instantiation exists for f32 only
-                    if (fast_path) {
-                        const dim3 gf((a.Q + FW - 1) / FW, nb[h]);
-                        if (a.N % WT == 0) pf_step_kernel<R, Model, true, true, false><<<gf, 32 * FW, 0, sh[h]>>>(ah[h], t);
-                        else pf_step_kernel<R, Model, true, true, true><<<gf, 32 * FW, 0, sh[h]>>>(ah[h], t);   // ragged last tile
-                        done = true;
-                    }
-                }
-                if (done) {}
-                else if (d->resample == SGM_RESAMPLE_MULTINOMIAL) pf_step_kernel<R, Model, false><<<gh, bs, 0, sh[h]>>>(ah[h], t);
-                else pf_step_kernel<R, Model, true><<<gh, bs, 0, sh[h]>>>(ah[h], t);
-                ++launches;
+                launch_header(h, t, 0);
+                launch_step(h, t);
             }
             if (pred) { pf_pred_kernel<R, Model><<<a.B, block, 0, stream>>>(a, t); ++launches; }
             if (d->pf == SGM_PF_POY_N2) launches += launch_poyiadjis_n2<R, Model>(a, t, stream);
             else if (d->pf == SGM_PF_PARIS) launches += launch_paris<R, Model>(a, t, stream);
         }
-        for (int h = 0; h < nh; ++h) {
-            if (big_hdr) pf_header_kernel<R, Model, 1024><<<nb[h], 1024, 0, sh[h]>>>(ah[h], a.max_T, 1);
-            else pf_header_kernel<R, Model><<<nb[h], block, 0, sh[h]>>>(ah[h], a.max_T, 1);
-            ++launches;
-        }
+        for (int h = 0; h < nh; ++h) launch_header(h, a.max_T, 1);
         if (piped) {
             cudaEventRecord(reinterpret_cast<cudaEvent_t>(d->ev_aux_join), sh[1]);
             cudaStreamWaitEvent(stream, reinterpret_cast<cudaEvent_t>(d->ev_aux_join), 0);
