@@ -126,10 +126,11 @@ struct ItemHdr {
     int Q;
     double M, total;
 };
-__device__ __forceinline__ ItemHdr load_hdr(const KArgs& a, int b) {
+// `local` != nullptr: a copy of the header somewhere else (the single-launch kernel keeps one per warp in shared memory)
+__device__ __forceinline__ ItemHdr load_hdr(const KArgs& a, int b, const double* local = nullptr) {
     ItemHdr h;
     h.Q = a.Q;
-    h.base = a.hdr + (size_t)b * hdr_stride(a.Q);
+    h.base = local ? local : a.hdr + (size_t)b * hdr_stride(a.Q);
     h.off = h.base + H_SCALARS;
     h.sc = h.off + (a.Q + 2);
     h.gam = h.sc + (a.Q + 2);
@@ -336,12 +337,13 @@ __global__ void __launch_bounds__(NT) pf_init_kernel(KArgs a) {
 // scalar tail of the header (one thread): totals, status flags, log-likelihood increment, final outputs
 template <class Model>
 __device__ __forceinline__ void header_finish(const KArgs& a, int b, int t_done, int final_pass, int nstat, double M, double total,
-                                              const double* sbar, double* base, double* off) {
+                                              const double* sbar, double* base, double* off, bool side_effects = true) {
     const int Q = a.Q, N = a.N;
     const double NEG_INF = -Mth<double>::inf();
     off[Q] = total;
     base[H_M] = M; base[H_TOTAL] = total;
     for (int j = 0; j < 4; ++j) base[H_SBAR + j] = sbar[j];
+    if (!side_effects) return;             // a redundant per-warp copy: status / log-likelihood are the first warp's job
     if (!(total > 0.0) || !(total < Mth<double>::inf()) || !(M == M) || !(fabs(M) < Mth<double>::inf()))
         a.status[b] |= (total == 0.0 || M == NEG_INF) ? SGM_STATUS_ZERO_WEIGHT : SGM_STATUS_NAN_WEIGHT;
     double* acc = a.acc + (size_t)b * ACC_STRIDE;
@@ -365,10 +367,13 @@ __device__ __forceinline__ void header_finish(const KArgs& a, int b, int t_done,
 
 // Header of an item with fewer than 32 warp tiles (N < 8192): ONE warp, shuffles only -- no block barrier.
 // This is the per-step latency of the single-launch kernel for small N (the SGLD-with-N~1000 regime).
+// `local` != nullptr: EVERY warp of the CTA calls this and builds its own copy of the header there (single-launch
+// kernel: no barrier and no global round trip between header and step; the copies are bit-identical -- same inputs,
+// counter-based Gamma draws, fixed shuffle trees); only the first warp applies the side effects.
 template <class R, class Model>
-__device__ __forceinline__ void header_warp(const KArgs& a, int b, int t, int final_pass) {
-    if (threadIdx.x >= 32) return;
-    const int lane = threadIdx.x;
+__device__ __forceinline__ void header_warp(const KArgs& a, int b, int t, int final_pass, double* local = nullptr) {
+    if (!local && threadIdx.x >= 32) return;
+    const int lane = threadIdx.x & 31;
     const int Tb = a.T_buf[b];
     const int par = final_pass ? (Tb & 1) : (t & 1);
     const int t_done = final_pass ? Tb - 1 : t - 1;
@@ -377,7 +382,7 @@ __device__ __forceinline__ void header_warp(const KArgs& a, int b, int t, int fi
     const bool shrink = (a.pf == SGM_PF_NEMETH) && (a.lambduh != 1.0);
     const int nws = (final_pass || shrink || a.pf == SGM_PF_FILTER) ? nstat : 0;
     const double* sub = a.sub[par] + (size_t)b * Q * SSTRIDE;
-    double* base = a.hdr + (size_t)b * hdr_stride(Q);
+    double* base = local ? local : a.hdr + (size_t)b * hdr_stride(Q);
     double* off = base + H_SCALARS;
     double* sc = off + (Q + 2);
     double* gam = sc + (Q + 2);
@@ -401,7 +406,8 @@ __device__ __forceinline__ void header_warp(const KArgs& a, int b, int t, int fi
         if (lane <= Q) gam[lane] = (gincl - g) * kk;
         if (lane == 0) gam[Q + 1] = total;
     }
-    if (lane == 0) header_finish<Model>(a, b, t_done, final_pass, nstat, M, total, sbar, base, off);
+    if (lane == 0) header_finish<Model>(a, b, t_done, final_pass, nstat, M, total, sbar, base, off, !local || threadIdx.x < 32);
+    if (local) __syncwarp();
 }
 
 // NTH = threads of the CTA: 256, or 1024 for items with more than 256 tiles (N > 65536), where the per-thread chunk of
@@ -603,7 +609,7 @@ __device__ __forceinline__ void search_levels(uint32_t* ad, const R* rt) {
 // i.e. N is not a multiple of 256 -- bound checks: ~9 % of the generic kernel's instructions); the arithmetic is
 // identical.
 template <class R, class Model, bool SORTED, bool FAST = false, bool RAGGED = false>
-__device__ __forceinline__ void step_body(const KArgs& a, int b, int t, int q_me, int lane, R* s_cdf) {
+__device__ __forceinline__ void step_body(const KArgs& a, int b, int t, int q_me, int lane, R* s_cdf, const double* hdr_local = nullptr) {
     static_assert(!FAST || SORTED, "FAST implies sorted resampling");
     R* const s_tr = s_cdf;                 // the warp's shared-memory slice doubles as the scan transposition buffer
     constexpr int NP = Model::NP, W = Model::NX + NP;
@@ -612,7 +618,7 @@ __device__ __forceinline__ void step_body(const KArgs& a, int b, int t, int q_me
     // every load that does not depend on the randoms is issued up front (one round trip for all of them):
     // activity flag, item header scalars, level-1 coarse probe, Gamma prefix, (y_t, w_t), model constants
     const int Tb = a.T_buf[b];
-    const ItemHdr hdr = load_hdr(a, b);
+    const ItemHdr hdr = load_hdr(a, b, hdr_local);
     const int s1c = (a.Q + 31) >> 5;
     const double c1 = (SORTED && lane * s1c < a.Q) ? hdr.off[lane * s1c] : Mth<double>::inf();
     const R* ywp = reinterpret_cast<const R*>(a.yw) + ((size_t)b * a.max_T + min(t, a.max_T - 1)) * 2;
@@ -866,14 +872,17 @@ template <class R, class Model, bool SORTED>
 __global__ void __launch_bounds__(NT, (sizeof(R) == 4 ? SGM_FUSED_CTAS : 2)) pf_fused_kernel(KArgs a) {
     __shared__ __align__(32) R s_cdf_all[NWARP][SORTED ? WIN_BYTES / sizeof(R) : WT];
     __shared__ double sh_d[NWARP];
+    __shared__ double s_hdr[NWARP][H_SCALARS + 3 * (NWARP + 2)];      // one private copy of the item header per warp
     const int b = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     init_body<R, Model>(a, b, 0, s_cdf_all[warp]);
     __syncthreads();
     const int Tb = a.T_buf[b];
     for (int t = 0; t < Tb; ++t) {
-        header_body<R, Model>(a, b, t, 0, sh_d);
-        __syncthreads();
-        step_body<R, Model, SORTED>(a, b, t, warp, lane, s_cdf_all[warp]);
+        // every warp that owns a tile builds the header itself, then runs its tile: ONE block barrier per time step
+        if (warp < a.Q) {
+            header_warp<R, Model>(a, b, t, 0, s_hdr[warp]);
+            step_body<R, Model, SORTED>(a, b, t, warp, lane, s_cdf_all[warp], s_hdr[warp]);
+        }
         __syncthreads();
     }
     header_body<R, Model>(a, b, Tb, 1, sh_d);
