@@ -228,3 +228,36 @@ def test_product_path_never_touches_the_oracle():
     gpu_arm = src[src.index("def run_gpu("):src.index("def extras(")]
     assert "import pf_oracle" not in gpu_arm and "po." not in gpu_arm.replace("cpu_rate", "")
     assert src.count("from oracle import pf_oracle") == 1 and "def _cpu_one_gradient" in src
+
+
+def test_prior_gradient_is_evaluated_while_the_filters_run(monkeypatch):
+    """noisy_gradient(kind='pf') hands the helper a `while_running` hook (host work between launch and wait); whether
+    or not the device layer calls it, the result is grad log-likelihood + grad log-prior, scaled by 1/T, and the
+    prior gradient is evaluated exactly once (sgmcmc_sampler.py:427-464)."""
+    from sgmcmc_ssm_b200.models.svm import SVMHelper
+    calls = []
+
+    def fake_batch(self, windows, parameters, while_running=None, **kwargs):
+        if fake_batch.use_hook and while_running is not None:
+            while_running()
+            while_running()                       # idempotent: a second device call must not re-evaluate it
+        return [dict(LRinv_vec=1.0, LQinv_vec=2.0, A=3.0) for _ in windows], None
+
+    monkeypatch.setattr(SVMHelper, "pf_gradient_estimate_batch", fake_batch)
+    np.random.seed(0)
+    y = np.random.normal(size=(300, 1))
+    s = SVMSampler(n=1, m=1, observations=y, parameters=svm_params())
+    prior_grad = s.prior.grad_logprior(parameters=s.parameters)
+    orig = type(s.prior).grad_logprior
+    monkeypatch.setattr(type(s.prior), "grad_logprior", lambda self, **kw: (calls.append(1), orig(self, **kw))[1])
+    out = {}
+    for use_hook in (True, False):
+        fake_batch.use_hook = use_hook
+        del calls[:]
+        np.random.seed(1)
+        out[use_hook] = s.noisy_gradient(kind="pf", N=16, subsequence_length=20, buffer_length=5, minibatch_size=1)
+        assert len(calls) == 1
+    for k, like in dict(LRinv_vec=1.0, LQinv_vec=2.0, A=3.0).items():
+        expect = (np.ravel(prior_grad[k])[0] + like) / 300.0
+        np.testing.assert_allclose(np.ravel(out[True][k])[0], expect, rtol=1e-13)
+        np.testing.assert_allclose(np.ravel(out[False][k])[0], expect, rtol=1e-13)
