@@ -20,6 +20,8 @@ def tril_indices_from(mat):
 def tril_vector_to_mat(vec):
     """Lower-triangular matrix from its row-major packed vector (_utils.py:134-139)."""
     vec = np.atleast_1d(vec)
+    if len(vec) == 1:                      # the n = 1 models of the PF path: skip the index machinery
+        return np.array(vec, dtype=float).reshape(1, 1)
     n = int(np.sqrt(len(vec) * 2))
     mat = np.zeros((n, n), dtype=float)
     mat[_tril_indices(n)] = vec

@@ -23,7 +23,11 @@ class SGMCMCHelper(object):
         (svm/helper.py:100-104, lgssm/helper.py:1098-1101)."""
         if forward_message is None:
             forward_message = self.default_forward_message
-        prior_var = np.linalg.inv(np.atleast_2d(forward_message["precision"]))
+        precision = np.atleast_2d(forward_message["precision"])
+        if precision.size == 1:             # n = 1: inv / solve are one division each (bitwise what LAPACK returns)
+            prior_var = 1.0 / float(precision[0, 0])
+            return float(np.ravel(forward_message["mean_precision"])[0]) / prior_var, prior_var
+        prior_var = np.linalg.inv(precision)
         prior_mean = np.linalg.solve(prior_var, np.atleast_1d(forward_message["mean_precision"]))
         return float(prior_mean[0]), float(prior_var[0, 0])
 

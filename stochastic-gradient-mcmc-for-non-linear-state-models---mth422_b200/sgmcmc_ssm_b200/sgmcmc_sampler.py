@@ -321,7 +321,8 @@ class SGMCMCSampler(object):
         for var in noisy_grad:
             if np.any(np.isnan(noisy_grad[var])):
                 raise ValueError("NaNs in gradient of {0}".format(var))
-            if np.linalg.norm(noisy_grad[var]) > 1e16:
+            g = noisy_grad[var]
+            if (abs(g.flat[0]) if np.size(g) == 1 else np.linalg.norm(g)) > 1e16:
                 logger.warning("Norm of noisy_grad_loglike[{1} > 1e16: {0}".format(noisy_grad[var], var))
         return noisy_grad
 
