@@ -215,6 +215,30 @@ def test_python_descriptor_mirror_has_the_size_the_library_expects():
     assert lib.sgm_pf_run(ctypes.byref(d), None) == -2 and b"optimal" in lib.sgm_last_error()   # NotImplementedError
 
 
+def test_python_constants_mirror_the_header():
+    """Enumerators and #defines of include/sgmpf.h against the Python mirror (a drifted constant would silently select
+    another smoother / statistic)."""
+    from sgmcmc_ssm_b200 import _native as nat
+    text = open(os.path.join(ROOT, "include", "sgmpf.h")).read()
+    defines = {k: int(v) for k, v in re.findall(r"#define\s+(SGM_[A-Z0-9_]+)\s+(\d+)", text)}
+    assert defines["SGM_PRED_SLOTS"] == nat.PRED_SLOTS and defines["SGM_PRED_MAX_STEPS"] == nat.PRED_MAX_STEPS
+    enums = {}
+    for body in re.findall(r"enum\s*\{(.*?)\}", text, flags=re.S):
+        body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+        for k, v in re.findall(r"(SGM_[A-Z0-9_]+)\s*=\s*(-?\d+)", body):
+            enums[k] = int(v)
+    expect = {"SGM_STAT_SCORE": nat.STAT["score"], "SGM_STAT_PRED": nat.STAT["pred"],
+              "SGM_PF_NEMETH": nat.PF["nemeth"], "SGM_PF_POY_N2": nat.PF["poyiadjis_N2"], "SGM_PF_PARIS": nat.PF["paris"],
+              "SGM_PF_FILTER": nat.PF["filter"], "SGM_MODEL_SVM": nat.MODEL["svm"], "SGM_MODEL_LGSSM": nat.MODEL["lgssm"],
+              "SGM_RNG_PHILOX": nat.RNG["philox"], "SGM_RNG_INJECTED": nat.RNG["injected"],
+              "SGM_RESAMPLE_MULTINOMIAL": nat.RESAMPLE["multinomial"],
+              "SGM_RESAMPLE_MULTINOMIAL_SORTED": nat.RESAMPLE["multinomial_sorted"],
+              "SGM_N2_TENSOR": nat.N2_MODE["tensor"], "SGM_N2_FP32_PIPE": nat.N2_MODE["fp32_pipe"]}
+    for k, v in expect.items():
+        assert enums[k] == v, k
+    assert nat.PF["poyiadjis_N"] == nat.PF["nemeth"]                  # buffered_smoother.py:175-180: nemeth with lambduh = 1
+
+
 def test_product_path_never_touches_the_oracle():
     """oracle/ is test infrastructure: nothing under the package, the drop-in alias or scripts/ may import it, and in
     bench.py only the CPU legs (cpu_baseline / --impl reference) do."""
