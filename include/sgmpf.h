@@ -71,6 +71,12 @@ enum { SGM_STAT_SCORE = 0,     /* complete-data log-likelihood gradient (pf_grad
  * otherwise; FP32_PIPE forces the CUDA-core kernel (any dtype); TENSOR requires SGM_F32. */
 enum { SGM_N2_AUTO = 0, SGM_N2_FP32_PIPE = 1, SGM_N2_TENSOR = 2 };
 
+/* Device random variates of an SGM_F64 run (Philox only; ignored for SGM_F32 and INJECTED).  NATIVE: 52-bit uniforms,
+ * f64 log / sincospi / sqrt transforms.  F32: the variates of the f32 path (32-bit uniforms, MUFU transforms), widened to
+ * f64 -- every operation on the particle system (propagation, weights, CDF, statistics) still runs in f64; only the
+ * resolution of the random inputs is 2^-24 instead of 2^-53 (a change of the sampling law far below Monte-Carlo error). */
+enum { SGM_VARIATES_NATIVE = 0, SGM_VARIATES_F32 = 1 };
+
 /* error codes */
 enum { SGM_OK = 0, SGM_ERR_INVALID = -1, SGM_ERR_UNSUPPORTED = -2, SGM_ERR_WORKSPACE = -3,
        SGM_ERR_CUDA = -4, SGM_ERR_DEVICE = -5 };
@@ -104,7 +110,7 @@ typedef struct sgm_pf_desc {
     int32_t pred_steps_ahead;      /* SGM_STAT_PRED: num_steps_ahead K (0..SGM_PRED_MAX_STEPS); K + 1 entries */
     int32_t pred_per_horizon;      /* SGM_STAT_PRED: 0 = the reference's log-sum over ALL horizons (pf.py:73-76),
                                     * 1 = one log-sum per horizon                                    */
-    int32_t reserved0;             /* must be 0                                                     */
+    int32_t variates;              /* SGM_VARIATES_*: precision the device random variates are generated in        */
     double lambduh;                /* Nemeth shrinkage (pf.py:140); 1.0 = Poyiadjis O(N)            */
     uint64_t seed, offset;         /* Philox key / call counter                                     */
     const uint64_t* offset_dev;    /* optional DEVICE pointer: when set the call counter is read from there by the

@@ -18,9 +18,13 @@ for model, (th, kern) in TH.items():
     for N in (300, 2500, 5000):                  # fused single-CTA path / multi-CTA ragged / 3 CTAs per item
         for pf, kw in (("poyiadjis_N", {}), ("nemeth", dict(lambduh=0.9)), ("filter", {}), ("poyiadjis_N2", {}),
                        ("poyiadjis_N2", dict(n2_mode="fp32_pipe")), ("paris", dict(Ntilde=3))):
-            for resample in ("multinomial_sorted", "multinomial"):
+            for resample in ("multinomial_sorted", "multinomial", "systematic", "stratified"):
                 r = sg.run_pf(model, kern, pf, it, N, dtype="f32", resample=resample, seed=1, offset=1, **kw)
-                assert np.all(np.isfinite(r.grad)), (model, pf, N)
+                assert np.all(np.isfinite(r.grad)), (model, pf, N, resample)
+        for pf, kw in (("poyiadjis_N", {}), ("nemeth", dict(lambduh=0.9)), ("filter", {})):      # f64 fast modes (ragged)
+            for variates in ("native", "f32"):
+                r = sg.run_pf(model, kern, pf, it, N, dtype="f64", variates=variates, seed=1, offset=1, **kw)
+                assert np.all(np.isfinite(r.grad)), (model, pf, N, variates)
         r = sg.run_pf(model, kern, "poyiadjis_N", it, N, dtype="f64", seed=1, offset=1, want=("x", "lw", "stats", "anc", "trace_x"))
         r = sg.run_pf(model, kern, "filter", it, N, dtype="f32", stat_kind="pred", num_steps_ahead=4, seed=1, offset=1)
         assert np.all(np.isfinite(r.grad))

@@ -58,6 +58,7 @@ struct KArgs {
     int B, N, G, Q, max_T;
     int pf, rng_mode, resample, stat_kind, Ntilde, accept_reject, max_ar, manual_thresh;
     int need_lw, n2_tensor;
+    int variates32;        // f64 runs: generate the random variates with the f32 transforms (see draw_normals)
     int pred_K, pred_per_horizon;  // SGM_STAT_PRED: num_steps_ahead, log-sum variant
     const double* inj_pred;
     int b0;                // first item of this launch (a batch may be split over two streams)
@@ -212,10 +213,13 @@ __device__ __forceinline__ void load_lane_major(const R* src, int lane, R* v) {
 
 // ---- per-warp-tile epilogue: tile max, tile-local scan of exp(lw - m), per-tile partials ---------------
 // lwn[c] belongs to particle tile_base + 32 c + lane; callers set -inf beyond N (zero weight).
+// `carried` != nullptr: the caller already holds the lane's weighted statistic sums sum_c stat[c] * exp(lwn[c] - carried->m)
+// (accumulated in registers while the particles were propagated, see WsCarry) -- no re-read of the new records.
+template <class R> struct WsCarry { R m; R s[4]; };
 template <class R, int W>
 __device__ __forceinline__ void warp_tile_epilogue(const R* lwn, int tile_base, int N, int lane, R* fine_out, double* sub_out,
                                                    const void* rec_new, const void* tail_new, size_t item_off,
-                                                   bool need_ws, int nws, R* s_tr) {
+                                                   bool need_ws, int nws, R* s_tr, const WsCarry<R>* carried = nullptr) {
     R m = -Mth<R>::inf();
 #pragma unroll
     for (int c = 0; c < KPT; ++c) m = nan_max(m, lwn[c]);
@@ -236,7 +240,12 @@ __device__ __forceinline__ void warp_tile_epilogue(const R* lwn, int tile_base, 
     store_lane_major<R>(fine_out + tile_base, lane, f);   // `fine` is padded to whole tiles (entries >= N repeat the total)
     __syncwarp();
     double ws[4] = {0.0, 0.0, 0.0, 0.0};
-    if (need_ws) {
+    if (carried) {
+        // lane-local reference -> tile reference (exp(-inf - msafe) = 0 for a lane that owns no live particle)
+        const R sc = Mth<R>::exp(carried->m - msafe);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) if (q < nws) ws[q] = (double)warp_sum(carried->s[q] * sc);
+    } else if (need_ws) {
         // weighted statistic sums of the tile (Nemeth shrinkage, filter statistic, final average): summed in R within
         // the tile (256 terms with weights <= 1), in f64 across tiles (header kernel)
         R wl[4] = {(R)0, (R)0, (R)0, (R)0};
@@ -492,13 +501,17 @@ __global__ void __launch_bounds__(NTH) pf_header_kernel(KArgs a, int t, int fina
 // ---- gather parents -> propagate -> reweight -> statistic update -> store (pf.py:30-36, 168-179) -----
 // Row c of the warp tile = particles tile_base + 32 c + lane: coalesced stores, and with ascending
 // ancestors the parent gathers of a row are (nearly) contiguous too.
-template <class R, class Model, bool FAST = false, bool RAGGED = false>
+// FM = fast mode of the instantiation (see step_body): FM_GENERIC reads every flag at run time.
+enum : int { FM_GENERIC = 0, FM_POY = 1, FM_SHRINK = 2, FM_FILTER = 3 };
+template <class R, class Model, int FM = FM_GENERIC, bool RAGGED = false>
 __device__ __forceinline__ void propagate_store(const KArgs& a, int b, int t, int par, int tile_base, int lane, size_t item_off,
                                                 const int* anc, const R* z, const ItemHdr& hdr, int nws,
                                                 bool carries, bool shrink, R* lwn,
-                                                const typename Model::template Theta<R>& th, R y, R wt) {
+                                                const typename Model::template Theta<R>& th, R y, R wt, WsCarry<R>* carry) {
     constexpr int NX = Model::NX, NP = Model::NP, W = NX + NP;
+    constexpr bool FAST = FM != FM_GENERIC;
     constexpr bool FULLT = FAST && !RAGGED;        // every tile of the item is complete: no bound checks
+    constexpr bool CARRY_WS = FM == FM_SHRINK || FM == FM_FILTER;   // weighted statistic sums accumulated in registers
     const int N = a.N;
     const bool in_sub = wt != (R)0;               // yw[1] is zero outside [t1, tL)
     const R lam = (R)a.lambduh;
@@ -511,7 +524,7 @@ __device__ __forceinline__ void propagate_store(const KArgs& a, int b, int t, in
     const R keep = carries ? (shrink ? lam : (R)1) : (R)0;
     const R hs = (FAST || carries || a.pf == SGM_PF_FILTER) ? wt : (R)0;
     const int stat_kind = (in_sub && hs != (R)0) ? (FAST ? (int)SGM_STAT_SCORE : a.stat_kind) : (int)SGM_STAT_NONE;
-    const bool plain = FAST || (carries && !shrink);
+    const bool plain = FM == FM_POY || (!FAST && carries && !shrink);
     // per-item base pointers: the particle index stays a 32-bit register (one IMAD.WIDE per address)
     const void* rec_old = reinterpret_cast<const Vec4T<R>*>(a.rec[par]) + item_off;
     const void* tail_old = reinterpret_cast<const R*>(a.tail[par]) + item_off * (W - 4);
@@ -520,6 +533,7 @@ __device__ __forceinline__ void propagate_store(const KArgs& a, int b, int t, in
     R* lw_new = reinterpret_cast<R*>(a.lw[par ^ 1]) + item_off;
     // keep the compiler from folding the item offset back into every 64-bit address computation
     asm volatile("" : "+l"(rec_old), "+l"(tail_old), "+l"(rec_new), "+l"(tail_new), "+l"(lw_new));
+    if (CARRY_WS) { carry->m = -Mth<R>::inf(); carry->s[0] = carry->s[1] = carry->s[2] = carry->s[3] = (R)0; }
 #pragma unroll
     for (int h0 = 0; h0 < KPT; h0 += GB) {
         R ra[GB][W];
@@ -540,11 +554,24 @@ __device__ __forceinline__ void propagate_store(const KArgs& a, int b, int t, in
                 if (plain) {
 #pragma unroll
                     for (int q = 0; q < NP; ++q) rn[q] = ra[c4][q] + h[q] * hs;           // Poyiadjis O(N): one FMA
+                } else if (FM == FM_FILTER) {
+#pragma unroll
+                    for (int q = 0; q < NP; ++q) rn[q] = h[q] * hs;                       // pf.py:70-71: nothing carried
                 } else {
 #pragma unroll
                     for (int q = 0; q < NP; ++q) rn[q] = keep * ra[c4][q] + (sbar[q] + h[q] * hs);
                 }
                 store_rec<R, W>(rec_new, tail_new, i, rn);
+                if (CARRY_WS) {
+                    // sum_c stat[c] * exp(lw[c] - m) with a lane-local running reference m (rescaled to the tile maximum
+                    // in the epilogue): the freshly written records are not read again
+                    const R mnew = nan_max(carry->m, lwn[c]);
+                    const R msf = (mnew == -Mth<R>::inf()) ? (R)0 : mnew;
+                    const R so = Mth<R>::exp(carry->m - msf), e = Mth<R>::exp(lwn[c] - msf);
+#pragma unroll
+                    for (int q = 0; q < NP; ++q) carry->s[q] = carry->s[q] * so + rn[q] * e;
+                    carry->m = mnew;
+                }
                 if (tracing) {
                     if (a.need_lw) lw_new[i] = lwn[c];
                     if (a.trace_anc) a.trace_anc[((size_t)b * a.max_T + t) * N + i] = anc[c];
@@ -561,8 +588,26 @@ __device__ __forceinline__ void propagate_store(const KArgs& a, int b, int t, in
 
 // Random numbers of a warp tile: one Philox call yields the values of rows 4h..4h+3 of a lane
 // (counter index = 64 q + 2 lane + h: a function of the particle index only).
+// a.variates32 (f64 runs only): the variates are generated with the f32 transforms (one Philox call per four values,
+// MUFU log / sin / cos) and widened -- exactly the random numbers an f32 run of the same call draws; all arithmetic on
+// the particle system stays f64.
+__device__ __forceinline__ void widen8(const float* s, double* d) {
+#pragma unroll
+    for (int c = 0; c < KPT; ++c) d[c] = (double)s[c];
+}
+__device__ __forceinline__ void widen8(const float* s, float* d) {
+#pragma unroll
+    for (int c = 0; c < KPT; ++c) d[c] = s[c];
+}
 template <class R>
 __device__ __forceinline__ void draw_normals(const KArgs& a, const RngKey& key, int b, int t, int q_me, int lane, R* z) {
+    if (sizeof(R) == 8 && a.variates32 && a.rng_mode != SGM_RNG_INJECTED) {
+        float zf[KPT];
+        rng_normal4(key, (uint32_t)(q_me * 64 + lane * 2), (uint32_t)t, zf);
+        rng_normal4(key, (uint32_t)(q_me * 64 + lane * 2 + 1), (uint32_t)t, zf + 4);
+        widen8(zf, z);
+        return;
+    }
     if (a.rng_mode == SGM_RNG_INJECTED) {
         const double* zz = a.inj_z + ((size_t)b * a.max_T + t) * a.N;
 #pragma unroll
@@ -573,7 +618,14 @@ __device__ __forceinline__ void draw_normals(const KArgs& a, const RngKey& key, 
     }
 }
 template <class R>
-__device__ __forceinline__ void draw_uniforms(const RngKey& key, int t, int q_me, int lane, R* u) {
+__device__ __forceinline__ void draw_uniforms(const RngKey& key, int t, int q_me, int lane, R* u, bool variates32 = false) {
+    if (sizeof(R) == 8 && variates32) {
+        float uf[KPT];
+        rng_uniform4(key, (uint32_t)(q_me * 64 + lane * 2), (uint32_t)t, STREAM_UNIFORM, uf);
+        rng_uniform4(key, (uint32_t)(q_me * 64 + lane * 2 + 1), (uint32_t)t, STREAM_UNIFORM, uf + 4);
+        widen8(uf, u);
+        return;
+    }
     rng_uniform4(key, (uint32_t)(q_me * 64 + lane * 2), (uint32_t)t, STREAM_UNIFORM, u);
     rng_uniform4(key, (uint32_t)(q_me * 64 + lane * 2 + 1), (uint32_t)t, STREAM_UNIFORM, u + 4);
 }
@@ -603,14 +655,20 @@ __device__ __forceinline__ void search_levels(uint32_t* ad, const R* rt) {
 //   [lo, hi]: a paired warp-cooperative search finds it, the CDF of the range is staged in the warp's slice
 //   of shared memory in global units, each child binary-searches that slice (8 interleaved searches per
 //   lane, neighbouring lanes read neighbouring words), and parent records are gathered as a stream.
-// FAST = the production configuration, checked by the host before it picks this instantiation: device randoms,
-// order-statistics resampling, Poyiadjis O(N) (lambduh = 1) with the model score, no traces / exported log-weights.
-// It only turns the run-time flags below into constants (fewer uniform branches, constant loads and -- unless RAGGED,
-// i.e. N is not a multiple of 256 -- bound checks: ~9 % of the generic kernel's instructions); the arithmetic is
-// identical.
-template <class R, class Model, bool SORTED, bool FAST = false, bool RAGGED = false>
+// FM != FM_GENERIC = the production configurations, checked by the host before it picks the instantiation: device
+// randoms, order-statistics resampling, the model score as the statistic, no traces / exported log-weights, and
+//   FM_POY    Poyiadjis O(N)  (pf = nemeth with lambduh = 1)
+//   FM_SHRINK Nemeth          (lambduh < 1)
+//   FM_FILTER pf = filter
+// They turn the run-time flags below into constants (fewer uniform branches, constant loads and -- unless RAGGED,
+// i.e. N is not a multiple of 256 -- bound checks: ~9 % of the generic kernel's instructions); the particle system
+// (positions, weights, genealogy) is bit-identical to the generic instantiation.  FM_SHRINK / FM_FILTER additionally
+// accumulate the per-tile weighted statistic sums in registers while they propagate (WsCarry) instead of re-reading
+// the freshly written records: same sums up to f32 / f64 rounding of the statistic (not of the particle system).
+template <class R, class Model, bool SORTED, int FM = FM_GENERIC, bool RAGGED = false, int WINB = WIN_BYTES>
 __device__ __forceinline__ void step_body(const KArgs& a, int b, int t, int q_me, int lane, R* s_cdf, const double* hdr_local = nullptr) {
-    static_assert(!FAST || SORTED, "FAST implies sorted resampling");
+    constexpr bool FAST = FM != FM_GENERIC;
+    static_assert(!FAST || SORTED, "the fast modes imply sorted resampling");
     R* const s_tr = s_cdf;                 // the warp's shared-memory slice doubles as the scan transposition buffer
     constexpr int NP = Model::NP, W = Model::NX + NP;
     const int N = a.N, par = t & 1;
@@ -631,8 +689,8 @@ __device__ __forceinline__ void step_body(const KArgs& a, int b, int t, int q_me
     if (t >= Tb) return;
     const size_t item_off = (size_t)b * N;
     const int nws = FAST ? NP : stat_width<Model>(a.stat_kind);
-    const bool carries = FAST || (a.pf == SGM_PF_NEMETH);    // stats follow the resampled genealogy here
-    const bool shrink = !FAST && carries && (a.lambduh != 1.0);
+    const bool carries = FAST ? (FM != FM_FILTER) : (a.pf == SGM_PF_NEMETH);    // stats follow the resampled genealogy here
+    const bool shrink = FAST ? (FM == FM_SHRINK) : (carries && (a.lambduh != 1.0));
     const R* fine_old = reinterpret_cast<const R*>(a.fine[par]) + (size_t)b * a.Q * WT;      // padded to whole tiles
     const int tile_base = q_me * WT;
     const int n_valid = (FAST && !RAGGED) ? WT : min(WT, N - tile_base);
@@ -650,7 +708,7 @@ __device__ __forceinline__ void step_body(const KArgs& a, int b, int t, int q_me
             for (int c = 0; c < KPT; ++c) { const int i = tile_base + 32 * c + lane; target[c] = (i < N) ? u[i] * total : 0.0; }
         } else {
             R u[KPT];
-            draw_uniforms<R>(key, t, q_me, lane, u);
+            draw_uniforms<R>(key, t, q_me, lane, u, a.variates32 != 0);
 #pragma unroll
             for (int c = 0; c < KPT; ++c) target[c] = (double)u[c] * total;
         }
@@ -692,11 +750,19 @@ __device__ __forceinline__ void step_body(const KArgs& a, int b, int t, int q_me
             // totals are drawn directly (pf_header_kernel), so no cross-tile scan is needed.
             // Lane l draws the spacings of ranks 8 l .. 8 l + 7 (lane-major scan), then the positions are
             // transposed to row-major (child slot 32 c + lane has rank 32 c + lane) for coalesced gathers.
-            draw_uniforms<R>(key, t, q_me, lane, u);
-#pragma unroll
             // Exp(1) spacings up to a common factor: the positions are normalised by the tile's total below, so
             // -ln u and log2 u (same sign throughout, no scaling multiply, no negation) give identical positions
-            for (int k = 0; k < KPT; ++k) u[k] = (8 * lane + k < n_valid) ? Mth<R>::log2(u[k]) : (R)0;
+            if (sizeof(R) == 8 && a.variates32) {
+                float uf[KPT];
+                draw_uniforms<float>(key, t, q_me, lane, uf);
+#pragma unroll
+                for (int k = 0; k < KPT; ++k) uf[k] = (8 * lane + k < n_valid) ? Mth<float>::log2(uf[k]) : 0.0f;
+                widen8(uf, u);
+            } else {
+                draw_uniforms<R>(key, t, q_me, lane, u);
+#pragma unroll
+                for (int k = 0; k < KPT; ++k) u[k] = (8 * lane + k < n_valid) ? Mth<R>::log2(u[k]) : (R)0;
+            }
             R etot;
             lane_major_incl_scan<R>(u, etot);
             const R inv = Mth<R>::rcp(etot);
@@ -718,7 +784,7 @@ __device__ __forceinline__ void step_body(const KArgs& a, int b, int t, int q_me
 #pragma unroll
                 for (int c = 0; c < KPT; ++c) u[c] = u4[0];
             } else {
-                draw_uniforms<R>(key, t, q_me, lane, u);
+                draw_uniforms<R>(key, t, q_me, lane, u, a.variates32 != 0);
             }
             tB = total / (double)N; tA = (double)tile_base * tB;
         }
@@ -752,7 +818,7 @@ __device__ __forceinline__ void step_body(const KArgs& a, int b, int t, int q_me
         tl = (tl < total) ? tl : tmax;
         int q_lo, q_hi;
         warp_search_tiles(tf, tl, c1, s1c, hdr, lane, q_lo, q_hi);
-        constexpr int MAXT = WIN_BYTES / (int)(WT * sizeof(R));         // tiles the window holds: f32 4, f64 2
+        constexpr int MAXT = WINB / (int)(WT * sizeof(R));              // tiles the window holds: 4 (2 for f64 in the single-launch kernel)
         const int nst = q_hi - q_lo + 1;
         if (nst >= 1 && nst <= MAXT) {
             // Stage the CDF of whole parent tiles q_lo .. q_lo + wt - 1 (wt = 1, 2 or 4: a power-of-two window, so
@@ -832,11 +898,13 @@ __device__ __forceinline__ void step_body(const KArgs& a, int b, int t, int q_me
         }
     }
     R lwn[KPT];
-    propagate_store<R, Model, FAST, RAGGED>(a, b, t, par, tile_base, lane, item_off, anc, z, hdr, nws, carries, shrink, lwn, th, y_t, w_t);
+    WsCarry<R> carry;
+    propagate_store<R, Model, FM, RAGGED>(a, b, t, par, tile_base, lane, item_off, anc, z, hdr, nws, carries, shrink, lwn, th, y_t, w_t, &carry);
+    constexpr bool CARRY_WS = FM == FM_SHRINK || FM == FM_FILTER;
     const bool need_ws = (nws > 0) && ((!FAST && a.pf == SGM_PF_FILTER) || shrink || (carries && t == Tb - 1));
     warp_tile_epilogue<R, W>(lwn, tile_base, N, lane, reinterpret_cast<R*>(a.fine[par ^ 1]) + (size_t)b * a.Q * WT,
                              a.sub[par ^ 1] + ((size_t)b * a.Q + q_me) * SSTRIDE, a.rec[par ^ 1], a.tail[par ^ 1],
-                             item_off, need_ws, nws, s_tr);
+                             item_off, need_ws, nws, s_tr, CARRY_WS ? &carry : nullptr);
 }
 
 // CTA shape of the step kernel: its warps are independent (no block barrier), so the CTA size only sets the
@@ -852,16 +920,25 @@ __device__ __forceinline__ void step_body(const KArgs& a, int b, int t, int q_me
 #ifndef SGM_FAST_CTAS
 #define SGM_FAST_CTAS 9
 #endif
-template <bool FAST> struct StepShape {
-    static constexpr int WARPS = FAST ? SGM_FAST_WARPS : SGM_STEP_WARPS;
-    template <class R> static constexpr int ctas() { return FAST ? SGM_FAST_CTAS : (sizeof(R) == 4 ? SGM_STEP_CTAS : 2 * 8 / SGM_STEP_WARPS); }
+#ifndef SGM_FAST64_WARPS
+#define SGM_FAST64_WARPS 4
+#endif
+#ifndef SGM_FAST64_CTAS
+#define SGM_FAST64_CTAS 5
+#endif
+template <class R, bool FAST> struct StepShape {
+    static constexpr int WARPS = FAST ? (sizeof(R) == 4 ? SGM_FAST_WARPS : SGM_FAST64_WARPS) : SGM_STEP_WARPS;
+    static constexpr int CTAS = FAST ? (sizeof(R) == 4 ? SGM_FAST_CTAS : SGM_FAST64_CTAS)
+                                     : (sizeof(R) == 4 ? SGM_STEP_CTAS : 2 * 8 / SGM_STEP_WARPS);
 };
-template <class R, class Model, bool SORTED, bool FAST = false, bool RAGGED = false>
-__global__ void __launch_bounds__(32 * StepShape<FAST>::WARPS, StepShape<FAST>::template ctas<R>()) pf_step_kernel(KArgs a, int t) {
-    constexpr int SW = StepShape<FAST>::WARPS;
-    __shared__ __align__(32) R s_cdf_all[SW][SORTED ? WIN_BYTES / sizeof(R) : WT];
+template <class R, class Model, bool SORTED, int FM = FM_GENERIC, bool RAGGED = false>
+__global__ void __launch_bounds__(32 * StepShape<R, FM != FM_GENERIC>::WARPS, StepShape<R, FM != FM_GENERIC>::CTAS) pf_step_kernel(KArgs a, int t) {
+    constexpr int SW = StepShape<R, FM != FM_GENERIC>::WARPS;
+    // four parent tiles per warp in the fast modes (4 KB f32 / 8 KB f64); the generic f64 instantiation keeps two
+    constexpr int WINB = (FM != FM_GENERIC) ? 4 * WT * (int)sizeof(R) : WIN_BYTES;
+    __shared__ __align__(32) R s_cdf_all[SW][SORTED ? WINB / sizeof(R) : WT];
     const int warp = threadIdx.x >> 5;
-    step_body<R, Model, SORTED, FAST, RAGGED>(a, a.b0 + blockIdx.y, t, blockIdx.x * SW + warp, threadIdx.x & 31, s_cdf_all[warp]);
+    step_body<R, Model, SORTED, FM, RAGGED, WINB>(a, a.b0 + blockIdx.y, t, blockIdx.x * SW + warp, threadIdx.x & 31, s_cdf_all[warp]);
 }
 
 // ---- fused kernel for small particle counts (N <= 2048: the item fits one CTA) -----------------------------

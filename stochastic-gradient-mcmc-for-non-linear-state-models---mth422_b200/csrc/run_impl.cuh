@@ -1,6 +1,7 @@
 // Launch orchestration of one sgm_pf_run call for arithmetic type R (template definitions; instantiated explicitly
 // in sgmpf_f32.cu and sgmpf_f64.cu).
 #pragma once
+#include <type_traits>
 #include "host_common.cuh"
 
 namespace sgmhost {
@@ -30,6 +31,7 @@ int run_impl(const sgm_pf_desc* d, cudaStream_t stream) {
                                          : (d->rng_mode == SGM_RNG_PHILOX ? PARIS_CAP : (int)(100.0 * l10));
     a.manual_thresh = d->manual_sample_threshold >= 0 ? d->manual_sample_threshold : (int)(10.0 * l10);  // pf.py:286-287
     if (a.max_ar < 0) a.max_ar = 0;
+    a.variates32 = (d->dtype == SGM_F64 && d->variates == SGM_VARIATES_F32) ? 1 : 0;
     a.need_lw = (backward_pf(d->pf) || d->out_lw || d->trace_lw || d->stat_kind == SGM_STAT_PRED) ? 1 : 0;
     a.pred_K = d->pred_steps_ahead; a.pred_per_horizon = d->pred_per_horizon; a.inj_pred = d->inj_pred;
     a.lambduh = d->lambduh;
@@ -79,10 +81,12 @@ int run_impl(const sgm_pf_desc* d, cudaStream_t stream) {
         const bool piped = d->aux_stream && d->ev_aux_fork && d->ev_aux_join && !backward_pf(d->pf) && !pred &&
                            (int64_t)a.B * a.G >= 2 * 148 * 4 && a.B >= 2;
         const int nh = piped ? 2 : 1;
-        // the production configuration runs the step kernel with its run-time flags folded to constants
-        const bool fast_path = sizeof(R) == 4 && d->rng_mode == SGM_RNG_PHILOX && d->resample == SGM_RESAMPLE_MULTINOMIAL_SORTED &&
-                               d->pf == SGM_PF_NEMETH && d->lambduh == 1.0 && d->stat_kind == SGM_STAT_SCORE &&
-                               !a.need_lw && !d->trace_anc && !d->trace_x && !d->trace_lw;
+        // the production configurations run the step kernel with their run-time flags folded to constants (FM_*)
+        const bool fast_cfg = d->rng_mode == SGM_RNG_PHILOX && d->resample == SGM_RESAMPLE_MULTINOMIAL_SORTED &&
+                              d->stat_kind == SGM_STAT_SCORE && !a.need_lw && !d->trace_anc && !d->trace_x && !d->trace_lw;
+        const int fm = !fast_cfg ? FM_GENERIC
+                                 : (d->pf == SGM_PF_NEMETH ? (d->lambduh == 1.0 ? FM_POY : FM_SHRINK)
+                                                           : (d->pf == SGM_PF_FILTER ? FM_FILTER : FM_GENERIC));
         cudaStream_t sh[2] = {stream, piped ? reinterpret_cast<cudaStream_t>(d->aux_stream) : stream};
         KArgs ah[2] = {a, a};
         int nb[2] = {piped ? a.B / 2 : a.B, piped ? a.B - a.B / 2 : 0};
@@ -97,17 +101,19 @@ int run_impl(const sgm_pf_desc* d, cudaStream_t stream) {
             else pf_header_kernel<R, Model><<<nb[h], block, 0, sh[h]>>>(ah[h], t, final_pass);
             ++launches;
         };
+        auto launch_fast = [&](auto fmc, int h, int t) {
+            constexpr int FMV = decltype(fmc)::value;
+            constexpr int FW = StepShape<R, true>::WARPS;
+            const dim3 gf((a.Q + FW - 1) / FW, nb[h]);
+            if (a.N % WT == 0) pf_step_kernel<R, Model, true, FMV, false><<<gf, 32 * FW, 0, sh[h]>>>(ah[h], t);
+            else pf_step_kernel<R, Model, true, FMV, true><<<gf, 32 * FW, 0, sh[h]>>>(ah[h], t);   // ragged last tile
+        };
         auto launch_step = [&](int h, int t) {
-            constexpr int SW = StepShape<false>::WARPS, FW = StepShape<true>::WARPS;
+            constexpr int SW = StepShape<R, false>::WARPS;
             ++launches;
-            if constexpr (sizeof(R) == 4) {                    // the FAST instantiations exist for f32 only
-                if (fast_path) {
-                    const dim3 gf((a.Q + FW - 1) / FW, nb[h]);
-                    if (a.N % WT == 0) pf_step_kernel<R, Model, true, true, false><<<gf, 32 * FW, 0, sh[h]>>>(ah[h], t);
-                    else pf_step_kernel<R, Model, true, true, true><<<gf, 32 * FW, 0, sh[h]>>>(ah[h], t);   // ragged last tile
-                    return;
-                }
-            }
+            if (fm == FM_POY) return launch_fast(std::integral_constant<int, FM_POY>{}, h, t);
+            if (fm == FM_SHRINK) return launch_fast(std::integral_constant<int, FM_SHRINK>{}, h, t);
+            if (fm == FM_FILTER) return launch_fast(std::integral_constant<int, FM_FILTER>{}, h, t);
             const dim3 gh((a.Q + SW - 1) / SW, nb[h]), bs(32 * SW);
             if (d->resample == SGM_RESAMPLE_MULTINOMIAL) pf_step_kernel<R, Model, false><<<gh, bs, 0, sh[h]>>>(ah[h], t);
             else pf_step_kernel<R, Model, true><<<gh, bs, 0, sh[h]>>>(ah[h], t);

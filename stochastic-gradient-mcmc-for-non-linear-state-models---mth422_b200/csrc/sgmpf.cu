@@ -59,7 +59,8 @@ int validate(const sgm_pf_desc* d) {
             return fail(SGM_ERR_INVALID, "INJECTED PaRIS needs inj_extra / inj_extra_off");
     }
     if (d->step_weights && !d->wts_off) return fail(SGM_ERR_INVALID, "step_weights given without wts_off");
-    if (d->n2_mode < SGM_N2_AUTO || d->n2_mode > SGM_N2_TENSOR || d->reserved0 != 0) return fail(SGM_ERR_INVALID, "unknown n2_mode");
+    if (d->n2_mode < SGM_N2_AUTO || d->n2_mode > SGM_N2_TENSOR) return fail(SGM_ERR_INVALID, "unknown n2_mode");
+    if (d->variates != SGM_VARIATES_NATIVE && d->variates != SGM_VARIATES_F32) return fail(SGM_ERR_INVALID, "unknown variates");
     if (d->n2_mode == SGM_N2_TENSOR && d->dtype != SGM_F32) return fail(SGM_ERR_UNSUPPORTED, "the tensor-core O(N^2) smoother needs dtype f32");
     return SGM_OK;
 }

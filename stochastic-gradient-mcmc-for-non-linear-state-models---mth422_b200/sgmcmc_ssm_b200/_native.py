@@ -17,6 +17,7 @@ RNG = dict(philox=0, injected=1)
 RESAMPLE = dict(multinomial=0, multinomial_sorted=1, sorted=1, systematic=2, stratified=3)
 STAT = dict(score=0, suff=1, none=2, pred=3)
 N2_MODE = dict(auto=0, fp32_pipe=1, tensor=2)
+VARIATES = dict(native=0, f32=1)
 STATUS_NAN_WEIGHT, STATUS_ZERO_WEIGHT, STATUS_AR_OVERFLOW = 1, 2, 4
 THETA_STRIDE = 12
 PRED_SLOTS, PRED_MAX_STEPS = 16, 14           # SGM_PRED_SLOTS, SGM_PRED_MAX_STEPS (include/sgmpf.h)
@@ -30,7 +31,7 @@ class SgmPfDesc(ctypes.Structure):
         ("n_items", c_i32), ("n_particles", c_i32), ("max_T", c_i32), ("Ntilde", c_i32),
         ("accept_reject", c_i32), ("max_accept_reject", c_i32), ("manual_sample_threshold", c_i32),
         ("item_id_base", c_i32), ("n2_mode", c_i32), ("pred_steps_ahead", c_i32),
-        ("pred_per_horizon", c_i32), ("reserved0", c_i32),
+        ("pred_per_horizon", c_i32), ("variates", c_i32),
         ("lambduh", c_f64), ("seed", c_u64), ("offset", c_u64), ("offset_dev", c_vp),
         ("obs", c_vp), ("obs_off", c_vp), ("T_buf", c_vp), ("t1", c_vp), ("tL", c_vp),
         ("step_weights", c_vp), ("wts_off", c_vp), ("theta", c_vp), ("prior_mean", c_vp), ("prior_var", c_vp),

@@ -5,6 +5,7 @@ PyTorch is used for device memory, pinned staging buffers and streams only.  One
 packed host buffer to the device and ONE packed result buffer back.
 """
 import ctypes
+import os
 
 import numpy as np
 import torch
@@ -24,6 +25,7 @@ class Config(object):
     device = None                    # torch device; default = current CUDA device
     two_streams = True               # split big O(N) batches over two streams (hides the per-step header kernel)
     cuda_graphs = True               # replay a captured CUDA graph for small launch-bound batches (one wave of CTAs)
+    variates = "native"              # dtype 'f64' + device randoms: 'native' (53-bit variates) or 'f32' (the f32 path's variates, widened)
 
 
 config = Config()
@@ -36,10 +38,19 @@ def set_seed(seed):
 
 
 def _next_seed_offset():
+    """(seed, call counter) of the next device-random call.  An unseeded process seeds itself from the OS -- never from
+    np.random: the global numpy stream belongs to the caller (the reference's samplers draw windows and SGLD noise from
+    it, and parity runs replay it draw for draw)."""
     if _SEED[0] is None:
-        _SEED[0] = int(np.random.randint(0, 2 ** 31 - 1))
+        _SEED[0] = int.from_bytes(os.urandom(8), "little")
     _CALLS[0] += 1
     return _SEED[0], _CALLS[0]
+
+
+def skip_call():
+    """Advance the call counter without launching (a rank whose shard of a distributed minibatch is empty), so the
+    Philox call offsets stay aligned across ranks."""
+    _next_seed_offset()
 
 
 def _device(device=None):
@@ -253,13 +264,15 @@ class PreparedPF(object):
     def __init__(self, model, kernel, pf, items, N, dtype=None, rng=None, resample=None, stat_kind="score",
                  lambduh=None, Ntilde=2, accept_reject=True, max_accept_reject=None,
                  manual_sample_threshold=None, seed=None, offset=None, item_id_base=0, injected=None,
-                 want=(), device=None, n2_mode="auto", num_steps_ahead=5, per_horizon=False):
+                 want=(), device=None, n2_mode="auto", num_steps_ahead=5, per_horizon=False, variates=None):
         lib = self.lib = nat.load()
         device = self.device = _device(device)
         st = self.st = _state(device)
         dtype = dtype or config.dtype
         rng = rng or config.rng
-        resample = resample or config.resample
+        if resample is None:
+            # recorded uniforms come in the reference's (iid) order: only the generic search is valid for them
+            resample = "multinomial" if rng == "injected" else config.resample
         if pf not in nat.PF:
             raise ValueError("Unrecognized pf = {0}".format(pf))
         if lambduh is None:
@@ -310,9 +323,12 @@ class PreparedPF(object):
         desc.manual_sample_threshold = -1 if manual_sample_threshold is None else int(manual_sample_threshold)
         desc.item_id_base = int(item_id_base)
         desc.n2_mode = nat.N2_MODE[n2_mode]
+        desc.variates = nat.VARIATES[variates or config.variates]
         desc.pred_steps_ahead, desc.pred_per_horizon = int(num_steps_ahead), int(bool(per_horizon))
         desc.lambduh = float(lambduh)
-        if seed is None or offset is None:
+        if rng == "injected":
+            seed, offset = 0, 0                          # no device randoms: the process-wide Philox state is untouched
+        elif seed is None or offset is None:
             s_, o_ = _next_seed_offset()
             seed = s_ if seed is None else seed
             offset = o_ if offset is None else offset
@@ -347,7 +363,12 @@ class PreparedPF(object):
                     return tns.data_ptr()
 
                 desc.inj_z0 = dev64(injected["z0"], (B, N))
-                desc.inj_u = dev64(injected["u"], (B, max_T, N))
+                u_inj = np.asarray(injected["u"], dtype=np.float64).reshape(B, max_T, N)
+                if resample != "multinomial" and N > 1 and np.any(np.diff(u_inj, axis=-1) < 0):
+                    # the streaming search stages the CDF window of a warp tile from its first and last target only
+                    raise ValueError("rng='injected' with resample='{0}' needs ascending uniforms per step; "
+                                     "use resample='multinomial' for uniforms in the reference's order".format(resample))
+                desc.inj_u = dev64(u_inj, (B, max_T, N))
                 desc.inj_z = dev64(injected["z"], (B, max_T, N))
                 if injected.get("zp") is not None:       # predictive-statistic normals, (B, max_T, PRED_SLOTS, N)
                     desc.inj_pred = dev64(injected["zp"], (B, max_T, nat.PRED_SLOTS, N))

@@ -290,6 +290,9 @@ class SGMCMCSampler(object):
                 packed = self.message_helper.packed_items(self.parameters, forward_message=fm, **arrays)
                 sums, _ = self.message_helper.pf_gradient_sum_packed(packed, self.parameters, item_id_base=lo, **kwargs)
                 local = np.array([sums[k] for k in keys])
+            else:
+                from . import engine
+                engine.skip_call()                   # empty shard: keep the Philox call offsets aligned across ranks
             total = parallel.allreduce_sum(local) if distributed else local
             for k, v in zip(keys, total):
                 noisy_grad[k] += v / minibatch_size
@@ -306,6 +309,9 @@ class SGMCMCSampler(object):
                 grads, _ = self.message_helper.pf_gradient_estimate_batch(
                     windows[lo:hi], self.parameters, item_id_base=lo, **kwargs)
                 local = np.array([sum(float(np.ravel(g[k])[0]) for g in grads) for k in keys])
+            else:
+                from . import engine
+                engine.skip_call()
             total = parallel.allreduce_sum(local)
             for k, v in zip(keys, total):
                 noisy_grad[k] += v / minibatch_size

@@ -12,14 +12,14 @@ def load(name):
     return _cache[name]
 
 
-def case_names(section):
-    z = load("ref_cases.npz")
+def case_names(section, file="ref_cases.npz"):
+    z = load(file)
     names = sorted({"/".join(k.split("/")[:2]) for k in z.files if k.startswith(section + "/")})
     return names
 
 
-def case(name):
-    z = load("ref_cases.npz")
+def case(name, file="ref_cases.npz"):
+    z = load(file)
     pre = name + "/"
     return {k[len(pre):]: z[k] for k in z.files if k.startswith(pre)}
 

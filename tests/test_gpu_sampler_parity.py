@@ -213,3 +213,16 @@ def test_stored_svm_truth_run_N_1e6_on_gpu():
     g = np.array([res.grad[0][2], res.grad[0][1], res.grad[0][0]])       # (A, LQinv_vec, LRinv_vec)
     mean, sd = TRUTH_RUNS.mean(axis=0), TRUTH_RUNS.std(axis=0, ddof=1)
     assert np.all(np.abs(g - mean) <= 5 * sd), (g, mean, sd)
+
+
+def test_sgld_parity_in_a_fresh_process_without_set_seed():
+    """Parity mode must not touch the caller's numpy stream: the engine used to seed its Philox state lazily with
+    np.random.randint on the first call of a process -- between the injected PF draws and the SGLD noise.  Run the
+    SGLD parity test alone in a fresh interpreter (no earlier test has called set_seed there)."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "pytest", "-x", "-q", "-m", "gpu", os.path.join(root, "tests", "test_gpu_sampler_parity.py"),
+                        "-k", "test_sampler_sgld_steps and lgssm"], cwd=root, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]

@@ -1,0 +1,95 @@
+"""Statistical parity of the PRODUCTION instantiations (device Philox randoms, order-statistics multinomial resampling,
+run-time flags folded: `pf_step_kernel<R, Model, SORTED, FM_POY | FM_SHRINK | FM_FILTER, RAGGED>`, the single-launch
+kernel for small batches, the Philox PaRIS kernels) against the UNMODIFIED reference, for every model / proposal kernel.
+
+Golden: tests/golden/model_sweep_stats.npz (tests/golden/make_model_sweep_stats.py) -- for each (model, kernel, smoother)
+group and each (N, buffer B) cell the mean and standard deviation over `reps` independent runs of the reference's
+`buffered_pf_wrapper` + `average_statistic` (the protocol of gradient_error_fig_scripts/*_grad_compare.py: an L = 16
+subsequence in the middle of a T = 100 series, B buffer steps on each side).  N = 1000 / 10000 are ragged (not a multiple
+of the 256-particle warp tile), N = 4096 is not.
+
+The GPU draws R repetitions of the same cell in ONE batched launch.  Same law iff, per gradient component,
+    |mean_gpu - mean_ref| <= 4.5 sqrt(std_ref^2 / reps + std_gpu^2 / R)      (both the bias in N and B and the centre)
+    LO <= std_gpu / std_ref <= HI                                            (a reps-sample std: +-9 % at 1 sigma for
+                                                                              reps = 64, +-10 % for 48)
+and the log-likelihood estimate obeys the same two rules.  A wrong score column, a wrong weight, a biased resampler or
+a broken ragged tile in any fast instantiation moves a mean by many sigma (the components differ by O(1) while
+std / sqrt(reps) is ~0.05).
+"""
+import numpy as np
+import pytest
+
+from tests import _cases as C
+
+pytestmark = pytest.mark.gpu
+LO, HI = 0.6, 1.6
+
+
+def _groups():
+    z = C.load("model_sweep_stats.npz")
+    return sorted({k.split("/")[0] for k in z.files if "/" in k})
+
+
+def _run_cell(group, N, B, R, dtype="f32", variates="native", seed=17, **kw):
+    import sgmcmc_ssm_b200 as sg
+    z = C.load("model_sweep_stats.npz")
+    model, kernel, pf = group.split("_", 2)
+    L, t0 = int(z["L"]), int(z["t0"])
+    obs = z[group + "/obs"].reshape(-1)
+    window = obs[t0 - B:t0 + L + B]
+    pk = sg.PackedItems(np.tile(window, R), np.full(R, window.shape[0]), np.full(R, B), np.full(R, L + B), None, None,
+                        z[group + "/theta"], float(z[group + "/prior_mean"]), float(z[group + "/prior_var"]))
+    res = sg.run_pf(model, kernel, pf, pk, N, dtype=dtype, rng="philox", resample="multinomial_sorted", seed=seed,
+                    offset=1000 * B + N % 977, variates=variates, **kw)
+    return res
+
+
+def _check(group, i, j, res, R, what):
+    z = C.load("model_sweep_stats.npz")
+    reps = int(z[group + "/reps"])
+    m_ref, s_ref = z[group + "/mean"][i, j], z[group + "/std"][i, j]
+    g = res.grad
+    m, s = g.mean(axis=0), g.std(axis=0, ddof=1)
+    tol = 4.5 * np.sqrt(s_ref ** 2 / reps + s ** 2 / R)
+    assert np.all(np.abs(m - m_ref) <= tol), (what, m, m_ref, tol)
+    assert np.all(s / s_ref > LO) and np.all(s / s_ref < HI), (what, s, s_ref)
+    lm_ref, ls_ref = z[group + "/loglik_mean"][i, j], z[group + "/loglik_std"][i, j]
+    lm, ls = res.loglik.mean(), res.loglik.std(ddof=1)
+    assert abs(lm - lm_ref) <= 4.5 * np.sqrt(ls_ref ** 2 / reps + ls ** 2 / R), (what, lm, lm_ref)
+    assert LO < ls / ls_ref < HI, (what, ls, ls_ref)
+
+
+@pytest.mark.parametrize("group", _groups())
+def test_production_path_matches_the_reference_distribution(group):
+    """f32: every (N, B) cell of the group.  R = 2048 items keeps N = 1000 on the per-step (fast-mode, ragged) kernels."""
+    z = C.load("model_sweep_stats.npz")
+    paris = group.endswith("paris")
+    R = 512 if paris else 2048
+    for i, N in enumerate(z[group + "/Ns"]):
+        for j, B in enumerate(z[group + "/buffer_sizes"]):
+            res = _run_cell(group, int(N), int(B), R)
+            _check(group, i, j, res, R, (group, int(N), int(B), "f32"))
+
+
+@pytest.mark.parametrize("group", [g for g in _groups() if not g.endswith("paris")])
+def test_single_launch_kernel_matches_the_reference_distribution(group):
+    """N = 1000 with 512 items runs the one-CTA-per-item single-launch kernel (pf_fused_kernel)."""
+    z = C.load("model_sweep_stats.npz")
+    i = list(z[group + "/Ns"]).index(1000)
+    for j, B in enumerate(z[group + "/buffer_sizes"]):
+        res = _run_cell(group, 1000, int(B), 512, seed=23)
+        assert res.launches <= 2, res.launches
+        _check(group, i, j, res, 512, (group, 1000, int(B), "fused"))
+
+
+@pytest.mark.parametrize("variates", ["native", "f32"])
+@pytest.mark.parametrize("group", [g for g in _groups() if not g.endswith("paris")])
+def test_f64_production_path_matches_the_reference_distribution(group, variates):
+    """The reference's own precision with device randoms (fast-mode f64 instantiations; `variates='f32'` generates the
+    random inputs with the f32 transforms and widens them): N = 4096 (full tiles) and N = 1000 (ragged)."""
+    z = C.load("model_sweep_stats.npz")
+    for N, R in ((4096, 1024), (1000, 2048)):
+        i = list(z[group + "/Ns"]).index(N)
+        for j, B in enumerate(z[group + "/buffer_sizes"]):
+            res = _run_cell(group, N, int(B), R, dtype="f64", variates=variates, seed=29)
+            _check(group, i, j, res, R, (group, N, int(B), "f64", variates))
