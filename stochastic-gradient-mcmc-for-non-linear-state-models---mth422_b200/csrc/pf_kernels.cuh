@@ -924,7 +924,7 @@ __device__ __forceinline__ void step_body(const KArgs& a, int b, int t, int q_me
 #define SGM_FAST64_WARPS 4
 #endif
 #ifndef SGM_FAST64_CTAS
-#define SGM_FAST64_CTAS 5
+#define SGM_FAST64_CTAS 4          /* measured (SVM f64, N = 2^16, 256 items): 4 -> 4.87e10, 5 -> 4.79e10, 6 -> 4.49e10 particle-steps/s */
 #endif
 template <class R, bool FAST> struct StepShape {
     static constexpr int WARPS = FAST ? (sizeof(R) == 4 ? SGM_FAST_WARPS : SGM_FAST64_WARPS) : SGM_STEP_WARPS;
