@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define SGM_VERSION 100 /* 0.1.0 */
+#define SGM_VERSION 200 /* 0.2.0 */
 
 /* model: models/{lgssm,svm,garch} */
 enum { SGM_MODEL_LGSSM = 0, SGM_MODEL_SVM = 1, SGM_MODEL_GARCH = 2 };
@@ -77,6 +77,11 @@ enum { SGM_N2_AUTO = 0, SGM_N2_FP32_PIPE = 1, SGM_N2_TENSOR = 2 };
  * resolution of the random inputs is 2^-24 instead of 2^-53 (a change of the sampling law far below Monte-Carlo error). */
 enum { SGM_VARIATES_NATIVE = 0, SGM_VARIATES_F32 = 1 };
 
+/* Kernel family of the O(N) smoothers.  AUTO: N <= 2048 runs the shared-memory-resident one-CTA-per-item kernel
+ * (whole time loop in one launch), larger N the per-step warp-tile kernels that stream the particle arrays through HBM.
+ * TILES forces the per-step kernels (any N), SMALL requires N <= 2048. */
+enum { SGM_PATH_AUTO = 0, SGM_PATH_TILES = 1, SGM_PATH_SMALL = 2 };
+
 /* error codes */
 enum { SGM_OK = 0, SGM_ERR_INVALID = -1, SGM_ERR_UNSUPPORTED = -2, SGM_ERR_WORKSPACE = -3,
        SGM_ERR_CUDA = -4, SGM_ERR_DEVICE = -5 };
@@ -111,6 +116,8 @@ typedef struct sgm_pf_desc {
     int32_t pred_per_horizon;      /* SGM_STAT_PRED: 0 = the reference's log-sum over ALL horizons (pf.py:73-76),
                                     * 1 = one log-sum per horizon                                    */
     int32_t variates;              /* SGM_VARIATES_*: precision the device random variates are generated in        */
+    int32_t path;                  /* SGM_PATH_*: kernel family for the O(N) smoothers (AUTO picks by N)            */
+    int32_t reserved1;             /* must be 0                                                     */
     double lambduh;                /* Nemeth shrinkage (pf.py:140); 1.0 = Poyiadjis O(N)            */
     uint64_t seed, offset;         /* Philox key / call counter                                     */
     const uint64_t* offset_dev;    /* optional DEVICE pointer: when set the call counter is read from there by the
@@ -181,8 +188,81 @@ int sgm_pf_run(const sgm_pf_desc* d, void* stream);
  * DEVICE array `partial`; KSD = sqrt(sum(partial)) / num_points. */
 int sgm_ksd_imq(const double* x, const double* gradlogp, int32_t num_points, int32_t dim, double c, double beta,
                 double* partial, void* stream);
-/* number of kernel launches the last sgm_pf_run on this thread issued (for bench accounting) */
+/* number of kernel launches the last sgm_pf_run / sgm_sgld_run on this thread issued (for bench accounting) */
 int64_t sgm_last_launch_count(void);
+
+/* ---- device-resident SG-MCMC iterations -------------------------------------------------------------------------
+ * K iterations of C independent chains without a host round trip.  Replaces, for the n = m = 1 models and kind='pf',
+ * the reference's per-iteration Python (relative to sgmcmc_ssm/):
+ *     sgmcmc_sampler.py:1969-2017  random_subsequence_and_weights        (window draw + importance weights)
+ *     sgmcmc_sampler.py:259-288    _random_subsequence_and_buffers       (buffers)
+ *     sgmcmc_sampler.py:390-464    _noisy_grad_loglikelihood / noisy_gradient (minibatch mean, + grad log-prior, / T)
+ *     sgmcmc_sampler.py:1249-1283  SeqSGMCMCSampler._noisy_grad_loglikelihood (sequence choice, T / S rescale)
+ *     sgmcmc_sampler.py:529-567    _get_sgmcmc_noise, sample_sgld;  :613-640 sample_sgrld;  :466-480 step_sgd
+ *     sgmcmc_sampler.py:650-656    project_parameters  (model defaults: |A| <= 0.9999, Cholesky diagonals > 0, LGSSM C = 1)
+ *     variables/covariance.py:229-243, variables/matrices.py:575-590, variables/garch_var.py:150-163   grad_logprior
+ * Every iteration = sgld_prepare_kernel -> the sgm_pf_run launch sequence for the C x sequences x minibatch work
+ * items -> sgld_update_kernel, all enqueued on `stream`; the Philox call counter lives in device memory and is advanced
+ * on the device, so a captured CUDA graph of this call replays with fresh random numbers. */
+enum { SGM_STEP_SGLD = 0, SGM_STEP_SGRLD = 1 /* LGSSM only (LGSSMPreconditioner) */, SGM_STEP_SGD = 2 };
+enum { SGM_PARTITION_UNIFORM = 0, SGM_PARTITION_NAIVE = 1, SGM_PARTITION_STRICT = 2 };
+#define SGM_PARAM_STRIDE 8
+#define SGM_HYPER_STRIDE 16
+/* parameter slots (var_dict order) and prior hyper-parameter slots per model:
+ *   SVM   : [A, LQinv, LRinv]                          hyper [mean_A, var_col_A, df_Qinv, scale_Qinv, df_Rinv, scale_Rinv]
+ *   LGSSM : [A, C, LQinv, LRinv]                       hyper [mean_A, var_col_A, mean_C, var_col_C, df_Qinv, scale_Qinv, df_Rinv, scale_Rinv]
+ *   GARCH : [log_mu, logit_phi, logit_lambduh, LRinv]  hyper [scale_mu, shape_mu, alpha_phi, beta_phi, alpha_lambduh, beta_lambduh, df_Rinv, scale_Rinv] */
+
+typedef struct sgm_sgld_desc {
+    int32_t struct_bytes;          /* sizeof(sgm_sgld_desc), checked */
+    int32_t method;                /* SGM_STEP_*                                                     */
+    int32_t n_chains;              /* C chains advanced in lock-step                                 */
+    int32_t minibatch;             /* M subsequences per (chain, sequence) and iteration             */
+    int32_t n_seqs;                /* observation sequences (1 for a plain sampler)                  */
+    int32_t num_sequences;         /* Seq samplers: sequences drawn per iteration without replacement (<= 8), -1 = all */
+    int32_t subsequence_length;    /* S, -1 = whole sequence                                         */
+    int32_t buffer_length;         /* B, -1 = whole sequence                                         */
+    int32_t partition;             /* SGM_PARTITION_* (options['partition_style'])                    */
+    int32_t n_iters;               /* K iterations in this call                                      */
+    int32_t project;               /* 1 = project_parameters after every step                        */
+    int32_t prior_x0;              /* 0 = prior_mean / prior_var per chain; 1 = GARCH: alpha / (1 - beta - gamma) of the
+                                    * chain's CURRENT parameters (garch/helper.py:324-332, forward_message None) */
+    int32_t trace_every;           /* > 0: parameters copied to `trace` every that many iterations   */
+    int32_t trace_rows;            /* rows of `trace` (row r = after r * trace_every iterations; row 0 is the caller's) */
+    int32_t max_seq_len;           /* longest sequence (bounds T_buf when S or B is -1)              */
+    int32_t no_persistent;         /* 1 = always one launch sequence per iteration (default 0: a batch with one work item
+                                    * per chain and N <= 2048 runs all K iterations inside ONE persistent kernel)     */
+    double epsilon;                /* step size                                                      */
+    double T_total;                /* sum of the sequence lengths (the 1 / T scaling of gradient and noise) */
+    const double* obs;             /* DEVICE flat observations, sequence after sequence              */
+    const int64_t* seq_off;        /* DEVICE [n_seqs + 1] offsets into obs                           */
+    double* params;                /* DEVICE [C][SGM_PARAM_STRIDE] in / out                          */
+    const double* hyper;           /* DEVICE [C][SGM_HYPER_STRIDE]                                   */
+    const double* prior_mean;      /* DEVICE [C] (prior_x0 == 0)                                     */
+    const double* prior_var;       /* DEVICE [C]                                                     */
+    int32_t* chain_status;         /* DEVICE [C]: SGM_STATUS_* bits; a flagged chain keeps its last finite parameters */
+    double* trace;                 /* DEVICE optional [trace_rows][C][SGM_PARAM_STRIDE]              */
+    uint64_t* offset_dev;          /* DEVICE Philox call counter (read by every kernel, + 1 per iteration) -- required */
+    int64_t* iter_dev;             /* DEVICE iterations completed so far (+ 1 per iteration) -- required */
+    /* INJECTED parity mode (pf.rng_mode == SGM_RNG_INJECTED): the draws the reference takes from the numpy stream */
+    const int32_t* inj_start;      /* [K][items] np.random.randint window starts (strict: block index) */
+    const int32_t* inj_seq;        /* [K][C][num_sequences] sequence picks (num_sequences != -1)      */
+    const double* inj_noise;       /* [K][C][SGM_PARAM_STRIDE] standard normals of _get_sgmcmc_noise / precondition_noise */
+    void* workspace;               /* >= sgm_sgld_workspace_bytes(desc), 256-byte aligned            */
+    uint64_t workspace_bytes;
+    /* particle-filter template: model, kernel, pf, dtype, rng_mode, resample, variates, n_particles, lambduh, Ntilde, ...,
+     * seed, item_id_base (global index of chain 0 x items per chain), aux stream / events.  stat_kind must be
+     * SGM_STAT_SCORE.  n_items, max_T, the per-item arrays, outputs, workspace and offset_dev are filled in by the
+     * library.  INJECTED: inj_z0 / inj_u / inj_z carry a leading [K] dimension ([K][items][N], [K][items][max_T][N]). */
+    sgm_pf_desc pf;
+} sgm_sgld_desc;
+
+/* items per iteration (C x sequences x M) and the max_T the library uses for this descriptor; negative on error */
+int32_t sgm_sgld_items(const sgm_sgld_desc* d);
+int32_t sgm_sgld_max_steps(const sgm_sgld_desc* d);
+uint64_t sgm_sgld_workspace_bytes(const sgm_sgld_desc* d);
+/* enqueue n_iters iterations on `stream`; asynchronous, no hidden synchronisation */
+int sgm_sgld_run(const sgm_sgld_desc* d, void* stream);
 
 #ifdef __cplusplus
 }

@@ -10,6 +10,8 @@
 #include "../../include/sgmpf.h"
 #include "pf_kernels.cuh"
 #include "backward_kernels.cuh"
+#include "small_kernels.cuh"
+#include "sgld_kernels.cuh"
 
 namespace sgmhost {
 using namespace sgm;
@@ -31,5 +33,8 @@ Layout make_layout(const sgm_pf_desc* d);
 template <class R> int run_model(const sgm_pf_desc* d, cudaStream_t s);
 extern template int run_model<float>(const sgm_pf_desc* d, cudaStream_t s);
 extern template int run_model<double>(const sgm_pf_desc* d, cudaStream_t s);
+template <class R> int run_sgld_persistent(const sgm_pf_desc* d, const sgm::SgldArgs& sa, int K, cudaStream_t s);
+extern template int run_sgld_persistent<float>(const sgm_pf_desc* d, const sgm::SgldArgs& sa, int K, cudaStream_t s);
+extern template int run_sgld_persistent<double>(const sgm_pf_desc* d, const sgm::SgldArgs& sa, int K, cudaStream_t s);
 
 }  // namespace sgmhost

@@ -34,9 +34,6 @@ namespace sgm {
 #ifndef SGM_STEP_CTAS
 #define SGM_STEP_CTAS 4
 #endif
-#ifndef SGM_FUSED_CTAS
-#define SGM_FUSED_CTAS 3          /* measured: 4 -> 0.425 ms, 3 -> 0.362 ms, 2 -> 0.350 ms per 60-step item at N = 1024; 3 is also best at 1024 items */
-#endif
 #ifndef SGM_GATHER_BATCH
 #define SGM_GATHER_BATCH 4
 #endif
@@ -939,30 +936,6 @@ __global__ void __launch_bounds__(32 * StepShape<R, FM != FM_GENERIC>::WARPS, St
     __shared__ __align__(32) R s_cdf_all[SW][SORTED ? WINB / sizeof(R) : WT];
     const int warp = threadIdx.x >> 5;
     step_body<R, Model, SORTED, FM, RAGGED, WINB>(a, a.b0 + blockIdx.y, t, blockIdx.x * SW + warp, threadIdx.x & 31, s_cdf_all[warp]);
-}
-
-// ---- fused kernel for small particle counts (N <= 2048: the item fits one CTA) -----------------------------
-// One CTA per item runs init, every (header, step) pair and the final header in ONE launch; the block
-// barrier replaces the kernel boundary (all global-memory traffic of an item stays on one SM, whose L1 is
-// coherent for its own writes).  This is the SGLD-with-N~1000 regime, where launch latency dominated.
-template <class R, class Model, bool SORTED>
-__global__ void __launch_bounds__(NT, (sizeof(R) == 4 ? SGM_FUSED_CTAS : 2)) pf_fused_kernel(KArgs a) {
-    __shared__ __align__(32) R s_cdf_all[NWARP][SORTED ? WIN_BYTES / sizeof(R) : WT];
-    __shared__ double sh_d[NWARP];
-    __shared__ double s_hdr[NWARP][H_SCALARS + 3 * (NWARP + 2)];      // one private copy of the item header per warp
-    const int b = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    init_body<R, Model>(a, b, 0, s_cdf_all[warp]);
-    __syncthreads();
-    const int Tb = a.T_buf[b];
-    for (int t = 0; t < Tb; ++t) {
-        // every warp that owns a tile builds the header itself, then runs its tile: ONE block barrier per time step
-        if (warp < a.Q) {
-            header_warp<R, Model>(a, b, t, 0, s_hdr[warp]);
-            step_body<R, Model, SORTED>(a, b, t, warp, lane, s_cdf_all[warp], s_hdr[warp]);
-        }
-        __syncthreads();
-    }
-    header_body<R, Model>(a, b, Tb, 1, sh_d);
 }
 
 // ---- optional export of the final particle system (out['x_t'], ['log_weights'], ['statistics']) ---

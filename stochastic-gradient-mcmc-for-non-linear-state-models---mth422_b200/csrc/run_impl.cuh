@@ -3,23 +3,50 @@
 #pragma once
 #include <type_traits>
 #include "host_common.cuh"
+#include "sgld_kernels.cuh"
 
 namespace sgmhost {
 
-// N <= 2048: the single-launch kernel (one CTA per item, whole time loop) wins while launch latency dominates; from
-// ~1000 items on the per-step kernels fill the machine better (measured, SVM f32, N = 1024: 512 items 0.70 vs 0.87 ms,
-// 2048 items 1.96 vs 1.47 ms, 8192 items 7.45 vs 4.58 ms; same crossover at N = 256 and 2048).
-#ifndef SGM_FUSED_MAX_ITEMS
-#define SGM_FUSED_MAX_ITEMS 1024
+// N <= 2048: the shared-memory-resident kernel (small_kernels.cuh), one CTA per item.  Thread count / particles per
+// thread by N; for N in (512, 1024] a latency-bound batch (at most two CTAs per SM) spreads an item over 1024 threads,
+// a throughput-bound one packs two particles per thread so that four items share an SM.
+#ifndef SGM_SMALL_MAX_N
+#define SGM_SMALL_MAX_N 2048
 #endif
-
+#ifndef SGM_SMALL_MAX_ITEMS
+#define SGM_SMALL_MAX_ITEMS 65535
+#endif
+template <class R, class Model, int NTH, int PPT>
+bool launch_small_shape(const KArgs& a, int nst, cudaStream_t stream) {
+    const size_t bytes = small_smem_bytes<R>(NTH * PPT, Model::NX, nst);
+    if (bytes > 227 * 1024) return false;
+    auto kern = pf_small_kernel<R, Model, NTH, PPT>;
+    if (bytes > 48 * 1024) {
+        static thread_local size_t granted = 0;            // per instantiation (and host thread): raise the limit once
+        if (granted < bytes) {
+            if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) { cudaGetLastError(); return false; }
+            granted = 227 * 1024;
+        }
+    }
+    kern<<<a.B, NTH, bytes, stream>>>(a);
+    return true;
+}
 template <class R, class Model>
-int run_impl(const sgm_pf_desc* d, cudaStream_t stream) {
+bool launch_small(const KArgs& a, cudaStream_t stream) {
+    const int nstat = a.stat_kind == SGM_STAT_SCORE ? Model::NP : (a.stat_kind == SGM_STAT_SUFF ? 3 : 0);
+    const int nst = a.pf == SGM_PF_NEMETH ? nstat : 0;
+    if (a.N <= 256) return launch_small_shape<R, Model, 256, 1>(a, nst, stream);
+    if (a.N <= 1024) return a.B <= 2 * 148 ? launch_small_shape<R, Model, 1024, 1>(a, nst, stream)
+                                            : launch_small_shape<R, Model, 512, 2>(a, nst, stream);
+    return launch_small_shape<R, Model, 1024, 2>(a, nst, stream);
+}
+
+// kernel arguments of one call (workspace carved up, descriptor fields copied)
+inline int make_kargs(const sgm_pf_desc* d, KArgs& a) {
     const Layout L = make_layout(d);
     if (!d->workspace || d->workspace_bytes < L.total) return fail(SGM_ERR_WORKSPACE, "workspace too small");
     if (((uintptr_t)d->workspace & 255) != 0) return fail(SGM_ERR_WORKSPACE, "workspace must be 256-byte aligned");
     char* ws = reinterpret_cast<char*>(d->workspace);
-    KArgs a;
     memset(&a, 0, sizeof(a));
     a.B = d->n_items; a.N = d->n_particles; a.G = (a.N + TILE - 1) / TILE; a.Q = (a.N + WT - 1) / WT; a.max_T = d->max_T;
     a.pf = d->pf; a.rng_mode = d->rng_mode; a.resample = d->resample; a.stat_kind = d->stat_kind;
@@ -64,17 +91,31 @@ int run_impl(const sgm_pf_desc* d, cudaStream_t stream) {
     a.out_x = d->out_x; a.out_lw = d->out_lw; a.out_stats = d->out_stats;
     a.trace_anc = d->trace_anc; a.trace_x = d->trace_x; a.trace_lw = d->trace_lw; a.trace_J = d->trace_J;
 
+    return SGM_OK;
+}
+
+template <class R, class Model>
+int run_impl(const sgm_pf_desc* d, cudaStream_t stream) {
+    KArgs a;
+    { const int rc = make_kargs(d, a); if (rc != SGM_OK) return rc; }
     const dim3 grid(a.G, a.B), block(NT);
     int64_t launches = 0;
     const bool pred = d->stat_kind == SGM_STAT_PRED;
-    const bool fused = (a.Q <= NWARP) && !backward_pf(d->pf) && !pred && a.B <= SGM_FUSED_MAX_ITEMS;
-    if (fused) {
-        // small N: the whole time loop of an item in one launch (one CTA per item)
+    const bool small_ok = a.N <= SGM_SMALL_MAX_N && !backward_pf(d->pf) && !pred && d->path != SGM_PATH_TILES &&
+                          (a.B <= SGM_SMALL_MAX_ITEMS || d->path == SGM_PATH_SMALL);
+    bool done_small = false;
+    if (small_ok) {
         if (d->ev_steps_begin) cudaEventRecord(reinterpret_cast<cudaEvent_t>(d->ev_steps_begin), stream);
-        if (d->resample == SGM_RESAMPLE_MULTINOMIAL) pf_fused_kernel<R, Model, false><<<a.B, block, 0, stream>>>(a);
-        else pf_fused_kernel<R, Model, true><<<a.B, block, 0, stream>>>(a);
-        ++launches;
+        done_small = launch_small<R, Model>(a, stream);
+        if (done_small) ++launches;
         if (d->ev_steps_end) cudaEventRecord(reinterpret_cast<cudaEvent_t>(d->ev_steps_end), stream);
+    }
+    if (done_small) {
+        // results written by the kernel itself (incl. the optional exports)
+        set_launch_count(launches);
+        const cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return fail(SGM_ERR_CUDA, "CUDA launch failed: %s", cudaGetErrorString(e));
+        return SGM_OK;
     } else {
         // Two-stream pipelining (O(N) smoothers, big batches): the halves alternate on `stream` / `aux_stream`, so
         // the one-CTA-per-item header kernel and the launch gap of one half overlap the step kernel of the other.
@@ -143,6 +184,81 @@ int run_impl(const sgm_pf_desc* d, cudaStream_t stream) {
     const cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail(SGM_ERR_CUDA, "CUDA launch failed: %s", cudaGetErrorString(e));
     return SGM_OK;
+}
+
+// ---- persistent SG-MCMC kernel: K whole iterations of a chain inside ONE launch ---------------------------------
+// One CTA per chain (one work item per chain and iteration: minibatch 1, one sequence, N <= 2048): thread 0 draws the
+// window and rebuilds theta (sgld_prepare_item), the CTA runs the shared-memory particle filter (small_pf_item), thread
+// 0 applies the SG-MCMC update (sgld_update_chain) -- no kernel boundary, no host, nothing but the chain's few scalars
+// in global memory.  Iteration k uses Philox call offset (*offset_dev + k): exactly the numbers the launch-per-iteration
+// path draws, so both paths give bit-identical chains.
+template <class R, class Model, int NTH, int PPT>
+__global__ void __launch_bounds__(NTH, 1024 / NTH) sgld_persistent_kernel(SgldArgs sa, KArgs a, int K) {
+    extern __shared__ __align__(16) unsigned char small_smem[];
+    const int c = blockIdx.x;
+    const uint64_t o0 = *sa.offset_dev;
+    const int64_t it0 = *sa.iter_dev;
+    const size_t B = (size_t)a.B, N = (size_t)a.N, T = (size_t)a.max_T;
+    const double *z0 = a.inj_z0, *iu = a.inj_u, *iz = a.inj_z;
+    a.offset_dev = nullptr;
+    const uint32_t k1 = a.key.k1;
+    for (int k = 0; k < K; ++k) {
+        const uint64_t o = o0 + (uint64_t)k;
+        if (threadIdx.x == 0) sgld_prepare_item(sa, c, k, o);
+        __syncthreads();
+        a.key.offset = (uint32_t)(o & 0xffffffffu);
+        a.key.k1 = k1 ^ (uint32_t)(o >> 32);
+        if (z0) { a.inj_z0 = z0 + (size_t)k * B * N; a.inj_u = iu + (size_t)k * B * T * N; a.inj_z = iz + (size_t)k * B * T * N; }
+        small_pf_item<R, Model, NTH, PPT>(a, c, small_smem);
+        __syncthreads();
+        if (threadIdx.x == 0) sgld_update_chain(sa, c, k, o, it0 + k);
+        __syncthreads();
+    }
+}
+
+template <class R, class Model, int NTH, int PPT>
+bool launch_persistent_shape(const SgldArgs& sa, const KArgs& a, int nst, int K, cudaStream_t stream) {
+    const size_t bytes = small_smem_bytes<R>(NTH * PPT, Model::NX, nst);
+    if (bytes > 227 * 1024) return false;
+    auto kern = sgld_persistent_kernel<R, Model, NTH, PPT>;
+    if (bytes > 48 * 1024) {
+        static thread_local size_t granted = 0;
+        if (granted < bytes) {
+            if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) { cudaGetLastError(); return false; }
+            granted = 227 * 1024;
+        }
+    }
+    kern<<<a.B, NTH, bytes, stream>>>(sa, a, K);
+    return true;
+}
+template <class R, class Model>
+bool launch_persistent(const SgldArgs& sa, const KArgs& a, int K, cudaStream_t stream) {
+    const int nstat = a.stat_kind == SGM_STAT_SCORE ? Model::NP : (a.stat_kind == SGM_STAT_SUFF ? 3 : 0);
+    const int nst = a.pf == SGM_PF_NEMETH ? nstat : 0;
+    if (a.N <= 256) return launch_persistent_shape<R, Model, 256, 1>(sa, a, nst, K, stream);
+    if (a.N <= 1024) return a.B <= 2 * 148 ? launch_persistent_shape<R, Model, 1024, 1>(sa, a, nst, K, stream)
+                                            : launch_persistent_shape<R, Model, 512, 2>(sa, a, nst, K, stream);
+    return launch_persistent_shape<R, Model, 1024, 2>(sa, a, nst, K, stream);
+}
+
+// 1 = launched, 0 = not eligible (the caller falls back to one launch sequence per iteration), < 0 = error
+template <class R>
+int run_sgld_persistent(const sgm_pf_desc* d, const SgldArgs& sa, int K, cudaStream_t s) {
+    if (sa.ipc != 1 || d->n_particles > SGM_SMALL_MAX_N || backward_pf(d->pf) || d->stat_kind != SGM_STAT_SCORE) return 0;
+    KArgs a;
+    { const int rc = make_kargs(d, a); if (rc != SGM_OK) return rc; }
+    bool ok;
+    switch (d->model) {
+        case SGM_MODEL_SVM: ok = launch_persistent<R, SvmPrior>(sa, a, K, s); break;
+        case SGM_MODEL_LGSSM: ok = d->kernel == SGM_KERNEL_PRIOR ? launch_persistent<R, LgssmPrior>(sa, a, K, s) : launch_persistent<R, LgssmOptimal>(sa, a, K, s); break;
+        default: ok = d->kernel == SGM_KERNEL_PRIOR ? launch_persistent<R, GarchPrior>(sa, a, K, s) : launch_persistent<R, GarchOptimal>(sa, a, K, s);
+    }
+    if (!ok) return 0;
+    sgld_advance_kernel<<<1, 1, 0, s>>>(sa, K);
+    set_launch_count(2);
+    const cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(SGM_ERR_CUDA, "CUDA launch failed: %s", cudaGetErrorString(e));
+    return 1;
 }
 
 template <class R>

@@ -4,6 +4,7 @@
 // arithmetic type in sgmpf_f32.cu / sgmpf_f64.cu.
 #include "host_common.cuh"
 #include "ksd_kernel.cuh"
+#include "sgld_kernels.cuh"
 
 using namespace sgm;
 
@@ -61,6 +62,9 @@ int validate(const sgm_pf_desc* d) {
     if (d->step_weights && !d->wts_off) return fail(SGM_ERR_INVALID, "step_weights given without wts_off");
     if (d->n2_mode < SGM_N2_AUTO || d->n2_mode > SGM_N2_TENSOR) return fail(SGM_ERR_INVALID, "unknown n2_mode");
     if (d->variates != SGM_VARIATES_NATIVE && d->variates != SGM_VARIATES_F32) return fail(SGM_ERR_INVALID, "unknown variates");
+    if (d->path < SGM_PATH_AUTO || d->path > SGM_PATH_SMALL || d->reserved1 != 0) return fail(SGM_ERR_INVALID, "unknown path");
+    if (d->path == SGM_PATH_SMALL && (d->n_particles > 2048 || d->pf == SGM_PF_POY_N2 || d->pf == SGM_PF_PARIS || d->stat_kind == SGM_STAT_PRED))
+        return fail(SGM_ERR_UNSUPPORTED, "path = SMALL needs N <= 2048 and an O(N) smoother");
     if (d->n2_mode == SGM_N2_TENSOR && d->dtype != SGM_F32) return fail(SGM_ERR_UNSUPPORTED, "the tensor-core O(N^2) smoother needs dtype f32");
     return SGM_OK;
 }
@@ -101,7 +105,178 @@ Layout sgmhost::make_layout(const sgm_pf_desc* d) {
     return L;
 }
 
+namespace {
+
+struct SgldLayout {
+    size_t obs_off, T_buf, t1, tL, wts_off, weights, theta, pm, pv, item_seq, grad, loglik, status, pf_ws, total;
+    int B, max_T, nsel, Smax;
+};
+
+int sgld_geometry(const sgm_sgld_desc* d, int& B, int& max_T, int& nsel, int& Smax) {
+    if (!d) return fail(SGM_ERR_INVALID, "null descriptor");
+    if (d->struct_bytes != (int32_t)sizeof(sgm_sgld_desc)) return fail(SGM_ERR_INVALID, "sgm_sgld_desc size mismatch (header / library out of sync)");
+    if (d->method < SGM_STEP_SGLD || d->method > SGM_STEP_SGD) return fail(SGM_ERR_INVALID, "unknown method");
+    if (d->method == SGM_STEP_SGRLD && d->pf.model != SGM_MODEL_LGSSM)
+        return fail(SGM_ERR_UNSUPPORTED, "No Default Preconditioner: SGRLD on the device covers the LGSSM preconditioner only");
+    if (d->n_chains < 1 || d->minibatch < 1 || d->n_seqs < 1 || d->n_iters < 0) return fail(SGM_ERR_INVALID, "n_chains / minibatch / n_seqs / n_iters out of range");
+    if (d->num_sequences != -1 && (d->num_sequences < 1 || d->num_sequences > 8 || d->num_sequences > d->n_seqs))
+        return fail(SGM_ERR_UNSUPPORTED, "num_sequences must be -1 or in [1, min(8, n_seqs)]");
+    if (d->partition < SGM_PARTITION_UNIFORM || d->partition > SGM_PARTITION_STRICT) return fail(SGM_ERR_INVALID, "unknown partition");
+    if (d->subsequence_length == 0 || d->subsequence_length < -1 || d->buffer_length < -1 || d->max_seq_len < 1)
+        return fail(SGM_ERR_INVALID, "subsequence_length / buffer_length / max_seq_len out of range");
+    if (d->pf.stat_kind != SGM_STAT_SCORE) return fail(SGM_ERR_INVALID, "the SG-MCMC loop needs stat_kind = SGM_STAT_SCORE");
+    if (d->pf.pf == SGM_PF_PARIS && d->pf.rng_mode == SGM_RNG_INJECTED) return fail(SGM_ERR_UNSUPPORTED, "INJECTED PaRIS inside the device loop");
+    nsel = d->num_sequences == -1 ? d->n_seqs : d->num_sequences;
+    const int64_t items = (int64_t)d->n_chains * nsel * d->minibatch;
+    if (items > 65535) return fail(SGM_ERR_INVALID, "more than 65535 work items per iteration");
+    B = (int)items;
+    const int S = d->subsequence_length;
+    if (S == -1 || d->buffer_length == -1) max_T = d->max_seq_len;
+    else { const int64_t w = (int64_t)S + 2 * (int64_t)d->buffer_length; max_T = (int)(w < d->max_seq_len ? w : d->max_seq_len); }
+    // a sequence shorter than S runs whole
+    if (S != -1 && max_T < (S < d->max_seq_len ? S : d->max_seq_len)) max_T = S < d->max_seq_len ? S : d->max_seq_len;
+    Smax = S == -1 ? 1 : S;
+    return SGM_OK;
+}
+
+void sgld_pf_template(const sgm_sgld_desc* d, int B, int max_T, sgm_pf_desc& pf) {
+    pf = d->pf;
+    pf.struct_bytes = (int32_t)sizeof(sgm_pf_desc);
+    pf.n_items = B; pf.max_T = max_T;
+    pf.out_x = pf.out_lw = pf.out_stats = nullptr;
+    pf.trace_anc = nullptr; pf.trace_x = pf.trace_lw = nullptr; pf.trace_J = nullptr;
+    pf.ev_steps_begin = pf.ev_steps_end = nullptr;
+    // placeholders so that the layout / validation see a complete descriptor
+    static const double dummy = 0.0;
+    pf.obs = &dummy; pf.obs_off = reinterpret_cast<const int64_t*>(&dummy); pf.T_buf = pf.t1 = pf.tL = reinterpret_cast<const int32_t*>(&dummy);
+    pf.theta = pf.prior_mean = pf.prior_var = &dummy;
+    pf.step_weights = &dummy; pf.wts_off = reinterpret_cast<const int64_t*>(&dummy);
+    pf.grad = pf.loglik = const_cast<double*>(&dummy); pf.status = reinterpret_cast<int32_t*>(const_cast<double*>(&dummy));
+}
+
+int sgld_layout(const sgm_sgld_desc* d, SgldLayout& L) {
+    memset(&L, 0, sizeof(L));
+    int rc = sgld_geometry(d, L.B, L.max_T, L.nsel, L.Smax);
+    if (rc != SGM_OK) return rc;
+    sgm_pf_desc pf;
+    sgld_pf_template(d, L.B, L.max_T, pf);
+    rc = validate(&pf);
+    if (rc != SGM_OK) return rc;
+    const size_t B = L.B;
+    size_t off = 0;
+    L.obs_off = off; off = align_up(off + B * 8);
+    L.T_buf = off; off = align_up(off + B * 4);
+    L.t1 = off; off = align_up(off + B * 4);
+    L.tL = off; off = align_up(off + B * 4);
+    L.wts_off = off; off = align_up(off + B * 8);
+    L.weights = off; off = align_up(off + B * (size_t)L.Smax * 8);
+    L.theta = off; off = align_up(off + B * SGM_THETA_STRIDE * 8);
+    L.pm = off; off = align_up(off + B * 8);
+    L.pv = off; off = align_up(off + B * 8);
+    L.item_seq = off; off = align_up(off + B * 4);
+    L.grad = off; off = align_up(off + B * 8 * 8);
+    L.loglik = off; off = align_up(off + B * 8);
+    L.status = off; off = align_up(off + B * 4);
+    L.pf_ws = off; off = align_up(off + make_layout(&pf).total);
+    L.total = off;
+    return SGM_OK;
+}
+
+}  // namespace
+
 extern "C" {
+
+int32_t sgm_sgld_items(const sgm_sgld_desc* d) {
+    int B, max_T, nsel, Smax;
+    const int rc = sgld_geometry(d, B, max_T, nsel, Smax);
+    return rc != SGM_OK ? rc : B;
+}
+int32_t sgm_sgld_max_steps(const sgm_sgld_desc* d) {
+    int B, max_T, nsel, Smax;
+    const int rc = sgld_geometry(d, B, max_T, nsel, Smax);
+    return rc != SGM_OK ? rc : max_T;
+}
+uint64_t sgm_sgld_workspace_bytes(const sgm_sgld_desc* d) {
+    SgldLayout L;
+    if (sgld_layout(d, L) != SGM_OK) return 0;
+    return (uint64_t)L.total;
+}
+
+int sgm_sgld_run(const sgm_sgld_desc* d, void* stream) {
+    SgldLayout L;
+    int rc = sgld_layout(d, L);
+    if (rc != SGM_OK) return rc;
+    g_err[0] = 0;
+    if (!d->obs || !d->seq_off || !d->params || !d->hyper || !d->chain_status || !d->offset_dev || !d->iter_dev)
+        return fail(SGM_ERR_INVALID, "missing array (obs / seq_off / params / hyper / chain_status / offset_dev / iter_dev)");
+    if (d->prior_x0 == 0 && (!d->prior_mean || !d->prior_var)) return fail(SGM_ERR_INVALID, "prior_mean / prior_var missing");
+    if (d->prior_x0 != 0 && (d->prior_x0 != 1 || d->pf.model != SGM_MODEL_GARCH)) return fail(SGM_ERR_INVALID, "prior_x0 = 1 is the GARCH stationary prior");
+    const bool injected = d->pf.rng_mode == SGM_RNG_INJECTED;
+    if (injected && ((d->subsequence_length != -1 && !d->inj_start) || (d->method != SGM_STEP_SGD && !d->inj_noise) ||
+                     (d->num_sequences != -1 && !d->inj_seq)))
+        return fail(SGM_ERR_INVALID, "INJECTED mode needs inj_start / inj_noise (/ inj_seq)");
+    if (!d->workspace || d->workspace_bytes < L.total) return fail(SGM_ERR_WORKSPACE, "workspace too small");
+    if (((uintptr_t)d->workspace & 255) != 0) return fail(SGM_ERR_WORKSPACE, "workspace must be 256-byte aligned");
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    char* ws = reinterpret_cast<char*>(d->workspace);
+
+    SgldArgs a;
+    memset(&a, 0, sizeof(a));
+    a.model = d->pf.model; a.method = d->method; a.C = d->n_chains; a.M = d->minibatch; a.nsel = L.nsel; a.n_seqs = d->n_seqs;
+    a.S = d->subsequence_length; a.Bf = d->buffer_length; a.partition = d->partition; a.project = d->project;
+    a.prior_x0 = d->prior_x0; a.injected = injected ? 1 : 0; a.ipc = L.nsel * d->minibatch; a.Smax = L.Smax;
+    a.pick_all = d->num_sequences == -1 ? 1 : 0;
+    a.epsilon = d->epsilon; a.T_total = d->T_total;
+    a.key.k0 = (uint32_t)(d->pf.seed & 0xffffffffu); a.key.k1 = (uint32_t)(d->pf.seed >> 32);
+    a.key.item = (uint32_t)(d->pf.item_id_base / (a.ipc > 0 ? a.ipc : 1)); a.key.offset = 0;
+    a.offset_dev = d->offset_dev; a.offset_rw = d->offset_dev; a.iter_dev = d->iter_dev;
+    a.obs = d->obs; a.seq_off = d->seq_off; a.params = d->params; a.hyper = d->hyper;
+    a.prior_mean = d->prior_mean; a.prior_var = d->prior_var; a.chain_status = d->chain_status;
+    a.trace = d->trace; a.trace_every = d->trace_every; a.trace_rows = d->trace_rows;
+    a.inj_start = d->inj_start; a.inj_seq = d->inj_seq; a.inj_noise = d->inj_noise;
+    a.obs_off = reinterpret_cast<int64_t*>(ws + L.obs_off); a.T_buf = reinterpret_cast<int32_t*>(ws + L.T_buf);
+    a.t1 = reinterpret_cast<int32_t*>(ws + L.t1); a.tL = reinterpret_cast<int32_t*>(ws + L.tL);
+    a.wts_off = reinterpret_cast<int64_t*>(ws + L.wts_off); a.weights = reinterpret_cast<double*>(ws + L.weights);
+    a.theta = reinterpret_cast<double*>(ws + L.theta); a.item_pm = reinterpret_cast<double*>(ws + L.pm);
+    a.item_pv = reinterpret_cast<double*>(ws + L.pv); a.item_seq = reinterpret_cast<int32_t*>(ws + L.item_seq);
+    a.grad = reinterpret_cast<double*>(ws + L.grad); a.loglik = reinterpret_cast<double*>(ws + L.loglik);
+    a.item_status = reinterpret_cast<int32_t*>(ws + L.status);
+
+    sgm_pf_desc pf;
+    sgld_pf_template(d, L.B, L.max_T, pf);
+    pf.obs = d->obs; pf.obs_off = a.obs_off; pf.T_buf = a.T_buf; pf.t1 = a.t1; pf.tL = a.tL;
+    pf.step_weights = a.weights; pf.wts_off = a.wts_off; pf.theta = a.theta; pf.prior_mean = a.item_pm; pf.prior_var = a.item_pv;
+    pf.grad = reinterpret_cast<double*>(ws + L.grad); pf.loglik = reinterpret_cast<double*>(ws + L.loglik);
+    pf.status = reinterpret_cast<int32_t*>(ws + L.status);
+    pf.workspace = ws + L.pf_ws; pf.workspace_bytes = L.total - L.pf_ws;
+    pf.offset_dev = d->offset_dev;
+
+    int64_t launches = 0;
+    const size_t N = (size_t)pf.n_particles, B = (size_t)L.B, T = (size_t)L.max_T;
+    if (d->n_iters > 0 && !d->no_persistent) {
+        // one item per chain and N <= 2048: all iterations inside one persistent launch
+        rc = pf.dtype == SGM_F64 ? sgmhost::run_sgld_persistent<double>(&pf, a, d->n_iters, s)
+                                 : sgmhost::run_sgld_persistent<float>(&pf, a, d->n_iters, s);
+        if (rc < 0) return rc;
+        if (rc == 1) return SGM_OK;
+    }
+    for (int k = 0; k < d->n_iters; ++k) {
+        sgld_prepare_kernel<<<(L.B + 127) / 128, 128, 0, s>>>(a, k);
+        if (injected) {
+            pf.inj_z0 = d->pf.inj_z0 + (size_t)k * B * N;
+            pf.inj_u = d->pf.inj_u + (size_t)k * B * T * N;
+            pf.inj_z = d->pf.inj_z + (size_t)k * B * T * N;
+        }
+        rc = pf.dtype == SGM_F64 ? sgmhost::run_model<double>(&pf, s) : sgmhost::run_model<float>(&pf, s);
+        if (rc != SGM_OK) return rc;
+        launches += g_launches + 2;
+        sgld_update_kernel<<<1, 256, 0, s>>>(a, k);
+    }
+    g_launches = launches;
+    const cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(SGM_ERR_CUDA, "CUDA launch failed: %s", cudaGetErrorString(e));
+    return SGM_OK;
+}
 
 int sgm_version(void) { return SGM_VERSION; }
 

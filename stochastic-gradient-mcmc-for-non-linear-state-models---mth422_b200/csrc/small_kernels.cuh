@@ -1,0 +1,294 @@
+// Small particle counts (N <= 2048): the whole buffered time loop of an item in ONE CTA with the particle system
+// resident in SHARED MEMORY -- no global-memory traffic inside the time loop at all (the per-step tile kernels stream
+// 40-56 B per particle-step through HBM / L2; here a time step is two block barriers and shared-memory accesses).
+// This is the SG-MCMC regime of the reference's own scripts (N = 1000, one subsequence per iteration), where a
+// gradient is latency-bound: every thread owns PPT (1 or 2) particles instead of a warp owning 256, so the dependent
+// instruction chain of a time step is ~1/8 as long as in the warp-tile kernels.
+//
+// One time step (reference pf.py:7-38 + :138-181 / :40-82, buffered_smoother.py:94-126):
+//   A  per warp: max of the log-weights, w = exp(lw - m_warp), inclusive scan (registers + shuffles), weighted
+//      statistic sums; lane 0 stores the warp summary                                             -> barrier 1
+//   B  every warp combines the <= 32 warp summaries itself (shuffles): global max M, total, offsets, scales,
+//      S-bar; writes the CDF entries of its particles to shared memory (c_i = off_w + sc_w * prefix_i: the same
+//      hierarchical form as the tile kernels); thread 0 adds the log-likelihood increment        -> barrier 2
+//   C  per particle: uniform -> binary search of the shared-memory CDF (np.random.choice == searchsorted(cdf, u,
+//      'right')), gather the parent from shared memory, propose, reweight, update the statistic, store the child
+// Resampling is the reference's plain multinomial (iid uniforms): parents are gathered from shared memory, so the
+// sorted-target trick of the streaming kernels has nothing to gain here ('multinomial_sorted' has the same law and
+// takes this path too); systematic / stratified targets are supported as in the tile kernels.
+#pragma once
+#include "pf_kernels.cuh"
+
+namespace sgm {
+
+enum : uint32_t { STREAM_SMALL = 9 };
+constexpr int SM_STRIDE = 8;          // R values per warp summary: m, s, ws[0..3]
+
+template <class R> __host__ __device__ inline size_t small_smem_bytes(int npad, int nx, int nst) {
+    return sizeof(R) * ((size_t)npad * (size_t)(1 + 2 * nx + 2 * nst) + 32 * SM_STRIDE);
+}
+
+// u[PPT] uniforms and z[PPT] standard normals of thread `tid` at `step`
+template <int PPT> __device__ __forceinline__ void small_draw(const RngKey& key, uint32_t tid, uint32_t step, float* u, float* z) {
+#pragma unroll
+    for (int h = 0; h < (PPT + 1) / 2; ++h) {
+        const uint4 r = rng_raw(key, tid, step, STREAM_SMALL, (uint32_t)h);
+        const float rad = sqrt_approx(__log2f(u01f(r.z)) * -1.3862943611198906f);
+        float s, c;
+        __sincosf(6.28318530717958647692f * u01f(r.w), &s, &c);
+        u[2 * h] = u01f(r.x); z[2 * h] = rad * c;
+        if (2 * h + 1 < PPT) { u[2 * h + 1] = u01f(r.y); z[2 * h + 1] = rad * s; }
+    }
+}
+template <int PPT> __device__ __forceinline__ void small_draw(const RngKey& key, uint32_t tid, uint32_t step, double* u, double* z) {
+#pragma unroll
+    for (int h = 0; h < (PPT + 1) / 2; ++h) {
+        const uint4 a = rng_raw(key, tid, step, STREAM_SMALL, (uint32_t)(2 * h)), b = rng_raw(key, tid, step, STREAM_SMALL, (uint32_t)(2 * h + 1));
+        const double rad = sqrt(-2.0 * log(u01d(b.x, b.y)));
+        double s, c;
+        sincospi(2.0 * u01d(b.z, b.w), &s, &c);
+        u[2 * h] = u01d(a.x, a.y); z[2 * h] = rad * c;
+        if (2 * h + 1 < PPT) { u[2 * h + 1] = u01d(a.z, a.w); z[2 * h + 1] = rad * s; }
+    }
+}
+
+// The whole time loop of item b by the calling CTA (NTH threads, every thread calls).  `smem` = small_smem_bytes<R>()
+// bytes of 16-byte aligned shared memory.  Results go to a.grad / a.loglik / a.status (and the optional outputs).
+template <class R, class Model, int NTH, int PPT>
+__device__ void small_pf_item(const KArgs& a, int b, unsigned char* smem) {
+    constexpr int NW = NTH / 32, NX = Model::NX, NP = Model::NP, NPAD = NTH * PPT;
+    static_assert(NW <= 32, "at most 32 warps");
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int N = a.N;
+    const int Tb = a.T_buf[b], t1 = a.t1[b], tL = a.tL[b];
+    const int nstat = stat_width<Model>(a.stat_kind);
+    const bool carries = a.pf == SGM_PF_NEMETH, filter = a.pf == SGM_PF_FILTER;
+    const bool shrink = carries && a.lambduh != 1.0;
+    const int nst = carries ? nstat : 0;                 // statistics stored per particle (followed along the genealogy)
+    R* const cdf = reinterpret_cast<R*>(smem);
+    R* const xs0 = cdf + NPAD;
+    R* const st0 = xs0 + 2 * NPAD * NX;
+    R* const summ = st0 + 2 * NPAD * nst;
+    const typename Model::template Theta<R> th = Model::template load<R>(a.theta + (size_t)b * SGM_THETA_STRIDE);
+    const RngKey key = item_key(a, b);
+    const bool injected = a.rng_mode == SGM_RNG_INJECTED;
+    const bool var32 = sizeof(R) == 8 && a.variates32 && !injected;
+    const R NEG_INF = -Mth<R>::inf();
+    const size_t item_off = (size_t)b * N;
+    const double* obs = a.obs + a.obs_off[b];
+    const double* wts = (a.wts_off && a.wts_off[b] >= 0) ? a.step_weights + a.wts_off[b] : nullptr;
+    const R lam = (R)a.lambduh;
+
+    auto draw = [&](uint32_t step, R* u, R* z) {
+        if (var32) {
+            float uf[PPT], zf[PPT];
+            small_draw<PPT>(key, (uint32_t)tid, step, uf, zf);
+#pragma unroll
+            for (int k = 0; k < PPT; ++k) { u[k] = (R)uf[k]; z[k] = (R)zf[k]; }
+        } else {
+            small_draw<PPT>(key, (uint32_t)tid, step, u, z);
+        }
+    };
+
+    R lw[PPT], sv[PPT][4];
+    int par = 0;
+    {   // ---- init: x0 ~ N(prior_mean, prior_var), lw = 0, statistics = 0  (buffered_smoother.py:67-75) ----
+        const R mean = (R)a.prior_mean[b], sd = (R)::sqrt(a.prior_var[b]);
+        R u[PPT], z[PPT];
+        if (!injected) draw(0xffffu, u, z);
+#pragma unroll
+        for (int k = 0; k < PPT; ++k) {
+            const int i = tid * PPT + k;
+            lw[k] = (i < N) ? (R)0 : NEG_INF;
+            sv[k][0] = sv[k][1] = sv[k][2] = sv[k][3] = (R)0;
+            if (i < N) {
+                if (injected) z[k] = (R)a.inj_z0[item_off + i];
+                R x[NX];
+                Model::init(mean, sd, z[k], x);
+#pragma unroll
+                for (int d = 0; d < NX; ++d) xs0[d * NPAD + i] = x[d];
+                for (int q = 0; q < nst; ++q) st0[q * NPAD + i] = (R)0;
+                if (a.trace_x) for (int d = 0; d < NX; ++d)
+                    reinterpret_cast<R*>(a.trace_x)[((size_t)b * (a.max_T + 1) * N + i) * NX + d] = x[d];
+                if (a.trace_lw) reinterpret_cast<R*>(a.trace_lw)[(size_t)b * (a.max_T + 1) * N + i] = (R)0;
+            }
+        }
+    }
+    double loglik = 0.0, accf[4] = {0.0, 0.0, 0.0, 0.0};
+    int status = 0;
+
+    for (int t = 0;; ++t) {
+        const bool final_pass = t >= Tb;
+        const bool need_ws = nstat > 0 && (filter || shrink || (carries && final_pass));
+        // ---- A: warp summary --------------------------------------------------------------------------
+        R m = NEG_INF;
+#pragma unroll
+        for (int k = 0; k < PPT; ++k) m = nan_max(m, lw[k]);
+        m = warp_max(m);
+        const R msafe = (m == NEG_INF) ? (R)0 : m;
+        R w[PPT], pre[PPT];
+#pragma unroll
+        for (int k = 0; k < PPT; ++k) { w[k] = Mth<R>::exp(lw[k] - msafe); pre[k] = w[k] + (k ? pre[k - 1] : (R)0); }
+        const R incl = warp_incl_scan(pre[PPT - 1]);
+        const R excl = incl - pre[PPT - 1];
+#pragma unroll
+        for (int k = 0; k < PPT; ++k) pre[k] += excl;
+        const R s_w = __shfl_sync(FULL, incl, 31);
+        R wsum[4] = {(R)0, (R)0, (R)0, (R)0};
+        if (need_ws) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                R acc = (R)0;
+#pragma unroll
+                for (int k = 0; k < PPT; ++k) acc += sv[k][q] * w[k];          // w = 0 beyond N
+                wsum[q] = (q < nstat) ? warp_sum(acc) : (R)0;
+            }
+        }
+        if (lane == 0) {
+            R* p = summ + warp * SM_STRIDE;
+            p[0] = m; p[1] = s_w; p[2] = wsum[0]; p[3] = wsum[1]; p[4] = wsum[2]; p[5] = wsum[3];
+        }
+        __syncthreads();                                                      // barrier 1
+        // ---- B: cross-warp combine (every warp, redundantly: fixed shuffle trees => identical results) ----
+        const bool has = lane < NW;
+        const R ml = has ? summ[lane * SM_STRIDE] : NEG_INF;
+        const R M = warp_max(ml);
+        const R el = (has && ml != NEG_INF) ? Mth<R>::exp(ml - M) : (R)0;
+        const R loc = has ? el * summ[lane * SM_STRIDE + 1] : (R)0;
+        const R lincl = warp_incl_scan(loc);
+        const R total = __shfl_sync(FULL, lincl, 31);
+        const R off_me = __shfl_sync(FULL, lincl - loc, warp);
+        const R sc_me = __shfl_sync(FULL, el, warp);
+        R sbar[4] = {(R)0, (R)0, (R)0, (R)0};
+        if (need_ws) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                if (q < nstat) sbar[q] = warp_sum(has ? el * summ[lane * SM_STRIDE + 2 + q] : (R)0) / total;
+        }
+        if (tid == 0) {
+            const double Md = (double)M, td = (double)total;
+            if (!(td > 0.0) || !(td < Mth<double>::inf()) || !(Md == Md) || !(fabs(Md) < Mth<double>::inf()))
+                status |= (td == 0.0 || Md == -Mth<double>::inf()) ? SGM_STATUS_ZERO_WEIGHT : SGM_STATUS_NAN_WEIGHT;
+            const int t_done = t - 1;
+            if (t_done >= 0) {
+                if (t_done >= t1 && t_done < tL)                                // buffered_smoother.py:124-126 (max-shifted)
+                    loglik += (wts ? wts[t_done - t1] : 1.0) * (Md + ::log(td / (double)N));
+                if (filter) for (int j = 0; j < nstat; ++j) accf[j] += (double)sbar[j];      // pf.py:77-80
+            }
+        }
+        if (final_pass) {
+            if (tid == 0) {
+                a.loglik[b] = loglik;
+                a.status[b] = status;
+                for (int j = 0; j < 8; ++j) a.grad[(size_t)b * 8 + j] = 0.0;
+                for (int j = 0; j < nstat; ++j) a.grad[(size_t)b * 8 + j] = filter ? accf[j] : (double)sbar[j];
+            }
+            break;
+        }
+#pragma unroll
+        for (int k = 0; k < PPT; ++k) {
+            const int i = tid * PPT + k;
+            if (i < N) cdf[i] = Mth<R>::fma(sc_me, pre[k], off_me);
+        }
+        __syncthreads();                                                      // barrier 2
+        // ---- C: resample -> propagate -> reweight -> statistic update ----------------------------------
+        const bool in_sub = t >= t1 && t < tL;
+        const R y = (R)obs[t];
+        const R wt = in_sub ? (R)(wts ? wts[t - t1] : 1.0) : (R)0;
+        const R hs = (carries || filter) ? wt : (R)0;
+        const int stat_kind = (in_sub && hs != (R)0) ? a.stat_kind : (int)SGM_STAT_NONE;
+        R u[PPT], z[PPT];
+        if (!injected) {
+            draw((uint32_t)t, u, z);
+            if (a.resample == SGM_RESAMPLE_SYSTEMATIC) {
+                R u4[4];
+                if (var32) { float f4[4]; rng_uniform4(key, 0u, (uint32_t)t, STREAM_GAMMA, f4); u4[0] = (R)f4[0]; }
+                else rng_uniform4(key, 0u, (uint32_t)t, STREAM_GAMMA, u4);
+#pragma unroll
+                for (int k = 0; k < PPT; ++k) u[k] = u4[0];
+            }
+        }
+        const R* xo = xs0 + par * NPAD * NX;
+        R* xn_s = xs0 + (par ^ 1) * NPAD * NX;
+        const R* so = st0 + par * NPAD * nst;
+        R* sn = st0 + (par ^ 1) * NPAD * nst;
+        const R cmax = cdf[N - 1];
+        const bool strat = !injected && (a.resample == SGM_RESAMPLE_SYSTEMATIC || a.resample == SGM_RESAMPLE_STRATIFIED);
+        int anc[PPT];
+        R tg[PPT];
+#pragma unroll
+        for (int k = 0; k < PPT; ++k) {
+            const int i = tid * PPT + k;
+            if (injected) { u[k] = (i < N) ? (R)a.inj_u[((size_t)b * a.max_T + t) * N + i] : (R)0; z[k] = (i < N) ? (R)a.inj_z[((size_t)b * a.max_T + t) * N + i] : (R)0; }
+            tg[k] = strat ? (((R)i + u[k]) / (R)N) * total : u[k] * total;
+            anc[k] = 0;
+        }
+        // searchsorted(cdf, target, 'right'): number of entries <= target; PPT searches interleaved, fixed trip count
+#pragma unroll 1
+        for (int step = NPAD / 2; step > 0; step >>= 1) {
+#pragma unroll
+            for (int k = 0; k < PPT; ++k) {
+                const int idx = anc[k] + step;
+                if (idx <= N && cdf[idx - 1] <= tg[k]) anc[k] = idx;
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < PPT; ++k) {
+            const int i = tid * PPT + k;
+            if (!(tg[k] < cmax)) anc[k] = N - 1;               // u * total rounded up to the total (or a NaN weight)
+            anc[k] = min(anc[k], N - 1);
+            lw[k] = NEG_INF;
+            if (i < N) {
+                R xa[NX], xn[NX], sa[4] = {(R)0, (R)0, (R)0, (R)0};
+#pragma unroll
+                for (int d = 0; d < NX; ++d) xa[d] = xo[d * NPAD + anc[k]];
+#pragma unroll
+                for (int q = 0; q < NP; ++q) if (q < nst) sa[q] = so[q * NPAD + anc[k]];
+                Model::propagate(th, xa, y, z[k], xn);
+                lw[k] = Model::log_weight(th, xa, xn, y);
+                R h[4] = {(R)0, (R)0, (R)0, (R)0};
+                if (stat_kind == SGM_STAT_SCORE) Model::score(th, xa, xn, y, h);
+                else if (stat_kind == SGM_STAT_SUFF) Model::suff(xa, xn, h);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    // pf.py:175-179 (Nemeth / Poyiadjis O(N)), pf.py:70-71 (filter: nothing carried)
+                    if (!carries) sv[k][q] = h[q] * hs;
+                    else if (!shrink) sv[k][q] = sa[q] + h[q] * hs;
+                    else sv[k][q] = lam * sa[q] + ((R)((1.0 - a.lambduh) * (double)sbar[q]) + h[q] * hs);
+                }
+#pragma unroll
+                for (int d = 0; d < NX; ++d) xn_s[d * NPAD + i] = xn[d];
+#pragma unroll
+                for (int q = 0; q < NP; ++q) if (q < nst) sn[q * NPAD + i] = sv[k][q];
+                if (a.trace_anc) a.trace_anc[((size_t)b * a.max_T + t) * N + i] = anc[k];
+                if (a.trace_x) for (int d = 0; d < NX; ++d)
+                    reinterpret_cast<R*>(a.trace_x)[(((size_t)b * (a.max_T + 1) + t + 1) * N + i) * NX + d] = xn[d];
+                if (a.trace_lw) reinterpret_cast<R*>(a.trace_lw)[((size_t)b * (a.max_T + 1) + t + 1) * N + i] = lw[k];
+            }
+        }
+        par ^= 1;
+        // no barrier here: the next step's barriers 1 and 2 order these stores before the next gathers, and every
+        // read of the old buffers / the CDF above precedes barrier 1 of the next step
+    }
+    // ---- optional export of the final particle system (each thread: its own particles) ----
+    if (a.out_x || a.out_lw || a.out_stats) {
+        const R* xc = xs0 + par * NPAD * NX;
+#pragma unroll
+        for (int k = 0; k < PPT; ++k) {
+            const int i = tid * PPT + k;
+            if (i < N) {
+                if (a.out_x) for (int d = 0; d < NX; ++d) reinterpret_cast<R*>(a.out_x)[(item_off + i) * NX + d] = xc[d * NPAD + i];
+                if (a.out_lw) reinterpret_cast<R*>(a.out_lw)[item_off + i] = lw[k];
+                if (a.out_stats) for (int q = 0; q < NP; ++q) reinterpret_cast<R*>(a.out_stats)[(item_off + i) * NP + q] = carries ? sv[k][q] : (R)0;
+            }
+        }
+    }
+}
+
+template <class R, class Model, int NTH, int PPT>
+__global__ void __launch_bounds__(NTH, 1024 / NTH) pf_small_kernel(KArgs a) {     // 64 registers: 1024 resident threads per SM
+    extern __shared__ __align__(16) unsigned char small_smem[];
+    small_pf_item<R, Model, NTH, PPT>(a, a.b0 + blockIdx.x, small_smem);
+}
+
+}  // namespace sgm

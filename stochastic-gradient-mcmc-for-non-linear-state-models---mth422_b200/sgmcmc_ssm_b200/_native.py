@@ -18,6 +18,7 @@ RESAMPLE = dict(multinomial=0, multinomial_sorted=1, sorted=1, systematic=2, str
 STAT = dict(score=0, suff=1, none=2, pred=3)
 N2_MODE = dict(auto=0, fp32_pipe=1, tensor=2)
 VARIATES = dict(native=0, f32=1)
+PATH = dict(auto=0, tiles=1, small=2)
 STATUS_NAN_WEIGHT, STATUS_ZERO_WEIGHT, STATUS_AR_OVERFLOW = 1, 2, 4
 THETA_STRIDE = 12
 PRED_SLOTS, PRED_MAX_STEPS = 16, 14           # SGM_PRED_SLOTS, SGM_PRED_MAX_STEPS (include/sgmpf.h)
@@ -31,7 +32,7 @@ class SgmPfDesc(ctypes.Structure):
         ("n_items", c_i32), ("n_particles", c_i32), ("max_T", c_i32), ("Ntilde", c_i32),
         ("accept_reject", c_i32), ("max_accept_reject", c_i32), ("manual_sample_threshold", c_i32),
         ("item_id_base", c_i32), ("n2_mode", c_i32), ("pred_steps_ahead", c_i32),
-        ("pred_per_horizon", c_i32), ("variates", c_i32),
+        ("pred_per_horizon", c_i32), ("variates", c_i32), ("path", c_i32), ("reserved1", c_i32),
         ("lambduh", c_f64), ("seed", c_u64), ("offset", c_u64), ("offset_dev", c_vp),
         ("obs", c_vp), ("obs_off", c_vp), ("T_buf", c_vp), ("t1", c_vp), ("tL", c_vp),
         ("step_weights", c_vp), ("wts_off", c_vp), ("theta", c_vp), ("prior_mean", c_vp), ("prior_var", c_vp),
@@ -45,8 +46,29 @@ class SgmPfDesc(ctypes.Structure):
     ]
 
 
+STEP = dict(SGLD=0, SGRLD=1, SGD=2)
+PARTITION = dict(uniform=0, naive=1, strict=2)
+PARAM_STRIDE, HYPER_STRIDE = 8, 16          # SGM_PARAM_STRIDE, SGM_HYPER_STRIDE
+
+
+class SgmSgldDesc(ctypes.Structure):
+    _fields_ = [
+        ("struct_bytes", c_i32), ("method", c_i32), ("n_chains", c_i32), ("minibatch", c_i32), ("n_seqs", c_i32),
+        ("num_sequences", c_i32), ("subsequence_length", c_i32), ("buffer_length", c_i32), ("partition", c_i32),
+        ("n_iters", c_i32), ("project", c_i32), ("prior_x0", c_i32), ("trace_every", c_i32), ("trace_rows", c_i32),
+        ("max_seq_len", c_i32), ("no_persistent", c_i32),
+        ("epsilon", c_f64), ("T_total", c_f64),
+        ("obs", c_vp), ("seq_off", c_vp), ("params", c_vp), ("hyper", c_vp), ("prior_mean", c_vp), ("prior_var", c_vp),
+        ("chain_status", c_vp), ("trace", c_vp), ("offset_dev", c_vp), ("iter_dev", c_vp),
+        ("inj_start", c_vp), ("inj_seq", c_vp), ("inj_noise", c_vp),
+        ("workspace", c_vp), ("workspace_bytes", c_u64),
+        ("pf", SgmPfDesc),
+    ]
+
+
 EXPORTS = ["sgm_version", "sgm_device_check", "sgm_last_error", "sgm_stat_dim", "sgm_state_dim",
-           "sgm_pf_workspace_bytes", "sgm_pf_run", "sgm_last_launch_count", "sgm_ksd_imq"]
+           "sgm_pf_workspace_bytes", "sgm_pf_run", "sgm_last_launch_count", "sgm_ksd_imq",
+           "sgm_sgld_items", "sgm_sgld_max_steps", "sgm_sgld_workspace_bytes", "sgm_sgld_run"]
 _lib = None
 
 
@@ -72,6 +94,14 @@ def load():
     lib.sgm_pf_run.restype = c_i32
     lib.sgm_pf_run.argtypes = [ctypes.POINTER(SgmPfDesc), c_vp]
     lib.sgm_last_launch_count.restype = c_i64
+    lib.sgm_sgld_items.restype = c_i32
+    lib.sgm_sgld_items.argtypes = [ctypes.POINTER(SgmSgldDesc)]
+    lib.sgm_sgld_max_steps.restype = c_i32
+    lib.sgm_sgld_max_steps.argtypes = [ctypes.POINTER(SgmSgldDesc)]
+    lib.sgm_sgld_workspace_bytes.restype = c_u64
+    lib.sgm_sgld_workspace_bytes.argtypes = [ctypes.POINTER(SgmSgldDesc)]
+    lib.sgm_sgld_run.restype = c_i32
+    lib.sgm_sgld_run.argtypes = [ctypes.POINTER(SgmSgldDesc), c_vp]
     lib.sgm_ksd_imq.restype = c_i32
     lib.sgm_ksd_imq.argtypes = [c_vp, c_vp, c_i32, c_i32, c_f64, c_f64, c_vp, c_vp]
     _lib = lib

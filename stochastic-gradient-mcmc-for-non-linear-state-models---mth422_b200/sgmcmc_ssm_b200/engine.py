@@ -25,6 +25,7 @@ class Config(object):
     device = None                    # torch device; default = current CUDA device
     two_streams = True               # split big O(N) batches over two streams (hides the per-step header kernel)
     cuda_graphs = True               # replay a captured CUDA graph for small launch-bound batches (one wave of CTAs)
+    device_loop = True               # sampler.fit(...) runs whole SG-MCMC iterations on the device when it can (device_loop.py)
     variates = "native"              # dtype 'f64' + device randoms: 'native' (53-bit variates) or 'f32' (the f32 path's variates, widened)
 
 
@@ -264,7 +265,7 @@ class PreparedPF(object):
     def __init__(self, model, kernel, pf, items, N, dtype=None, rng=None, resample=None, stat_kind="score",
                  lambduh=None, Ntilde=2, accept_reject=True, max_accept_reject=None,
                  manual_sample_threshold=None, seed=None, offset=None, item_id_base=0, injected=None,
-                 want=(), device=None, n2_mode="auto", num_steps_ahead=5, per_horizon=False, variates=None):
+                 want=(), device=None, n2_mode="auto", num_steps_ahead=5, per_horizon=False, variates=None, path="auto"):
         lib = self.lib = nat.load()
         device = self.device = _device(device)
         st = self.st = _state(device)
@@ -324,6 +325,7 @@ class PreparedPF(object):
         desc.item_id_base = int(item_id_base)
         desc.n2_mode = nat.N2_MODE[n2_mode]
         desc.variates = nat.VARIATES[variates or config.variates]
+        desc.path = nat.PATH[path]
         desc.pred_steps_ahead, desc.pred_per_horizon = int(num_steps_ahead), int(bool(per_horizon))
         desc.lambduh = float(lambduh)
         if rng == "injected":

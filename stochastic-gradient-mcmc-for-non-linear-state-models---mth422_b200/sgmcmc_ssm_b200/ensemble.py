@@ -101,3 +101,20 @@ class ChainEnsemble(object):
 
     def step_adagrad(self, epsilon, **kwargs):
         return self._step("step_adagrad", epsilon, **kwargs)
+
+    def fit(self, iter_type, num_iters, epsilon, output_all=False, trace_every=None, **kwargs):
+        """`num_iters` iterations of every chain on the device with no host round trip (device_loop.DeviceChains: windows,
+        particle filters, prior gradient, Langevin noise, update and projection in one launch sequence per iteration, all
+        chains batched).  Randomness comes from the device Philox streams (keyed by chain index, so sharding the
+        chains over GPUs does not change a chain's stream).  Returns the parameter trace (rows, chains, n_params) when
+        output_all, else the list of final Parameters."""
+        from .device_loop import DeviceChains
+        pfk = dict(kwargs.pop("pf_kwargs", {}))
+        pfk.update(kwargs)
+        every = (trace_every or 1) if output_all else 0
+        chains = DeviceChains(self.samplers, method=iter_type, epsilon=epsilon, trace_every=every,
+                              max_trace_rows=(num_iters // every if every else 0), **pfk)
+        chains.run(num_iters)
+        params = chains.pull_parameters()
+        self.device_chains = chains
+        return chains.trace() if output_all else params

@@ -20,7 +20,7 @@ from . import statistics as S
 
 _PF_NAMES = ("nemeth", "poyiadjis_N", "poyiadjis_N2", "paris", "filter")
 _ENGINE_KW = ("dtype", "rng", "resample", "lambduh", "Ntilde", "accept_reject", "max_accept_reject",
-              "manual_sample_threshold", "seed", "offset", "device", "item_id_base", "n2_mode", "num_steps_ahead", "per_horizon", "variates")
+              "manual_sample_threshold", "seed", "offset", "device", "item_id_base", "n2_mode", "num_steps_ahead", "per_horizon", "variates", "path")
 
 
 def _theta(model, parameters):

@@ -443,6 +443,8 @@ class SGMCMCSampler(object):
             self.observations = observations
         if init_parameters is not None:
             self.parameters = init_parameters.copy()
+        if self._device_loop_eligible(iter_type, kwargs):
+            return self._fit_device(iter_type, num_iters, output_all=output_all, **kwargs)
         names, kws = self.get_iter_step(iter_type, tqdm=tqdm, **kwargs)
         parameters_list = [None] * (num_iters + 1)
         parameters_list[0] = self.parameters.copy()
@@ -462,6 +464,48 @@ class SGMCMCSampler(object):
                 logger.warning("Interrupt in fit:\n{0}\nStopping early after {1} iters".format(e, it))
                 return parameters_list[:it] if output_all else self.parameters.copy()
         return parameters_list if output_all else self.parameters.copy()
+
+    def _device_loop_eligible(self, iter_type, kwargs):
+        """The whole loop runs on the device (device_loop.DeviceChains) when nothing in it needs the host: particle-filter
+        gradients with device randoms, a plain SGLD / SGD / LGSSM-SGRLD step, default projection options."""
+        from . import engine
+        from .device_loop import _supported_options
+        pfk = kwargs.get("pf_kwargs", {})
+        if not kwargs.get("device_loop", engine.config.device_loop) or kwargs.get("kind") != "pf":
+            return False
+        if iter_type not in ("SGLD", "SGD", "SGRLD") or kwargs.get("steps_per_iteration", 1) != 1:
+            return False
+        if pfk.get("rng", engine.config.rng) != "philox" or kwargs.get("project_kwargs") or pfk.get("distributed"):
+            return False
+        if iter_type == "SGRLD":
+            from .models.lgssm import LGSSMPreconditioner
+            if not isinstance(kwargs.get("preconditioner"), LGSSMPreconditioner):
+                return False
+        return _supported_options(getattr(self, "options", {})) and getattr(self.parameters, "n", 1) == 1 \
+            and getattr(self.parameters, "m", 1) == 1
+
+    def _fit_device(self, iter_type, num_iters, output_all=False, **kwargs):
+        """fit() with every iteration on the device (same arguments; windows, filter randoms and Langevin noise come
+        from the device Philox streams instead of np.random)."""
+        from .device_loop import DeviceChains
+        pfk = dict(kwargs.get("pf_kwargs", {}))
+        chains = DeviceChains([self], method=iter_type, epsilon=kwargs["epsilon"],
+                              subsequence_length=kwargs["subsequence_length"], buffer_length=kwargs["buffer_length"],
+                              minibatch_size=kwargs.get("minibatch_size", 1), num_sequences=kwargs.get("num_sequences"),
+                              num_samples=kwargs.get("num_samples"), preconditioner=kwargs.get("preconditioner"),
+                              trace_every=1 if output_all else 0, max_trace_rows=num_iters if output_all else 0, **pfk)
+        chains.run(num_iters)
+        chains.pull_parameters()
+        if not output_all:
+            return self.parameters.copy()
+        tr = chains.trace()                                   # (num_iters + 1, 1, n_params)
+        out = []
+        for row in tr[:, 0, :]:
+            p = self.parameters.copy()
+            for i, k in enumerate(chains.slots):
+                p.var_dict[k] = np.full_like(np.asarray(p.var_dict[k], dtype=float), row[i])
+            out.append(p)
+        return out
 
     def fit_timed(self, iter_type, max_time=60, min_save_time=1, observations=None, init_parameters=None,
                   tqdm=None, tqdm_iter=False, catch_interrupt=False, **kwargs):

@@ -11,7 +11,7 @@ THETA = dict(A=0.95, LQinv=np.sqrt(2.0), Qinv=2.0 + 1e-16, LRinv=np.sqrt(2.0), R
 TH = [THETA[k] for k in ("A", "LQinv", "Qinv", "LRinv", "Rinv")]
 
 
-def _run(N, obs, t1, tL, pf="poyiadjis_N", resample="multinomial", seed=3, weights=None, **kw):
+def _run(N, obs, t1, tL, pf="poyiadjis_N", resample="multinomial", seed=3, weights=None, path="auto", **kw):
     import sgmcmc_ssm_b200 as sg
     K = po.make_kernel("svm", "prior", THETA)
     if resample == "multinomial":
@@ -28,16 +28,19 @@ def _run(N, obs, t1, tL, pf="poyiadjis_N", resample="multinomial", seed=3, weigh
                              t1=t1, tL=tL, weights=weights, prior_mean=0.0, prior_var=10.0, **kw)
         inj = dict(z0=z0, u=u, z=z)
     items = sg.PFItems().add(obs, TH, t1=t1, tL=tL, weights=weights, prior_mean=0.0, prior_var=10.0)
-    res = sg.run_pf("svm", "prior", pf, items, N, dtype="f64", rng="injected", resample=resample, injected=inj, **kw)
+    res = sg.run_pf("svm", "prior", pf, items, N, dtype="f64", rng="injected", resample=resample, injected=inj, path=path, **kw)
     expect = ref["statistics"] if pf == "filter" else po.average_statistic(ref)
     return res, expect, ref
 
 
+@pytest.mark.parametrize("path", ["auto", "tiles"])      # auto: N <= 2048 runs the shared-memory kernel (thread-count boundaries 256 / 1024 / 2048)
 @pytest.mark.parametrize("resample", ["multinomial", "multinomial_sorted"])
-@pytest.mark.parametrize("N", [1, 2, 31, 255, 256, 257, 511, 513, 2047, 2049, 8191, 65537, 70000])   # 65537+: 1024-thread header
-def test_tiny_and_tile_boundary_particle_counts(N, resample):
+@pytest.mark.parametrize("N", [1, 2, 31, 255, 256, 257, 511, 513, 1023, 1024, 1025, 2047, 2048, 2049, 8191, 65537, 70000])   # 65537+: 1024-thread header
+def test_tiny_and_tile_boundary_particle_counts(N, resample, path):
+    if path == "tiles" and N > 2048:
+        pytest.skip("same kernels as path='auto'")
     obs = np.array([0.3, -1.2, 0.8, 2.0, -0.1, 0.4])
-    res, expect, ref = _run(N, obs, 1, 5, resample=resample, weights=np.array([1.0, 2.0, 0.5, 3.0]))
+    res, expect, ref = _run(N, obs, 1, 5, resample=resample, weights=np.array([1.0, 2.0, 0.5, 3.0]), path=path)
     np.testing.assert_allclose(res.grad[0], expect, rtol=1e-8, atol=1e-9)
     np.testing.assert_allclose(res.loglik[0], ref["loglikelihood_estimate"], rtol=1e-9, atol=1e-10)
 

@@ -15,7 +15,7 @@ from tests import _cases as C
 pytestmark = pytest.mark.gpu
 
 
-def _run_case(name, dtype="f64"):
+def _run_case(name, dtype="f64", path="auto"):
     import sgmcmc_ssm_b200 as sg
     c = C.case(name)
     model, kernel, pf = C.parse_kernel_case(name)
@@ -33,13 +33,16 @@ def _run_case(name, dtype="f64"):
     want = ("x", "lw", "stats", "anc") + (("J",) if pf == "paris" else ())
     res = sg.run_pf(model, kernel, pf, items, N, dtype=dtype, rng="injected", resample="multinomial",
                     injected=dict(z0=parts["z0"], u=parts["u"], z=parts["z"], extra=parts["extra"]),
-                    want=want, **opts)
+                    want=want, path=path, **opts)
     return c, ref, res, K
 
 
+@pytest.mark.parametrize("path", ["auto", "tiles"])      # auto: the O(N) smoothers at N <= 2048 run the shared-memory kernel
 @pytest.mark.parametrize("name", C.case_names("k"))
-def test_kernel_case_f64_matches_oracle_and_reference(name):
-    c, ref, res, K = _run_case(name)
+def test_kernel_case_f64_matches_oracle_and_reference(name, path):
+    if path == "tiles" and ("poyiadjis_N2" in name or "paris" in name):
+        pytest.skip("backward smoothers always run the tile kernels")
+    c, ref, res, K = _run_case(name, path=path)
     model, kernel, pf = C.parse_kernel_case(name)
     anc = res.tensor("anc")[0].cpu().numpy()
     np.testing.assert_array_equal(anc, np.array(ref["trace"]["ancestors"]))
@@ -109,7 +112,7 @@ def test_sorted_uniform_path_f64(name, N):
     ref = po.buffered_pf(pf, c["obs"], K, N, K.score, K.p, po.InjectedStream(u.ravel(), flat_z), save_all=True, **kw, **opts)
     items = sg.PFItems().add(c["obs"], c["theta"], **kw)
     res = sg.run_pf(model, kernel, pf, items, N, dtype="f64", rng="injected", resample="multinomial_sorted",
-                    injected=dict(z0=z0, u=u, z=z), want=("x", "stats", "anc"), **opts)
+                    injected=dict(z0=z0, u=u, z=z), want=("x", "stats", "anc"), path="tiles", **opts)
     np.testing.assert_array_equal(res.tensor("anc")[0].cpu().numpy(), np.array(ref["trace"]["ancestors"]))
     np.testing.assert_allclose(res.grad[0], po.average_statistic(ref), rtol=1e-8, atol=1e-9)
     np.testing.assert_allclose(res.loglik[0], ref["loglikelihood_estimate"], rtol=1e-9, atol=1e-10)

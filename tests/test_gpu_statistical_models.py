@@ -39,6 +39,8 @@ def _run_cell(group, N, B, R, dtype="f32", variates="native", seed=17, **kw):
     window = obs[t0 - B:t0 + L + B]
     pk = sg.PackedItems(np.tile(window, R), np.full(R, window.shape[0]), np.full(R, B), np.full(R, L + B), None, None,
                         z[group + "/theta"], float(z[group + "/prior_mean"]), float(z[group + "/prior_var"]))
+    # N <= 2048 would run the shared-memory kernel (its own test below): the tile kernels are forced unless asked otherwise
+    kw.setdefault("path", "tiles" if (N <= 2048 and not pf == "paris") else "auto")
     res = sg.run_pf(model, kernel, pf, pk, N, dtype=dtype, rng="philox", resample="multinomial_sorted", seed=seed,
                     offset=1000 * B + N % 977, variates=variates, **kw)
     return res
@@ -61,7 +63,7 @@ def _check(group, i, j, res, R, what):
 
 @pytest.mark.parametrize("group", _groups())
 def test_production_path_matches_the_reference_distribution(group):
-    """f32: every (N, B) cell of the group.  R = 2048 items keeps N = 1000 on the per-step (fast-mode, ragged) kernels."""
+    """f32: every (N, B) cell of the group on the per-step tile kernels (fast modes; N = 1000 / 10000 ragged)."""
     z = C.load("model_sweep_stats.npz")
     paris = group.endswith("paris")
     R = 512 if paris else 2048
@@ -72,14 +74,16 @@ def test_production_path_matches_the_reference_distribution(group):
 
 
 @pytest.mark.parametrize("group", [g for g in _groups() if not g.endswith("paris")])
-def test_single_launch_kernel_matches_the_reference_distribution(group):
-    """N = 1000 with 512 items runs the one-CTA-per-item single-launch kernel (pf_fused_kernel)."""
+@pytest.mark.parametrize("dtype,R", [("f32", 1024), ("f32", 200), ("f64", 512)])
+def test_shared_memory_kernel_matches_the_reference_distribution(group, dtype, R):
+    """N = 1000: the one-CTA-per-item shared-memory kernel (small_kernels.cuh; 1024 threads x 1 particle for R <= 296
+    items, 512 threads x 2 particles above)."""
     z = C.load("model_sweep_stats.npz")
     i = list(z[group + "/Ns"]).index(1000)
     for j, B in enumerate(z[group + "/buffer_sizes"]):
-        res = _run_cell(group, 1000, int(B), 512, seed=23)
-        assert res.launches <= 2, res.launches
-        _check(group, i, j, res, 512, (group, 1000, int(B), "fused"))
+        res = _run_cell(group, 1000, int(B), R, dtype=dtype, seed=23, path="auto")
+        assert res.launches == 1, res.launches
+        _check(group, i, j, res, R, (group, 1000, int(B), "small", dtype, R))
 
 
 @pytest.mark.parametrize("variates", ["native", "f32"])

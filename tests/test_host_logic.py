@@ -48,7 +48,7 @@ def test_cabi_library_exports_every_declared_symbol():
     assert declared == set(nat.EXPORTS), declared ^ set(nat.EXPORTS)
     for sym in declared:
         assert getattr(lib, sym) is not None
-    assert lib.sgm_version() == 100
+    assert lib.sgm_version() == 200
     assert lib.sgm_stat_dim(nat.MODEL["svm"], 0) == 3 and lib.sgm_stat_dim(nat.MODEL["garch"], 0) == 4
     assert lib.sgm_state_dim(nat.MODEL["garch"]) == 2
     # descriptor validation happens before any CUDA call
