@@ -13,14 +13,17 @@ namespace sgmhost {
 #ifndef SGM_SMALL_MAX_N
 #define SGM_SMALL_MAX_N 2048
 #endif
-#ifndef SGM_SMALL_MAX_ITEMS
-#define SGM_SMALL_MAX_ITEMS 65535
+// ... while the batch is small enough: the shared-memory kernel is bound by instruction issue and shared-memory
+// wavefronts (random parent gathers), the tile kernels by HBM -- measured crossover (SVM / LGSSM f32, 60 steps):
+// N = 256: never; N = 1000: ~1650 items (4096 items: 3.7 vs 2.8 ms); N = 2048: ~480 items (9.4 vs 4.4 ms).
+#ifndef SGM_SMALL_MAX_PARTICLES
+#define SGM_SMALL_MAX_PARTICLES 1200000
 #endif
-template <class R, class Model, int NTH, int PPT>
-bool launch_small_shape(const KArgs& a, int nst, cudaStream_t stream) {
-    const size_t bytes = small_smem_bytes<R>(NTH * PPT, Model::NX, nst);
+template <class R, class Model, int NTH, int PPT, bool FAST>
+bool launch_small_shape(const KArgs& a, cudaStream_t stream) {
+    const size_t bytes = small_smem_bytes<R>(NTH * PPT, Model::NX, Model::NP);
     if (bytes > 227 * 1024) return false;
-    auto kern = pf_small_kernel<R, Model, NTH, PPT>;
+    auto kern = pf_small_kernel<R, Model, NTH, PPT, FAST>;
     if (bytes > 48 * 1024) {
         static thread_local size_t granted = 0;            // per instantiation (and host thread): raise the limit once
         if (granted < bytes) {
@@ -33,12 +36,15 @@ bool launch_small_shape(const KArgs& a, int nst, cudaStream_t stream) {
 }
 template <class R, class Model>
 bool launch_small(const KArgs& a, cudaStream_t stream) {
-    const int nstat = a.stat_kind == SGM_STAT_SCORE ? Model::NP : (a.stat_kind == SGM_STAT_SUFF ? 3 : 0);
-    const int nst = a.pf == SGM_PF_NEMETH ? nstat : 0;
-    if (a.N <= 256) return launch_small_shape<R, Model, 256, 1>(a, nst, stream);
-    if (a.N <= 1024) return a.B <= 2 * 148 ? launch_small_shape<R, Model, 1024, 1>(a, nst, stream)
-                                            : launch_small_shape<R, Model, 512, 2>(a, nst, stream);
-    return launch_small_shape<R, Model, 1024, 2>(a, nst, stream);
+    if (small_fast_config(a)) {
+        if (a.N <= 256) return launch_small_shape<R, Model, 256, 1, true>(a, stream);
+        if (a.N <= 1024) return a.B <= 2 * 148 ? launch_small_shape<R, Model, 1024, 1, true>(a, stream)
+                                                : launch_small_shape<R, Model, 512, 2, true>(a, stream);
+        return launch_small_shape<R, Model, 1024, 2, true>(a, stream);
+    }
+    // every other configuration (injected randoms, Nemeth shrinkage, filter, traces, ...): two shapes, flags read at run time
+    if (a.N <= 1024) return launch_small_shape<R, Model, 1024, 1, false>(a, stream);
+    return launch_small_shape<R, Model, 1024, 2, false>(a, stream);
 }
 
 // kernel arguments of one call (workspace carved up, descriptor fields copied)
@@ -102,7 +108,7 @@ int run_impl(const sgm_pf_desc* d, cudaStream_t stream) {
     int64_t launches = 0;
     const bool pred = d->stat_kind == SGM_STAT_PRED;
     const bool small_ok = a.N <= SGM_SMALL_MAX_N && !backward_pf(d->pf) && !pred && d->path != SGM_PATH_TILES &&
-                          (a.B <= SGM_SMALL_MAX_ITEMS || d->path == SGM_PATH_SMALL);
+                          (a.N <= 512 || (int64_t)a.B * a.N <= SGM_SMALL_MAX_PARTICLES || d->path == SGM_PATH_SMALL);
     bool done_small = false;
     if (small_ok) {
         if (d->ev_steps_begin) cudaEventRecord(reinterpret_cast<cudaEvent_t>(d->ev_steps_begin), stream);
@@ -192,7 +198,7 @@ int run_impl(const sgm_pf_desc* d, cudaStream_t stream) {
 // 0 applies the SG-MCMC update (sgld_update_chain) -- no kernel boundary, no host, nothing but the chain's few scalars
 // in global memory.  Iteration k uses Philox call offset (*offset_dev + k): exactly the numbers the launch-per-iteration
 // path draws, so both paths give bit-identical chains.
-template <class R, class Model, int NTH, int PPT>
+template <class R, class Model, int NTH, int PPT, bool FAST>
 __global__ void __launch_bounds__(NTH, 1024 / NTH) sgld_persistent_kernel(SgldArgs sa, KArgs a, int K) {
     extern __shared__ __align__(16) unsigned char small_smem[];
     const int c = blockIdx.x;
@@ -209,18 +215,18 @@ __global__ void __launch_bounds__(NTH, 1024 / NTH) sgld_persistent_kernel(SgldAr
         a.key.offset = (uint32_t)(o & 0xffffffffu);
         a.key.k1 = k1 ^ (uint32_t)(o >> 32);
         if (z0) { a.inj_z0 = z0 + (size_t)k * B * N; a.inj_u = iu + (size_t)k * B * T * N; a.inj_z = iz + (size_t)k * B * T * N; }
-        small_pf_item<R, Model, NTH, PPT>(a, c, small_smem);
+        small_pf_item<R, Model, NTH, PPT, FAST>(a, c, small_smem);
         __syncthreads();
         if (threadIdx.x == 0) sgld_update_chain(sa, c, k, o, it0 + k);
         __syncthreads();
     }
 }
 
-template <class R, class Model, int NTH, int PPT>
-bool launch_persistent_shape(const SgldArgs& sa, const KArgs& a, int nst, int K, cudaStream_t stream) {
-    const size_t bytes = small_smem_bytes<R>(NTH * PPT, Model::NX, nst);
+template <class R, class Model, int NTH, int PPT, bool FAST>
+bool launch_persistent_shape(const SgldArgs& sa, const KArgs& a, int K, cudaStream_t stream) {
+    const size_t bytes = small_smem_bytes<R>(NTH * PPT, Model::NX, Model::NP);
     if (bytes > 227 * 1024) return false;
-    auto kern = sgld_persistent_kernel<R, Model, NTH, PPT>;
+    auto kern = sgld_persistent_kernel<R, Model, NTH, PPT, FAST>;
     if (bytes > 48 * 1024) {
         static thread_local size_t granted = 0;
         if (granted < bytes) {
@@ -233,12 +239,14 @@ bool launch_persistent_shape(const SgldArgs& sa, const KArgs& a, int nst, int K,
 }
 template <class R, class Model>
 bool launch_persistent(const SgldArgs& sa, const KArgs& a, int K, cudaStream_t stream) {
-    const int nstat = a.stat_kind == SGM_STAT_SCORE ? Model::NP : (a.stat_kind == SGM_STAT_SUFF ? 3 : 0);
-    const int nst = a.pf == SGM_PF_NEMETH ? nstat : 0;
-    if (a.N <= 256) return launch_persistent_shape<R, Model, 256, 1>(sa, a, nst, K, stream);
-    if (a.N <= 1024) return a.B <= 2 * 148 ? launch_persistent_shape<R, Model, 1024, 1>(sa, a, nst, K, stream)
-                                            : launch_persistent_shape<R, Model, 512, 2>(sa, a, nst, K, stream);
-    return launch_persistent_shape<R, Model, 1024, 2>(sa, a, nst, K, stream);
+    if (small_fast_config(a)) {
+        if (a.N <= 256) return launch_persistent_shape<R, Model, 256, 1, true>(sa, a, K, stream);
+        if (a.N <= 1024) return a.B <= 2 * 148 ? launch_persistent_shape<R, Model, 1024, 1, true>(sa, a, K, stream)
+                                                : launch_persistent_shape<R, Model, 512, 2, true>(sa, a, K, stream);
+        return launch_persistent_shape<R, Model, 1024, 2, true>(sa, a, K, stream);
+    }
+    if (a.N <= 1024) return launch_persistent_shape<R, Model, 1024, 1, false>(sa, a, K, stream);
+    return launch_persistent_shape<R, Model, 1024, 2, false>(sa, a, K, stream);
 }
 
 // 1 = launched, 0 = not eligible (the caller falls back to one launch sequence per iteration), < 0 = error

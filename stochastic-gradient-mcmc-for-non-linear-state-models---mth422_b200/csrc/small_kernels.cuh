@@ -11,11 +11,14 @@
 //   B  every warp combines the <= 32 warp summaries itself (shuffles): global max M, total, offsets, scales,
 //      S-bar; writes the CDF entries of its particles to shared memory (c_i = off_w + sc_w * prefix_i: the same
 //      hierarchical form as the tile kernels); thread 0 adds the log-likelihood increment        -> barrier 2
-//   C  per particle: uniform -> binary search of the shared-memory CDF (np.random.choice == searchsorted(cdf, u,
-//      'right')), gather the parent from shared memory, propose, reweight, update the statistic, store the child
+//   C  per particle: uniform -> branch-free binary search of the shared-memory CDF (np.random.choice ==
+//      searchsorted(cdf, u, 'right')), gather the parent record (one 16-byte shared-memory load), propose, reweight,
+//      update the statistic, store the child
 // Resampling is the reference's plain multinomial (iid uniforms): parents are gathered from shared memory, so the
 // sorted-target trick of the streaming kernels has nothing to gain here ('multinomial_sorted' has the same law and
 // takes this path too); systematic / stratified targets are supported as in the tile kernels.
+// FAST = the production configuration (device randoms, multinomial law, Poyiadjis O(N) with the model score, no traces /
+// exports) with its run-time flags folded to constants; the generic instantiation reads every flag at run time.
 #pragma once
 #include "pf_kernels.cuh"
 
@@ -24,8 +27,9 @@ namespace sgm {
 enum : uint32_t { STREAM_SMALL = 9 };
 constexpr int SM_STRIDE = 8;          // R values per warp summary: m, s, ws[0..3]
 
-template <class R> __host__ __device__ inline size_t small_smem_bytes(int npad, int nx, int nst) {
-    return sizeof(R) * ((size_t)npad * (size_t)(1 + 2 * nx + 2 * nst) + 32 * SM_STRIDE);
+template <class R> __host__ __device__ inline size_t small_smem_bytes(int npad, int nx, int np) {
+    // cdf | rec[2] (16-byte records) | tail[2][KT] | warp summaries
+    return sizeof(R) * ((size_t)npad * (size_t)(1 + 2 * 4 + 2 * (nx + np - 4)) + 32 * SM_STRIDE);
 }
 
 // u[PPT] uniforms and z[PPT] standard normals of thread `tid` at `step`
@@ -52,27 +56,39 @@ template <int PPT> __device__ __forceinline__ void small_draw(const RngKey& key,
     }
 }
 
+// PPT interleaved branch-free binary searches over a power-of-two CDF kept as shared-memory byte addresses
+template <class R, int PPT, int STEP>
+__device__ __forceinline__ void small_search(uint32_t* ad, const R* tg) {
+    if constexpr (STEP > 0) {
+#pragma unroll
+        for (int k = 0; k < PPT; ++k)
+            if (lds_at<(STEP - 1) * (int)sizeof(R)>(ad[k], (R)0) <= tg[k]) ad[k] += STEP * (int)sizeof(R);
+        small_search<R, PPT, STEP / 2>(ad, tg);
+    }
+}
+
 // The whole time loop of item b by the calling CTA (NTH threads, every thread calls).  `smem` = small_smem_bytes<R>()
 // bytes of 16-byte aligned shared memory.  Results go to a.grad / a.loglik / a.status (and the optional outputs).
-template <class R, class Model, int NTH, int PPT>
+template <class R, class Model, int NTH, int PPT, bool FAST>
 __device__ void small_pf_item(const KArgs& a, int b, unsigned char* smem) {
-    constexpr int NW = NTH / 32, NX = Model::NX, NP = Model::NP, NPAD = NTH * PPT;
+    constexpr int NW = NTH / 32, NX = Model::NX, NP = Model::NP, W = NX + NP, KT = W - 4, NPAD = NTH * PPT;
     static_assert(NW <= 32, "at most 32 warps");
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int N = a.N;
     const int Tb = a.T_buf[b], t1 = a.t1[b], tL = a.tL[b];
-    const int nstat = stat_width<Model>(a.stat_kind);
-    const bool carries = a.pf == SGM_PF_NEMETH, filter = a.pf == SGM_PF_FILTER;
-    const bool shrink = carries && a.lambduh != 1.0;
-    const int nst = carries ? nstat : 0;                 // statistics stored per particle (followed along the genealogy)
+    const int nstat = FAST ? NP : stat_width<Model>(a.stat_kind);
+    const bool carries = FAST || a.pf == SGM_PF_NEMETH, filter = !FAST && a.pf == SGM_PF_FILTER;
+    const bool shrink = !FAST && carries && a.lambduh != 1.0;
+    const bool injected = !FAST && a.rng_mode == SGM_RNG_INJECTED;
+    const bool strat = !FAST && !injected && (a.resample == SGM_RESAMPLE_SYSTEMATIC || a.resample == SGM_RESAMPLE_STRATIFIED);
+    const bool tracing = !FAST && (a.trace_anc || a.trace_x || a.trace_lw);
+    const bool var32 = sizeof(R) == 8 && a.variates32 && !injected;
     R* const cdf = reinterpret_cast<R*>(smem);
-    R* const xs0 = cdf + NPAD;
-    R* const st0 = xs0 + 2 * NPAD * NX;
-    R* const summ = st0 + 2 * NPAD * nst;
+    Vec4T<R>* const rec0 = reinterpret_cast<Vec4T<R>*>(cdf + NPAD);
+    R* const tail0 = reinterpret_cast<R*>(rec0 + 2 * NPAD);
+    R* const summ = tail0 + 2 * NPAD * KT;
     const typename Model::template Theta<R> th = Model::template load<R>(a.theta + (size_t)b * SGM_THETA_STRIDE);
     const RngKey key = item_key(a, b);
-    const bool injected = a.rng_mode == SGM_RNG_INJECTED;
-    const bool var32 = sizeof(R) == 8 && a.variates32 && !injected;
     const R NEG_INF = -Mth<R>::inf();
     const size_t item_off = (size_t)b * N;
     const double* obs = a.obs + a.obs_off[b];
@@ -89,6 +105,19 @@ __device__ void small_pf_item(const KArgs& a, int b, unsigned char* smem) {
             small_draw<PPT>(key, (uint32_t)tid, step, u, z);
         }
     };
+    // record of particle i: r[0..NP) statistics, r[NP..W) state -- first four components as one 16-byte vector
+    auto load_p = [&](int buf, int i, R* r) {
+        const Vec4T<R> v = rec0[buf * NPAD + i];
+        r[0] = v.x; r[1] = v.y; r[2] = v.z; r[3] = v.w;
+#pragma unroll
+        for (int q = 0; q < KT; ++q) r[4 + q] = tail0[(buf * KT + q) * NPAD + i];
+    };
+    auto store_p = [&](int buf, int i, const R* r) {
+        Vec4T<R> v; v.x = r[0]; v.y = r[1]; v.z = r[2]; v.w = r[3];
+        rec0[buf * NPAD + i] = v;
+#pragma unroll
+        for (int q = 0; q < KT; ++q) tail0[(buf * KT + q) * NPAD + i] = r[4 + q];
+    };
 
     R lw[PPT], sv[PPT][4];
     int par = 0;
@@ -101,25 +130,33 @@ __device__ void small_pf_item(const KArgs& a, int b, unsigned char* smem) {
             const int i = tid * PPT + k;
             lw[k] = (i < N) ? (R)0 : NEG_INF;
             sv[k][0] = sv[k][1] = sv[k][2] = sv[k][3] = (R)0;
+            cdf[i] = Mth<R>::inf();                       // entries >= N stay +inf: the searches need no bound check
             if (i < N) {
                 if (injected) z[k] = (R)a.inj_z0[item_off + i];
-                R x[NX];
-                Model::init(mean, sd, z[k], x);
+                R r[W];
 #pragma unroll
-                for (int d = 0; d < NX; ++d) xs0[d * NPAD + i] = x[d];
-                for (int q = 0; q < nst; ++q) st0[q * NPAD + i] = (R)0;
-                if (a.trace_x) for (int d = 0; d < NX; ++d)
-                    reinterpret_cast<R*>(a.trace_x)[((size_t)b * (a.max_T + 1) * N + i) * NX + d] = x[d];
-                if (a.trace_lw) reinterpret_cast<R*>(a.trace_lw)[(size_t)b * (a.max_T + 1) * N + i] = (R)0;
+                for (int q = 0; q < W; ++q) r[q] = (R)0;
+                Model::init(mean, sd, z[k], r + NP);
+                store_p(0, i, r);
+                if (tracing) {
+                    if (a.trace_x) for (int d = 0; d < NX; ++d)
+                        reinterpret_cast<R*>(a.trace_x)[((size_t)b * (a.max_T + 1) * N + i) * NX + d] = r[NP + d];
+                    if (a.trace_lw) reinterpret_cast<R*>(a.trace_lw)[(size_t)b * (a.max_T + 1) * N + i] = (R)0;
+                }
             }
         }
     }
     double loglik = 0.0, accf[4] = {0.0, 0.0, 0.0, 0.0};
     int status = 0;
+    R wt_prev = (R)0;                                  // log-likelihood weight of the step that produced the current weights
 
     for (int t = 0;; ++t) {
         const bool final_pass = t >= Tb;
         const bool need_ws = nstat > 0 && (filter || shrink || (carries && final_pass));
+        // this step's observation and statistic weight: issued first, consumed in phase C
+        const bool in_sub = !final_pass && t >= t1 && t < tL;
+        const R y = final_pass ? (R)0 : (R)obs[t];
+        const R wt = in_sub ? (R)(wts ? wts[t - t1] : 1.0) : (R)0;
         // ---- A: warp summary --------------------------------------------------------------------------
         R m = NEG_INF;
 #pragma unroll
@@ -146,7 +183,8 @@ __device__ void small_pf_item(const KArgs& a, int b, unsigned char* smem) {
         }
         if (lane == 0) {
             R* p = summ + warp * SM_STRIDE;
-            p[0] = m; p[1] = s_w; p[2] = wsum[0]; p[3] = wsum[1]; p[4] = wsum[2]; p[5] = wsum[3];
+            p[0] = m; p[1] = s_w;
+            if (need_ws) { p[2] = wsum[0]; p[3] = wsum[1]; p[4] = wsum[2]; p[5] = wsum[3]; }
         }
         __syncthreads();                                                      // barrier 1
         // ---- B: cross-warp combine (every warp, redundantly: fixed shuffle trees => identical results) ----
@@ -166,15 +204,14 @@ __device__ void small_pf_item(const KArgs& a, int b, unsigned char* smem) {
                 if (q < nstat) sbar[q] = warp_sum(has ? el * summ[lane * SM_STRIDE + 2 + q] : (R)0) / total;
         }
         if (tid == 0) {
-            const double Md = (double)M, td = (double)total;
-            if (!(td > 0.0) || !(td < Mth<double>::inf()) || !(Md == Md) || !(fabs(Md) < Mth<double>::inf()))
-                status |= (td == 0.0 || Md == -Mth<double>::inf()) ? SGM_STATUS_ZERO_WEIGHT : SGM_STATUS_NAN_WEIGHT;
-            const int t_done = t - 1;
-            if (t_done >= 0) {
-                if (t_done >= t1 && t_done < tL)                                // buffered_smoother.py:124-126 (max-shifted)
-                    loglik += (wts ? wts[t_done - t1] : 1.0) * (Md + ::log(td / (double)N));
+            if (!(total > (R)0) || !(total < Mth<R>::inf()) || !(M == M) || !(M > NEG_INF && M < Mth<R>::inf()))
+                status |= (total == (R)0 || M == NEG_INF) ? SGM_STATUS_ZERO_WEIGHT : SGM_STATUS_NAN_WEIGHT;
+            if (t > 0) {
+                // buffered_smoother.py:124-126, max-shifted; the logarithm in the arithmetic type of the run
+                if (wt_prev != (R)0) loglik += (double)wt_prev * ((double)M + (double)Mth<R>::log(total / (R)N));
                 if (filter) for (int j = 0; j < nstat; ++j) accf[j] += (double)sbar[j];      // pf.py:77-80
             }
+            wt_prev = in_sub ? (wts ? (R)wts[t - t1] : (R)1) : (R)0;
         }
         if (final_pass) {
             if (tid == 0) {
@@ -192,15 +229,12 @@ __device__ void small_pf_item(const KArgs& a, int b, unsigned char* smem) {
         }
         __syncthreads();                                                      // barrier 2
         // ---- C: resample -> propagate -> reweight -> statistic update ----------------------------------
-        const bool in_sub = t >= t1 && t < tL;
-        const R y = (R)obs[t];
-        const R wt = in_sub ? (R)(wts ? wts[t - t1] : 1.0) : (R)0;
         const R hs = (carries || filter) ? wt : (R)0;
-        const int stat_kind = (in_sub && hs != (R)0) ? a.stat_kind : (int)SGM_STAT_NONE;
+        const int stat_kind = (in_sub && hs != (R)0) ? (FAST ? (int)SGM_STAT_SCORE : a.stat_kind) : (int)SGM_STAT_NONE;
         R u[PPT], z[PPT];
         if (!injected) {
             draw((uint32_t)t, u, z);
-            if (a.resample == SGM_RESAMPLE_SYSTEMATIC) {
+            if (!FAST && a.resample == SGM_RESAMPLE_SYSTEMATIC) {
                 R u4[4];
                 if (var32) { float f4[4]; rng_uniform4(key, 0u, (uint32_t)t, STREAM_GAMMA, f4); u4[0] = (R)f4[0]; }
                 else rng_uniform4(key, 0u, (uint32_t)t, STREAM_GAMMA, u4);
@@ -208,62 +242,51 @@ __device__ void small_pf_item(const KArgs& a, int b, unsigned char* smem) {
                 for (int k = 0; k < PPT; ++k) u[k] = u4[0];
             }
         }
-        const R* xo = xs0 + par * NPAD * NX;
-        R* xn_s = xs0 + (par ^ 1) * NPAD * NX;
-        const R* so = st0 + par * NPAD * nst;
-        R* sn = st0 + (par ^ 1) * NPAD * nst;
         const R cmax = cdf[N - 1];
-        const bool strat = !injected && (a.resample == SGM_RESAMPLE_SYSTEMATIC || a.resample == SGM_RESAMPLE_STRATIFIED);
-        int anc[PPT];
         R tg[PPT];
+        uint32_t ad[PPT];
+        const uint32_t ad0 = (uint32_t)__cvta_generic_to_shared(cdf);
 #pragma unroll
         for (int k = 0; k < PPT; ++k) {
             const int i = tid * PPT + k;
             if (injected) { u[k] = (i < N) ? (R)a.inj_u[((size_t)b * a.max_T + t) * N + i] : (R)0; z[k] = (i < N) ? (R)a.inj_z[((size_t)b * a.max_T + t) * N + i] : (R)0; }
             tg[k] = strat ? (((R)i + u[k]) / (R)N) * total : u[k] * total;
-            anc[k] = 0;
+            ad[k] = ad0;
         }
-        // searchsorted(cdf, target, 'right'): number of entries <= target; PPT searches interleaved, fixed trip count
-#pragma unroll 1
-        for (int step = NPAD / 2; step > 0; step >>= 1) {
-#pragma unroll
-            for (int k = 0; k < PPT; ++k) {
-                const int idx = anc[k] + step;
-                if (idx <= N && cdf[idx - 1] <= tg[k]) anc[k] = idx;
-            }
-        }
+        // searchsorted(cdf, target, 'right') = number of entries <= target (entries >= N are +inf)
+        small_search<R, PPT, NPAD / 2>(ad, tg);
 #pragma unroll
         for (int k = 0; k < PPT; ++k) {
             const int i = tid * PPT + k;
-            if (!(tg[k] < cmax)) anc[k] = N - 1;               // u * total rounded up to the total (or a NaN weight)
-            anc[k] = min(anc[k], N - 1);
+            int anc = (int)((ad[k] - ad0) / (uint32_t)sizeof(R));
+            if (!(tg[k] < cmax)) anc = N - 1;                  // u * total rounded up to the total (or a NaN weight)
+            anc = min(anc, N - 1);
             lw[k] = NEG_INF;
             if (i < N) {
-                R xa[NX], xn[NX], sa[4] = {(R)0, (R)0, (R)0, (R)0};
-#pragma unroll
-                for (int d = 0; d < NX; ++d) xa[d] = xo[d * NPAD + anc[k]];
-#pragma unroll
-                for (int q = 0; q < NP; ++q) if (q < nst) sa[q] = so[q * NPAD + anc[k]];
-                Model::propagate(th, xa, y, z[k], xn);
-                lw[k] = Model::log_weight(th, xa, xn, y);
+                R ra[W], rn[W];
+                load_p(par, anc, ra);
+                Model::propagate(th, ra + NP, y, z[k], rn + NP);
+                lw[k] = Model::log_weight(th, ra + NP, rn + NP, y);
                 R h[4] = {(R)0, (R)0, (R)0, (R)0};
-                if (stat_kind == SGM_STAT_SCORE) Model::score(th, xa, xn, y, h);
-                else if (stat_kind == SGM_STAT_SUFF) Model::suff(xa, xn, h);
+                if (stat_kind == SGM_STAT_SCORE) Model::score(th, ra + NP, rn + NP, y, h);
+                else if (stat_kind == SGM_STAT_SUFF) Model::suff(ra + NP, rn + NP, h);
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
                     // pf.py:175-179 (Nemeth / Poyiadjis O(N)), pf.py:70-71 (filter: nothing carried)
+                    const R sa = (q < NP) ? ra[q] : (R)0;
                     if (!carries) sv[k][q] = h[q] * hs;
-                    else if (!shrink) sv[k][q] = sa[q] + h[q] * hs;
-                    else sv[k][q] = lam * sa[q] + ((R)((1.0 - a.lambduh) * (double)sbar[q]) + h[q] * hs);
+                    else if (!shrink) sv[k][q] = sa + h[q] * hs;
+                    else sv[k][q] = lam * sa + ((R)((1.0 - a.lambduh) * (double)sbar[q]) + h[q] * hs);
                 }
 #pragma unroll
-                for (int d = 0; d < NX; ++d) xn_s[d * NPAD + i] = xn[d];
-#pragma unroll
-                for (int q = 0; q < NP; ++q) if (q < nst) sn[q * NPAD + i] = sv[k][q];
-                if (a.trace_anc) a.trace_anc[((size_t)b * a.max_T + t) * N + i] = anc[k];
-                if (a.trace_x) for (int d = 0; d < NX; ++d)
-                    reinterpret_cast<R*>(a.trace_x)[(((size_t)b * (a.max_T + 1) + t + 1) * N + i) * NX + d] = xn[d];
-                if (a.trace_lw) reinterpret_cast<R*>(a.trace_lw)[((size_t)b * (a.max_T + 1) + t + 1) * N + i] = lw[k];
+                for (int q = 0; q < NP; ++q) rn[q] = carries ? sv[k][q] : (R)0;
+                store_p(par ^ 1, i, rn);
+                if (tracing) {
+                    if (a.trace_anc) a.trace_anc[((size_t)b * a.max_T + t) * N + i] = anc;
+                    if (a.trace_x) for (int d = 0; d < NX; ++d)
+                        reinterpret_cast<R*>(a.trace_x)[(((size_t)b * (a.max_T + 1) + t + 1) * N + i) * NX + d] = rn[NP + d];
+                    if (a.trace_lw) reinterpret_cast<R*>(a.trace_lw)[((size_t)b * (a.max_T + 1) + t + 1) * N + i] = lw[k];
+                }
             }
         }
         par ^= 1;
@@ -271,24 +294,32 @@ __device__ void small_pf_item(const KArgs& a, int b, unsigned char* smem) {
         // read of the old buffers / the CDF above precedes barrier 1 of the next step
     }
     // ---- optional export of the final particle system (each thread: its own particles) ----
-    if (a.out_x || a.out_lw || a.out_stats) {
-        const R* xc = xs0 + par * NPAD * NX;
+    if (!FAST && (a.out_x || a.out_lw || a.out_stats)) {
 #pragma unroll
         for (int k = 0; k < PPT; ++k) {
             const int i = tid * PPT + k;
             if (i < N) {
-                if (a.out_x) for (int d = 0; d < NX; ++d) reinterpret_cast<R*>(a.out_x)[(item_off + i) * NX + d] = xc[d * NPAD + i];
+                R r[W];
+                load_p(par, i, r);
+                if (a.out_x) for (int d = 0; d < NX; ++d) reinterpret_cast<R*>(a.out_x)[(item_off + i) * NX + d] = r[NP + d];
                 if (a.out_lw) reinterpret_cast<R*>(a.out_lw)[item_off + i] = lw[k];
-                if (a.out_stats) for (int q = 0; q < NP; ++q) reinterpret_cast<R*>(a.out_stats)[(item_off + i) * NP + q] = carries ? sv[k][q] : (R)0;
+                if (a.out_stats) for (int q = 0; q < NP; ++q) reinterpret_cast<R*>(a.out_stats)[(item_off + i) * NP + q] = r[q];
             }
         }
     }
 }
 
-template <class R, class Model, int NTH, int PPT>
+// host-side eligibility of the FAST instantiation
+inline bool small_fast_config(const KArgs& a) {
+    return a.rng_mode == SGM_RNG_PHILOX && a.pf == SGM_PF_NEMETH && a.lambduh == 1.0 && a.stat_kind == SGM_STAT_SCORE &&
+           (a.resample == SGM_RESAMPLE_MULTINOMIAL || a.resample == SGM_RESAMPLE_MULTINOMIAL_SORTED) &&
+           !a.trace_anc && !a.trace_x && !a.trace_lw && !a.out_x && !a.out_lw && !a.out_stats;
+}
+
+template <class R, class Model, int NTH, int PPT, bool FAST>
 __global__ void __launch_bounds__(NTH, 1024 / NTH) pf_small_kernel(KArgs a) {     // 64 registers: 1024 resident threads per SM
     extern __shared__ __align__(16) unsigned char small_smem[];
-    small_pf_item<R, Model, NTH, PPT>(a, a.b0 + blockIdx.x, small_smem);
+    small_pf_item<R, Model, NTH, PPT, FAST>(a, a.b0 + blockIdx.x, small_smem);
 }
 
 }  // namespace sgm
