@@ -139,7 +139,9 @@ def run_reference(args):
     line = {"metric": METRIC, "value": rate, "unit": UNIT, "impl": "reference", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": min(args.warmup, 1), "ms_per_step": 1e3 * dt / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": workload_config(args.gpus, args.minibatch),
+            "config": dict(workload_config(args.gpus, args.minibatch), reference_arm_work_per_step=(
+                "{0} subsequence gradients per step (one per host core), not the GPU arm's minibatch: a RATE comparison "
+                "on the same per-item workload".format(cores)), reference_arm_items_per_step=cores),
             "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -271,24 +273,32 @@ def run_gpu(args):
     torch.cuda.synchronize()
     parallel.barrier()
     t0 = time.perf_counter()
+    e2e_local_ps, e2e_h2d, e2e_d2h = 0, 0, 0
     for _ in range(args.steps):
         g = sampler.noisy_gradient(**api_kw)
+        e2e_local_ps += sampler.last_pf_info["particle_steps"]      # N x sum(T_buf) of this rank's packed windows
+        e2e_h2d, e2e_d2h = sampler.last_pf_info["h2d_bytes"], sampler.last_pf_info["d2h_bytes"]
     torch.cuda.synchronize()
     parallel.barrier()
     e2e_s = parallel.allreduce_max(time.perf_counter() - t0)
-    e2e_ps = M * world * N_PARTICLES * (SUBSEQ + 2 * BUFFER)      # interior windows; edge windows are shorter
-    e2e_value = e2e_ps * args.steps / e2e_s
+    e2e_value = parallel.allreduce_sum(np.array([float(e2e_local_ps)]))[0] / e2e_s
+    assert all(np.all(np.isfinite(v)) for v in g.values())
 
-    if world > 1:
-        torch.distributed.destroy_process_group()
-    if rank != 0:
-        return 0
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
     hbm = float(peaks.get("hbm_gbs", 6650.0))
+    multi = {}
+    if not args.no_extras:                      # every rank takes part (sharded work + all-reduce inside)
+        multi["f64"] = f64_block(sg, torch, parallel, items, lo, args, world, hbm, sampler, api_kw)
+        multi["config5_strong"] = config5_strong(sg, torch, parallel, theta, world, hbm)
+        multi["config4_chains"] = config4_chains(sg, torch, parallel, world)
+    if world > 1:
+        torch.distributed.destroy_process_group()
+    if rank != 0:
+        return 0
     achieved = ALG_BYTES * prep.B * N_PARTICLES / (step_kernel_ms * 1e-3) / 1e9
     traffic = None
     try:
@@ -300,14 +310,17 @@ def run_gpu(args):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic", "config": workload_config(world, M),
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(res.h2d_bytes),
-                "d2h_bytes_per_step": int(res.d2h_bytes), "ms_per_step": 1e3 * e2e_s / args.steps,
-                "api": "SVMSampler.noisy_gradient(kind='pf', minibatch_size=M*n_gpus, ...)"},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(e2e_h2d),
+                "d2h_bytes_per_step": int(e2e_d2h), "ms_per_step": 1e3 * e2e_s / args.steps,
+                "api": "SVMSampler.noisy_gradient(kind='pf', minibatch_size=M*n_gpus, ...): numpy window draws, packing, one "
+                       "H2D copy, kernels, device-side sum of the item gradients, in-place NCCL all-reduce, one D2H copy"},
         "gpu_launches": int(launches_per_step * args.steps),
         "clocks": clk,
         "roofline": {"bound": "hbm", "kernel": "pf_step_kernel<float, SvmPrior, SORTED=true> (+ pf_header_kernel; the batch runs as two halves "
                                                "on two streams, avg_launch_ms = time of one time step of the whole batch)", "achieved": achieved, "peak": hbm,
                      "unit": "GB/s", "frac": achieved / hbm, "traffic": traffic,
+                     "traffic_source": "ncu --set full capture of this command (profiles/step_kernel_traffic.json: dram bytes per "
+                                       "particle-step x particles per time step), not measured in this run",
                      "peak_source": "MEASURED_PEAKS.json (measured)" if peaks else "fallback 6650 GB/s",
                      "alg_bytes_per_particle_step": ALG_BYTES, "particles_per_launch": prep.B * N_PARTICLES,
                      "avg_launch_ms": step_kernel_ms, "step_kernel_share_of_step": step_kernel_ms * prep.max_T * args.steps / dev_ms},
@@ -322,10 +335,138 @@ def run_gpu(args):
                                 "sample": "{0} subsequence gradient(s) of the same workload (N=2^16, T_buf<=60), "
                                           "numpy oracle port incl. np.random.choice, {1:.1f} s; host has {2} cores".format(
                                               n_grad, dt, os.cpu_count())}
-    if world == 1 and not args.no_extras:
-        line["extra"] = extras(sg, y, theta, windows_all, torch)
+    if not args.no_extras:
+        f64 = multi.pop("f64")
+        line["f64"] = f64
+        line["roofline_f64"] = f64["native"]["roofline"]
+        line["extra"] = multi
+        if world == 1:
+            line["extra"].update(extras(sg, y, theta, windows_all, torch))
     print(json.dumps(line), flush=True)
     return 0
+
+
+def _timed_launches(prep, torch, parallel, world, warm, steps):
+    """Device-timed launches of a prepared batch (+ the all-reduce of the gradient sums): (ms per launch, ms per time step)."""
+    st = prep.st
+    so = prep.base_out - st.dev_out.data_ptr()
+    grad_view = st.dev_out[so:so + prep.B * 64].view(torch.float64).view(prep.B, 8)
+    gsum = torch.zeros(8, dtype=torch.float64, device=grad_view.device)
+
+    def one(k, ev=None):
+        prep.launch(offset=k + 1, step_events=ev)
+        torch.sum(grad_view, dim=0, out=gsum)
+        if world > 1:
+            torch.distributed.all_reduce(gsum)
+    for k in range(warm):
+        one(k)
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    for a, b in ev:
+        a.record(); b.record()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    parallel.barrier()
+    e0.record()
+    for k in range(steps):
+        one(warm + k, ev[k])
+    e1.record()
+    torch.cuda.synchronize()
+    parallel.barrier()
+    ms = parallel.allreduce_max(e0.elapsed_time(e1)) / steps
+    step_ms = parallel.allreduce_max(float(np.mean([a.elapsed_time(b) for a, b in ev])) / prep.max_T)
+    assert bool(torch.all(torch.isfinite(gsum)))
+    return ms, step_ms
+
+
+def f64_block(sg, torch, parallel, items, lo, args, world, hbm, sampler, api_kw):
+    """The headline workload in the reference's precision: float64 particle arithmetic and storage (80 B / particle-step),
+    device-timed and through the public API; `native` = 53-bit device variates, `variates_f32` = the f32 path's random
+    variates widened to f64 (every operation on the particle system still f64; include/sgmpf.h SGM_VARIATES_F32)."""
+    out = {}
+    for name, variates in (("native", "native"), ("variates_f32", "f32")):
+        prep = sg.engine.PreparedPF("svm", "prior", "poyiadjis_N", items, N_PARTICLES, dtype="f64", rng="philox",
+                                    resample="multinomial_sorted", item_id_base=lo, variates=variates).upload()
+        ms, step_ms = _timed_launches(prep, torch, parallel, world, 2, 3)
+        total_ps = parallel.allreduce_sum(np.array([float(prep.particle_steps)]))[0]
+        achieved = 2 * ALG_BYTES * prep.B * N_PARTICLES / (step_ms * 1e-3) / 1e9
+        kw = dict(api_kw, dtype="f64", variates=variates)
+        sampler.noisy_gradient(**kw)
+        torch.cuda.synchronize(); parallel.barrier()
+        t0 = time.perf_counter()
+        ps = 0
+        for _ in range(2):
+            sampler.noisy_gradient(**kw)
+            ps += sampler.last_pf_info["particle_steps"]
+        torch.cuda.synchronize(); parallel.barrier()
+        dt = parallel.allreduce_max(time.perf_counter() - t0)
+        out[name] = {"dtype": "f64", "variates": variates, "value": total_ps / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms,
+                     "e2e": {"value": parallel.allreduce_sum(np.array([float(ps)]))[0] / dt, "unit": UNIT, "ms_per_step": 1e3 * dt / 2},
+                     "roofline": {"bound": "hbm", "kernel": "pf_step_kernel<double, SvmPrior, SORTED=true, FM_POY> (+ pf_header_kernel)",
+                                  "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm, "traffic": None,
+                                  "alg_bytes_per_particle_step": 2 * ALG_BYTES, "particles_per_launch": prep.B * N_PARTICLES,
+                                  "avg_launch_ms": step_ms}}
+    return out
+
+
+def config5_strong(sg, torch, parallel, theta, world, hbm):
+    """BASELINE configs[4] as written (strong scaling): SVM T = 10^6, minibatch 1024 subsequences of S=40 / B=10, N = 2^20
+    particles each, the 1024 items split over the ranks, one all-reduce of the gradient sums per gradient."""
+    from scipy.signal import lfilter
+    from sgmcmc_ssm_b200.sgmcmc_sampler import random_subsequences_packed
+    N5, M5, T5 = 1 << 20, 1024, 1000000
+    rs = np.random.RandomState(2020)
+    x = lfilter([1.0], [1.0, -0.95], np.sqrt(0.5) * rs.normal(size=T5))
+    y5 = (np.sqrt(0.5) * np.exp(0.5 * x) * rs.normal(size=T5)).reshape(-1, 1)
+    lo, hi = parallel.shard_bounds(M5)
+    state = np.random.get_state()
+    np.random.seed(555)
+    arrays = random_subsequences_packed(y5, SUBSEQ, M5, BUFFER, None, lo, hi)
+    np.random.set_state(state)
+    pk = sg.PackedItems(theta=theta, prior_mean=0.0, prior_var=10.0, **arrays)
+    prep = sg.engine.PreparedPF("svm", "prior", "poyiadjis_N", pk, N5, dtype="f32", rng="philox",
+                                resample="multinomial_sorted", item_id_base=lo).upload()
+    ms, step_ms = _timed_launches(prep, torch, parallel, world, 1, 2)
+    total_ps = parallel.allreduce_sum(np.array([float(prep.particle_steps)]))[0]
+    achieved = ALG_BYTES * prep.B * N5 / (step_ms * 1e-3) / 1e9
+    out = {"workload": "SVM T=1e6, 1024 subsequences x N=2^20 particles, S=40 B=10, split over the ranks (strong scaling)",
+           "items_per_gpu": hi - lo, "n_gpus": world, "ms_per_gradient": ms, "particle_steps_per_s": total_ps / (ms * 1e-3),
+           "frac": achieved / hbm, "workspace_gb_per_gpu": prep.ws_bytes / 1e9}
+    prep.st.workspace = None                    # hand the 43 GB (1 GPU) back before the next block
+    del prep
+    torch.cuda.empty_cache()
+    return out
+
+
+def config4_chains(sg, torch, parallel, world):
+    """BASELINE configs[3]: 64 independent SGLD chains of a Seq SVM sampler on the EUR/USD hourly returns (49 sequences /
+    5907 observations, demo/exchange_rate/exchange_rate_full_demo.py:16-42, 96-102), chains sharded over the ranks with no
+    collective per iteration, every iteration on the device (device_loop.DeviceChains)."""
+    from sgmcmc_ssm_b200.device_loop import DeviceChains
+    from sgmcmc_ssm_b200.models.svm import SeqSVMSampler
+    sys.path.insert(0, os.path.join(ROOT, "scripts"))
+    from chains_demo import eurus_sequences, chain
+    seqs = eurus_sequences()
+    n_chains = 64
+    lo, hi = parallel.shard_bounds(n_chains)
+    out = {"workload": "64 SeqSVMSampler SGLD chains on EUR/USD hourly returns (49 seq / 5907 obs), eps=1e-3, S=16, B=4, "
+                       "num_sequences=1, pf=poyiadjis_N; chains sharded over the ranks, device-resident loop", "n_gpus": world}
+    state = np.random.get_state()
+    for N, iters in ((1000, 2000), (10000, 200)):
+        chains = DeviceChains([chain(seqs, 12345 + c) for c in range(lo, hi)], method="SGLD", epsilon=1e-3, chain_id_base=lo,
+                              kind="pf", pf="poyiadjis_N", N=N, subsequence_length=16, buffer_length=4, minibatch_size=1,
+                              num_sequences=1)
+        chains.run(max(16, iters // 10)).synchronize()
+        parallel.barrier()
+        t0 = time.perf_counter()
+        chains.run(iters).synchronize()
+        parallel.barrier()
+        dt = parallel.allreduce_max(time.perf_counter() - t0)
+        params = chains.pull_parameters()
+        ok = all(np.isfinite(float(np.ravel(p.A)[0])) for p in params)
+        out["N%d" % N] = {"chain_iterations_per_sec": n_chains * iters / dt, "ms_per_iteration_all_chains": 1e3 * dt / iters,
+                          "chains_per_gpu": hi - lo, "persistent_kernel": bool(chains.persistent), "finite": bool(ok)}
+    np.random.set_state(state)
+    return out
 
 
 def extras(sg, y, theta, windows, torch):
@@ -350,11 +491,27 @@ def extras(sg, y, theta, windows, torch):
     out["minibatch1_ms_per_gradient"] = ms
     out["minibatch1_particle_steps_per_sec"] = prep.particle_steps / (ms * 1e-3)
     out["minibatch1_cuda_graph"] = bool(prep.graph_eligible())
-    # SGLD iterations / s, BASELINE configs[0]: LGSSM T=1000, N=1000, S=40, B=10, minibatch 1
+    # SGLD iterations / s ("full sample_sgld + project_parameters iterations per second").
+    # configs[0]: LGSSM T=1000, N=1000, S=40, B=10, minibatch 1 -- through the public API: sampler.fit(iter_type='SGLD', ...)
+    # runs the iterations on the device (device_loop.DeviceChains; persistent kernel), timed with host wall clock
+    # incl. set-up, the single enqueue and the parameter read-back; `host_loop` = one Python iteration per step (round 1).
     from sgmcmc_ssm_b200.models.lgssm import LGSSMSampler, LGSSMParameters, generate_lgssm_data
+    from sgmcmc_ssm_b200.models.svm import SVMSampler, SVMParameters
     np.random.seed(12345)
     p = LGSSMParameters(A=np.eye(1) * 0.9, C=np.eye(1), LQinv=np.eye(1) * np.sqrt(10.0), LRinv=np.eye(1))
     data = generate_lgssm_data(T=1000, parameters=p)
+    fit_kw = dict(epsilon=0.01, subsequence_length=40, buffer_length=10, minibatch_size=1, kind="pf")
+
+    def fit_rate(sampler, iters, N):
+        sampler.fit("SGLD", max(8, iters // 20), pf_kwargs=dict(pf="poyiadjis_N", N=N), **fit_kw)      # warm-up
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        sampler.fit("SGLD", iters, pf_kwargs=dict(pf="poyiadjis_N", N=N), **fit_kw)
+        dt = time.perf_counter() - t0
+        assert all(np.all(np.isfinite(v)) for v in sampler.parameters.var_dict.values())
+        return iters / dt
+    s = LGSSMSampler(n=1, m=1, observations=data["observations"], parameters=p.copy())
+    out["sgld_iters_per_sec_lgssm_T1000_N1000"] = fit_rate(s, 4000, 1000)
     s = LGSSMSampler(n=1, m=1, observations=data["observations"], parameters=p.copy())
     kw = dict(epsilon=0.01, kind="pf", pf="poyiadjis_N", N=1000, subsequence_length=40, buffer_length=10, minibatch_size=1)
     for _ in range(5):
@@ -364,7 +521,12 @@ def extras(sg, y, theta, windows, torch):
     for _ in range(100):
         s.sample_sgld(**kw); s.project_parameters()
     torch.cuda.synchronize()
-    out["sgld_iters_per_sec_lgssm_T1000_N1000"] = 100 / (time.perf_counter() - t0)
+    out["sgld_iters_per_sec_lgssm_T1000_N1000_host_loop"] = 100 / (time.perf_counter() - t0)
+    # configs[1]: SVM T=10000, minibatch 1, N = 2^10 (persistent kernel), 2^13, 2^16 (tile kernels, CUDA graph per 8 iterations)
+    ps = SVMParameters(A=np.eye(1) * 0.95, LQinv=np.eye(1) * np.sqrt(2.0), LRinv=np.eye(1) * np.sqrt(2.0))
+    for N, iters in ((1 << 10, 4000), (1 << 13, 400), (1 << 16, 200)):
+        s = SVMSampler(n=1, m=1, observations=y, parameters=ps.copy())
+        out["sgld_iters_per_sec_svm_T10000_N%d" % N] = fit_rate(s, iters, N)
 
     # O(N^2) smoother (configs[1]: N up to 2^16) and PaRIS (configs[2]: GARCH N = 2^14), device-timed
     def timed(model, kern, pf, th, N, B, T, **kw):

@@ -44,6 +44,10 @@ class BaseParameters(_Dims):
     def from_vector(self, vector):
         self.var_dict.update(self.from_vector_to_dict(vector, **self.dim))
 
+    # `parameters.vector` is what metric_functions.average_input_decorator reads and assigns (metric_functions.py:239-261
+    # of the reference, whose containers lack the attribute: the decorator raises AttributeError there)
+    vector = property(lambda self: self.as_vector(), lambda self, value: self.from_vector(np.asarray(value, dtype=float)))
+
     @classmethod
     def from_dict_to_vector(cls, var_dict, **dim):
         return np.concatenate([np.ravel(v) for var in cls._variables for v in var.flatten(var_dict)])

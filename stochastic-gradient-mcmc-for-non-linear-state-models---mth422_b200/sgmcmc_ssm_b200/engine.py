@@ -75,6 +75,7 @@ class _DeviceState(object):
         self.pin_out = None
         self.dev_out = None
         self.checked = False
+        self.generation = 0        # bumped by every download(): a PFResult whose staging buffer was reused says so
         self.aux = None            # (stream, fork event, join event) for the two-stream pipelining of big batches
 
     @staticmethod
@@ -84,6 +85,13 @@ class _DeviceState(object):
         return t
 
     def buffers(self, ws_bytes, in_bytes, out_bytes):
+        before = tuple(None if t is None else t.data_ptr() for t in (self.workspace, self.dev_in, self.dev_out))
+        self._buffers(ws_bytes, in_bytes, out_bytes)
+        after = tuple(t.data_ptr() for t in (self.workspace, self.dev_in, self.dev_out))
+        if before != after:
+            _GRAPHS.clear()            # captured graphs hold the old device addresses
+
+    def _buffers(self, ws_bytes, in_bytes, out_bytes):
         self.workspace = self._grow(self.workspace, ws_bytes + 256, device=self.device)
         self.pin_in = self._grow(self.pin_in, in_bytes, pin_memory=True)
         self.dev_in = self._grow(self.dev_in, in_bytes + 256, device=self.device)
@@ -236,6 +244,9 @@ class PFResult(object):
     def wait(self, check=True):
         if self._done:
             return self
+        if self._state.generation != self._generation:
+            raise RuntimeError("this PFResult was not waited for before the next run_pf on the same device reused its "
+                               "staging buffer (one call may be outstanding per device)")
         self._event.synchronize()
         B = self.B
         out = self._pin_out.numpy()
@@ -304,9 +315,11 @@ class PreparedPF(object):
         has_w = pk.wts_flat is not None
         wts_off = pk.wts_off
         wlen = pk.wts_flat.shape[0] if has_w else 0
-        sections = [("obs", n_obs * 8), ("wts", max(wlen, 1) * 8), ("theta", B * nat.THETA_STRIDE * 8),
-                    ("prior_mean", B * 8), ("prior_var", B * 8), ("obs_off", B * 8), ("wts_off", B * 8),
-                    ("T_buf", B * 4), ("t1", B * 4), ("tL", B * 4)]
+        # fixed-size sections first and the variable-length ones padded to their maxima, so that batches of the same
+        # shape (B, max_T) always land on the same device addresses -- the CUDA-graph cache key holds these pointers
+        sections = [("theta", B * nat.THETA_STRIDE * 8), ("prior_mean", B * 8), ("prior_var", B * 8), ("obs_off", B * 8),
+                    ("wts_off", B * 8), ("T_buf", B * 4), ("t1", B * 4), ("tL", B * 4),
+                    ("obs", max(n_obs, B * max_T) * 8), ("wts", max(wlen, B * max_T, 1) * 8)]
         offs, tot = {}, 0
         for name, nb in sections:
             offs[name] = tot
@@ -497,7 +510,8 @@ class PreparedPF(object):
             st.pin_out[:self.out_bytes].copy_(st.dev_out[so:so + self.out_bytes], non_blocking=True)
             ev = torch.cuda.Event()
             ev.record(stream)
-        return PFResult(B=self.B, N=self.N, p=self.p, n=self.n, max_T=self.max_T, T_buf=self.T_buf, _event=ev,
+            st.generation += 1
+        return PFResult(_state=st, _generation=st.generation, seed=int(self.desc.seed), offset=int(self.desc.offset), B=self.B, N=self.N, p=self.p, n=self.n, max_T=self.max_T, T_buf=self.T_buf, _event=ev,
                         _pin_out=st.pin_out, _extra=self.extra, _keep=self.keep, launches=self.launches,
                         h2d_bytes=self.in_bytes, d2h_bytes=self.out_bytes, particle_steps=self.particle_steps,
                         ws_bytes=self.ws_bytes, grad_slots=self.grad_slots)
@@ -518,3 +532,41 @@ def run_pf(model, kernel, pf, items, N, sync=True, check=True, while_running=Non
     if sync:
         res.wait(check=check)
     return res
+
+
+def run_pf_sum(model, kernel, pf, items, N, allreduce=False, while_running=None, **kwargs):
+    """Sum over the items of a batch of their gradient estimates, reduced ON THE DEVICE (and, with allreduce=True, over
+    the ranks of the process group by ONE in-place NCCL all-reduce of the same device buffer), then one small D2H copy:
+    the minibatch path of the samplers (sgmcmc_sampler.py:411-418).  `items` may be None on a rank whose shard is empty.
+    Returns (sums (p,) float64, info dict)."""
+    import torch.distributed as dist
+    device = _device(kwargs.get("device"))
+    info = dict(particle_steps=0, h2d_bytes=0, d2h_bytes=0, launches=0)
+    with torch.cuda.device(device):
+        if items is not None and len(items) > 0:
+            prep = PreparedPF(model, kernel, pf, items, N, **kwargs).upload()
+            (prep.launch_graph() if prep.graph_eligible() else prep.launch())
+            st = prep.st
+            so = prep.base_out - st.dev_out.data_ptr()
+            B, gs = prep.B, prep.grad_slots
+            g = st.dev_out[so:so + B * 8 * gs].view(torch.float64).view(B, gs)
+            status = st.dev_out[so + B * (8 * gs + 8):so + B * (8 * gs + 12)].view(torch.int32)
+            buf = torch.empty(gs + 1, dtype=torch.float64, device=device)
+            torch.sum(g, dim=0, out=buf[:gs])
+            buf[gs] = (status & (nat.STATUS_NAN_WEIGHT | nat.STATUS_ZERO_WEIGHT)).ne(0).sum().to(torch.float64)
+            info.update(particle_steps=prep.particle_steps, h2d_bytes=prep.in_bytes, launches=prep.launches + 2, p=prep.p)
+        else:
+            skip_call()
+            gs = nat.PRED_SLOTS if kwargs.get("stat_kind") == "pred" else 8
+            buf = torch.zeros(gs + 1, dtype=torch.float64, device=device)
+        if allreduce and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            dist.all_reduce(buf, op=dist.ReduceOp.SUM)
+            info["launches"] += 1
+        info["allreduced"] = bool(allreduce)
+        if while_running is not None:
+            while_running()
+        host = buf.cpu().numpy()                      # the only synchronisation and D2H copy of the call
+        info["d2h_bytes"] = int(host.nbytes)
+    if host[gs] != 0:
+        raise ValueError("probabilities contain NaN (degenerate particle weights in {0} item(s))".format(int(host[gs])))
+    return host[:gs], info

@@ -63,10 +63,17 @@ class SGMCMCHelper(object):
         K.set_parameters(parameters)
         if N is None:
             raise TypeError("N (number of particles) must be given for kind='pf'")
-        res = batched_pf(pf, K.model, K.kernel, packed, N, stat_kind="score", **kwargs)
         keys = S.MODEL_SPECS[self._model]["grad_keys"]
-        total = res.grad.sum(axis=0)
-        return {k: float(total[i]) for i, k in enumerate(keys)}, res
+        rng = kwargs.get("rng", engine.config.rng)
+        if rng == "injected":          # parity mode: the host draws the recorded stream item by item
+            res = batched_pf(pf, K.model, K.kernel, packed, N, stat_kind="score", **kwargs)
+            total = res.grad.sum(axis=0)
+            return {k: float(total[i]) for i, k in enumerate(keys)}, res
+        from .particle_filters.buffered_smoother import _ENGINE_KW
+        kw = {k: kwargs[k] for k in _ENGINE_KW if k in kwargs and kwargs[k] is not None}
+        total, info = engine.run_pf_sum(K.model, K.kernel, pf, packed, N, allreduce=kwargs.get("allreduce", False),
+                                        while_running=kwargs.get("while_running"), stat_kind="score", **kw)
+        return {k: float(total[i]) for i, k in enumerate(keys)}, info
 
     def packed_items(self, parameters, forward_message=None, **arrays):
         prior_mean, prior_var = self._prior_moments(forward_message, parameters)
@@ -119,7 +126,8 @@ class SGMCMCHelper(object):
                                   additive_statistic_func=stat, statistic_dim=3, t1=subsequence_start,
                                   tL=subsequence_end, weights=weights, prior_mean=prior_mean,
                                   prior_var=prior_var, elementwise_statistic=True, **kwargs)
-        avg = np.reshape(average_statistic(out), (-1, 3))
+        # lag = 0: the filter's statistic is already the weighted average (pf.py:77-80)
+        avg = np.reshape(out["statistics"] if pf == "filter" else average_statistic(out), (-1, 3))
         if self._model == "garch" and squared:
             x_mean, x_cov = avg[:, 1], avg[:, 2] - avg[:, 1] ** 2
         else:

@@ -23,6 +23,9 @@ _ENGINE_KW = ("dtype", "rng", "resample", "lambduh", "Ntilde", "accept_reject", 
               "manual_sample_threshold", "seed", "offset", "device", "item_id_base", "n2_mode", "num_steps_ahead", "per_horizon", "variates", "path")
 
 
+_LAST_INJECTED = {}        # randoms drawn by the last rng='injected' call without explicit arrays (save_all replays prefixes)
+
+
 def _theta(model, parameters):
     return S.MODEL_SPECS[model]["theta"](parameters)
 
@@ -68,7 +71,7 @@ def batched_pf(pf, model, kernel, items, N, stat_kind="score", want=(), sync=Tru
         pred = None
         if stat_kind == "pred" and model != "lgssm":      # the LGSSM predictive statistic is analytic (no draws)
             pred = (int(kw.get("num_steps_ahead", 5)), [int(v) for v in pk.t1], [int(v) for v in pk.tL])
-        kw["injected"] = _draw_injected(int(N), [int(T) for T in pk.T_buf], pred=pred)
+        kw["injected"] = _LAST_INJECTED["value"] = _draw_injected(int(N), [int(T) for T in pk.T_buf], pred=pred)
         kw.setdefault("resample", "multinomial")
     elif "injected" in kwargs:
         kw["injected"] = kwargs["injected"]
@@ -108,8 +111,38 @@ def buffered_pf_wrapper(pf, observations=None, parameters=None, N=1000, kernel=N
         out["statistics"] = res.tensor("stats")[0][:, :p].double().cpu().numpy()
         out["_average_statistic"] = res.grad[0].copy()
     if save_all:
+        # buffered_smoother.py:128-147: the particle system, statistics and running log-likelihood after every step
         out["all_x_t"] = res.tensor("trace_x")[0].double().cpu().numpy()
-        out["all_log_weights"] = res.tensor("trace_lw")[0].double().cpu().numpy()
+        out["all_log_weights"] = alw = res.tensor("trace_lw")[0].double().cpu().numpy()
+        wts = None if weights is None else np.asarray(weights, dtype=float).reshape(-1)
+        ll, all_ll = 0.0, [0.0]
+        for t in range(T):
+            if t1 <= t < tL:          # :124-126 (here max-shifted like the kernels)
+                m = np.max(alw[t + 1])
+                ll += (1.0 if wts is None else wts[t - t1]) * (m + np.log(np.mean(np.exp(alw[t + 1] - m))))
+            all_ll.append(ll)
+        out["all_loglikelihood_estimate"] = np.array(all_ll)
+        # The statistics after step t are what a run over the first t observations returns: with the same random
+        # numbers (Philox seed / call offset, or the recorded stream) the particle system of a prefix is identical.
+        kw2 = dict(kwargs)
+        if kw2.get("rng", engine.config.rng) == "injected":
+            inj = kw2.get("injected") or _LAST_INJECTED.get("value")
+        else:
+            inj = None
+            kw2.update(seed=int(res.seed), offset=int(res.offset))
+        zero = np.zeros(p) if pf == "filter" else np.zeros((int(N), p))
+        all_stats = [zero]
+        for t in range(1, T + 1):
+            sub = engine.PFItems().add(observations[:t], _theta(model, parameters), t1=min(t1, t), tL=min(tL, t),
+                                       weights=weights, prior_mean=float(np.ravel(prior_mean)[0]),
+                                       prior_var=float(np.ravel(prior_var)[0]))
+            if inj is not None:
+                kw2["injected"] = {k: (np.asarray(v)[:, :t] if k in ("u", "z", "zp") else
+                                       (list(v)[:t] if k == "extra" else v)) for k, v in inj.items() if v is not None}
+            r2 = batched_pf(pf, model, kernel.kernel, sub, N, stat_kind=stat_kind,
+                            want=() if pf == "filter" else ("stats",), **kw2)
+            all_stats.append(r2.grad[0].copy() if pf == "filter" else r2.tensor("stats")[0][:, :p].double().cpu().numpy())
+        out["all_statistics"] = np.array(all_stats)
     return out
 
 

@@ -66,9 +66,27 @@ def elementwise_run(pf, model, kernel, items, N, stat_kind, t1, tL, **kwargs):
     lambduh = 1) the wide statistic of particle i is h_s evaluated along i's ancestral line, so it is
     rebuilt from the ancestor and particle traces (T gathers) instead of widening the records."""
     from .buffered_smoother import batched_pf
-    if pf != "poyiadjis_N" or stat_kind != "suff":
-        raise NotImplementedError("elementwise statistics are implemented for pf='poyiadjis_N' with the "
-                                  "sufficient statistics (what pf_latent_var_distr uses)")
+    if pf not in ("poyiadjis_N", "filter") or stat_kind != "suff":
+        raise NotImplementedError("elementwise statistics are implemented for pf='poyiadjis_N' (smoothing) and "
+                                  "pf='filter' (lag = 0) with the sufficient statistics (what pf_latent_var_distr uses)")
+    if pf == "filter":
+        # pf.py:40-82 with the wide statistic: block s of the (3 L,) vector is sum_i h_s(x_anc_i, x'_i) softmax(lw')_i of
+        # step s, from the traced particle system
+        res = batched_pf(pf, model, kernel, items, N, stat_kind="none", want=("lw", "anc", "trace_x", "trace_lw", "x"), **kwargs)
+        anc = res.tensor("anc")[0].long()
+        tx = res.tensor("trace_x")[0].double()
+        tlw = res.tensor("trace_lw")[0].double()
+        L = tL - t1
+        stats = torch.zeros(3 * L, dtype=torch.float64, device=anc.device)
+        wts = items.weights[0]
+        for t in range(t1, min(tL, anc.shape[0])):
+            xn, xa = tx[t + 1][:, 0], tx[t][anc[t]][:, 0]
+            w = torch.softmax(tlw[t + 1], dim=0)
+            s = t - t1
+            h = torch.stack([xn, xn * xn, (xn ** 4) if model == "garch" else xa * xn])
+            stats[3 * s:3 * s + 3] = (h * w).sum(dim=1) * (1.0 if wts is None else float(wts[s]))
+        return dict(x_t=res.tensor("x")[0].double().cpu().numpy(), log_weights=res.tensor("lw")[0].double().cpu().numpy(),
+                    statistics=stats.cpu().numpy(), loglikelihood_estimate=float(res.loglik[0]))
     res = batched_pf(pf, model, kernel, items, N, stat_kind="none", want=("lw", "anc", "trace_x", "x"), **kwargs)
     anc = res.tensor("anc")[0].long()            # (T, N)
     tx = res.tensor("trace_x")[0].double()       # (T + 1, N, n)

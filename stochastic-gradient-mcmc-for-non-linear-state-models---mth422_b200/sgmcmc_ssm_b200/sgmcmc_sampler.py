@@ -285,15 +285,24 @@ class SGMCMCSampler(object):
             fm = kwargs.pop("forward_message", None)
             arrays = random_subsequences_packed(obs_all, subsequence_length, minibatch_size, buffer_length, style, lo, hi)
             keys = list(noisy_grad)
-            local = np.zeros(len(keys))
-            if hi > lo:
-                packed = self.message_helper.packed_items(self.parameters, forward_message=fm, **arrays)
-                sums, _ = self.message_helper.pf_gradient_sum_packed(packed, self.parameters, item_id_base=lo, **kwargs)
-                local = np.array([sums[k] for k in keys])
+            from . import engine
+            if kwargs.get("rng", engine.config.rng) == "injected":
+                local = np.zeros(len(keys))
+                if hi > lo:
+                    packed = self.message_helper.packed_items(self.parameters, forward_message=fm, **arrays)
+                    sums, _ = self.message_helper.pf_gradient_sum_packed(packed, self.parameters, item_id_base=lo, **kwargs)
+                    local = np.array([sums[k] for k in keys])
+                total = parallel.allreduce_sum(local) if distributed else local
             else:
-                from . import engine
-                engine.skip_call()                   # empty shard: keep the Philox call offsets aligned across ranks
-            total = parallel.allreduce_sum(local) if distributed else local
+                # device randoms: the item gradients are summed on the device, all-reduced in place over the ranks
+                # (one NCCL call on the same buffer) and read back with a single small D2H copy
+                packed = self.message_helper.packed_items(self.parameters, forward_message=fm, **arrays) if hi > lo else None
+                sums, info = self.message_helper.pf_gradient_sum_packed(packed, self.parameters, item_id_base=lo,
+                                                                        allreduce=distributed, **kwargs)
+                self.last_pf_info = info
+                total = np.array([sums[k] for k in keys])
+                if distributed and not (isinstance(info, dict) and info.get("allreduced")):
+                    total = parallel.allreduce_sum(total)
             for k, v in zip(keys, total):
                 noisy_grad[k] += v / minibatch_size
             return self._check_noisy_grad(noisy_grad)

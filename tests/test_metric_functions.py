@@ -119,3 +119,23 @@ def test_metric_factories_drive_the_real_samplers(model):
     assert all(np.isfinite(r["value"]) for r in rec)
     one = mf.metric_function_from_sampler("noisy_loglikelihood", **kw)(s)
     assert np.isfinite(one["value"]) and one["metric"] == "noisy_loglikelihood"
+
+
+def test_average_input_decorator_with_a_real_sampler():
+    """The decorator reads / assigns `parameters.vector`: works on the real Parameters containers (not only on a stub)
+    and restores the sampler's own parameters afterwards."""
+    from sgmcmc_ssm_b200 import metric_functions as mf
+    from sgmcmc_ssm_b200.models.svm import SVMSampler, SVMParameters
+    p = SVMParameters(A=np.eye(1) * 0.9, LQinv=np.eye(1) * 1.5, LRinv=np.eye(1) * 2.0)
+    s = SVMSampler(n=1, m=1, observations=np.zeros((10, 1)), parameters=p)
+    avg = mf.average_input_decorator(mf.metric_function_parameter("A", np.array([[1.0]]), "mae"))
+    out1 = avg(s)
+    s.parameters.A = np.eye(1) * 0.5
+    out2 = avg(s)
+    rec1 = out1 if isinstance(out1, dict) else out1[0]
+    rec2 = out2 if isinstance(out2, dict) else out2[0]
+    assert rec1["variable"].startswith("avg_")
+    np.testing.assert_allclose(rec1["value"], 0.1, atol=1e-12)
+    np.testing.assert_allclose(rec2["value"], 0.3, atol=1e-12)          # running mean of A: (0.9 + 0.5) / 2 = 0.7
+    np.testing.assert_allclose(s.parameters.A, [[0.5]])                  # restored
+    np.testing.assert_allclose(s.parameters.vector, [0.5, 1.5, 2.0])
