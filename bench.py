@@ -90,10 +90,33 @@ def draw_windows(n, T=T_SERIES, seed=777):
 
 
 # ------------------------------------------------------------------------------------------------------
-# reference arm: the reference's algorithm (oracle port, numpy) on all host cores
+# reference arm: the reference's own CPU implementation (oracle/_ref, the unmodified package; else the oracle port) on all host cores
 # ------------------------------------------------------------------------------------------------------
+REF_DIR = os.path.join(ROOT, "oracle", "_ref")
+
+
+def ref_kind():
+    """"reference" when the vendored copy of the unmodified reference (oracle/make_ref.py) is present, else "port"."""
+    return "reference" if os.path.isdir(os.path.join(REF_DIR, "sgmcmc_ssm")) else "port"
+
+
 def _cpu_one_gradient(args):
     y, w, seed = args
+    if ref_kind() == "reference":
+        # the UNMODIFIED reference: sgmcmc_ssm.models.svm.SVMHelper.pf_gradient_estimate (svm/helper.py:67-128)
+        if REF_DIR not in sys.path:
+            sys.path.insert(0, REF_DIR)
+        import warnings
+        warnings.filterwarnings("ignore")
+        from sgmcmc_ssm.models.svm import SVMHelper, SVMParameters
+        th = svm_theta()
+        params = SVMParameters(A=np.eye(1) * th["A"], LQinv=np.eye(1) * th["LQinv"], LRinv=np.eye(1) * th["LRinv"])
+        obs = y[w["lo"]:w["hi"]]
+        np.random.seed(seed)
+        g = SVMHelper(n=1, m=1).pf_gradient_estimate(
+            observations=obs, parameters=params, subsequence_start=w["start"] - w["lo"],
+            subsequence_end=w["start"] - w["lo"] + SUBSEQ, weights=w["weights"], pf="poyiadjis_N", N=N_PARTICLES)
+        return obs.shape[0] * N_PARTICLES, [float(g["LRinv_vec"]), float(g["LQinv_vec"]), float(np.ravel(g["A"])[0])]
     from oracle import pf_oracle as po
     rng = po.LegacyStream(seed, native_choice=True)       # np.random.choice(range(N), p=...) like pf.py:28-29
     obs = y[w["lo"]:w["hi"]]
@@ -142,7 +165,7 @@ def run_reference(args):
             "config": dict(workload_config(args.gpus, args.minibatch), reference_arm_work_per_step=(
                 "{0} subsequence gradients per step (one per host core), not the GPU arm's minibatch: a RATE comparison "
                 "on the same per-item workload".format(cores)), reference_arm_items_per_step=cores),
-            "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": ref_kind(), "sample": sample},
             "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
@@ -331,10 +354,12 @@ def run_gpu(args):
         _, dt1, _ = cpu_rate(y, windows, 1, 1, 0)
         n_grad = int(min(64, max(2, args.cpu_seconds / max(dt1, 1e-3))))
         rate, dt, done = cpu_rate(y, windows, 1, n_grad, 0)
-        line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": 1, "kind": "port",
-                                "sample": "{0} subsequence gradient(s) of the same workload (N=2^16, T_buf<=60), "
-                                          "numpy oracle port incl. np.random.choice, {1:.1f} s; host has {2} cores".format(
-                                              n_grad, dt, os.cpu_count())}
+        line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": 1, "kind": ref_kind(),
+                                "sample": "{0} subsequence gradient(s) of the same workload (N=2^16, T_buf<=60), {3}, "
+                                          "{1:.1f} s; host has {2} cores".format(
+                                              n_grad, dt, os.cpu_count(),
+                                              "the unmodified reference (oracle/_ref: SVMHelper.pf_gradient_estimate)"
+                                              if ref_kind() == "reference" else "numpy oracle port incl. np.random.choice")}
     if not args.no_extras:
         f64 = multi.pop("f64")
         line["f64"] = f64
