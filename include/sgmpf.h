@@ -77,10 +77,14 @@ enum { SGM_N2_AUTO = 0, SGM_N2_FP32_PIPE = 1, SGM_N2_TENSOR = 2 };
  * resolution of the random inputs is 2^-24 instead of 2^-53 (a change of the sampling law far below Monte-Carlo error). */
 enum { SGM_VARIATES_NATIVE = 0, SGM_VARIATES_F32 = 1 };
 
-/* Kernel family of the O(N) smoothers.  AUTO: N <= 2048 runs the shared-memory-resident one-CTA-per-item kernel
- * (whole time loop in one launch), larger N the per-step warp-tile kernels that stream the particle arrays through HBM.
- * TILES forces the per-step kernels (any N), SMALL requires N <= 2048. */
-enum { SGM_PATH_AUTO = 0, SGM_PATH_TILES = 1, SGM_PATH_SMALL = 2 };
+/* Kernel family of the O(N) smoothers.
+ *   TILES   per-step warp-tile kernels streaming the particle arrays through HBM / L2 (any N; the throughput path)
+ *   SMALL   one CTA per item, particle system resident in shared memory, whole time loop in one launch (N <= 2048)
+ *   CLUSTER one thread-block cluster (2..8 CTAs) per item, particle system in distributed shared memory, whole time loop
+ *           in one launch (256 < N <= 16384 and few enough items that all clusters are resident: items x CTAs <= 148)
+ *   AUTO    CLUSTER for 1024 < N <= 2048 with items x CTAs <= 148 (256 particles per CTA: where it beats one CTA), else
+ *           SMALL while the batch is small (N <= 512 or items x N <= 1.2e6), else TILES */
+enum { SGM_PATH_AUTO = 0, SGM_PATH_TILES = 1, SGM_PATH_SMALL = 2, SGM_PATH_CLUSTER = 3 };
 
 /* error codes */
 enum { SGM_OK = 0, SGM_ERR_INVALID = -1, SGM_ERR_UNSUPPORTED = -2, SGM_ERR_WORKSPACE = -3,

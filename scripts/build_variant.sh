@@ -7,7 +7,7 @@ name="$1"; extra="$2"
 obj="$PKG/build_$name"; mkdir -p "$obj"
 FLAGS="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC -Xptxas -v $extra"
 pids=()
-for u in sgmpf sgmpf_f32 sgmpf_f64; do
+for u in sgmpf sgmpf_f32 sgmpf_f64 sgmpf_cl32 sgmpf_cl64; do
   /usr/local/cuda/bin/nvcc $FLAGS -c -o "$obj/$u.o" "$PKG/csrc/$u.cu" > "$obj/$u.log" 2>&1 &
   pids+=($!)
 done

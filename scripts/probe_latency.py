@@ -45,21 +45,24 @@ def go(p):
     return f
 for model in ("svm", "lgssm"):
     for N in (256, 1000, 1024, 2048):
-        for B, reps in ((1, 50), (64, 20), (296, 10), (4096, 3)):
-            for path in ("auto", "tiles"):
+        for B, reps in ((1, 50), (8, 30), (64, 20), (296, 10), (4096, 3)):
+            for path in ("auto", "small", "tiles"):
                 if args.quick and (B == 296 or (path == "tiles" and B == 64)):
                     continue
+                if path == "small" and (N <= 512 or B > 64):
+                    continue                    # auto already is the shared-memory kernel there
                 p = prep(model, N, B, path)
                 ms = timed(go(p), reps)
                 key = "grad_ms_%s_N%d_B%d_%s" % (model, N, B, path)
                 out[key] = ms
                 print("%-34s %9.4f ms  %.3e particle-steps/s  launches %d" % (key, ms, N * 60 * B / (ms * 1e-3), p.launches), flush=True)
 # larger N single item (tile kernels + CUDA graph)
-for N in (4096, 8192, 65536):
-    p = prep("svm", N, 1)
-    ms = timed(go(p), 20)
-    out["grad_ms_svm_N%d_B1" % N] = ms
-    print("grad_ms_svm_N%d_B1  %9.4f ms" % (N, ms), flush=True)
+for N in (4096, 8192, 16384, 65536):
+    for path in ("auto", "tiles"):
+        p = prep("svm", N, 1, path)
+        ms = timed(go(p), 20)
+        out["grad_ms_svm_N%d_B1_%s" % (N, path)] = ms
+        print("grad_ms_svm_N%d_B1_%s  %9.4f ms  launches %d" % (N, path, ms, p.launches), flush=True)
 
 # ---- 2. SGLD iterations / s ------------------------------------------------------------------------------------------
 np.random.seed(12345)

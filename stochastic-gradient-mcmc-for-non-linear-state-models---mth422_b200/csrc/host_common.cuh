@@ -33,6 +33,13 @@ Layout make_layout(const sgm_pf_desc* d);
 template <class R> int run_model(const sgm_pf_desc* d, cudaStream_t s);
 extern template int run_model<float>(const sgm_pf_desc* d, cudaStream_t s);
 extern template int run_model<double>(const sgm_pf_desc* d, cudaStream_t s);
+// thread-block-cluster kernels (cluster_impl.cuh, own translation units)
+template <class R> bool run_cluster(const sgm_pf_desc* d, const sgm::KArgs& a, cudaStream_t s);
+extern template bool run_cluster<float>(const sgm_pf_desc* d, const sgm::KArgs& a, cudaStream_t s);
+extern template bool run_cluster<double>(const sgm_pf_desc* d, const sgm::KArgs& a, cudaStream_t s);
+template <class R> int run_sgld_cluster(const sgm_pf_desc* d, const sgm::SgldArgs& sa, const sgm::KArgs& a, int K, cudaStream_t s);
+extern template int run_sgld_cluster<float>(const sgm_pf_desc* d, const sgm::SgldArgs& sa, const sgm::KArgs& a, int K, cudaStream_t s);
+extern template int run_sgld_cluster<double>(const sgm_pf_desc* d, const sgm::SgldArgs& sa, const sgm::KArgs& a, int K, cudaStream_t s);
 template <class R> int run_sgld_persistent(const sgm_pf_desc* d, const sgm::SgldArgs& sa, int K, cudaStream_t s);
 extern template int run_sgld_persistent<float>(const sgm_pf_desc* d, const sgm::SgldArgs& sa, int K, cudaStream_t s);
 extern template int run_sgld_persistent<double>(const sgm_pf_desc* d, const sgm::SgldArgs& sa, int K, cudaStream_t s);

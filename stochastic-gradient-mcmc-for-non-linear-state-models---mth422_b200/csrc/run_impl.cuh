@@ -112,10 +112,14 @@ int run_impl(const sgm_pf_desc* d, cudaStream_t stream) {
     const bool pred = d->stat_kind == SGM_STAT_PRED;
     const bool small_ok = a.N <= SGM_SMALL_MAX_N && !backward_pf(d->pf) && !pred && d->path != SGM_PATH_TILES &&
                           (a.N <= 512 || (int64_t)a.B * a.N <= SGM_SMALL_MAX_PARTICLES || d->path == SGM_PATH_SMALL);
+    // few items (all clusters resident at once): a cluster of CTAs per item, particle system in distributed shared memory
+    const bool cluster_ok = !backward_pf(d->pf) && !pred && (d->path == SGM_PATH_AUTO || d->path == SGM_PATH_CLUSTER) &&
+                            (a.N > 1024 || d->path == SGM_PATH_CLUSTER);
     bool done_small = false;
-    if (small_ok) {
+    if (cluster_ok || small_ok) {
         if (d->ev_steps_begin) cudaEventRecord(reinterpret_cast<cudaEvent_t>(d->ev_steps_begin), stream);
-        done_small = launch_small<R, Model>(a, stream);
+        if (cluster_ok) done_small = run_cluster<R>(d, a, stream);
+        if (!done_small && small_ok) done_small = launch_small<R, Model>(a, stream);
         if (done_small) ++launches;
         if (d->ev_steps_end) cudaEventRecord(reinterpret_cast<cudaEvent_t>(d->ev_steps_end), stream);
     }
@@ -255,11 +259,14 @@ bool launch_persistent(const SgldArgs& sa, const KArgs& a, int K, cudaStream_t s
 // 1 = launched, 0 = not eligible (the caller falls back to one launch sequence per iteration), < 0 = error
 template <class R>
 int run_sgld_persistent(const sgm_pf_desc* d, const SgldArgs& sa, int K, cudaStream_t s) {
-    if (sa.ipc != 1 || d->n_particles > SGM_SMALL_MAX_N || backward_pf(d->pf) || d->stat_kind != SGM_STAT_SCORE) return 0;
+    if (sa.ipc != 1 || backward_pf(d->pf) || d->stat_kind != SGM_STAT_SCORE) return 0;
     KArgs a;
     { const int rc = make_kargs(d, a); if (rc != SGM_OK) return rc; }
-    bool ok;
-    switch (d->model) {
+    bool ok = false;
+    // few chains: one cluster of CTAs per chain (N up to 8 x 2048); else one CTA per chain (N <= 2048)
+    if (d->path == SGM_PATH_CLUSTER || (d->path == SGM_PATH_AUTO && a.N > 1024)) ok = run_sgld_cluster<R>(d, sa, a, K, s) == 1;
+    if (!ok && (d->n_particles > SGM_SMALL_MAX_N || d->path == SGM_PATH_TILES || d->path == SGM_PATH_CLUSTER)) return 0;
+    if (!ok) switch (d->model) {
         case SGM_MODEL_SVM: ok = launch_persistent<R, SvmPrior>(sa, a, K, s); break;
         case SGM_MODEL_LGSSM: ok = d->kernel == SGM_KERNEL_PRIOR ? launch_persistent<R, LgssmPrior>(sa, a, K, s) : launch_persistent<R, LgssmOptimal>(sa, a, K, s); break;
         default: ok = d->kernel == SGM_KERNEL_PRIOR ? launch_persistent<R, GarchPrior>(sa, a, K, s) : launch_persistent<R, GarchOptimal>(sa, a, K, s);

@@ -12,7 +12,7 @@ LIB_PATH = os.environ.get("SGM_LIB_PATH") or os.path.join(PKG_DIR, "libsgmpf.so"
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC"]
 # translation units: the C-ABI + the two per-dtype instantiations of the launch orchestration (compiled in parallel)
-UNITS = ["sgmpf.cu", "sgmpf_f32.cu", "sgmpf_f64.cu"]
+UNITS = ["sgmpf.cu", "sgmpf_f32.cu", "sgmpf_f64.cu", "sgmpf_cl32.cu", "sgmpf_cl64.cu"]
 OBJ_DIR = os.path.join(PKG_DIR, "build")
 
 

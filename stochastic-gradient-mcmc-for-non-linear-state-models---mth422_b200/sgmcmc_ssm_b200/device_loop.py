@@ -32,6 +32,9 @@ def _f(a):
     return float(np.ravel(a)[0])
 
 
+cluster_plan = engine.cluster_plan
+
+
 def _supported_options(options):
     """project_parameters runs with the models' defaults on the device; custom projection options stay on the host."""
     return all(k == "partition_style" for k in (options or {}))
@@ -44,7 +47,7 @@ class DeviceChains(object):
                  num_sequences=None, pf="poyiadjis_N", N=None, num_samples=None, kernel=None, preconditioner=None,
                  dtype=None, rng=None, resample=None, variates=None, seed=None, lambduh=None, Ntilde=2,
                  trace_every=0, max_trace_rows=0, project=True, device=None, chain_id_base=0, kind="pf",
-                 persistent=True, **unused):
+                 persistent=True, path="auto", **unused):
         if kind != "pf":
             raise NotImplementedError("the device loop covers the particle-filter gradient (kind='pf')")
         self.samplers = list(samplers)
@@ -150,6 +153,7 @@ class DeviceChains(object):
             pf_d.n_particles, pf_d.Ntilde, pf_d.accept_reject = self.N, int(Ntilde), 1
             pf_d.max_accept_reject = pf_d.manual_sample_threshold = -1
             pf_d.variates = nat.VARIATES[variates or engine.config.variates]
+            pf_d.path = nat.PATH[path]
             pf_d.lambduh = float(lambduh)
             if self.rng == "injected":
                 seed, offset = 0, 0
@@ -165,7 +169,11 @@ class DeviceChains(object):
             self.ipc = B // C
             # one work item per chain and a shared-memory-sized particle system: the library runs all iterations of a
             # call inside one persistent kernel (no per-iteration launches to put into a graph)
-            self.persistent = bool(persistent) and self.ipc == 1 and self.N <= 2048 and pf in ("nemeth", "poyiadjis_N", "filter")
+            fast = pf == "poyiadjis_N" and self.rng == "philox" and resample in ("multinomial", "multinomial_sorted", "sorted")
+            self.cluster = bool(persistent) and self.ipc == 1 and fast and path in ("auto", "cluster") and (
+                cluster_plan(self.N, B, path == "cluster") is not None)
+            self.persistent = bool(persistent) and self.ipc == 1 and pf in ("nemeth", "poyiadjis_N", "filter") and (
+                self.N <= 2048 or self.cluster)
             pf_d.item_id_base = int(chain_id_base) * self.ipc
             if engine.config.two_streams:
                 st = engine._state(device)

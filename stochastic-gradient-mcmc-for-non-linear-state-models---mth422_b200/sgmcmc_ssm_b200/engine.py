@@ -115,6 +115,20 @@ def _state(device):
     return st
 
 
+def cluster_plan(N, B, forced=False):
+    """Mirror of cluster_plan() in csrc/cluster_impl.cuh: (cluster size, particles per CTA) when a batch of B items with N
+    particles runs the thread-block-cluster kernel (path='auto': 1024 < N <= 2048 only; forced: path='cluster'), else None."""
+    if N <= 256 or (not forced and not 1024 < N <= 2048):
+        return None
+    for nl in ((256, 512, 1024, 2048) if forced else (256,)):
+        C = 2
+        while C * nl < N:
+            C *= 2
+        if C <= 8 and B * C <= 148:
+            return C, nl
+    return None
+
+
 def _align(x, a=256):
     return (x + a - 1) // a * a
 
@@ -470,6 +484,9 @@ class PreparedPF(object):
         d = self.desc
         if not config.cuda_graphs or d.rng_mode != nat.RNG["philox"] or self.extra or self.N <= 2048:
             return False
+        if d.path in (nat.PATH["auto"], nat.PATH["cluster"]) and d.pf in (nat.PF["nemeth"], nat.PF["filter"]) and \
+                d.stat_kind != nat.STAT["pred"] and cluster_plan(self.N, self.B, d.path == nat.PATH["cluster"]) is not None:
+            return False                       # one cluster launch runs the whole time loop: nothing to put into a graph
         return self.B * ((self.N + 2047) // 2048) <= 148
 
     def _graph_key(self):

@@ -97,8 +97,9 @@ def test_graph_replay_equals_plain_enqueue_and_draws_fresh_randoms():
     assert len(np.unique(steps)) == len(steps)          # every replayed iteration moved A by a different amount
 
 
-@pytest.mark.parametrize("model,N", [("lgssm", 1000), ("svm", 200), ("garch", 2048)])
-def test_persistent_kernel_equals_one_launch_sequence_per_iteration(model, N):
+@pytest.mark.parametrize("model,N,path", [("lgssm", 1000, "auto"), ("svm", 200, "auto"), ("garch", 2048, "auto"), ("lgssm", 1000, "cluster"),
+                                          ("svm", 8192, "cluster")])   # auto: one CTA per chain up to N = 1024, a cluster of 8 x 256 at 2048
+def test_persistent_kernel_equals_one_launch_sequence_per_iteration(model, N, path):
     """One work item per chain and N <= 2048: all iterations run inside ONE persistent kernel.  Iteration k uses the
     Philox call offset (base + k) either way, so the chains must be bit-identical to the launch-per-iteration path."""
     import sgmcmc_ssm_b200 as sg
@@ -106,15 +107,15 @@ def test_persistent_kernel_equals_one_launch_sequence_per_iteration(model, N):
     make, _, Sampler = MODELS[model]
     obs = C.case("s/sgld_" + model)["obs"]
     kw = dict(method="SGLD", epsilon=0.005, pf="poyiadjis_N", N=N, subsequence_length=16, buffer_length=4, minibatch_size=1,
-              trace_every=1, max_trace_rows=12)
+              trace_every=1, max_trace_rows=12, path=path)
     out = []
     for persistent in (True, False):
         sg.set_seed(77)
         ch = DeviceChains([Sampler(n=1, m=1, observations=obs, parameters=make()) for _ in range(5)], persistent=persistent, **kw)
-        assert ch.persistent == persistent
+        assert ch.persistent == persistent and ch.cluster == (persistent and (N > 1024 or path == "cluster"))
         ch.run(7); ch.run(5)
         ch.pull_parameters()
-        assert ch.launches == (2 if persistent else 3 * 5)
+        assert ch.launches == (2 if persistent else (3 if N <= 16384 else 124) * 5)
         out.append(ch.trace())
     assert out[0].shape == (13, 5, len(ch.slots))
     np.testing.assert_array_equal(out[0], out[1])

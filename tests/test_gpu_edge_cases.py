@@ -33,12 +33,12 @@ def _run(N, obs, t1, tL, pf="poyiadjis_N", resample="multinomial", seed=3, weigh
     return res, expect, ref
 
 
-@pytest.mark.parametrize("path", ["auto", "tiles"])      # auto: N <= 2048 runs the shared-memory kernel (thread-count boundaries 256 / 1024 / 2048)
+@pytest.mark.parametrize("path", ["auto", "small", "tiles", "cluster"])      # shared-memory kernel (N <= 2048), tile kernels, cluster kernel (256 < N <= 16384)
 @pytest.mark.parametrize("resample", ["multinomial", "multinomial_sorted"])
 @pytest.mark.parametrize("N", [1, 2, 31, 255, 256, 257, 511, 513, 1023, 1024, 1025, 2047, 2048, 2049, 8191, 65537, 70000])   # 65537+: 1024-thread header
 def test_tiny_and_tile_boundary_particle_counts(N, resample, path):
-    if path == "tiles" and N > 2048:
-        pytest.skip("same kernels as path='auto'")
+    if (path == "small" and N > 2048) or (path == "cluster" and not 256 < N <= 16384) or (path == "tiles" and N > 16384):
+        pytest.skip("path does not apply / same kernels as path='auto'")
     obs = np.array([0.3, -1.2, 0.8, 2.0, -0.1, 0.4])
     res, expect, ref = _run(N, obs, 1, 5, resample=resample, weights=np.array([1.0, 2.0, 0.5, 3.0]), path=path)
     np.testing.assert_allclose(res.grad[0], expect, rtol=1e-8, atol=1e-9)

@@ -89,7 +89,7 @@ def test_shared_memory_kernel_and_tile_kernels_have_the_same_law(N, dtype):
     pk = sg.PackedItems(np.tile(it.obs_flat, R), np.tile(it.T_buf, R), np.tile(it.t1, R), np.tile(it.tL, R),
                         np.tile(it.wts_flat, R), np.arange(R, dtype=np.int64) * it.wts_flat.shape[0], it.theta[0], 0.0, 10.0)
     kw = dict(dtype=dtype, rng="philox", offset=1)
-    a = sg.run_pf("svm", "prior", "poyiadjis_N", pk, N, seed=4, **kw)                       # shared-memory kernel
+    a = sg.run_pf("svm", "prior", "poyiadjis_N", pk, N, seed=4, path="small", **kw)         # shared-memory kernel
     b = sg.run_pf("svm", "prior", "poyiadjis_N", pk, N, seed=5, path="tiles", **kw)         # per-step tile kernels
     assert a.launches == 1 and b.launches > 100
     ga, gb = np.column_stack([a.grad, a.loglik]), np.column_stack([b.grad, b.loglik])

@@ -37,11 +37,13 @@ def _run_case(name, dtype="f64", path="auto"):
     return c, ref, res, K
 
 
-@pytest.mark.parametrize("path", ["auto", "tiles"])      # auto: the O(N) smoothers at N <= 2048 run the shared-memory kernel
+@pytest.mark.parametrize("path", ["auto", "small", "tiles", "cluster"])      # the three kernel families of the O(N) smoothers
 @pytest.mark.parametrize("name", C.case_names("k"))
 def test_kernel_case_f64_matches_oracle_and_reference(name, path):
-    if path == "tiles" and ("poyiadjis_N2" in name or "paris" in name):
+    if path != "auto" and ("poyiadjis_N2" in name or "paris" in name):
         pytest.skip("backward smoothers always run the tile kernels")
+    if path == "cluster" and int(C.case(name)["N"]) <= 256:
+        pytest.skip("clusters need N > 256")
     c, ref, res, K = _run_case(name, path=path)
     model, kernel, pf = C.parse_kernel_case(name)
     anc = res.tensor("anc")[0].cpu().numpy()

@@ -97,3 +97,30 @@ def test_f64_production_path_matches_the_reference_distribution(group, variates)
         for j, B in enumerate(z[group + "/buffer_sizes"]):
             res = _run_cell(group, N, int(B), R, dtype="f64", variates=variates, seed=29)
             _check(group, i, j, res, R, (group, N, int(B), "f64", variates))
+
+
+@pytest.mark.parametrize("group", [g for g in _groups() if not g.endswith("paris")])
+def test_cluster_kernel_matches_the_reference_distribution(group):
+    """The thread-block-cluster kernel (cluster_kernels.cuh: particle system in the distributed shared memory of 2-8 CTAs)
+    in every (N, B) cell: N = 1000 -> 4 CTAs x 256 particles, N = 4096 -> 8 x 512, N = 10000 -> 8 x 2048.  A launch holds
+    at most 148 / C items, so R = 288 repetitions come from several launches with different call offsets."""
+    import sgmcmc_ssm_b200 as sg
+    z = C.load("model_sweep_stats.npz")
+    model, kernel, pf = group.split("_", 2)
+    L, t0 = int(z["L"]), int(z["t0"])
+    obs = z[group + "/obs"].reshape(-1)
+    for i, N in enumerate(z[group + "/Ns"]):
+        per = 36 if N <= 1024 else 18
+        for j, B in enumerate(z[group + "/buffer_sizes"]):
+            window = obs[t0 - int(B):t0 + L + int(B)]
+            pk = sg.PackedItems(np.tile(window, per), np.full(per, window.shape[0]), np.full(per, int(B)), np.full(per, L + int(B)),
+                                None, None, z[group + "/theta"], float(z[group + "/prior_mean"]), float(z[group + "/prior_var"]))
+            grads, lls = [], []
+            for rep in range(288 // per):
+                res = sg.run_pf(model, kernel, pf, pk, int(N), dtype="f32", rng="philox", seed=31, offset=100 * rep + int(B) + 1, path="cluster")
+                assert res.launches == 1
+                grads.append(res.grad); lls.append(res.loglik)
+
+            class _R(object):
+                grad, loglik = np.concatenate(grads), np.concatenate(lls)
+            _check(group, i, j, _R, 288, (group, int(N), int(B), "cluster"))
