@@ -16,8 +16,11 @@ namespace sgmhost {
 // ... while the batch is small enough: the shared-memory kernel is bound by instruction issue and shared-memory
 // wavefronts (random parent gathers), the tile kernels by HBM -- measured crossover (SVM / LGSSM f32, 60 steps):
 // N = 256: never; N = 1000: ~1650 items (4096 items: 3.7 vs 2.8 ms); N = 2048: ~480 items (9.4 vs 4.4 ms).
+// N in (256, 1024]: 512 threads x 2 particles for every batch size.  A/B against 1024 threads x 1 particle (LGSSM f32, 60
+// steps): N = 1000, 1 item 0.171 vs 0.182 ms, 296 items 0.29 vs 0.36 ms, persistent SGLD 5.5e3 vs 5.2e3 it/s (one Philox
+// call and one Box-Muller pair serve both particles of a thread; half as many warps meet at the two barriers).
 #ifndef SGM_SMALL_LATENCY_ITEMS
-#define SGM_SMALL_LATENCY_ITEMS (2 * 148)     /* up to two CTAs per SM: 1024 threads x 1 particle; above: 512 x 2 */
+#define SGM_SMALL_LATENCY_ITEMS 0
 #endif
 #ifndef SGM_SMALL_MAX_PARTICLES
 #define SGM_SMALL_MAX_PARTICLES 1200000
@@ -41,8 +44,10 @@ template <class R, class Model>
 bool launch_small(const KArgs& a, cudaStream_t stream) {
     if (small_fast_config(a)) {
         if (a.N <= 256) return launch_small_shape<R, Model, 256, 1, true>(a, stream);
-        if (a.N <= 1024) return a.B <= SGM_SMALL_LATENCY_ITEMS ? launch_small_shape<R, Model, 1024, 1, true>(a, stream)
-                                                                : launch_small_shape<R, Model, 512, 2, true>(a, stream);
+#if SGM_SMALL_LATENCY_ITEMS > 0
+        if (a.N <= 1024 && a.B <= SGM_SMALL_LATENCY_ITEMS) return launch_small_shape<R, Model, 1024, 1, true>(a, stream);
+#endif
+        if (a.N <= 1024) return launch_small_shape<R, Model, 512, 2, true>(a, stream);
         return launch_small_shape<R, Model, 1024, 2, true>(a, stream);
     }
     // every other configuration (injected randoms, Nemeth shrinkage, filter, traces, ...): two shapes, flags read at run time
@@ -248,8 +253,10 @@ template <class R, class Model>
 bool launch_persistent(const SgldArgs& sa, const KArgs& a, int K, cudaStream_t stream) {
     if (small_fast_config(a)) {
         if (a.N <= 256) return launch_persistent_shape<R, Model, 256, 1, true>(sa, a, K, stream);
-        if (a.N <= 1024) return a.B <= SGM_SMALL_LATENCY_ITEMS ? launch_persistent_shape<R, Model, 1024, 1, true>(sa, a, K, stream)
-                                                                : launch_persistent_shape<R, Model, 512, 2, true>(sa, a, K, stream);
+#if SGM_SMALL_LATENCY_ITEMS > 0
+        if (a.N <= 1024 && a.B <= SGM_SMALL_LATENCY_ITEMS) return launch_persistent_shape<R, Model, 1024, 1, true>(sa, a, K, stream);
+#endif
+        if (a.N <= 1024) return launch_persistent_shape<R, Model, 512, 2, true>(sa, a, K, stream);
         return launch_persistent_shape<R, Model, 1024, 2, true>(sa, a, K, stream);
     }
     if (a.N <= 1024) return launch_persistent_shape<R, Model, 1024, 1, false>(sa, a, K, stream);
