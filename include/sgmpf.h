@@ -82,7 +82,7 @@ enum { SGM_VARIATES_NATIVE = 0, SGM_VARIATES_F32 = 1 };
  *   SMALL   one CTA per item, particle system resident in shared memory, whole time loop in one launch (N <= 2048)
  *   CLUSTER one thread-block cluster (2..8 CTAs) per item, particle system in distributed shared memory, whole time loop
  *           in one launch (256 < N <= 16384 and few enough items that all clusters are resident: items x CTAs <= 148)
- *   AUTO    CLUSTER for 1024 < N <= 2048 with items x CTAs <= 148 (256 particles per CTA: where it beats one CTA), else
+ *   AUTO    CLUSTER for 1024 < N <= 4096 with items x CTAs <= 148 (<= 512 particles per CTA: where it wins), else
  *           SMALL while the batch is small (N <= 512 or items x N <= 1.2e6), else TILES */
 enum { SGM_PATH_AUTO = 0, SGM_PATH_TILES = 1, SGM_PATH_SMALL = 2, SGM_PATH_CLUSTER = 3 };
 
@@ -150,7 +150,9 @@ typedef struct sgm_pf_desc {
                                     * (svm/helper.py:379, garch/kernels.py:66), horizon-major        */
 
     /* outputs */
-    double* grad;                  /* [B][8]  final weighted-average statistic (average_statistic);
+    double* grad;                  /* [B][8]  final weighted-average statistic (average_statistic) in slots 0..p-1; PaRIS with
+                                    * device randoms also reports in slots 6, 7 the accept-reject proposals made and the entries
+                                    * resolved by the exact sampler (sums over the item's time steps);
                                     * SGM_STAT_PRED: [B][SGM_PRED_SLOTS], entries 0..K               */
     double* loglik;                /* [B]     log-likelihood estimate over [t1, tL)                 */
     int32_t* status;               /* [B]                                                           */

@@ -32,7 +32,15 @@ for l in sass[start + 1:]:
 out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(out.split("\n")))
 st = [i for i, r in enumerate(rows) if r and r[0] == "Kernel Name"]
-seg = rows[st[0] + 1:st[1]] if len(st) > 1 else rows[st[0] + 1:]
+# several kernels in the report: take the segment whose kernel name matches argv[4] (substring), default the first
+want = sys.argv[4] if len(sys.argv) > 4 else None
+pick = 0
+if want:
+    for n, i in enumerate(st):
+        if want in " ".join(rows[i + 1]) or (i + 2 < len(rows) and want in " ".join(rows[i + 2])):
+            pick = n
+            break
+seg = rows[st[pick] + 1:st[pick + 1]] if pick + 1 < len(st) else rows[st[pick] + 1:]
 hdr, data = seg[0], [r for r in seg[1:] if len(r) > 5]
 iE, iS = hdr.index("Instructions Executed"), hdr.index("# Samples")
 print("sass instrs: nvdisasm", len(seq), "ncu", len(data))

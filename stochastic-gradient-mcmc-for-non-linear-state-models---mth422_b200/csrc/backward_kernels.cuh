@@ -583,6 +583,10 @@ constexpr int PARIS_CH = 1024;         // children per CTA of the accept-reject 
 #define SGM_PARIS_CAP 512
 #endif
 constexpr int PARIS_CAP = SGM_PARIS_CAP;   // proposals per entry before it falls back to the exact sampler (x Ntilde <= 8 fits the 12-bit Philox sub-counter)
+#ifndef SGM_PARIS_U
+#define SGM_PARIS_U 2      /* A/B (64 items, N = 2^14, ms per 60-step gradient; U = 1 / 2 / 4): GARCH 27.3 / 24.1 / 23.8, SVM 27.0 / 25.0 / 27.1, LGSSM 23.0 / 20.4 / 22.1 */
+#endif
+constexpr int PARIS_U = SGM_PARIS_U;   // queue entries a thread works on at once (memory-level parallelism)
 constexpr int PARIS_MAXQ = 4096;       // queue capacity >= children per CTA * Ntilde (Ntilde > 4: fewer children per CTA)
 
 template <class R, class Model>
@@ -638,7 +642,7 @@ __global__ void __launch_bounds__(NT) paris_ar_kernel(KArgs a, int t, int ch) {
         s_x[0][k] = bb; s_x[1][k] = aa - Model::pair_bound(th, rn + NP);       // accept w.p. q(x'|x_I) / sup_j q(x'|x_j)
     }
     int qlen = nch * Nt;
-    for (int e = tid; e < qlen; e += NT) s_q[0][e] = (uint16_t)e;
+    for (int e = tid; e < qlen; e += NT) s_q[0][e] = (uint16_t)(((e / Nt) << 3) | (e % Nt));      // entry = (child << 3) | replicate
     if (tid == 0) { s_n[0] = qlen; s_n[1] = 0; }
     __syncthreads();
     // Proposal budget per entry (PARIS_CAP; the reference's max_accept_reject only lowers it).  While the queue is
@@ -647,41 +651,70 @@ __global__ void __launch_bounds__(NT) paris_ar_kernel(KArgs a, int t, int ch) {
     // proposal order wins -- the same draw sequential accept-reject would have taken, in 1 / tpr of the rounds.
     const int cap = a.accept_reject ? min(a.max_ar, PARIS_CAP) : 0;
     int cur = 0, tries_done = 0;
+    int n_prop = 0;                                  // proposals made by this thread (diagnostic: grad[6] of the item)
     while (tries_done < cap && qlen > 0) {
         int tpr = 1;
         while (tpr < 32 && qlen * tpr * 2 <= NT && tries_done + tpr * 2 <= cap) tpr *= 2;
         const int r = tid & (tpr - 1), gshift = (tid & 31) & ~(tpr - 1), per_round = NT / tpr;
-        for (int base = 0; base < qlen; base += per_round) {          // warp-uniform trip count: full-warp ballots
-            const int e = base + tid / tpr;
-            const bool live = e < qlen;
-            bool ok = false;
-            int entry = 0, I = 0, i = 0, jt = 0;
-            if (live) {
-                entry = s_q[cur][e];
-                const int k = entry / Nt;
-                jt = entry - k * Nt; i = c0 + k;
-                const uint4 raw = rng_raw(key, (uint32_t)i, (uint32_t)t, STREAM_PARIS, (uint32_t)(jt * PARIS_CAP + tries_done + r));
-                const double u = u01d(raw.x, raw.y);
-                double target = u * total;
-                if (!(target < total)) target = total * (1.0 - 1.2e-16);
-                const int kb = min((int)(u * (double)N), N - 1);
-                I = guide[kb];
-                int hi = guide[kb + 1];
-                // first particle in [guide[kb], guide[kb + 1]] whose cumulative mass exceeds the target: usually 0-2
-                // bisections; a bucket holds many particles only where the weights are tiny (degenerate steps)
-                while (I < hi) {
-                    const int mid = (I + hi) >> 1;
-                    if (cdf[mid] <= target) I = mid + 1; else hi = mid;
+        // PARIS_U entries per thread and pass with their dependent load chains (guide -> CDF bisection -> key) issued side by
+        // side: the kernel is bound by L2 latency, not by bandwidth or issue (ncu round 2: issue active 25 %, long-scoreboard
+        // stalls 16.7 per issue with all 64 warps resident), so memory-level parallelism per thread is the lever
+        for (int base = 0; base < qlen; base += per_round * PARIS_U) {          // warp-uniform trip count: full-warp ballots
+            bool live[PARIS_U], ok[PARIS_U];
+            int entry[PARIS_U], I[PARIS_U], hi[PARIS_U], kk[PARIS_U], jt[PARIS_U];
+            double target[PARIS_U];
+            R ua[PARIS_U];
+#pragma unroll
+            for (int u = 0; u < PARIS_U; ++u) {
+                const int e = base + u * per_round + tid / tpr;
+                live[u] = e < qlen;
+                ok[u] = false;
+                entry[u] = 0; I[u] = 0; hi[u] = 0; kk[u] = 0; jt[u] = 0; target[u] = 0.0; ua[u] = (R)2;
+                if (live[u]) {
+                    ++n_prop;
+                    entry[u] = s_q[cur][e];
+                    kk[u] = entry[u] >> 3;
+                    jt[u] = entry[u] & 7;
+                    const uint4 raw = rng_raw(key, (uint32_t)(c0 + kk[u]), (uint32_t)t, STREAM_PARIS, (uint32_t)(jt[u] * PARIS_CAP + tries_done + r));
+                    const double uu = u01d(raw.x, raw.y);
+                    target[u] = uu * total;
+                    if (!(target[u] < total)) target[u] = total * (1.0 - 1.2e-16);
+                    const int kb = min((int)(uu * (double)N), N - 1);
+                    I[u] = guide[kb];
+                    hi[u] = guide[kb + 1];
+                    ua[u] = (R)u01d(raw.z, raw.w);
                 }
-                const Vec4T<R> pk = pkey[I];
-                const R thr = Mth<R>::exp(s_x[0][k] * pk.x + pk.y + s_x[1][k]);        // q(x'_i | x_I) / (per-child bound)
-                ok = (R)u01d(raw.z, raw.w) <= thr;
             }
-            // first accepted proposal of the group, in proposal order
-            const unsigned grp = (__ballot_sync(FULL, ok) >> gshift) & (tpr == 32 ? 0xffffffffu : ((1u << tpr) - 1u));
-            if (live) {
-                if (grp) { if (r == __ffs(grp) - 1) a.Jidx[(item_off + i) * Nt + jt] = I; }
-                else if (r == 0) s_q[cur ^ 1][atomicAdd(&s_n[cur ^ 1], 1)] = (uint16_t)entry;
+            // first particle in [guide[kb], guide[kb + 1]] whose cumulative mass exceeds the target: usually 0-2
+            // bisections; a bucket holds many particles only where the weights are tiny (degenerate steps)
+            bool any = true;
+            while (any) {
+                any = false;
+#pragma unroll
+                for (int u = 0; u < PARIS_U; ++u) {
+                    if (I[u] < hi[u]) {
+                        const int mid = (I[u] + hi[u]) >> 1;
+                        if (cdf[mid] <= target[u]) I[u] = mid + 1; else hi[u] = mid;
+                        any = any || (I[u] < hi[u]);
+                    }
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < PARIS_U; ++u) {
+                if (live[u]) {
+                    const Vec4T<R> pk = pkey[I[u]];
+                    const R thr = Mth<R>::exp(s_x[0][kk[u]] * pk.x + pk.y + s_x[1][kk[u]]);        // q(x'_i | x_I) / (per-child bound)
+                    ok[u] = ua[u] <= thr;
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < PARIS_U; ++u) {
+                // first accepted proposal of the group, in proposal order
+                const unsigned grp = (__ballot_sync(FULL, ok[u]) >> gshift) & (tpr == 32 ? 0xffffffffu : ((1u << tpr) - 1u));
+                if (live[u]) {
+                    if (grp) { if (r == __ffs(grp) - 1) a.Jidx[(item_off + c0 + kk[u]) * Nt + jt[u]] = I[u]; }
+                    else if (r == 0) s_q[cur ^ 1][atomicAdd(&s_n[cur ^ 1], 1)] = (uint16_t)entry[u];
+                }
             }
         }
         tries_done += tpr;
@@ -692,12 +725,14 @@ __global__ void __launch_bounds__(NT) paris_ar_kernel(KArgs a, int t, int ch) {
         cur ^= 1;
         __syncthreads();
     }
+    n_prop = warp_sum(n_prop);
+    if ((tid & 31) == 0) atomicAdd(a.counters + b * 16 + 1, n_prop);
     if (qlen > 0) {                                                  // leftovers -> exact sampler
         __shared__ int s_base;
-        if (tid == 0) s_base = atomicAdd(a.counters + b * 16, qlen);
+        if (tid == 0) { s_base = atomicAdd(a.counters + b * 16, qlen); atomicAdd(a.counters + b * 16 + 2, qlen); }
         __syncthreads();
         for (int e = tid; e < qlen; e += NT) {
-            const int entry = s_q[cur][e], k = entry / Nt, jt = entry - k * Nt;
+            const int entry = s_q[cur][e], k = entry >> 3, jt = entry & 7;
             a.Llist[0][item_off * Nt + s_base + e] = (c0 + k) * Nt + jt;
         }
     }
@@ -708,10 +743,13 @@ __global__ void __launch_bounds__(NT) paris_ar_kernel(KArgs a, int t, int ch) {
 // the per-parent keys with one FMA + one exp.  Pass 1 streams all parents (coalesced), keeping the total of every
 // 2048-parent segment; the segment holding the target is then re-scanned with warp prefix sums.
 constexpr int PSEG = 2048;
+// Round 2: a whole CTA per entry (warp w takes the segments w, w + 8, ...) instead of one warp per entry -- the leftover
+// lists are short (tens of entries per item), so one-warp-per-entry left 3/4 of the launched warps idle while a few ran
+// 512 dependent iterations each (ncu round 2: 89 us per step, issue active 12 %, warps active 26 %).
 template <class R, class Model>
 __global__ void __launch_bounds__(NT) paris_exact_kernel(KArgs a, int t) {
     constexpr int NX = Model::NX, NP = Model::NP, W = NX + NP;
-    __shared__ double s_seg[NWARP][MAX_Q * WT / PSEG];
+    __shared__ double s_seg[MAX_Q * WT / PSEG];
     const int b = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (t >= a.T_buf[b]) return;
     const int N = a.N, par = t & 1, Nt = a.Ntilde;
@@ -720,20 +758,18 @@ __global__ void __launch_bounds__(NT) paris_exact_kernel(KArgs a, int t) {
     const typename Model::template Theta<R> th = load_thc<R, Model>(a, b);
     const Vec4T<R>* pkey = reinterpret_cast<const Vec4T<R>*>(a.pkey) + item_off;
     const RngKey key = item_key(a, b);
-    const int nwarps = gridDim.x * NWARP, nseg = (N + PSEG - 1) / PSEG;
-    double* seg = s_seg[warp];
-    for (int e = blockIdx.x * NWARP + warp; e < count; e += nwarps) {
+    const int nseg = (N + PSEG - 1) / PSEG;
+    for (int e = blockIdx.x; e < count; e += gridDim.x) {
         const int entry = a.Llist[0][item_off * Nt + e];
         const int i = entry / Nt, jt = entry - i * Nt;
         R rn[W], bb, aa;
         load_rec<R, W>(a.rec[par ^ 1], a.tail[par ^ 1], item_off + i, rn);
         Model::pair_child(th, rn + NP, bb, aa);
-        double tot = 0.0;
-        for (int sg = 0; sg < nseg; ++sg) {
+        for (int sg = warp; sg < nseg; sg += NWARP) {
             R loc = (R)0;
             const int jend = min(N, (sg + 1) * PSEG);
             if (jend - sg * PSEG == PSEG) {
-                // full segment: 8 independent key loads in flight per lane (one entry alone is latency-bound otherwise)
+                // full segment: 8 independent key loads in flight per lane
 #pragma unroll 8
                 for (int j = sg * PSEG + lane; j < (sg + 1) * PSEG; j += 32) {
                     const Vec4T<R> pk = pkey[j];
@@ -746,31 +782,34 @@ __global__ void __launch_bounds__(NT) paris_exact_kernel(KArgs a, int t) {
                 }
             }
             const double st = warp_sum((double)loc);
-            if (lane == 0) seg[sg] = st;
-            tot += st;
+            if (lane == 0) s_seg[sg] = st;
         }
-        __syncwarp();
-        const uint4 raw = rng_raw(key, (uint32_t)i, (uint32_t)t, STREAM_EXACT, (uint32_t)jt);
-        double target = u01d(raw.x, raw.y) * tot;
-        if (!(target < tot)) target = tot * (1.0 - 1.2e-16);
-        // segment of the crossing (sequential over <= 512 segment totals, warp-uniform)
-        int sg = 0;
-        double run = 0.0;
-        while (sg < nseg - 1 && run + seg[sg] <= target) { run += seg[sg]; ++sg; }
-        int J = min(N, (sg + 1) * PSEG) - 1;                         // rounding guard: last parent of the segment
-        bool done = false;
-        const int jend = min(N, (sg + 1) * PSEG);
-        for (int j0 = sg * PSEG; j0 < jend && !done; j0 += 32) {
-            const int j = j0 + lane;
-            double w = 0.0;
-            if (j < jend) { const Vec4T<R> pk = pkey[j]; w = (double)Mth<R>::exp(bb * pk.x + pk.y + pk.z + aa); }
-            const double incl = warp_incl_scan(w);
-            const unsigned hit = __ballot_sync(FULL, (j < jend) && (run + incl > target));
-            if (hit) { J = j0 + __ffs(hit) - 1; done = true; }
-            run += __shfl_sync(FULL, incl, 31);
+        __syncthreads();
+        if (warp == 0) {
+            double tot = 0.0;
+            for (int sg = 0; sg < nseg; ++sg) tot += s_seg[sg];          // fixed order: independent of the warp schedule
+            const uint4 raw = rng_raw(key, (uint32_t)i, (uint32_t)t, STREAM_EXACT, (uint32_t)jt);
+            double target = u01d(raw.x, raw.y) * tot;
+            if (!(target < tot)) target = tot * (1.0 - 1.2e-16);
+            // segment of the crossing (sequential over <= 512 segment totals, warp-uniform)
+            int sg = 0;
+            double run = 0.0;
+            while (sg < nseg - 1 && run + s_seg[sg] <= target) { run += s_seg[sg]; ++sg; }
+            int J = min(N, (sg + 1) * PSEG) - 1;                         // rounding guard: last parent of the segment
+            bool done = false;
+            const int jend = min(N, (sg + 1) * PSEG);
+            for (int j0 = sg * PSEG; j0 < jend && !done; j0 += 32) {
+                const int j = j0 + lane;
+                double w = 0.0;
+                if (j < jend) { const Vec4T<R> pk = pkey[j]; w = (double)Mth<R>::exp(bb * pk.x + pk.y + pk.z + aa); }
+                const double incl = warp_incl_scan(w);
+                const unsigned hit = __ballot_sync(FULL, (j < jend) && (run + incl > target));
+                if (hit) { J = j0 + __ffs(hit) - 1; done = true; }
+                run += __shfl_sync(FULL, incl, 31);
+            }
+            if (lane == 0) a.Jidx[(item_off + i) * Nt + jt] = J;
         }
-        if (lane == 0) a.Jidx[(item_off + i) * Nt + jt] = J;
-        __syncwarp();
+        __syncthreads();
     }
 }
 

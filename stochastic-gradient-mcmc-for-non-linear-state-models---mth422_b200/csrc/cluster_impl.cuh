@@ -11,15 +11,18 @@ struct ClusterPlan { int C, nl; };
 
 // Smallest per-CTA share NL (= most SMs per item) such that a cluster of C <= 8 CTAs holds the item and all B clusters
 // are resident at once (one wave: the regime where a gradient is latency-, not throughput-bound).
-// Measured (SVM / LGSSM f32, one item, 60 steps): N = 2048 as 8 x 256: 0.24 ms (one CTA: 0.35 ms, tile kernels 0.72 ms);
-// N = 1000 as 4 x 256: 0.19 ms (one CTA: 0.18 ms); N = 8192 as 8 x 1024: 1.28 ms (tile kernels + CUDA graph: 0.55 ms).
-// The two random DSMEM reads per child (fine-CDF group, parent record) cost ~10-16 cycles of the SM's DSMEM port EACH
-// (they do not coalesce), i.e. time grows with the particles per CTA; so AUTO takes the cluster kernel only where the
-// item is spread thin (256 particles per CTA) and one SM is not enough (N > 1024).  `forced` (SGM_PATH_CLUSTER) takes any plan.
+// Measured (SVM f32, one item, 60 steps, ms per gradient; cluster / one CTA / tile kernels):
+//   N = 1000 (4 x 256): 0.177 / 0.163 / 0.71      N = 2048 (8 x 256): 0.218 / 0.338 / 0.71      N = 4096 (8 x 512): 0.476 / - / 0.65
+//   N = 8192 (8 x 1024): 1.27 / - / 0.75 (0.55 as a CUDA graph)      N = 16384 (8 x 2048): 1.60 / - / 0.75
+// The two random DSMEM reads per child (fine-CDF group, parent record) do not coalesce and cost ~10-16 cycles of the SM's
+// DSMEM port EACH, i.e. time grows with the particles per CTA (with barrier.cluster's release / acquire -- MEMBAR.ALL.GPU +
+// CCTL.IVALL in SASS -- replaced by relaxed arrive / wait the N = 1000 gradient is still 0.156 ms: the fences are ~12 %).  So
+// AUTO takes the cluster kernel where the item is spread thin (<= 512 particles per CTA) and one SM is not enough:
+// 1024 < N <= 4096.  `forced` (SGM_PATH_CLUSTER) takes any plan.
 inline bool cluster_plan(int N, int B, ClusterPlan& p, bool forced = true) {
-    if (N <= 256 || (!forced && (N <= 1024 || N > 2048))) return false;
+    if (N <= 256 || (!forced && (N <= 1024 || N > 4096))) return false;
     static const int NLS[4] = {256, 512, 1024, 2048};
-    for (int k = 0; k < (forced ? 4 : 1); ++k) {
+    for (int k = 0; k < (forced ? 4 : 2); ++k) {
         int C = 2;
         while (C * NLS[k] < N) C *= 2;
         if (C <= 8 && (int64_t)B * C <= 148) { p.C = C; p.nl = NLS[k]; return true; }

@@ -25,6 +25,40 @@ namespace cg = cooperative_groups;
 constexpr int CL_MAX_GW = 256;                    // warps per cluster (C * NTH / 32) the summary combine handles
 constexpr int CL_JMAX = CL_MAX_GW / 32;
 
+// ---- distributed shared memory, explicit PTX --------------------------------------------------------------------
+// cooperative_groups' cluster.sync() compiles to MEMBAR.ALL.GPU + CCTL.IVALL + UCGABAR (a GPU-scope fence and an L1
+// flush: ~1 us with remote stores in flight) and map_shared_rank() to generic LD.E / ST.E.  The time loop only exchanges
+// SHARED memory inside the cluster, so it uses the cluster barrier with release / acquire at cluster scope and
+// ld / st.shared::cluster on addresses mapped with `mapa`.
+__device__ __forceinline__ void cluster_barrier() {
+#ifdef SGM_CLUSTER_RELAXED      /* measurement only: no memory ordering, NOT a correct exchange */
+    asm volatile("barrier.cluster.arrive.relaxed.aligned;\n\tbarrier.cluster.wait.aligned;" ::: "memory");
+#else
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+#endif
+}
+__device__ __forceinline__ uint32_t dsmem_map(const void* local, int rank) {
+    const uint32_t a = (uint32_t)__cvta_generic_to_shared(local);
+    uint32_t r;
+    asm("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void dsmem_st(uint32_t addr, float v) { asm volatile("st.shared::cluster.f32 [%0], %1;" :: "r"(addr), "f"(v) : "memory"); }
+__device__ __forceinline__ void dsmem_st(uint32_t addr, double v) { asm volatile("st.shared::cluster.f64 [%0], %1;" :: "r"(addr), "d"(v) : "memory"); }
+__device__ __forceinline__ float dsmem_ld(uint32_t addr, float) { float v; asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory"); return v; }
+__device__ __forceinline__ double dsmem_ld(uint32_t addr, double) { double v; asm volatile("ld.shared::cluster.f64 %0, [%1];" : "=d"(v) : "r"(addr) : "memory"); return v; }
+__device__ __forceinline__ Vec4T<float> dsmem_ld4(uint32_t addr, float) {
+    Vec4T<float> v;
+    asm volatile("ld.shared::cluster.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ Vec4T<double> dsmem_ld4(uint32_t addr, double) {
+    Vec4T<double> v;
+    asm volatile("ld.shared::cluster.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr) : "memory");
+    asm volatile("ld.shared::cluster.v2.f64 {%0, %1}, [%2];" : "=d"(v.z), "=d"(v.w) : "r"(addr + 16) : "memory");
+    return v;
+}
+
 template <class R> __host__ __device__ inline size_t cluster_smem_bytes(int nl, int C, int nthreads, int nx, int np) {
     // coarse[C nl / 8] | fine[nl] | rec[2][nl] (16-byte records) | tail[2][KT][nl] | summaries[C NW][8]
     return sizeof(R) * ((size_t)C * nl / 8 + (size_t)nl * (size_t)(1 + 2 * 4 + 2 * (nx + np - 4)) + (size_t)C * (nthreads / 32) * SM_STRIDE);
@@ -77,14 +111,10 @@ __device__ void cluster_pf_item(const KArgs& a, int b, unsigned char* smem) {
         for (int q = 0; q < KT; ++q) tail0[(buf * KT + q) * NL + li] = r[4 + q];
     };
     auto load_remote = [&](int owner, int buf, int li, R* r) {       // DSMEM gather of a parent record
-        const Vec4T<R>* rr = cluster.map_shared_rank(rec0, owner);
-        const Vec4T<R> v = rr[buf * NL + li];
+        const Vec4T<R> v = dsmem_ld4(dsmem_map(rec0 + buf * NL + li, owner), (R)0);
         r[0] = v.x; r[1] = v.y; r[2] = v.z; r[3] = v.w;
-        if (KT > 0) {
-            const R* tt = cluster.map_shared_rank(tail0, owner);
 #pragma unroll
-            for (int q = 0; q < KT; ++q) r[4 + q] = tt[(buf * KT + q) * NL + li];
-        }
+        for (int q = 0; q < KT; ++q) r[4 + q] = dsmem_ld(dsmem_map(tail0 + (buf * KT + q) * NL + li, owner), (R)0);
     };
 
     R lw[PPT], sv[PPT][4];
@@ -151,11 +181,14 @@ __device__ void cluster_pf_item(const KArgs& a, int b, unsigned char* smem) {
             }
         }
         if (lane < C) {
-            R* p = cluster.map_shared_rank(summ, lane) + gw * SM_STRIDE;
-            p[0] = m; p[1] = s_w;
-            if (need_ws) { p[2] = wsum[0]; p[3] = wsum[1]; p[4] = wsum[2]; p[5] = wsum[3]; }
+            const uint32_t p = dsmem_map(summ + gw * SM_STRIDE, lane);
+            dsmem_st(p, m); dsmem_st(p + (uint32_t)sizeof(R), s_w);
+            if (need_ws) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) dsmem_st(p + (uint32_t)((2 + q) * sizeof(R)), wsum[q]);
+            }
         }
-        cluster.sync();                                                       // cluster barrier 1
+        cluster_barrier();                                                    // cluster barrier 1
         // ---- B: combine the GW warp summaries (lane l: warps l J .. l J + J - 1) ------------------------------
         R mloc = NEG_INF;
 #pragma unroll
@@ -210,10 +243,10 @@ __device__ void cluster_pf_item(const KArgs& a, int b, unsigned char* smem) {
             if (i < N) {
                 const R c = Mth<R>::fma(sc_me, pre[k], off_me);
                 fine[li] = c;
-                if ((i & 7) == 7) for (int r = 0; r < C; ++r) cluster.map_shared_rank(coarse, r)[i >> 3] = c;
+                if ((i & 7) == 7) for (int r = 0; r < C; ++r) dsmem_st(dsmem_map(coarse + (i >> 3), r), c);
             }
         }
-        cluster.sync();                                                       // cluster barrier 2
+        cluster_barrier();                                                    // cluster barrier 2
         // ---- C: resample -> propagate -> reweight -> statistic update ----------------------------------
         const R hs = (carries || filter) ? wt : (R)0;
         const int stat_kind = (in_sub && hs != (R)0) ? (FAST ? (int)SGM_STAT_SCORE : a.stat_kind) : (int)SGM_STAT_NONE;
@@ -241,8 +274,8 @@ __device__ void cluster_pf_item(const KArgs& a, int b, unsigned char* smem) {
                 if (coarse[g + step - 1] <= tg) g += step;
             g = min(g, g_last);
             const int owner = (g * 8) / NL, lo8 = (g * 8) % NL;
-            const R* rf = cluster.map_shared_rank(fine, owner) + lo8;
-            const Vec4T<R> f0 = reinterpret_cast<const Vec4T<R>*>(rf)[0], f1 = reinterpret_cast<const Vec4T<R>*>(rf)[1];
+            const uint32_t rf = dsmem_map(fine + lo8, owner);
+            const Vec4T<R> f0 = dsmem_ld4(rf, (R)0), f1 = dsmem_ld4(rf + (uint32_t)(4 * sizeof(R)), (R)0);
             int cnt = (f0.x <= tg) + (f0.y <= tg) + (f0.z <= tg) + (f0.w <= tg) + (f1.x <= tg) + (f1.y <= tg) + (f1.z <= tg) + (f1.w <= tg);
             int anc = min(g * 8 + cnt, N - 1);
             if (!(tg < total)) anc = N - 1;

@@ -288,7 +288,7 @@ __device__ __forceinline__ void init_body(const KArgs& a, int b, int g, R* s_tr)
                 Model::template load<R>(a.theta + (size_t)b * SGM_THETA_STRIDE);
             for (int q = 0; q < ACC_STRIDE; ++q) a.acc[(size_t)b * ACC_STRIDE + q] = 0.0;
             a.status[b] = 0;
-            if (a.counters) a.counters[b * 16] = 0;
+            if (a.counters) for (int q = 0; q < 16; ++q) a.counters[b * 16 + q] = 0;
         }
     }
     const int q_me = g * NWARP + warp;
@@ -367,6 +367,12 @@ __device__ __forceinline__ void header_finish(const KArgs& a, int b, int t_done,
         } else {
             for (int j = 0; j < 8; ++j) a.grad[(size_t)b * 8 + j] = 0.0;
             for (int j = 0; j < nstat; ++j) a.grad[(size_t)b * 8 + j] = (a.pf == SGM_PF_FILTER) ? acc[1 + j] : sbar[j];
+            if (a.pf == SGM_PF_PARIS && a.counters && a.rng_mode == SGM_RNG_PHILOX) {
+                // diagnostics of the device-random PaRIS sampler: accept-reject proposals made and entries that fell back to
+                // the exact sampler, summed over the item's time steps (slots 6, 7 of the row: never part of a statistic)
+                a.grad[(size_t)b * 8 + 6] = (double)a.counters[b * 16 + 1];
+                a.grad[(size_t)b * 8 + 7] = (double)a.counters[b * 16 + 2];
+            }
         }
     }
 }
@@ -758,7 +764,7 @@ __device__ __forceinline__ void step_body(const KArgs& a, int b, int t, int q_me
             } else {
                 draw_uniforms<R>(key, t, q_me, lane, u);
 #pragma unroll
-                for (int k = 0; k < KPT; ++k) u[k] = (8 * lane + k < n_valid) ? Mth<R>::log2(u[k]) : (R)0;
+                for (int k = 0; k < KPT; ++k) u[k] = (8 * lane + k < n_valid) ? Mth<R>::logb(u[k]) : (R)0;
             }
             R etot;
             lane_major_incl_scan<R>(u, etot);

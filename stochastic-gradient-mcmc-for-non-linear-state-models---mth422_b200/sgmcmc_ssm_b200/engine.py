@@ -117,10 +117,10 @@ def _state(device):
 
 def cluster_plan(N, B, forced=False):
     """Mirror of cluster_plan() in csrc/cluster_impl.cuh: (cluster size, particles per CTA) when a batch of B items with N
-    particles runs the thread-block-cluster kernel (path='auto': 1024 < N <= 2048 only; forced: path='cluster'), else None."""
-    if N <= 256 or (not forced and not 1024 < N <= 2048):
+    particles runs the thread-block-cluster kernel (path='auto': 1024 < N <= 4096 only; forced: path='cluster'), else None."""
+    if N <= 256 or (not forced and not 1024 < N <= 4096):
         return None
-    for nl in ((256, 512, 1024, 2048) if forced else (256,)):
+    for nl in ((256, 512, 1024, 2048) if forced else (256, 512)):
         C = 2
         while C * nl < N:
             C *= 2
@@ -265,7 +265,9 @@ class PFResult(object):
         B = self.B
         out = self._pin_out.numpy()
         gb = 8 * self.grad_slots                         # bytes of one row of `grad`
-        self.grad = out[:B * gb].view(np.float64).reshape(B, self.grad_slots)[:, :max(self.p, 0)].copy()
+        rows = out[:B * gb].view(np.float64).reshape(B, self.grad_slots)
+        self.grad = rows[:, :max(self.p, 0)].copy()
+        self.diag = rows[:, 6:8].copy() if self.grad_slots == 8 else None      # PaRIS (device randoms): proposals, exact fallbacks
         self.loglik = out[B * gb:B * (gb + 8)].view(np.float64).copy()
         self.status = out[B * (gb + 8):B * (gb + 12)].view(np.int32).copy()
         self._done = True

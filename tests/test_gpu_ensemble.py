@@ -25,8 +25,10 @@ def _make(kind, c):
     return LGSSMSampler(n=1, m=1, observations=rs.normal(size=(300, 1)), parameters=lgssm_params())
 
 
-KW = dict(seqsvm=dict(kind="pf", pf="poyiadjis_N", N=4000, subsequence_length=16, buffer_length=4, minibatch_size=2, num_sequences=2),
-          lgssm=dict(kind="pf", pf="poyiadjis_N", N=4000, subsequence_length=20, buffer_length=5, minibatch_size=3))
+# path='tiles': bit-for-bit reproducibility of an item across batch compositions holds within ONE kernel family -- with
+# path='auto' the family (cluster / shared-memory / tile kernels, each with its own random streams) follows the batch size
+KW = dict(seqsvm=dict(kind="pf", pf="poyiadjis_N", N=4000, subsequence_length=16, buffer_length=4, minibatch_size=2, num_sequences=2, path="tiles"),
+          lgssm=dict(kind="pf", pf="poyiadjis_N", N=4000, subsequence_length=20, buffer_length=5, minibatch_size=3, path="tiles"))
 
 
 def _vec(p):
