@@ -78,11 +78,12 @@ enum { SGM_N2_AUTO = 0, SGM_N2_FP32_PIPE = 1, SGM_N2_TENSOR = 2 };
 enum { SGM_VARIATES_NATIVE = 0, SGM_VARIATES_F32 = 1 };
 
 /* Kernel family of the O(N) smoothers.
- *   TILES   per-step warp-tile kernels streaming the particle arrays through HBM / L2 (any N; the throughput path)
+ *   TILES   warp-tile kernels streaming the particle arrays through HBM / L2 (any N; the throughput path): one header + one step
+ *           launch per time step, or ONE cooperative launch (grid barrier per step) when all CTAs of the batch are resident
  *   SMALL   one CTA per item, particle system resident in shared memory, whole time loop in one launch (N <= 2048)
  *   CLUSTER one thread-block cluster (2..8 CTAs) per item, particle system in distributed shared memory, whole time loop
  *           in one launch (256 < N <= 16384 and few enough items that all clusters are resident: items x CTAs <= 148)
- *   AUTO    CLUSTER for 1024 < N <= 4096 with items x CTAs <= 148 (<= 512 particles per CTA: where it wins), else
+ *   AUTO    CLUSTER for 1024 < N <= 2048 with items x CTAs <= 148 (256 particles per CTA: where it wins), else
  *           SMALL while the batch is small (N <= 512 or items x N <= 1.2e6), else TILES */
 enum { SGM_PATH_AUTO = 0, SGM_PATH_TILES = 1, SGM_PATH_SMALL = 2, SGM_PATH_CLUSTER = 3 };
 

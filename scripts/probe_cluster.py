@@ -8,9 +8,9 @@ rs = np.random.RandomState(0)
 th = [0.95, np.sqrt(2.0), 2.0, np.sqrt(2.0), 2.0]
 print("lib", os.environ.get("SGM_LIB_PATH", "default"))
 ref = {}
-for N in (1000, 2048, 4096, 8192, 16384):
+for N in (1000, 1500, 2048, 3000, 4096, 8192, 16384, 65536):
     for path in ("cluster", "small", "tiles"):
-        if path == "small" and N > 2048:
+        if (path == "small" and N > 2048) or (path == "cluster" and N > 16384):
             continue
         it = sg.PFItems()
         it.add(rs.normal(size=60) * 0.7, th, t1=10, tL=50, weights=np.ones(40) * 25.0, prior_mean=0.0, prior_var=10.0)

@@ -17,12 +17,13 @@ struct ClusterPlan { int C, nl; };
 // The two random DSMEM reads per child (fine-CDF group, parent record) do not coalesce and cost ~10-16 cycles of the SM's
 // DSMEM port EACH, i.e. time grows with the particles per CTA (with barrier.cluster's release / acquire -- MEMBAR.ALL.GPU +
 // CCTL.IVALL in SASS -- replaced by relaxed arrive / wait the N = 1000 gradient is still 0.156 ms: the fences are ~12 %).  So
-// AUTO takes the cluster kernel where the item is spread thin (<= 512 particles per CTA) and one SM is not enough:
-// 1024 < N <= 4096.  `forced` (SGM_PATH_CLUSTER) takes any plan.
+// AUTO takes the cluster kernel where the item is spread thin (256 particles per CTA) and one SM is not enough:
+// 1024 < N <= 2048; from N = 4096 on the cooperative single-launch form of the tile kernels (coop_kernels.cuh) is faster
+// (N = 4096, one item: 0.41 ms against 0.48 ms).  `forced` (SGM_PATH_CLUSTER) takes any plan.
 inline bool cluster_plan(int N, int B, ClusterPlan& p, bool forced = true) {
-    if (N <= 256 || (!forced && (N <= 1024 || N > 4096))) return false;
+    if (N <= 256 || (!forced && (N <= 1024 || N > 2048))) return false;
     static const int NLS[4] = {256, 512, 1024, 2048};
-    for (int k = 0; k < (forced ? 4 : 2); ++k) {
+    for (int k = 0; k < (forced ? 4 : 1); ++k) {
         int C = 2;
         while (C * NLS[k] < N) C *= 2;
         if (C <= 8 && (int64_t)B * C <= 148) { p.C = C; p.nl = NLS[k]; return true; }

@@ -383,7 +383,7 @@ __device__ __forceinline__ void header_finish(const KArgs& a, int b, int t_done,
 // kernel: no barrier and no global round trip between header and step; the copies are bit-identical -- same inputs,
 // counter-based Gamma draws, fixed shuffle trees); only the first warp applies the side effects.
 template <class R, class Model>
-__device__ __forceinline__ void header_warp(const KArgs& a, int b, int t, int final_pass, double* local = nullptr) {
+__device__ __forceinline__ void header_warp(const KArgs& a, int b, int t, int final_pass, double* local = nullptr, bool side = true) {
     if (!local && threadIdx.x >= 32) return;
     const int lane = threadIdx.x & 31;
     const int Tb = a.T_buf[b];
@@ -418,18 +418,22 @@ __device__ __forceinline__ void header_warp(const KArgs& a, int b, int t, int fi
         if (lane <= Q) gam[lane] = (gincl - g) * kk;
         if (lane == 0) gam[Q + 1] = total;
     }
-    if (lane == 0) header_finish<Model>(a, b, t_done, final_pass, nstat, M, total, sbar, base, off, !local || threadIdx.x < 32);
+    if (lane == 0) header_finish<Model>(a, b, t_done, final_pass, nstat, M, total, sbar, base, off, side && (!local || threadIdx.x < 32));
     if (local) __syncwarp();
 }
 
 // NTH = threads of the CTA: 256, or 1024 for items with more than 256 tiles (N > 65536), where the per-thread chunk of
 // tiles (and with it the serial part of the scans) shrinks 4x.
 template <class R, class Model, int NTH = NT>
-__device__ __forceinline__ void header_body(const KArgs& a, int b, int t, int final_pass, double* sh_d) {
+__device__ __forceinline__ void header_body(const KArgs& a, int b, int t, int final_pass, double* sh_d, double* local = nullptr,
+                                            bool side = true) {
+    // `local` != nullptr: the header goes to that (shared-memory) copy instead of the item's global one -- the cooperative
+    // kernel lets every CTA of an item build its own; `side` = this caller applies the log-likelihood / status / output
+    // side effects (exactly one CTA per item may)
     const int tid = threadIdx.x;
     const int Tb = a.T_buf[b];
     if (!final_pass && t >= Tb) return;
-    if (a.Q < 32) { header_warp<R, Model>(a, b, t, final_pass); return; }
+    if (a.Q < 32) { if (!local || tid < 32) header_warp<R, Model>(a, b, t, final_pass, local, side); return; }
     const int par = final_pass ? (Tb & 1) : (t & 1);
     const int t_done = final_pass ? Tb - 1 : t - 1;
     const int Q = a.Q, N = a.N;
@@ -437,7 +441,7 @@ __device__ __forceinline__ void header_body(const KArgs& a, int b, int t, int fi
     const bool shrink = (a.pf == SGM_PF_NEMETH) && (a.lambduh != 1.0);
     const int nws = (final_pass || shrink || a.pf == SGM_PF_FILTER) ? nstat : 0;
     const double* sub = a.sub[par] + (size_t)b * Q * SSTRIDE;
-    double* base = a.hdr + (size_t)b * hdr_stride(Q);
+    double* base = local ? local : a.hdr + (size_t)b * hdr_stride(Q);
     double* off = base + H_SCALARS;
     double* sc = off + (Q + 2);
     double* gam = sc + (Q + 2);
@@ -492,7 +496,7 @@ __device__ __forceinline__ void header_body(const KArgs& a, int b, int t, int fi
         }
         if (tid == 0) gam[Q + 1] = total;
     }
-    if (tid == 0) header_finish<Model>(a, b, t_done, final_pass, nstat, M, total, sbar, base, off);
+    if (tid == 0) header_finish<Model>(a, b, t_done, final_pass, nstat, M, total, sbar, base, off, side);
 }
 
 template <class R, class Model, int NTH = NT>

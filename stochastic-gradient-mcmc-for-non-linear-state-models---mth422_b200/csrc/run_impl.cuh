@@ -4,6 +4,8 @@
 #include <type_traits>
 #include "host_common.cuh"
 #include "sgld_kernels.cuh"
+#include "coop_kernels.cuh"
+#include <stdlib.h>
 
 namespace sgmhost {
 
@@ -108,6 +110,35 @@ inline int make_kargs(const sgm_pf_desc* d, KArgs& a) {
     return SGM_OK;
 }
 
+// ---- cooperative single-launch form of the tile kernels (coop_kernels.cuh) ------------------------------------------
+template <class K>
+bool launch_coop_kernel(K kern, const KArgs& a, cudaStream_t stream) {
+    const size_t dyn = hdr_stride(a.Q) * sizeof(double);
+    static thread_local int per_sm = -1;                 // per instantiation: co-resident CTAs per SM at the largest header
+    if (per_sm < 0) {
+        int n = 0;
+        const size_t dyn_max = hdr_stride(COOP_MAX_Q) * sizeof(double);       // + 32 KB static: above the 48 KB default limit
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_max) != cudaSuccess ||
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kern, NT, dyn_max) != cudaSuccess) { cudaGetLastError(); n = 0; }
+        per_sm = n;
+    }
+    int dev = 0, sms = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if ((int64_t)a.G * a.B > (int64_t)per_sm * sms) return false;
+    KArgs args = a;
+    void* params[1] = {&args};
+    if (cudaLaunchCooperativeKernel((const void*)kern, dim3(a.G, a.B), dim3(NT), params, dyn, stream) != cudaSuccess) { cudaGetLastError(); return false; }
+    return true;
+}
+template <class R, class Model>
+bool launch_coop(const sgm_pf_desc* d, const KArgs& a, int fm, cudaStream_t stream) {
+    if (fm == FM_POY) return (a.N % WT == 0) ? launch_coop_kernel(pf_coop_kernel<R, Model, true, FM_POY, false>, a, stream)
+                                             : launch_coop_kernel(pf_coop_kernel<R, Model, true, FM_POY, true>, a, stream);
+    if (d->resample == SGM_RESAMPLE_MULTINOMIAL) return launch_coop_kernel(pf_coop_kernel<R, Model, false, FM_GENERIC, false>, a, stream);
+    return launch_coop_kernel(pf_coop_kernel<R, Model, true, FM_GENERIC, false>, a, stream);
+}
+
 template <class R, class Model>
 int run_impl(const sgm_pf_desc* d, cudaStream_t stream) {
     KArgs a;
@@ -177,6 +208,19 @@ int run_impl(const sgm_pf_desc* d, cudaStream_t stream) {
             if (d->resample == SGM_RESAMPLE_MULTINOMIAL) pf_step_kernel<R, Model, false><<<gh, bs, 0, sh[h]>>>(ah[h], t);
             else pf_step_kernel<R, Model, true><<<gh, bs, 0, sh[h]>>>(ah[h], t);
         };
+        // few items (every CTA of the batch resident at once, at most one CTA per SM): the whole time loop in ONE
+        // cooperative launch, grid barrier instead of the kernel boundary; same arithmetic, bit-identical results
+        static const bool no_coop = getenv("SGM_NO_COOP") != nullptr;            // A/B switch for the benches
+        // (Q <= 256: above that the per-step path builds its headers with 1024 threads, i.e. another summation order)
+        const bool coop_ok = !no_coop && !piped && !backward_pf(d->pf) && !pred && a.Q <= NT && a.max_T > 0 &&
+                             (int64_t)a.G * a.B <= 148;
+        bool done_coop = false;
+        if (coop_ok) {
+            if (d->ev_steps_begin) cudaEventRecord(reinterpret_cast<cudaEvent_t>(d->ev_steps_begin), stream);
+            done_coop = launch_coop<R, Model>(d, a, fm == FM_POY ? FM_POY : FM_GENERIC, stream);
+            if (done_coop) { ++launches; if (d->ev_steps_end) cudaEventRecord(reinterpret_cast<cudaEvent_t>(d->ev_steps_end), stream); }
+        }
+        if (!done_coop) {
         for (int h = 0; h < nh; ++h) { pf_init_kernel<R, Model><<<dim3(a.G, nb[h]), block, 0, sh[h]>>>(ah[h]); ++launches; }
         if (d->ev_steps_begin) cudaEventRecord(reinterpret_cast<cudaEvent_t>(d->ev_steps_begin), stream);
         for (int t = 0; t < a.max_T; ++t) {
@@ -194,6 +238,7 @@ int run_impl(const sgm_pf_desc* d, cudaStream_t stream) {
             cudaStreamWaitEvent(stream, reinterpret_cast<cudaEvent_t>(d->ev_aux_join), 0);
         }
         if (d->ev_steps_end) cudaEventRecord(reinterpret_cast<cudaEvent_t>(d->ev_steps_end), stream);
+        }
     }
     if (d->out_x || d->out_lw || d->out_stats) {
         pf_export_kernel<R, Model><<<dim3((a.N + NT - 1) / NT, a.B), block, 0, stream>>>(a); ++launches;

@@ -117,10 +117,10 @@ def _state(device):
 
 def cluster_plan(N, B, forced=False):
     """Mirror of cluster_plan() in csrc/cluster_impl.cuh: (cluster size, particles per CTA) when a batch of B items with N
-    particles runs the thread-block-cluster kernel (path='auto': 1024 < N <= 4096 only; forced: path='cluster'), else None."""
-    if N <= 256 or (not forced and not 1024 < N <= 4096):
+    particles runs the thread-block-cluster kernel (path='auto': 1024 < N <= 2048 only; forced: path='cluster'), else None."""
+    if N <= 256 or (not forced and not 1024 < N <= 2048):
         return None
-    for nl in ((256, 512, 1024, 2048) if forced else (256, 512)):
+    for nl in ((256, 512, 1024, 2048) if forced else (256,)):
         C = 2
         while C * nl < N:
             C *= 2
@@ -480,15 +480,16 @@ class PreparedPF(object):
 
     # ---- CUDA-graph replay for launch-bound batches ----------------------------------------------------------
     def graph_eligible(self):
-        """2 * max_T + 2 tiny launches per call: worth a graph when the whole batch is at most one wave of CTAs and the
-        item does not already run in the single-launch kernel (N <= 2048).  Device randoms only (a graph bakes the
+        """2 * max_T + 2 (+ backward kernels) tiny launches per call: worth a graph when the whole batch is at most one wave of
+        CTAs and the call is not a single launch anyway (shared-memory / cluster / cooperative kernels of the O(N) smoothers).  Device randoms only (a graph bakes the
         kernel arguments in; the Philox call offset is then read from device memory, sgm_pf_desc.offset_dev)."""
         d = self.desc
         if not config.cuda_graphs or d.rng_mode != nat.RNG["philox"] or self.extra or self.N <= 2048:
             return False
-        if d.path in (nat.PATH["auto"], nat.PATH["cluster"]) and d.pf in (nat.PF["nemeth"], nat.PF["filter"]) and \
-                d.stat_kind != nat.STAT["pred"] and cluster_plan(self.N, self.B, d.path == nat.PATH["cluster"]) is not None:
-            return False                       # one cluster launch runs the whole time loop: nothing to put into a graph
+        if d.pf in (nat.PF["nemeth"], nat.PF["filter"]) and d.stat_kind != nat.STAT["pred"] and self.N <= 65536:
+            # the O(N) smoothers run such a batch in ONE launch (cluster kernel or the cooperative form of the tile kernels,
+            # csrc/coop_kernels.cuh): nothing to put into a graph
+            return False
         return self.B * ((self.N + 2047) // 2048) <= 148
 
     def _graph_key(self):
