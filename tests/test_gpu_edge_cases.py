@@ -66,6 +66,25 @@ def test_degenerate_weights_raise_like_the_reference():
     assert res.status[0] != 0 and res.status[1] == 0 and np.all(np.isfinite(res.grad[1]))
 
 
+def test_injected_uniforms_default_to_the_generic_search_and_sorted_modes_need_ascending_uniforms():
+    """Recorded uniforms come in the reference's iid order: with rng='injected' the resampling mode defaults to 'multinomial'
+    (per-child search); the streaming modes stage a CDF window from a tile's first and last target only, so unsorted
+    uniforms are refused instead of silently clamped (N > 256: more than one tile)."""
+    import sgmcmc_ssm_b200 as sg
+    N, obs = 700, np.array([0.3, -1.2, 0.8, 2.0])
+    K = po.make_kernel("svm", "prior", THETA)
+    rec = po.LegacyStream(5, record=True)
+    ref = po.buffered_pf("poyiadjis_N", obs, K, N, K.score, K.p, rec, t1=0, tL=4, prior_mean=0.0, prior_var=10.0)
+    parts = po.split_events(rec.events, N)
+    inj = dict(z0=parts["z0"], u=parts["u"], z=parts["z"])
+    items = sg.PFItems().add(obs, TH, prior_mean=0.0, prior_var=10.0)
+    for path in ("tiles", "small", "cluster"):
+        res = sg.run_pf("svm", "prior", "poyiadjis_N", items, N, dtype="f64", rng="injected", injected=inj, path=path)   # no resample= given
+        np.testing.assert_allclose(res.grad[0], po.average_statistic(ref), rtol=1e-8, atol=1e-9)
+    with pytest.raises(ValueError, match="ascending"):
+        sg.run_pf("svm", "prior", "poyiadjis_N", items, N, dtype="f64", rng="injected", injected=inj, resample="multinomial_sorted")
+
+
 def test_invalid_arguments():
     import sgmcmc_ssm_b200 as sg
     items = sg.PFItems().add(np.array([0.3, 0.2]), TH)

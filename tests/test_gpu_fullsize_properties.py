@@ -9,7 +9,8 @@ of (observations, theta, prior), so:
   * shard invariance: a batch run in one call == the same items run as two calls with item_id_base (what the
                      multi-GPU sharding does), bit for bit;
   * stream invariance: the two-stream pipelining of half batches is bit-identical to the single-stream run;
-  * consistency    : f32 and f64 batch-mean gradients agree within Monte-Carlo error at N = 2^16;
+  * consistency    : f32 and f64 gradients of the same 512 windows agree within the standard error of their paired
+                     differences at N = 2^16;
   * N = 2^20       : the largest supported particle count runs and agrees with N = 2^16 on the log-likelihood."""
 import numpy as np
 import pytest
@@ -115,16 +116,26 @@ def test_shared_memory_kernel_and_tile_kernels_have_the_same_law(N, dtype):
     assert np.all(np.abs(ga.std(axis=0) / gb.std(axis=0) - 1) < 0.15), (ga.std(axis=0), gb.std(axis=0))
 
 
-def test_f32_and_f64_agree_within_monte_carlo_error_at_full_size():
+@pytest.mark.parametrize("variates", ["native", "f32"])
+def test_f32_and_f64_agree_within_standard_error_at_full_size(variates):
+    """N = 2^16, the SAME 512 heterogeneous windows in f32 and in f64 (independent random streams).  Paired differences
+    d_i = g32_i - g64_i have mean zero iff the two arithmetic types estimate the same quantity; with 512 items the mean of
+    d is resolved to std(d) / sqrt(512), i.e. a bias of ~4 % of ONE item's Monte-Carlo standard deviation -- or of 0.2 % of
+    a gradient component's typical size -- fails:   |mean d| <= 4.5 std(d) / sqrt(512)  per gradient component and for the
+    log-likelihood, and the spreads of the two samples agree within 15 %."""
     import sgmcmc_ssm_b200 as sg
-    it = _items(32, seed=11)
+    B = 512
+    it = _items(B, seed=11)
     a = sg.run_pf("svm", "prior", "poyiadjis_N", it, N16, dtype="f32", seed=1, offset=1)
-    b = sg.run_pf("svm", "prior", "poyiadjis_N", it, N16, dtype="f64", seed=2, offset=1)
-    # log-likelihood: ~40 weighted increments, each with Monte-Carlo error ~ cv / sqrt(N) ~ 1e-2 -> ~0.1 absolute
-    # (observed max 0.17 between two independent runs); a broken weight path is off by O(10)
-    np.testing.assert_allclose(a.loglik, b.loglik, rtol=0, atol=0.6)
-    spread = np.abs(b.grad - b.grad.mean(axis=0)).mean(axis=0) + 1.0
-    assert np.all(np.abs(a.grad.mean(axis=0) - b.grad.mean(axis=0)) <= 0.5 * spread)
+    b = sg.run_pf("svm", "prior", "poyiadjis_N", it, N16, dtype="f64", seed=2, offset=1, variates=variates)
+    c = sg.run_pf("svm", "prior", "poyiadjis_N", it, N16, dtype="f32", seed=3, offset=1)      # a second f32 draw: the noise floor
+    ga, gb, gc = (np.column_stack([r.grad, r.loglik]) for r in (a, b, c))
+    d = ga - gb
+    se = d.std(axis=0, ddof=1) / np.sqrt(B)
+    assert np.all(np.abs(d.mean(axis=0)) <= 4.5 * se), (d.mean(axis=0), se)
+    # the f32-f64 differences are no wider than the differences between two f32 runs (pure Monte-Carlo noise)
+    ratio = d.std(axis=0, ddof=1) / (ga - gc).std(axis=0, ddof=1)
+    assert np.all(np.abs(ratio - 1) < 0.15), ratio
 
 
 def test_largest_particle_count_runs_and_agrees():
