@@ -28,8 +28,8 @@ enum : uint32_t { STREAM_SMALL = 9 };
 constexpr int SM_STRIDE = 8;          // R values per warp summary: m, s, ws[0..3]
 
 template <class R> __host__ __device__ inline size_t small_smem_bytes(int npad, int nx, int np) {
-    // cdf | rec[2] (16-byte records) | tail[2][KT] | warp summaries
-    return sizeof(R) * ((size_t)npad * (size_t)(1 + 2 * 4 + 2 * (nx + np - 4)) + 32 * SM_STRIDE);
+    // cdf | sampled CDF levels (npad / 2) | rec[2] (16-byte records) | tail[2][KT] | warp summaries
+    return sizeof(R) * ((size_t)npad * (size_t)(1 + 2 * 4 + 2 * (nx + np - 4)) + (size_t)npad / 2 + 32 * SM_STRIDE);
 }
 
 // u[PPT] uniforms and z[PPT] standard normals of thread `tid` at `step`
@@ -56,14 +56,60 @@ template <int PPT> __device__ __forceinline__ void small_draw(const RngKey& key,
     }
 }
 
-// PPT interleaved branch-free binary searches over a power-of-two CDF kept as shared-memory byte addresses
-template <class R, int PPT, int STEP>
-__device__ __forceinline__ void small_search(uint32_t* ad, const R* tg) {
-    if constexpr (STEP > 0) {
+// ---- 4-ary search on sampled copies of the CDF ---------------------------------------------------------------------
+// ncu (round 2): half of the shared-memory kernel's stall samples sat on the 10 dependent LDS of the binary search.  The CDF
+// is therefore kept with sampled copies  L1[j] = cdf[4 j + 3], L2[j] = cdf[16 j + 15], ...  down to a top level of 4 or 8
+// entries; a search reads ONE 16-byte group per level (5 dependent loads for 1024 entries instead of 10) and counts the
+// entries <= target among its first three (the fourth is the parent level's entry, already known to exceed the target).
+// Entries beyond N are +inf on every level.  Same result as searchsorted(cdf, target, 'right').
+__host__ __device__ constexpr int samp_off(int npad, int sz) {      // offset of the level with `sz` entries inside the sampled area
+    int off = 0;
+    for (int s = npad / 4; s > sz; s /= 4) off += s;
+    return off;
+}
+__host__ __device__ constexpr int samp_top(int npad) {               // size of the top level: 4 or 8
+    int s = npad / 4;
+    while (s > 8) s /= 4;
+    return s;
+}
+template <class R> __device__ __forceinline__ int count3(const Vec4T<R>& v, R tg) { return (v.x <= tg) + (v.y <= tg) + (v.z <= tg); }
+template <class R, int PPT, int NPAD, int SZ>
+__device__ __forceinline__ void samp_descend(const R* cdf, const R* samp, const R* tg, int* pos) {
+    // pos[k] = group index at the level with SZ entries (or the CDF itself when SZ == NPAD)
+    const R* lvl = (SZ == NPAD) ? cdf : samp + samp_off(NPAD, SZ);
 #pragma unroll
-        for (int k = 0; k < PPT; ++k)
-            if (lds_at<(STEP - 1) * (int)sizeof(R)>(ad[k], (R)0) <= tg[k]) ad[k] += STEP * (int)sizeof(R);
-        small_search<R, PPT, STEP / 2>(ad, tg);
+    for (int k = 0; k < PPT; ++k) {
+        const Vec4T<R> v = reinterpret_cast<const Vec4T<R>*>(lvl)[pos[k]];
+        pos[k] = 4 * pos[k] + count3(v, tg[k]);
+    }
+    if constexpr (SZ < NPAD) samp_descend<R, PPT, NPAD, SZ * 4>(cdf, samp, tg, pos);
+}
+template <class R, int PPT, int NPAD>
+__device__ __forceinline__ void samp_search(const R* cdf, const R* samp, const R* tg, int* anc) {
+    constexpr int TOP = samp_top(NPAD);
+    const R* top = samp + samp_off(NPAD, TOP);
+#pragma unroll
+    for (int k = 0; k < PPT; ++k) {
+        const Vec4T<R> v0 = reinterpret_cast<const Vec4T<R>*>(top)[0];
+        int c = count3(v0, tg[k]);
+        if (TOP == 8) {
+            const Vec4T<R> v1 = reinterpret_cast<const Vec4T<R>*>(top)[1];
+            c += (v0.w <= tg[k]) + count3(v1, tg[k]);
+        }
+        anc[k] = c;
+    }
+    samp_descend<R, PPT, NPAD, TOP * 4>(cdf, samp, tg, anc);
+}
+// store CDF entry i and its sampled copies
+template <class R, int NPAD>
+__device__ __forceinline__ void samp_store(R* cdf, R* samp, int i, R c) {
+    cdf[i] = c;
+    int sz = NPAD / 4, off = 0, sh = 2;
+#pragma unroll
+    for (; sz >= 4; sz /= 4, sh += 2) {
+        if ((i & ((1 << sh) - 1)) == (1 << sh) - 1) samp[off + (i >> sh)] = c;
+        off += sz;
+        if (sz <= 8) break;
     }
 }
 
@@ -84,7 +130,8 @@ __device__ void small_pf_item(const KArgs& a, int b, unsigned char* smem) {
     const bool tracing = !FAST && (a.trace_anc || a.trace_x || a.trace_lw);
     const bool var32 = sizeof(R) == 8 && a.variates32 && !injected;
     R* const cdf = reinterpret_cast<R*>(smem);
-    Vec4T<R>* const rec0 = reinterpret_cast<Vec4T<R>*>(cdf + NPAD);
+    R* const samp = cdf + NPAD;                        // sampled CDF levels (NPAD / 2 entries reserved)
+    Vec4T<R>* const rec0 = reinterpret_cast<Vec4T<R>*>(samp + NPAD / 2);
     R* const tail0 = reinterpret_cast<R*>(rec0 + 2 * NPAD);
     R* const summ = tail0 + 2 * NPAD * KT;
     const typename Model::template Theta<R> th = Model::template load<R>(a.theta + (size_t)b * SGM_THETA_STRIDE);
@@ -131,6 +178,7 @@ __device__ void small_pf_item(const KArgs& a, int b, unsigned char* smem) {
             lw[k] = (i < N) ? (R)0 : NEG_INF;
             sv[k][0] = sv[k][1] = sv[k][2] = sv[k][3] = (R)0;
             cdf[i] = Mth<R>::inf();                       // entries >= N stay +inf: the searches need no bound check
+            if (i < NPAD / 2) samp[i] = Mth<R>::inf();
             if (i < N) {
                 if (injected) z[k] = (R)a.inj_z0[item_off + i];
                 R r[W];
@@ -157,6 +205,20 @@ __device__ void small_pf_item(const KArgs& a, int b, unsigned char* smem) {
         const bool in_sub = !final_pass && t >= t1 && t < tL;
         const R y = final_pass ? (R)0 : (R)obs[t];
         const R wt = in_sub ? (R)(wts ? wts[t - t1] : 1.0) : (R)0;
+        // this step's random numbers do not depend on the weights: drawn here, in the same basic block as phase A, so that
+        // the Philox rounds and the Box-Muller transforms interleave with the max / exp / scan chain below (a step of this
+        // kernel is a chain of dependent latencies on 4 warps per scheduler, not a throughput problem)
+        R u[PPT], z[PPT];
+        if (!injected && !final_pass) {
+            draw((uint32_t)t, u, z);
+            if (!FAST && a.resample == SGM_RESAMPLE_SYSTEMATIC) {
+                R u4[4];
+                if (var32) { float f4[4]; rng_uniform4(key, 0u, (uint32_t)t, STREAM_GAMMA, f4); u4[0] = (R)f4[0]; }
+                else rng_uniform4(key, 0u, (uint32_t)t, STREAM_GAMMA, u4);
+#pragma unroll
+                for (int k = 0; k < PPT; ++k) u[k] = u4[0];
+            }
+        }
         // ---- A: warp summary --------------------------------------------------------------------------
         R m = NEG_INF;
 #pragma unroll
@@ -225,42 +287,29 @@ __device__ void small_pf_item(const KArgs& a, int b, unsigned char* smem) {
 #pragma unroll
         for (int k = 0; k < PPT; ++k) {
             const int i = tid * PPT + k;
-            if (i < N) cdf[i] = Mth<R>::fma(sc_me, pre[k], off_me);
+            if (i < N) samp_store<R, NPAD>(cdf, samp, i, Mth<R>::fma(sc_me, pre[k], off_me));
         }
         __syncthreads();                                                      // barrier 2
         // ---- C: resample -> propagate -> reweight -> statistic update ----------------------------------
         const R hs = (carries || filter) ? wt : (R)0;
         const int stat_kind = (in_sub && hs != (R)0) ? (FAST ? (int)SGM_STAT_SCORE : a.stat_kind) : (int)SGM_STAT_NONE;
-        R u[PPT], z[PPT];
-        if (!injected) {
-            draw((uint32_t)t, u, z);
-            if (!FAST && a.resample == SGM_RESAMPLE_SYSTEMATIC) {
-                R u4[4];
-                if (var32) { float f4[4]; rng_uniform4(key, 0u, (uint32_t)t, STREAM_GAMMA, f4); u4[0] = (R)f4[0]; }
-                else rng_uniform4(key, 0u, (uint32_t)t, STREAM_GAMMA, u4);
-#pragma unroll
-                for (int k = 0; k < PPT; ++k) u[k] = u4[0];
-            }
-        }
         const R cmax = cdf[N - 1];
         R tg[PPT];
-        uint32_t ad[PPT];
-        const uint32_t ad0 = (uint32_t)__cvta_generic_to_shared(cdf);
+        int ancs[PPT];
+        bool over[PPT];
 #pragma unroll
         for (int k = 0; k < PPT; ++k) {
             const int i = tid * PPT + k;
             if (injected) { u[k] = (i < N) ? (R)a.inj_u[((size_t)b * a.max_T + t) * N + i] : (R)0; z[k] = (i < N) ? (R)a.inj_z[((size_t)b * a.max_T + t) * N + i] : (R)0; }
             tg[k] = strat ? (((R)i + u[k]) / (R)N) * total : u[k] * total;
-            ad[k] = ad0;
+            over[k] = !(tg[k] < cmax);                         // u * total rounded up to the total (or a NaN weight)
         }
         // searchsorted(cdf, target, 'right') = number of entries <= target (entries >= N are +inf)
-        small_search<R, PPT, NPAD / 2>(ad, tg);
+        samp_search<R, PPT, NPAD>(cdf, samp, tg, ancs);
 #pragma unroll
         for (int k = 0; k < PPT; ++k) {
             const int i = tid * PPT + k;
-            int anc = (int)((ad[k] - ad0) / (uint32_t)sizeof(R));
-            if (!(tg[k] < cmax)) anc = N - 1;                  // u * total rounded up to the total (or a NaN weight)
-            anc = min(anc, N - 1);
+            const int anc = over[k] ? N - 1 : min(ancs[k], N - 1);
             lw[k] = NEG_INF;
             if (i < N) {
                 R ra[W], rn[W];
