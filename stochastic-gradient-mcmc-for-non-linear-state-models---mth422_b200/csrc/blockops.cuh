@@ -32,6 +32,13 @@ template <class T> __device__ __forceinline__ T warp_max(T v) {
     for (int d = 16; d > 0; d >>= 1) v = nan_max(v, __shfl_xor_sync(FULL, v, d));
     return v;
 }
+// f32: sm_100a reduces a float max over the warp in ONE instruction (CREDUX.MAX.F32, NaNs dropped like fmaxf) instead of five
+// dependent shuffle + FMNMX pairs.  Called by all 32 lanes, converged.
+template <> __device__ __forceinline__ float warp_max<float>(float v) {
+    float r;
+    asm volatile("redux.sync.max.f32 %0, %1, 0xffffffff;" : "=f"(r) : "f"(v));
+    return r;
+}
 
 // Block max.  `sh` needs NW elements.  Result valid in all threads.
 template <int NW = NWARP, class T> __device__ __forceinline__ T block_max(T v, T* sh) {

@@ -72,33 +72,78 @@ __host__ __device__ constexpr int samp_top(int npad) {               // size of 
     while (s > 8) s /= 4;
     return s;
 }
-template <class R> __device__ __forceinline__ int count3(const Vec4T<R>& v, R tg) { return (v.x <= tg) + (v.y <= tg) + (v.z <= tg); }
+// Searches run on shared-memory BYTE addresses: with  ad = base + OFF(level) + 16 g  the group of the next level is at
+// 4 ad + K + 16 #{entries <= target},  K a per-level constant; nvcc turns this into one LEA and three predicated adds.
+__device__ __forceinline__ Vec4T<float> lds_group(uint32_t ad, float) {
+    Vec4T<float> v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(ad));
+    return v;
+}
+__device__ __forceinline__ Vec4T<double> lds_group(uint32_t ad, double) {
+    Vec4T<double> v;
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(ad));
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2+16];" : "=d"(v.z), "=d"(v.w) : "r"(ad));
+    return v;
+}
+template <class R, int NPAD> __host__ __device__ constexpr int samp_level_bytes(int sz) {      // byte offset of a level from the CDF
+    return sz == NPAD ? 0 : (NPAD + samp_off(NPAD, sz)) * (int)sizeof(R);
+}
 template <class R, int PPT, int NPAD, int SZ>
-__device__ __forceinline__ void samp_descend(const R* cdf, const R* samp, const R* tg, int* pos) {
-    // pos[k] = group index at the level with SZ entries (or the CDF itself when SZ == NPAD)
-    const R* lvl = (SZ == NPAD) ? cdf : samp + samp_off(NPAD, SZ);
+__device__ __forceinline__ void samp_descend(uint32_t base, const R* tg, uint32_t* ad) {
+    constexpr int GB = 4 * (int)sizeof(R);
+    if constexpr (SZ == NPAD) {                        // the CDF itself: ad becomes sizeof(R) * searchsorted index
 #pragma unroll
-    for (int k = 0; k < PPT; ++k) {
-        const Vec4T<R> v = reinterpret_cast<const Vec4T<R>*>(lvl)[pos[k]];
-        pos[k] = 4 * pos[k] + count3(v, tg[k]);
+        for (int k = 0; k < PPT; ++k) {
+            const Vec4T<R> v = lds_group(ad[k], (R)0);
+            uint32_t n = ad[k] - base;
+            if (v.x <= tg[k]) n += (uint32_t)sizeof(R);
+            if (v.y <= tg[k]) n += (uint32_t)sizeof(R);
+            if (v.z <= tg[k]) n += (uint32_t)sizeof(R);
+            ad[k] = n;
+        }
+    } else {
+        const uint32_t K = (uint32_t)(samp_level_bytes<R, NPAD>(SZ * 4) - 4 * samp_level_bytes<R, NPAD>(SZ)) - 3u * base;
+#pragma unroll
+        for (int k = 0; k < PPT; ++k) {
+            const Vec4T<R> v = lds_group(ad[k], (R)0);
+            uint32_t n = 4u * ad[k] + K;
+            if (v.x <= tg[k]) n += GB;
+            if (v.y <= tg[k]) n += GB;
+            if (v.z <= tg[k]) n += GB;
+            ad[k] = n;
+        }
+        samp_descend<R, PPT, NPAD, SZ * 4>(base, tg, ad);
     }
-    if constexpr (SZ < NPAD) samp_descend<R, PPT, NPAD, SZ * 4>(cdf, samp, tg, pos);
 }
 template <class R, int PPT, int NPAD>
-__device__ __forceinline__ void samp_search(const R* cdf, const R* samp, const R* tg, int* anc) {
+__device__ __forceinline__ void samp_search(const R* cdf, const R* tg, int* anc) {
     constexpr int TOP = samp_top(NPAD);
-    const R* top = samp + samp_off(NPAD, TOP);
+    constexpr int GB = 4 * (int)sizeof(R);
+    const uint32_t base = (uint32_t)__cvta_generic_to_shared(cdf);
+    uint32_t ad[PPT];
+    if constexpr (TOP == 4) {
 #pragma unroll
-    for (int k = 0; k < PPT; ++k) {
-        const Vec4T<R> v0 = reinterpret_cast<const Vec4T<R>*>(top)[0];
-        int c = count3(v0, tg[k]);
-        if (TOP == 8) {
-            const Vec4T<R> v1 = reinterpret_cast<const Vec4T<R>*>(top)[1];
-            c += (v0.w <= tg[k]) + count3(v1, tg[k]);
+        for (int k = 0; k < PPT; ++k) ad[k] = base + samp_level_bytes<R, NPAD>(TOP);
+        samp_descend<R, PPT, NPAD, TOP>(base, tg, ad);
+    } else {                                           // 8 top entries: two groups, seven of the entries counted
+#pragma unroll
+        for (int k = 0; k < PPT; ++k) {
+            const Vec4T<R> v0 = lds_group(base + samp_level_bytes<R, NPAD>(TOP), (R)0);
+            const Vec4T<R> v1 = lds_group(base + samp_level_bytes<R, NPAD>(TOP) + GB, (R)0);
+            uint32_t n = base + samp_level_bytes<R, NPAD>(TOP * 4);
+            if (v0.x <= tg[k]) n += GB;
+            if (v0.y <= tg[k]) n += GB;
+            if (v0.z <= tg[k]) n += GB;
+            if (v0.w <= tg[k]) n += GB;
+            if (v1.x <= tg[k]) n += GB;
+            if (v1.y <= tg[k]) n += GB;
+            if (v1.z <= tg[k]) n += GB;
+            ad[k] = n;
         }
-        anc[k] = c;
+        samp_descend<R, PPT, NPAD, TOP * 4>(base, tg, ad);
     }
-    samp_descend<R, PPT, NPAD, TOP * 4>(cdf, samp, tg, anc);
+#pragma unroll
+    for (int k = 0; k < PPT; ++k) anc[k] = (int)(ad[k] / (uint32_t)sizeof(R));
 }
 // store CDF entry i and its sampled copies
 template <class R, int NPAD>
@@ -305,7 +350,7 @@ __device__ void small_pf_item(const KArgs& a, int b, unsigned char* smem) {
             over[k] = !(tg[k] < cmax);                         // u * total rounded up to the total (or a NaN weight)
         }
         // searchsorted(cdf, target, 'right') = number of entries <= target (entries >= N are +inf)
-        samp_search<R, PPT, NPAD>(cdf, samp, tg, ancs);
+        samp_search<R, PPT, NPAD>(cdf, tg, ancs);
 #pragma unroll
         for (int k = 0; k < PPT; ++k) {
             const int i = tid * PPT + k;
