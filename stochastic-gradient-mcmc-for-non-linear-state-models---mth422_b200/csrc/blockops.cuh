@@ -18,6 +18,17 @@ template <class T> __device__ __forceinline__ T warp_incl_scan(T v) {
     }
     return v;
 }
+// the same scan when only lanes < NL hold data (zeros elsewhere): levels d >= NL add nothing to lanes < NL and are skipped,
+// so lanes < NL get bit-identical results; lanes >= NL are NOT valid
+template <int NL, class T> __device__ __forceinline__ T warp_incl_scan_low(T v) {
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int d = 1; d < NL; d <<= 1) {
+        T n = __shfl_up_sync(FULL, v, d);
+        if (lane >= d) v += n;
+    }
+    return v;
+}
 template <class T> __device__ __forceinline__ T warp_sum(T v) {
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(FULL, v, d);

@@ -21,6 +21,10 @@ namespace sgmhost {
 // N in (256, 1024]: 512 threads x 2 particles for every batch size.  A/B against 1024 threads x 1 particle (LGSSM f32, 60
 // steps): N = 1000, 1 item 0.171 vs 0.182 ms, 296 items 0.29 vs 0.36 ms, persistent SGLD 5.5e3 vs 5.2e3 it/s (one Philox
 // call and one Box-Muller pair serve both particles of a thread; half as many warps meet at the two barriers).
+#ifndef SGM_SMALL_MID_NTH            // thread shape of the shared-memory kernel for 256 < N <= 1024 (A/B: scripts/build_variant.sh)
+#define SGM_SMALL_MID_NTH 512
+#define SGM_SMALL_MID_PPT 2
+#endif
 #ifndef SGM_SMALL_LATENCY_ITEMS
 #define SGM_SMALL_LATENCY_ITEMS 0
 #endif
@@ -49,7 +53,7 @@ bool launch_small(const KArgs& a, cudaStream_t stream) {
 #if SGM_SMALL_LATENCY_ITEMS > 0
         if (a.N <= 1024 && a.B <= SGM_SMALL_LATENCY_ITEMS) return launch_small_shape<R, Model, 1024, 1, true>(a, stream);
 #endif
-        if (a.N <= 1024) return launch_small_shape<R, Model, 512, 2, true>(a, stream);
+        if (a.N <= 1024) return launch_small_shape<R, Model, SGM_SMALL_MID_NTH, SGM_SMALL_MID_PPT, true>(a, stream);
         return launch_small_shape<R, Model, 1024, 2, true>(a, stream);
     }
     // every other configuration (injected randoms, Nemeth shrinkage, filter, traces, ...): two shapes, flags read at run time
@@ -301,7 +305,7 @@ bool launch_persistent(const SgldArgs& sa, const KArgs& a, int K, cudaStream_t s
 #if SGM_SMALL_LATENCY_ITEMS > 0
         if (a.N <= 1024 && a.B <= SGM_SMALL_LATENCY_ITEMS) return launch_persistent_shape<R, Model, 1024, 1, true>(sa, a, K, stream);
 #endif
-        if (a.N <= 1024) return launch_persistent_shape<R, Model, 512, 2, true>(sa, a, K, stream);
+        if (a.N <= 1024) return launch_persistent_shape<R, Model, SGM_SMALL_MID_NTH, SGM_SMALL_MID_PPT, true>(sa, a, K, stream);
         return launch_persistent_shape<R, Model, 1024, 2, true>(sa, a, K, stream);
     }
     if (a.N <= 1024) return launch_persistent_shape<R, Model, 1024, 1, false>(sa, a, K, stream);

@@ -277,7 +277,6 @@ __device__ void small_pf_item(const KArgs& a, int b, unsigned char* smem) {
         const R excl = incl - pre[PPT - 1];
 #pragma unroll
         for (int k = 0; k < PPT; ++k) pre[k] += excl;
-        const R s_w = __shfl_sync(FULL, incl, 31);
         R wsum[4] = {(R)0, (R)0, (R)0, (R)0};
         if (need_ws) {
 #pragma unroll
@@ -288,9 +287,9 @@ __device__ void small_pf_item(const KArgs& a, int b, unsigned char* smem) {
                 wsum[q] = (q < nstat) ? warp_sum(acc) : (R)0;
             }
         }
-        if (lane == 0) {
+        if (lane == 31) {                                  // the lane that holds the warp's weight sum; m is warp-uniform
             R* p = summ + warp * SM_STRIDE;
-            p[0] = m; p[1] = s_w;
+            p[0] = m; p[1] = incl;
             if (need_ws) { p[2] = wsum[0]; p[3] = wsum[1]; p[4] = wsum[2]; p[5] = wsum[3]; }
         }
         __syncthreads();                                                      // barrier 1
@@ -300,10 +299,10 @@ __device__ void small_pf_item(const KArgs& a, int b, unsigned char* smem) {
         const R M = warp_max(ml);
         const R el = (has && ml != NEG_INF) ? Mth<R>::exp(ml - M) : (R)0;
         const R loc = has ? el * summ[lane * SM_STRIDE + 1] : (R)0;
-        const R lincl = warp_incl_scan(loc);
-        const R total = __shfl_sync(FULL, lincl, 31);
+        const R lincl = warp_incl_scan_low<NW>(loc);       // valid in lanes < NW
+        const R total = __shfl_sync(FULL, lincl, NW - 1);
         const R off_me = __shfl_sync(FULL, lincl - loc, warp);
-        const R sc_me = __shfl_sync(FULL, el, warp);
+        const R sc_me = (m != NEG_INF) ? Mth<R>::exp(m - M) : (R)0;       // = lane `warp`'s el (same operands)
         R sbar[4] = {(R)0, (R)0, (R)0, (R)0};
         if (need_ws) {
 #pragma unroll
