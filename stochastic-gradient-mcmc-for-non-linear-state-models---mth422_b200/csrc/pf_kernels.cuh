@@ -644,6 +644,29 @@ template <int OFF> __device__ __forceinline__ float lds_at(uint32_t addr, float)
 template <int OFF> __device__ __forceinline__ double lds_at(uint32_t addr, double) {
     double v; asm volatile("ld.shared.f64 %0, [%1+%2];" : "=d"(v) : "r"(addr), "n"(OFF)); return v;
 }
+// ---- experiment (VERDICT W10 / W11): stage the RAW parent-CDF window with one bulk copy (TMA, cp.async.bulk + mbarrier) -------
+// Compile with -DSGM_TMA_WINDOW=1.  The window's whole tiles are contiguous in `fine`, so one elected lane issues ONE 1-4 KB
+// bulk copy instead of every lane's 2 LDG.128 + 8 FMA + 2 STS.128 per tile; the children then pick their parent tile by
+// comparing against the <= 4 tile offsets in registers and search in tile-local units with a rescaled TARGET.
+#ifndef SGM_TMA_WINDOW
+#define SGM_TMA_WINDOW 0
+#endif
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_load_window(void* dst_smem, const void* src, uint32_t bytes, uint64_t* bar) {
+    const uint32_t b = (uint32_t)__cvta_generic_to_shared(bar), d = (uint32_t)__cvta_generic_to_shared(dst_smem);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(b), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(d), "l"(src), "r"(bytes), "r"(b) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    const uint32_t b = (uint32_t)__cvta_generic_to_shared(bar);
+    asm volatile("{\n .reg .pred p;\n W_LOOP:\n mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n @p bra W_DONE;\n bra W_LOOP;\n W_DONE:\n}"
+                 :: "r"(b), "r"(parity) : "memory");
+}
+
 template <class R, int STEP>
 __device__ __forceinline__ void search_levels(uint32_t* ad, const R* rt) {
     if constexpr (STEP > 0) {
@@ -673,7 +696,8 @@ __device__ __forceinline__ void search_levels(uint32_t* ad, const R* rt) {
 // accumulate the per-tile weighted statistic sums in registers while they propagate (WsCarry) instead of re-reading
 // the freshly written records: same sums up to f32 / f64 rounding of the statistic (not of the particle system).
 template <class R, class Model, bool SORTED, int FM = FM_GENERIC, bool RAGGED = false, int WINB = WIN_BYTES>
-__device__ __forceinline__ void step_body(const KArgs& a, int b, int t, int q_me, int lane, R* s_cdf, const double* hdr_local = nullptr) {
+__device__ __forceinline__ void step_body(const KArgs& a, int b, int t, int q_me, int lane, R* s_cdf, const double* hdr_local = nullptr,
+                                          uint64_t* mbar = nullptr) {
     constexpr bool FAST = FM != FM_GENERIC;
     static_assert(!FAST || SORTED, "the fast modes imply sorted resampling");
     R* const s_tr = s_cdf;                 // the warp's shared-memory slice doubles as the scan transposition buffer
@@ -827,7 +851,42 @@ __device__ __forceinline__ void step_body(const KArgs& a, int b, int t, int q_me
         warp_search_tiles(tf, tl, c1, s1c, hdr, lane, q_lo, q_hi);
         constexpr int MAXT = WINB / (int)(WT * sizeof(R));              // tiles the window holds: 4 (2 for f64 in the single-launch kernel)
         const int nst = q_hi - q_lo + 1;
-        if (nst >= 1 && nst <= MAXT) {
+        if (SGM_TMA_WINDOW && FAST && mbar != nullptr && nst >= 1 && nst <= MAXT) {
+            const int wt = (nst <= 1) ? 1 : ((nst <= 2) ? 2 : 4);
+            const int live_t = min(wt, a.Q - q_lo);
+            constexpr int ES = (int)sizeof(R);
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // the slice was the transposition buffer (generic proxy)
+            __syncwarp();
+            if (lane == 0) bulk_load_window(s_cdf, fine_old + (size_t)q_lo * WT, (uint32_t)(live_t * WT * ES), mbar);
+            const double cbase = hdr.off[q_lo];
+            R o[MAXT], isc[MAXT];
+#pragma unroll
+            for (int j = 0; j < MAXT; ++j) {
+                const bool live = j < live_t;
+                o[j] = live ? (R)(hdr.off[q_lo + (live ? j : 0)] - cbase) : Mth<R>::inf();
+                isc[j] = live ? Mth<R>::rcp((R)hdr.sc[q_lo + (live ? j : 0)]) : (R)0;
+            }
+            const R rA = (R)(tA - cbase), rB = (R)tB;
+            R rt[KPT];
+            uint32_t ad[KPT];
+            const uint32_t ad0 = (uint32_t)__cvta_generic_to_shared(s_cdf);
+#pragma unroll
+            for (int c = 0; c < KPT; ++c) {
+                const R g = Mth<R>::fma(rB, u[c], rA);                       // spacings (fast modes)
+                R oj = o[0], ij = isc[0];
+                uint32_t adj = ad0;
+#pragma unroll
+                for (int j = 1; j < MAXT; ++j)
+                    if (g >= o[j]) { oj = o[j]; ij = isc[j]; adj = ad0 + j * WT * ES; }
+                rt[c] = Mth<R>::mul(g - oj, ij);
+                ad[c] = adj;
+            }
+            mbar_wait(mbar, 0u);
+            search_levels<R, WT / 2>(ad, rt);
+#pragma unroll
+            for (int c = 0; c < KPT; ++c) anc[c] = min(q_lo * WT + (int)((ad[c] - ad0) / ES), N - 1);
+            __syncwarp();
+        } else if (nst >= 1 && nst <= MAXT) {
             // Stage the CDF of whole parent tiles q_lo .. q_lo + wt - 1 (wt = 1, 2 or 4: a power-of-two window, so
             // the searches below need neither bound checks nor a run-time step) in global units relative to
             // cbase = off[q_lo]; f32 is enough, the window spans a few tiles.  `fine` is padded to whole tiles, so
@@ -945,7 +1004,17 @@ __global__ void __launch_bounds__(32 * StepShape<R, FM != FM_GENERIC>::WARPS, St
     constexpr int WINB = (FM != FM_GENERIC) ? 4 * WT * (int)sizeof(R) : WIN_BYTES;
     __shared__ __align__(32) R s_cdf_all[SW][SORTED ? WINB / sizeof(R) : WT];
     const int warp = threadIdx.x >> 5;
+#if SGM_TMA_WINDOW
+    __shared__ __align__(8) uint64_t s_mbar[SW];
+    if (FM != FM_GENERIC) {
+        if ((threadIdx.x & 31) == 0) mbar_init(&s_mbar[warp], 1);
+        __syncwarp();
+    }
+    step_body<R, Model, SORTED, FM, RAGGED, WINB>(a, a.b0 + blockIdx.y, t, blockIdx.x * SW + warp, threadIdx.x & 31, s_cdf_all[warp], nullptr,
+                                                  FM != FM_GENERIC ? &s_mbar[warp] : nullptr);
+#else
     step_body<R, Model, SORTED, FM, RAGGED, WINB>(a, a.b0 + blockIdx.y, t, blockIdx.x * SW + warp, threadIdx.x & 31, s_cdf_all[warp]);
+#endif
 }
 
 // ---- optional export of the final particle system (out['x_t'], ['log_weights'], ['statistics']) ---
