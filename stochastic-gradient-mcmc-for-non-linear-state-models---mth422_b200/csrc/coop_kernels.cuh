@@ -8,6 +8,7 @@
 // The arithmetic is that of the per-step kernels (same init_body / header_body / step_body): results are bit-identical.
 #pragma once
 #include <cooperative_groups.h>
+#include <utility>
 #include "pf_kernels.cuh"
 
 namespace sgm {
@@ -23,12 +24,19 @@ __global__ void __launch_bounds__(NT, 2) pf_coop_kernel(KArgs a) {
     extern __shared__ double s_hdr[];                 // hdr_stride(Q) doubles
     const int b = a.b0 + blockIdx.y, g = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     init_body<R, Model>(a, b, g, s_cdf_all[warp]);
+    // the header's Gamma draws of the NEXT step do not depend on this step's weights: they are drawn between the arrive and
+    // the wait of the grid barrier (same values as header_body would draw: counter-based), off the step's critical path
+    const bool pre = a.Q >= 32 && (FM != FM_GENERIC || (SORTED && uses_spacings(a)));
+    double gv[2] = {0.0, 0.0};
+    if (pre) header_gammas<NT>(a, b, 0, gv);
     grid.sync();
     for (int t = 0; t < a.max_T; ++t) {
-        header_body<R, Model, NT>(a, b, t, 0, sh_d, s_hdr, g == 0);
+        header_body<R, Model, NT>(a, b, t, 0, sh_d, s_hdr, g == 0, pre ? gv : nullptr);
         __syncthreads();
         step_body<R, Model, SORTED, FM, RAGGED, WIN_BYTES>(a, b, t, g * NWARP + warp, lane, s_cdf_all[warp], s_hdr);
-        grid.sync();
+        auto token = grid.barrier_arrive();
+        if (pre && t + 1 < a.max_T) header_gammas<NT>(a, b, t + 1, gv);
+        grid.barrier_wait(std::move(token));
     }
     if (g == 0) header_body<R, Model, NT>(a, b, a.max_T, 1, sh_d);
 }

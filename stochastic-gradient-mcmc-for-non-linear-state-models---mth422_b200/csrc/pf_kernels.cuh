@@ -422,11 +422,25 @@ __device__ __forceinline__ void header_warp(const KArgs& a, int b, int t, int fi
     if (local) __syncwarp();
 }
 
+// The calling thread's Gamma draws of step t when a header thread owns at most two of the Q + 1 draws (Q <= 2 NTH - 1):
+// they do not depend on the weights, so the cooperative kernel draws them while it waits at the grid barrier.
+template <int NTH>
+__device__ __forceinline__ void header_gammas(const KArgs& a, int b, int t, double* gv) {
+    const int Q = a.Q, N = a.N;
+    const int perg = (Q + 1 + NTH - 1) / NTH, g0 = threadIdx.x * perg;
+    const RngKey key = item_key(a, b);
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+        const int q = g0 + k;
+        gv[k] = (k < perg && q <= Q) ? rng_gamma(key, (uint32_t)q, (uint32_t)t, (q == Q) ? 1.0 : (double)min(WT, N - q * WT)) : 0.0;
+    }
+}
+
 // NTH = threads of the CTA: 256, or 1024 for items with more than 256 tiles (N > 65536), where the per-thread chunk of
 // tiles (and with it the serial part of the scans) shrinks 4x.
 template <class R, class Model, int NTH = NT>
 __device__ __forceinline__ void header_body(const KArgs& a, int b, int t, int final_pass, double* sh_d, double* local = nullptr,
-                                            bool side = true) {
+                                            bool side = true, const double* gpre = nullptr) {
     // `local` != nullptr: the header goes to that (shared-memory) copy instead of the item's global one -- the cooperative
     // kernel lets every CTA of an item build its own; `side` = this caller applies the log-likelihood / status / output
     // side effects (exactly one CTA per item may)
@@ -479,10 +493,21 @@ __device__ __forceinline__ void header_body(const KArgs& a, int b, int t, int fi
     if (!final_pass && uses_spacings(a)) {
         const RngKey key = item_key(a, b);
         const int perg = (Q + 1 + NTH - 1) / NTH, g0 = tid * perg;
+        // a thread with at most two draws keeps them in registers (gpre: already drawn by the caller) instead of drawing
+        // them again for the running sums below: same values, same order of additions
+        const bool cached = perg <= 2;
+        double gv[2] = {0.0, 0.0};
+        if (cached) {
+            if (gpre) { gv[0] = gpre[0]; gv[1] = gpre[1]; }
+            else header_gammas<NTH>(a, b, t, gv);
+        }
         double gl = 0.0;
-        for (int k = 0; k < perg; ++k) {
-            const int q = g0 + k;
-            if (q <= Q) gl += rng_gamma(key, (uint32_t)q, (uint32_t)t, (q == Q) ? 1.0 : (double)min(WT, N - q * WT));
+        if (cached) { gl += gv[0]; if (perg == 2 && g0 + 1 <= Q) gl += gv[1]; }
+        else {
+            for (int k = 0; k < perg; ++k) {
+                const int q = g0 + k;
+                if (q <= Q) gl += rng_gamma(key, (uint32_t)q, (uint32_t)t, (q == Q) ? 1.0 : (double)min(WT, N - q * WT));
+            }
         }
         double gtot;
         double grun = block_excl_scan<NTH / 32>(gl, sh_d, gtot);
@@ -491,7 +516,7 @@ __device__ __forceinline__ void header_body(const KArgs& a, int b, int t, int fi
             const int q = g0 + k;
             if (q <= Q) {
                 gam[q] = grun * kk;
-                grun += rng_gamma(key, (uint32_t)q, (uint32_t)t, (q == Q) ? 1.0 : (double)min(WT, N - q * WT));
+                grun += cached ? gv[k & 1] : rng_gamma(key, (uint32_t)q, (uint32_t)t, (q == Q) ? 1.0 : (double)min(WT, N - q * WT));
             }
         }
         if (tid == 0) gam[Q + 1] = total;
