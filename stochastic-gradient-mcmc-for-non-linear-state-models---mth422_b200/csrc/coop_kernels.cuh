@@ -9,6 +9,7 @@
 #pragma once
 #include <cooperative_groups.h>
 #include <utility>
+#include <cstdio>
 #include "pf_kernels.cuh"
 
 namespace sgm {
@@ -24,21 +25,41 @@ __global__ void __launch_bounds__(NT, 2) pf_coop_kernel(KArgs a) {
     extern __shared__ double s_hdr[];                 // hdr_stride(Q) doubles
     const int b = a.b0 + blockIdx.y, g = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     init_body<R, Model>(a, b, g, s_cdf_all[warp]);
-    // the header's Gamma draws of the NEXT step do not depend on this step's weights: they are drawn between the arrive and
-    // the wait of the grid barrier (same values as header_body would draw: counter-based), off the step's critical path
+    // Off the critical path of a step: T_buf is loaded once; the log-likelihood accumulator of the item lives in shared memory
+    // (CTA 0 of the item); the header's Gamma draws of the NEXT step and their block scan do not depend on this step's
+    // weights and are made between the arrive and the wait of the grid barrier (counter-based: the same values)
+    __shared__ double s_acc[ACC_STRIDE];
+    if (threadIdx.x < ACC_STRIDE) s_acc[threadIdx.x] = 0.0;
+    HeaderCoop hc;
+    hc.Tb = a.T_buf[b]; hc.scanned = false; hc.gv[0] = hc.gv[1] = hc.grun = hc.gtot = 0.0; hc.acc = s_acc;
     const bool pre = a.Q >= 32 && (FM != FM_GENERIC || (SORTED && uses_spacings(a)));
-    double gv[2] = {0.0, 0.0};
-    if (pre) header_gammas<NT>(a, b, 0, gv);
+    if (pre) header_gamma_scan<NT>(a, b, 0, sh_d, hc);
     grid.sync();
+#ifdef SGM_COOP_TIMING
+    long long tc[5] = {0, 0, 0, 0, 0}, c0 = clock64(), c1;
+#define SGM_TICK(i) { c1 = clock64(); tc[i] += c1 - c0; c0 = c1; }
+#else
+#define SGM_TICK(i)
+#endif
     for (int t = 0; t < a.max_T; ++t) {
-        header_body<R, Model, NT>(a, b, t, 0, sh_d, s_hdr, g == 0, pre ? gv : nullptr);
+        header_body<R, Model, NT>(a, b, t, 0, sh_d, s_hdr, g == 0, &hc);
         __syncthreads();
+        SGM_TICK(0)
         step_body<R, Model, SORTED, FM, RAGGED, WIN_BYTES>(a, b, t, g * NWARP + warp, lane, s_cdf_all[warp], s_hdr);
+        SGM_TICK(1)
         auto token = grid.barrier_arrive();
-        if (pre && t + 1 < a.max_T) header_gammas<NT>(a, b, t + 1, gv);
+        SGM_TICK(2)
+        if (pre && t + 1 < a.max_T) header_gamma_scan<NT>(a, b, t + 1, sh_d, hc);
+        SGM_TICK(3)
         grid.barrier_wait(std::move(token));
+        SGM_TICK(4)
     }
-    if (g == 0) header_body<R, Model, NT>(a, b, a.max_T, 1, sh_d);
+#ifdef SGM_COOP_TIMING
+    if (threadIdx.x == 0 && (blockIdx.x == 0 || blockIdx.x == gridDim.x - 1) && blockIdx.y == 0)
+        printf("coop timing cta %d (cycles/step): header %lld  step %lld  arrive %lld  gamma %lld  wait %lld\n", (int)blockIdx.x,
+               tc[0] / a.max_T, tc[1] / a.max_T, tc[2] / a.max_T, tc[3] / a.max_T, tc[4] / a.max_T);
+#endif
+    if (g == 0) header_body<R, Model, NT>(a, b, a.max_T, 1, sh_d, nullptr, true, &hc);
 }
 
 }  // namespace sgm

@@ -343,7 +343,8 @@ __global__ void __launch_bounds__(NT) pf_init_kernel(KArgs a) {
 // scalar tail of the header (one thread): totals, status flags, log-likelihood increment, final outputs
 template <class Model>
 __device__ __forceinline__ void header_finish(const KArgs& a, int b, int t_done, int final_pass, int nstat, double M, double total,
-                                              const double* sbar, double* base, double* off, bool side_effects = true) {
+                                              const double* sbar, double* base, double* off, bool side_effects = true,
+                                              double* acc_local = nullptr) {
     const int Q = a.Q, N = a.N;
     const double NEG_INF = -Mth<double>::inf();
     off[Q] = total;
@@ -352,7 +353,7 @@ __device__ __forceinline__ void header_finish(const KArgs& a, int b, int t_done,
     if (!side_effects) return;             // a redundant per-warp copy: status / log-likelihood are the first warp's job
     if (!(total > 0.0) || !(total < Mth<double>::inf()) || !(M == M) || !(fabs(M) < Mth<double>::inf()))
         a.status[b] |= (total == 0.0 || M == NEG_INF) ? SGM_STATUS_ZERO_WEIGHT : SGM_STATUS_NAN_WEIGHT;
-    double* acc = a.acc + (size_t)b * ACC_STRIDE;
+    double* acc = acc_local ? acc_local : a.acc + (size_t)b * ACC_STRIDE;       // acc_local: the cooperative kernel's shared-memory copy
     if (t_done >= 0) {
         if (t_done >= a.t1[b] && t_done < a.tL[b]) {
             const double wt = (a.wts_off && a.wts_off[b] >= 0) ? a.step_weights[a.wts_off[b] + (t_done - a.t1[b])] : 1.0;
@@ -422,6 +423,15 @@ __device__ __forceinline__ void header_warp(const KArgs& a, int b, int t, int fi
     if (local) __syncwarp();
 }
 
+// What the cooperative kernel hands to header_body: values it loaded once (T_buf) or prepared while it waited at the grid
+// barrier (the Gamma draws of the step and their block scan, none of which depends on the weights), and its shared-memory
+// log-likelihood accumulator.  Same values and the same order of operations as header_body computes on its own.
+struct HeaderCoop {
+    int Tb;
+    bool scanned;              // gv / grun / gtot hold this step's draws and their exclusive block scan
+    double gv[2], grun, gtot;
+    double* acc;               // ACC_STRIDE doubles in shared memory (CTA 0 of the item applies the side effects)
+};
 // The calling thread's Gamma draws of step t when a header thread owns at most two of the Q + 1 draws (Q <= 2 NTH - 1):
 // they do not depend on the weights, so the cooperative kernel draws them while it waits at the grid barrier.
 template <int NTH>
@@ -436,16 +446,28 @@ __device__ __forceinline__ void header_gammas(const KArgs& a, int b, int t, doub
     }
 }
 
+// draws + block scan of step t (all threads of the CTA; sh_d as in header_body)
+template <int NTH>
+__device__ __forceinline__ void header_gamma_scan(const KArgs& a, int b, int t, double* sh_d, HeaderCoop& hc) {
+    header_gammas<NTH>(a, b, t, hc.gv);
+    const int perg = (a.Q + 1 + NTH - 1) / NTH, g0 = threadIdx.x * perg;
+    double gl = 0.0;
+    gl += hc.gv[0];
+    if (perg == 2 && g0 + 1 <= a.Q) gl += hc.gv[1];
+    hc.grun = block_excl_scan<NTH / 32>(gl, sh_d, hc.gtot);
+    hc.scanned = true;
+}
+
 // NTH = threads of the CTA: 256, or 1024 for items with more than 256 tiles (N > 65536), where the per-thread chunk of
 // tiles (and with it the serial part of the scans) shrinks 4x.
 template <class R, class Model, int NTH = NT>
 __device__ __forceinline__ void header_body(const KArgs& a, int b, int t, int final_pass, double* sh_d, double* local = nullptr,
-                                            bool side = true, const double* gpre = nullptr) {
+                                            bool side = true, const HeaderCoop* hc = nullptr) {
     // `local` != nullptr: the header goes to that (shared-memory) copy instead of the item's global one -- the cooperative
     // kernel lets every CTA of an item build its own; `side` = this caller applies the log-likelihood / status / output
     // side effects (exactly one CTA per item may)
     const int tid = threadIdx.x;
-    const int Tb = a.T_buf[b];
+    const int Tb = hc ? hc->Tb : a.T_buf[b];
     if (!final_pass && t >= Tb) return;
     if (a.Q < 32) { if (!local || tid < 32) header_warp<R, Model>(a, b, t, final_pass, local, side); return; }
     const int par = final_pass ? (Tb & 1) : (t & 1);
@@ -466,25 +488,31 @@ __device__ __forceinline__ void header_body(const KArgs& a, int b, int t, int fi
     for (int k = 0; k < per; ++k) if (q0 + k < Q) m = fmax(m, sub[(size_t)(q0 + k) * SSTRIDE]);
     const double M = block_max<NTH / 32>(m, sh_d);
     double loc = 0.0, ws[4] = {0.0, 0.0, 0.0, 0.0};
+    double e_first = 0.0;                         // scale of the thread's first tile: kept for the loop below when it is the only one
     for (int k = 0; k < per; ++k) {
         const int q = q0 + k;
         if (q < Q) {
             const double* p = sub + (size_t)q * SSTRIDE;
             const double e = (p[0] == NEG_INF) ? 0.0 : ::exp(p[0] - M);
+            if (k == 0) e_first = e;
             loc += e * p[1];
             for (int j = 0; j < nws; ++j) ws[j] += e * p[2 + j];
         }
     }
     double total;
     double run = block_excl_scan<NTH / 32>(loc, sh_d, total);
-    for (int k = 0; k < per; ++k) {
-        const int q = q0 + k;
-        if (q < Q) {
-            const double* p = sub + (size_t)q * SSTRIDE;
-            const double e = (p[0] == NEG_INF) ? 0.0 : ::exp(p[0] - M);
-            off[q] = run;
-            sc[q] = e;
-            run += e * p[1];
+    if (per == 1) {
+        if (q0 < Q) { off[q0] = run; sc[q0] = e_first; }
+    } else {
+        for (int k = 0; k < per; ++k) {
+            const int q = q0 + k;
+            if (q < Q) {
+                const double* p = sub + (size_t)q * SSTRIDE;
+                const double e = (p[0] == NEG_INF) ? 0.0 : ::exp(p[0] - M);
+                off[q] = run;
+                sc[q] = e;
+                run += e * p[1];
+            }
         }
     }
     double sbar[4] = {0.0, 0.0, 0.0, 0.0};
@@ -496,21 +524,23 @@ __device__ __forceinline__ void header_body(const KArgs& a, int b, int t, int fi
         // a thread with at most two draws keeps them in registers (gpre: already drawn by the caller) instead of drawing
         // them again for the running sums below: same values, same order of additions
         const bool cached = perg <= 2;
+        const bool scanned = cached && hc && hc->scanned;
         double gv[2] = {0.0, 0.0};
-        if (cached) {
-            if (gpre) { gv[0] = gpre[0]; gv[1] = gpre[1]; }
-            else header_gammas<NTH>(a, b, t, gv);
-        }
-        double gl = 0.0;
-        if (cached) { gl += gv[0]; if (perg == 2 && g0 + 1 <= Q) gl += gv[1]; }
+        if (scanned) { gv[0] = hc->gv[0]; gv[1] = hc->gv[1]; }
+        else if (cached) header_gammas<NTH>(a, b, t, gv);
+        double gtot, grun;
+        if (scanned) { grun = hc->grun; gtot = hc->gtot; }
         else {
-            for (int k = 0; k < perg; ++k) {
-                const int q = g0 + k;
-                if (q <= Q) gl += rng_gamma(key, (uint32_t)q, (uint32_t)t, (q == Q) ? 1.0 : (double)min(WT, N - q * WT));
+            double gl = 0.0;
+            if (cached) { gl += gv[0]; if (perg == 2 && g0 + 1 <= Q) gl += gv[1]; }
+            else {
+                for (int k = 0; k < perg; ++k) {
+                    const int q = g0 + k;
+                    if (q <= Q) gl += rng_gamma(key, (uint32_t)q, (uint32_t)t, (q == Q) ? 1.0 : (double)min(WT, N - q * WT));
+                }
             }
+            grun = block_excl_scan<NTH / 32>(gl, sh_d, gtot);
         }
-        double gtot;
-        double grun = block_excl_scan<NTH / 32>(gl, sh_d, gtot);
         const double kk = total / gtot;                  // stored in target units: gam[q] = total * G_q / G_total
         for (int k = 0; k < perg; ++k) {
             const int q = g0 + k;
@@ -521,7 +551,7 @@ __device__ __forceinline__ void header_body(const KArgs& a, int b, int t, int fi
         }
         if (tid == 0) gam[Q + 1] = total;
     }
-    if (tid == 0) header_finish<Model>(a, b, t_done, final_pass, nstat, M, total, sbar, base, off, side);
+    if (tid == 0) header_finish<Model>(a, b, t_done, final_pass, nstat, M, total, sbar, base, off, side, hc ? hc->acc : nullptr);
 }
 
 template <class R, class Model, int NTH = NT>
