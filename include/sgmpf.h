@@ -195,6 +195,9 @@ int sgm_pf_run(const sgm_pf_desc* d, void* stream);
  * DEVICE array `partial`; KSD = sqrt(sum(partial)) / num_points. */
 int sgm_ksd_imq(const double* x, const double* gradlogp, int32_t num_points, int32_t dim, double c, double beta,
                 double* partial, void* stream);
+/* self-test hook: y[i] = the table-driven natural logarithm the f64 variate transforms use (csrc/fastlog.cuh), for DEVICE
+ * arrays of n normal positive doubles; lets the parity tests pin it against the host's log (<= 4 ulp on (0, 1)) */
+int sgm_selftest_log(const double* x, double* y, int64_t n, void* stream);
 /* number of kernel launches the last sgm_pf_run / sgm_sgld_run on this thread issued (for bench accounting) */
 int64_t sgm_last_launch_count(void);
 

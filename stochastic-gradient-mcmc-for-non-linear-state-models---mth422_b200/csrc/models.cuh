@@ -4,6 +4,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include "../../include/sgmpf.h"
+#include "fastlog.cuh"
 
 namespace sgm {
 
@@ -41,9 +42,9 @@ template <> struct Mth<double> {
     static __device__ __forceinline__ double exp(double x) { return ::exp(x); }
     static __device__ __forceinline__ double exp2(double x) { return ::exp2(x); }
     static __device__ __forceinline__ double log2(double x) { return ::log2(x); }
-    // any fixed-base logarithm serves the exponential spacings (they are normalised by their sum): the natural one is the
-    // cheapest in f64 (::log2 was 21 % of the f64 step kernel's instructions, profiles/ncu_r02_f64_step_kernel_source_lines.txt)
-    static __device__ __forceinline__ double logb(double x) { return ::log(x); }
+    // any fixed-base logarithm serves the exponential spacings (they are normalised by their sum): the table-driven natural
+    // one (fastlog.cuh; ::log2 was 21 % of the f64 step kernel's instructions, profiles/ncu_r02_f64_step_kernel_source_lines.txt)
+    static __device__ __forceinline__ double logb(double x) { return fast_log(x); }
     static __device__ __forceinline__ double log(double x) { return ::log(x); }
     static __device__ __forceinline__ double sqrt(double x) { return ::sqrt(x); }
     static __device__ __forceinline__ double rcp(double x) { return 1.0 / x; }

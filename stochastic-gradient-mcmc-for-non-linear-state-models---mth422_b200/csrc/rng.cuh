@@ -8,6 +8,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include "fastlog.cuh"
 
 namespace sgm {
 
@@ -58,7 +59,7 @@ __device__ __forceinline__ void rng_normal4(const RngKey& k, uint32_t q, uint32_
 }
 __device__ __forceinline__ void rng_normal4(const RngKey& k, uint32_t q, uint32_t step, double* z) {
     const uint4 a = rng_raw(k, q, step, STREAM_NORMAL, 0), b = rng_raw(k, q, step, STREAM_NORMAL, 1);
-    const double r0 = sqrt(-2.0 * log(u01d(a.x, a.y))), r1 = sqrt(-2.0 * log(u01d(b.x, b.y)));
+    const double r0 = sqrt(-2.0 * fast_log(u01d(a.x, a.y))), r1 = sqrt(-2.0 * fast_log(u01d(b.x, b.y)));
     double s0, c0, s1, c1;
     sincospi(2.0 * u01d(a.z, a.w), &s0, &c0);
     sincospi(2.0 * u01d(b.z, b.w), &s1, &c1);

@@ -312,6 +312,22 @@ int sgm_stat_dim(int32_t model, int32_t stat_kind) {
     return SGM_ERR_INVALID;
 }
 
+namespace {
+__global__ void selftest_log_kernel(const double* x, double* y, int64_t n) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) y[i] = sgm::fast_log(x[i]);
+}
+}  // namespace
+
+int sgm_selftest_log(const double* x, double* y, int64_t n, void* stream) {
+    if (!x || !y || n < 0) return fail(SGM_ERR_INVALID, "sgm_selftest_log: null pointer or negative size");
+    if (n == 0) return SGM_OK;
+    selftest_log_kernel<<<(unsigned)((n + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(x, y, n);
+    const cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(SGM_ERR_CUDA, "CUDA launch failed: %s", cudaGetErrorString(e));
+    return SGM_OK;
+}
+
 int sgm_ksd_imq(const double* x, const double* gradlogp, int32_t num_points, int32_t dim, double c, double beta,
                 double* partial, void* stream) {
     if (!x || !gradlogp || !partial) return fail(SGM_ERR_INVALID, "sgm_ksd_imq: null pointer");
