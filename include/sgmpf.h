@@ -195,9 +195,14 @@ int sgm_pf_run(const sgm_pf_desc* d, void* stream);
  * DEVICE array `partial`; KSD = sqrt(sum(partial)) / num_points. */
 int sgm_ksd_imq(const double* x, const double* gradlogp, int32_t num_points, int32_t dim, double c, double beta,
                 double* partial, void* stream);
-/* self-test hook: y[i] = the table-driven natural logarithm the f64 variate transforms use (csrc/fastlog.cuh), for DEVICE
- * arrays of n normal positive doubles; lets the parity tests pin it against the host's log (<= 4 ulp on (0, 1)) */
-int sgm_selftest_log(const double* x, double* y, int64_t n, void* stream);
+/* self-test hook for the table-driven functions of the f64 variate transforms (csrc/fastlog.cuh), DEVICE arrays:
+ *   SGM_SELFTEST_LOG        y[i] = ln(x[i]) for n normal positive doubles                      (<= 4 ulp on (0, 1))
+ *   SGM_SELFTEST_SINCOS2PI  (y[2i], y[2i+1]) = (sin, cos)(2 pi v), v = the 60 top bits of the 64-bit PATTERN of x[i]
+ *                           read as a binary fraction (k = top 8 bits, f = next 52)            (|error| <= 1e-15)
+ * so that the parity tests can pin them against the host's libm */
+#define SGM_SELFTEST_LOG 0
+#define SGM_SELFTEST_SINCOS2PI 1
+int sgm_selftest_math(int32_t what, const double* x, double* y, int64_t n, void* stream);
 /* number of kernel launches the last sgm_pf_run / sgm_sgld_run on this thread issued (for bench accounting) */
 int64_t sgm_last_launch_count(void);
 

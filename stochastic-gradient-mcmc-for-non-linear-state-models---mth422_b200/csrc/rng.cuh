@@ -34,7 +34,9 @@ __device__ __forceinline__ uint4 rng_raw(const RngKey& k, uint32_t index, uint32
 // uniforms: f32 in (0, 1] (x * 2^-32 + 2^-33, rounds to 1 with probability 2^-25; every consumer tolerates 1), f64 in (0, 1)
 __device__ __forceinline__ float u01f(uint32_t x) { return fmaf((float)x, 2.3283064365386963e-10f, 1.1641532182693481e-10f); }  // (0,1]: I2FP + FFMA
 __device__ __forceinline__ double u01d(uint32_t a, uint32_t b) {                                                         // (0,1), 52 bits
-    return ((double)(((uint64_t)(a >> 6) << 26) | (uint64_t)(b >> 6)) + 0.5) * (1.0 / 4503599627370496.0);
+    // (2 k + 1) 2^-53 for the 52-bit k = (top 20 bits of a, b): built as a double in [1, 2) and shifted down (exact), which
+    // avoids the 64-bit integer -> double conversion
+    return __hiloint2double((int)(0x3ff00000u | (a >> 12)), (int)b) - 0.99999999999999989;
 }
 
 // 4 uniforms in (0,1) for particle quad q
@@ -61,8 +63,8 @@ __device__ __forceinline__ void rng_normal4(const RngKey& k, uint32_t q, uint32_
     const uint4 a = rng_raw(k, q, step, STREAM_NORMAL, 0), b = rng_raw(k, q, step, STREAM_NORMAL, 1);
     const double r0 = sqrt(-2.0 * fast_log(u01d(a.x, a.y))), r1 = sqrt(-2.0 * fast_log(u01d(b.x, b.y)));
     double s0, c0, s1, c1;
-    sincospi(2.0 * u01d(a.z, a.w), &s0, &c0);
-    sincospi(2.0 * u01d(b.z, b.w), &s1, &c1);
+    fast_sincos2pi(a.z, a.w, &s0, &c0);
+    fast_sincos2pi(b.z, b.w, &s1, &c1);
     z[0] = r0 * c0; z[1] = r0 * s0; z[2] = r1 * c1; z[3] = r1 * s1;
 }
 // one standard normal for (index, step, stream, sub)

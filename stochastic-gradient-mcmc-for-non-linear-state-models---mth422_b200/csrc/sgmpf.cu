@@ -313,16 +313,22 @@ int sgm_stat_dim(int32_t model, int32_t stat_kind) {
 }
 
 namespace {
-__global__ void selftest_log_kernel(const double* x, double* y, int64_t n) {
+__global__ void selftest_math_kernel(int what, const double* x, double* y, int64_t n) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) y[i] = sgm::fast_log(x[i]);
+    if (i >= n) return;
+    if (what == SGM_SELFTEST_LOG) y[i] = sgm::fast_log(x[i]);
+    else {
+        const unsigned long long bits = (unsigned long long)__double_as_longlong(x[i]);
+        sgm::fast_sincos2pi((uint32_t)(bits >> 32), (uint32_t)bits, &y[2 * i], &y[2 * i + 1]);
+    }
 }
 }  // namespace
 
-int sgm_selftest_log(const double* x, double* y, int64_t n, void* stream) {
-    if (!x || !y || n < 0) return fail(SGM_ERR_INVALID, "sgm_selftest_log: null pointer or negative size");
+int sgm_selftest_math(int32_t what, const double* x, double* y, int64_t n, void* stream) {
+    if (!x || !y || n < 0) return fail(SGM_ERR_INVALID, "sgm_selftest_math: null pointer or negative size");
+    if (what != SGM_SELFTEST_LOG && what != SGM_SELFTEST_SINCOS2PI) return fail(SGM_ERR_INVALID, "sgm_selftest_math: unknown function");
     if (n == 0) return SGM_OK;
-    selftest_log_kernel<<<(unsigned)((n + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(x, y, n);
+    selftest_math_kernel<<<(unsigned)((n + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(what, x, y, n);
     const cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail(SGM_ERR_CUDA, "CUDA launch failed: %s", cudaGetErrorString(e));
     return SGM_OK;

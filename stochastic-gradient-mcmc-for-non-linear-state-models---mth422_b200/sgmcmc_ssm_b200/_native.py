@@ -68,7 +68,7 @@ class SgmSgldDesc(ctypes.Structure):
 
 EXPORTS = ["sgm_version", "sgm_device_check", "sgm_last_error", "sgm_stat_dim", "sgm_state_dim",
            "sgm_pf_workspace_bytes", "sgm_pf_run", "sgm_last_launch_count", "sgm_ksd_imq",
-           "sgm_sgld_items", "sgm_sgld_max_steps", "sgm_sgld_workspace_bytes", "sgm_sgld_run", "sgm_selftest_log"]
+           "sgm_sgld_items", "sgm_sgld_max_steps", "sgm_sgld_workspace_bytes", "sgm_sgld_run", "sgm_selftest_math"]
 _lib = None
 
 
@@ -102,8 +102,8 @@ def load():
     lib.sgm_sgld_workspace_bytes.argtypes = [ctypes.POINTER(SgmSgldDesc)]
     lib.sgm_sgld_run.restype = c_i32
     lib.sgm_sgld_run.argtypes = [ctypes.POINTER(SgmSgldDesc), c_vp]
-    lib.sgm_selftest_log.restype = c_i32
-    lib.sgm_selftest_log.argtypes = [c_vp, c_vp, c_i64, c_vp]
+    lib.sgm_selftest_math.restype = c_i32
+    lib.sgm_selftest_math.argtypes = [c_i32, c_vp, c_vp, c_i64, c_vp]
     lib.sgm_ksd_imq.restype = c_i32
     lib.sgm_ksd_imq.argtypes = [c_vp, c_vp, c_i32, c_i32, c_f64, c_f64, c_vp, c_vp]
     _lib = lib
