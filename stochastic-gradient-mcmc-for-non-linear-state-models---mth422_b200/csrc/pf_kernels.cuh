@@ -1045,16 +1045,21 @@ __device__ __forceinline__ void step_body(const KArgs& a, int b, int t, int q_me
 #define SGM_FAST64_WARPS 4
 #endif
 #ifndef SGM_FAST64_CTAS
-#define SGM_FAST64_CTAS 4          /* measured (SVM f64, N = 2^16, 256 items): 4 -> 4.87e10, 5 -> 4.79e10, 6 -> 4.49e10 particle-steps/s */
+#define SGM_FAST64_CTAS 4          /* Nemeth / filter fast modes: 4 CTAs; 5 costs GARCH Nemeth 8 % (92 registers) */
 #endif
-template <class R, bool FAST> struct StepShape {
+#ifndef SGM_FAST64_CTAS_POY
+/* FM_POY, measured with the table-driven variate transforms (N = 2^16, 256 items, same box, % of the HBM roofline):
+ * 4 CTAs -> SVM 63.0, LGSSM 69.6, GARCH 65.2;  5 -> 65.1, 73.1, 63.8-66.0;  6 (80 registers, no spills) -> 58.5, 64.7, 54.6 */
+#define SGM_FAST64_CTAS_POY 5
+#endif
+template <class R, bool FAST, int FM = FM_GENERIC> struct StepShape {
     static constexpr int WARPS = FAST ? (sizeof(R) == 4 ? SGM_FAST_WARPS : SGM_FAST64_WARPS) : SGM_STEP_WARPS;
-    static constexpr int CTAS = FAST ? (sizeof(R) == 4 ? SGM_FAST_CTAS : SGM_FAST64_CTAS)
+    static constexpr int CTAS = FAST ? (sizeof(R) == 4 ? SGM_FAST_CTAS : (FM == FM_POY ? SGM_FAST64_CTAS_POY : SGM_FAST64_CTAS))
                                      : (sizeof(R) == 4 ? SGM_STEP_CTAS : 2 * 8 / SGM_STEP_WARPS);
 };
 template <class R, class Model, bool SORTED, int FM = FM_GENERIC, bool RAGGED = false>
-__global__ void __launch_bounds__(32 * StepShape<R, FM != FM_GENERIC>::WARPS, StepShape<R, FM != FM_GENERIC>::CTAS) pf_step_kernel(KArgs a, int t) {
-    constexpr int SW = StepShape<R, FM != FM_GENERIC>::WARPS;
+__global__ void __launch_bounds__(32 * StepShape<R, FM != FM_GENERIC, FM>::WARPS, StepShape<R, FM != FM_GENERIC, FM>::CTAS) pf_step_kernel(KArgs a, int t) {
+    constexpr int SW = StepShape<R, FM != FM_GENERIC, FM>::WARPS;
     // four parent tiles per warp in the fast modes (4 KB f32 / 8 KB f64); the generic f64 instantiation keeps two
     constexpr int WINB = (FM != FM_GENERIC) ? 4 * WT * (int)sizeof(R) : WIN_BYTES;
     __shared__ __align__(32) R s_cdf_all[SW][SORTED ? WINB / sizeof(R) : WT];
