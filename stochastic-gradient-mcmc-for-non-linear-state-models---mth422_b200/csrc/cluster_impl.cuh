@@ -89,7 +89,7 @@ __global__ void __launch_bounds__(NTH, 1) sgld_cluster_kernel(SgldArgs sa, KArgs
     const uint32_t k1 = a.key.k1;
     for (int k = 0; k < K; ++k) {
         const uint64_t o = o0 + (uint64_t)k;
-        if (rank == 0 && threadIdx.x == 0) sgld_prepare_item(sa, c, k, o);
+        if (rank == 0) sgld_prepare_item(sa, c, k, o, (int)threadIdx.x, (int)blockDim.x);
         cluster.sync();                                  // the item arrays (global memory) are visible to every CTA
         a.key.offset = (uint32_t)(o & 0xffffffffu);
         a.key.k1 = k1 ^ (uint32_t)(o >> 32);

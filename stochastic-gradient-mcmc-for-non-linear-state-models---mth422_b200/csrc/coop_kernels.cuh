@@ -34,6 +34,8 @@ __global__ void __launch_bounds__(NT, 2) pf_coop_kernel(KArgs a) {
     hc.Tb = a.T_buf[b]; hc.scanned = false; hc.gv[0] = hc.gv[1] = hc.grun = hc.gtot = 0.0; hc.acc = s_acc;
     const bool pre = a.Q >= 32 && (FM != FM_GENERIC || (SORTED && uses_spacings(a)));
     if (pre) header_gamma_scan<NT>(a, b, 0, sh_d, hc);
+    // (drawing the warp tile's own variates of the next step there as well was tried and is slower: 0.47 -> 0.50 ms at N = 2^16 --
+    // 16 more live registers across the header push the kernel to 128 registers with spills, and the wait is not idle enough)
     grid.sync();
 #ifdef SGM_COOP_TIMING
     long long tc[5] = {0, 0, 0, 0, 0}, c0 = clock64(), c1;

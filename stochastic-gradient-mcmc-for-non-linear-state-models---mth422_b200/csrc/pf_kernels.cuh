@@ -750,6 +750,36 @@ __device__ __forceinline__ void search_levels(uint32_t* ad, const R* rt) {
 // (positions, weights, genealogy) is bit-identical to the generic instantiation.  FM_SHRINK / FM_FILTER additionally
 // accumulate the per-tile weighted statistic sums in registers while they propagate (WsCarry) instead of re-reading
 // the freshly written records: same sums up to f32 / f64 rounding of the statistic (not of the particle system).
+// Order statistics of N iid uniforms via exponential spacings.  Within a tile the normalised partial sums of P Exp(1) draws
+// are independent of their total, which is Gamma(P, 1); the tile totals are drawn directly (pf_header_kernel), so no
+// cross-tile scan is needed.  Lane l draws the spacings of ranks 8 l .. 8 l + 7 (lane-major scan), then the positions are
+// transposed to row-major (child slot 32 c + lane has rank 32 c + lane) for coalesced gathers.
+// Exp(1) spacings up to a common factor: the positions are normalised by the tile's total, so -ln u and log2 u (same sign
+// throughout, no scaling multiply, no negation) give identical positions.
+template <class R>
+__device__ __forceinline__ void draw_spacings(const KArgs& a, const RngKey& key, int t, int q_me, int lane, int n_valid, R* s_tr, R* u) {
+    if (sizeof(R) == 8 && a.variates32) {
+        float uf[KPT];
+        draw_uniforms<float>(key, t, q_me, lane, uf);
+#pragma unroll
+        for (int k = 0; k < KPT; ++k) uf[k] = (8 * lane + k < n_valid) ? Mth<float>::log2(uf[k]) : 0.0f;
+        widen8(uf, u);
+    } else {
+        draw_uniforms<R>(key, t, q_me, lane, u);
+#pragma unroll
+        for (int k = 0; k < KPT; ++k) u[k] = (8 * lane + k < n_valid) ? Mth<R>::logb(u[k]) : (R)0;
+    }
+    R etot;
+    lane_major_incl_scan<R>(u, etot);
+    const R inv = Mth<R>::rcp(etot);
+#pragma unroll
+    for (int k = 0; k < KPT; ++k) u[k] = Mth<R>::mul(u[k], inv);
+    __syncwarp();
+    store_lane_major<R>(s_tr, lane, u);
+    __syncwarp();
+#pragma unroll
+    for (int c = 0; c < KPT; ++c) u[c] = s_tr[32 * c + lane];
+}
 template <class R, class Model, bool SORTED, int FM = FM_GENERIC, bool RAGGED = false, int WINB = WIN_BYTES>
 __device__ __forceinline__ void step_body(const KArgs& a, int b, int t, int q_me, int lane, R* s_cdf, const double* hdr_local = nullptr,
                                           uint64_t* mbar = nullptr) {
@@ -831,34 +861,7 @@ __device__ __forceinline__ void step_body(const KArgs& a, int b, int t, int q_me
         R u[KPT];
         double tA, tB;
         if (spacings) {
-            // Order statistics of N iid uniforms via exponential spacings.  Within a tile the normalised
-            // partial sums of P Exp(1) draws are independent of their total, which is Gamma(P, 1); the tile
-            // totals are drawn directly (pf_header_kernel), so no cross-tile scan is needed.
-            // Lane l draws the spacings of ranks 8 l .. 8 l + 7 (lane-major scan), then the positions are
-            // transposed to row-major (child slot 32 c + lane has rank 32 c + lane) for coalesced gathers.
-            // Exp(1) spacings up to a common factor: the positions are normalised by the tile's total below, so
-            // -ln u and log2 u (same sign throughout, no scaling multiply, no negation) give identical positions
-            if (sizeof(R) == 8 && a.variates32) {
-                float uf[KPT];
-                draw_uniforms<float>(key, t, q_me, lane, uf);
-#pragma unroll
-                for (int k = 0; k < KPT; ++k) uf[k] = (8 * lane + k < n_valid) ? Mth<float>::log2(uf[k]) : 0.0f;
-                widen8(uf, u);
-            } else {
-                draw_uniforms<R>(key, t, q_me, lane, u);
-#pragma unroll
-                for (int k = 0; k < KPT; ++k) u[k] = (8 * lane + k < n_valid) ? Mth<R>::logb(u[k]) : (R)0;
-            }
-            R etot;
-            lane_major_incl_scan<R>(u, etot);
-            const R inv = Mth<R>::rcp(etot);
-#pragma unroll
-            for (int k = 0; k < KPT; ++k) u[k] = Mth<R>::mul(u[k], inv);
-            __syncwarp();
-            store_lane_major<R>(s_tr, lane, u);
-            __syncwarp();
-#pragma unroll
-            for (int c = 0; c < KPT; ++c) u[c] = s_tr[32 * c + lane];
+            draw_spacings<R>(a, key, t, q_me, lane, n_valid, s_tr, u);
             tA = gam_lo; tB = gam_hi - gam_lo;
         } else {
             if (injected) {

@@ -271,7 +271,7 @@ __global__ void __launch_bounds__(NTH, 1024 / NTH) sgld_persistent_kernel(SgldAr
     const uint32_t k1 = a.key.k1;
     for (int k = 0; k < K; ++k) {
         const uint64_t o = o0 + (uint64_t)k;
-        if (threadIdx.x == 0) sgld_prepare_item(sa, c, k, o);
+        sgld_prepare_item(sa, c, k, o, (int)threadIdx.x, (int)blockDim.x);      // all threads: the stores are shared out
         __syncthreads();
         a.key.offset = (uint32_t)(o & 0xffffffffu);
         a.key.k1 = k1 ^ (uint32_t)(o >> 32);

@@ -93,7 +93,9 @@ __device__ inline int sgld_pick_sequence(const SgldArgs& a, const RngKey& k, int
 }
 
 // work item b of iteration k_call (Philox call offset `off`): window, weights, theta, x_0 prior -> the item arrays
-__device__ inline void sgld_prepare_item(const SgldArgs& a, int b, int k_call, uint64_t off) {
+// (tid, nth): the nth threads that call this together for the SAME item (persistent kernels: the whole CTA) share the stores --
+// the S window weights are strided over them, thread 0 writes the scalars; every thread recomputes the few scalars itself
+__device__ inline void sgld_prepare_item(const SgldArgs& a, int b, int k_call, uint64_t off, int tid = 0, int nth = 1) {
     const int B = a.C * a.ipc;
     const int c = b / a.ipc, j = b % a.ipc, s = j / a.M;
     const RngKey key = sgld_key(a, c, off);
@@ -112,7 +114,7 @@ __device__ inline void sgld_prepare_item(const SgldArgs& a, int b, int k_call, u
         start = (a.partition == SGM_PARTITION_STRICT) ? r * S : r;
         end = start + S;
         double* w = a.weights + (size_t)b * a.Smax;
-        for (int i = 0; i < S; ++i) {
+        for (int i = tid; i < S; i += nth) {
             double wt;
             if (a.partition == SGM_PARTITION_UNIFORM) {           // :1994-2008
                 const int t = start + i, cap = min(S, Tq - S + 1);
@@ -128,16 +130,17 @@ __device__ inline void sgld_prepare_item(const SgldArgs& a, int b, int k_call, u
         }
     }
     const int left = max(0, start - Bf), right = min(Tq, end + Bf);
+    const double* p = a.params + (size_t)c * SGM_PARAM_STRIDE;
+    double th[SGM_THETA_STRIDE];
+    sgld_theta(a.model, p, th);
+    for (int i = tid; i < SGM_THETA_STRIDE; i += nth) a.theta[(size_t)b * SGM_THETA_STRIDE + i] = th[i];
+    if (tid != 0) return;
     a.obs_off[b] = base + left;
     a.T_buf[b] = right - left;
     a.t1[b] = start - left;
     a.tL[b] = end - left;
     a.wts_off[b] = weighted ? (int64_t)b * a.Smax : -1;
     a.item_seq[b] = q;
-    const double* p = a.params + (size_t)c * SGM_PARAM_STRIDE;
-    double th[SGM_THETA_STRIDE];
-    sgld_theta(a.model, p, th);
-    for (int i = 0; i < SGM_THETA_STRIDE; ++i) a.theta[(size_t)b * SGM_THETA_STRIDE + i] = th[i];
     if (a.prior_x0 == 1) {                                        // garch/helper.py:324-332
         a.item_pm[b] = 0.0;
         a.item_pv[b] = th[0] / (1.0 - th[1] - th[2]);
