@@ -1055,9 +1055,16 @@ __device__ __forceinline__ void step_body(const KArgs& a, int b, int t, int q_me
  * 4 CTAs -> SVM 63.0, LGSSM 69.6, GARCH 65.2;  5 -> 65.1, 73.1, 63.8-66.0;  6 (80 registers, no spills) -> 58.5, 64.7, 54.6 */
 #define SGM_FAST64_CTAS_POY 5
 #endif
+#ifndef SGM_FAST_CTAS_SHRINK
+/* f32 Nemeth-with-shrinkage fast mode (carries the weighted statistic sums in registers): 8 CTAs = 64 registers, no spill.
+ * Same box, % of the HBM roofline, 9 -> 8 CTAs: SVM 79.4 -> 79.2, LGSSM 82.2 -> 84.0, GARCH 83.1 -> 89.5 (7 CTAs: 73 / 80 / 86).
+ * The filter fast mode stays at 9 (8: SVM 81 -> 78.5, GARCH 99.6 -> 97). */
+#define SGM_FAST_CTAS_SHRINK 8
+#endif
 template <class R, bool FAST, int FM = FM_GENERIC> struct StepShape {
     static constexpr int WARPS = FAST ? (sizeof(R) == 4 ? SGM_FAST_WARPS : SGM_FAST64_WARPS) : SGM_STEP_WARPS;
-    static constexpr int CTAS = FAST ? (sizeof(R) == 4 ? SGM_FAST_CTAS : (FM == FM_POY ? SGM_FAST64_CTAS_POY : SGM_FAST64_CTAS))
+    static constexpr int CTAS = FAST ? (sizeof(R) == 4 ? (FM == FM_SHRINK ? SGM_FAST_CTAS_SHRINK : SGM_FAST_CTAS)
+                                                       : (FM == FM_POY ? SGM_FAST64_CTAS_POY : SGM_FAST64_CTAS))
                                      : (sizeof(R) == 4 ? SGM_STEP_CTAS : 2 * 8 / SGM_STEP_WARPS);
 };
 template <class R, class Model, bool SORTED, int FM = FM_GENERIC, bool RAGGED = false>
