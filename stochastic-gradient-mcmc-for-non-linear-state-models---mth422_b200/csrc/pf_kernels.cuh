@@ -8,7 +8,8 @@
 // kernel contains NO block barrier, so the 32+ resident warps of an SM hide each other's memory latency.
 // All cross-tile work of a step (global max, tile offsets, log-likelihood, Gamma prefix) is done by a
 // tiny per-item header kernel between two step kernels (a single warp for items with < 32 tiles); items with
-// N <= 2048 run the whole time loop in one launch (pf_fused_kernel).
+// N <= 2048 and a small batch run the whole time loop in one launch out of shared memory (small_kernels.cuh), few items with
+// N <= 65536 in one cooperative launch of these same device functions (coop_kernels.cuh).
 //
 // Data layout in HBM (caller workspace; B items, N particles, Q = ceil(N / 256) warp tiles per item):
 //   rec [2][B][N][4]   R   first four components of the particle record  (stats..., then state)
@@ -124,7 +125,7 @@ struct ItemHdr {
     int Q;
     double M, total;
 };
-// `local` != nullptr: a copy of the header somewhere else (the single-launch kernel keeps one per warp in shared memory)
+// `local` != nullptr: a copy of the header somewhere else (the cooperative kernel keeps one per CTA -- for fewer than 32 tiles one per warp -- in shared memory)
 __device__ __forceinline__ ItemHdr load_hdr(const KArgs& a, int b, const double* local = nullptr) {
     ItemHdr h;
     h.Q = a.Q;
@@ -379,7 +380,7 @@ __device__ __forceinline__ void header_finish(const KArgs& a, int b, int t_done,
 }
 
 // Header of an item with fewer than 32 warp tiles (N < 8192): ONE warp, shuffles only -- no block barrier.
-// This is the per-step latency of the single-launch kernel for small N (the SGLD-with-N~1000 regime).
+// This is the header path of items with 2048 < N < 8192 (per-step launches and the cooperative kernel).
 // `local` != nullptr: EVERY warp of the CTA calls this and builds its own copy of the header there (single-launch
 // kernel: no barrier and no global round trip between header and step; the copies are bit-identical -- same inputs,
 // counter-based Gamma draws, fixed shuffle trees); only the first warp applies the side effects.
@@ -907,7 +908,7 @@ __device__ __forceinline__ void step_body(const KArgs& a, int b, int t, int q_me
         tl = (tl < total) ? tl : tmax;
         int q_lo, q_hi;
         warp_search_tiles(tf, tl, c1, s1c, hdr, lane, q_lo, q_hi);
-        constexpr int MAXT = WINB / (int)(WT * sizeof(R));              // tiles the window holds: 4 (2 for f64 in the single-launch kernel)
+        constexpr int MAXT = WINB / (int)(WT * sizeof(R));              // tiles the window holds: 4 (2 for f64 in the generic and cooperative kernels)
         const int nst = q_hi - q_lo + 1;
         if (SGM_TMA_WINDOW && FAST && mbar != nullptr && nst >= 1 && nst <= MAXT) {
             const int wt = (nst <= 1) ? 1 : ((nst <= 2) ? 2 : 4);
