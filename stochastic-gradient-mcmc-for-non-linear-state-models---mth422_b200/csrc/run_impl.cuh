@@ -31,11 +31,20 @@ namespace sgmhost {
 #ifndef SGM_SMALL_MAX_PARTICLES
 #define SGM_SMALL_MAX_PARTICLES 1200000
 #endif
-template <class R, class Model, int NTH, int PPT, bool FAST>
+// number of SMs of the current device (batches of at most that many items take the latency instantiations)
+inline int sm_count() {
+    static thread_local int n = 0;
+    if (n == 0) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) { cudaGetLastError(); n = 148; }
+    }
+    return n;
+}
+template <class R, class Model, int NTH, int PPT, bool FAST, bool LAT = false>
 bool launch_small_shape(const KArgs& a, cudaStream_t stream) {
     const size_t bytes = small_smem_bytes<R>(NTH * PPT, Model::NX, Model::NP);
     if (bytes > 227 * 1024) return false;
-    auto kern = pf_small_kernel<R, Model, NTH, PPT, FAST>;
+    auto kern = pf_small_kernel<R, Model, NTH, PPT, FAST, LAT>;
     if (bytes > 48 * 1024) {
         static thread_local size_t granted = 0;            // per instantiation (and host thread): raise the limit once
         if (granted < bytes) {
@@ -49,11 +58,13 @@ bool launch_small_shape(const KArgs& a, cudaStream_t stream) {
 template <class R, class Model>
 bool launch_small(const KArgs& a, cudaStream_t stream) {
     if (small_fast_config(a)) {
-        if (a.N <= 256) return launch_small_shape<R, Model, 256, 1, true>(a, stream);
+        const bool lat = a.B <= sm_count();            // at most one item per SM: the latency instantiation (no register cap)
+        if (a.N <= 256) return lat ? launch_small_shape<R, Model, 256, 1, true, true>(a, stream) : launch_small_shape<R, Model, 256, 1, true>(a, stream);
 #if SGM_SMALL_LATENCY_ITEMS > 0
         if (a.N <= 1024 && a.B <= SGM_SMALL_LATENCY_ITEMS) return launch_small_shape<R, Model, 1024, 1, true>(a, stream);
 #endif
-        if (a.N <= 1024) return launch_small_shape<R, Model, SGM_SMALL_MID_NTH, SGM_SMALL_MID_PPT, true>(a, stream);
+        if (a.N <= 1024) return lat ? launch_small_shape<R, Model, SGM_SMALL_MID_NTH, SGM_SMALL_MID_PPT, true, true>(a, stream)
+                                    : launch_small_shape<R, Model, SGM_SMALL_MID_NTH, SGM_SMALL_MID_PPT, true>(a, stream);
         return launch_small_shape<R, Model, 1024, 2, true>(a, stream);
     }
     // every other configuration (injected randoms, Nemeth shrinkage, filter, traces, ...): two shapes, flags read at run time
@@ -259,8 +270,8 @@ int run_impl(const sgm_pf_desc* d, cudaStream_t stream) {
 // 0 applies the SG-MCMC update (sgld_update_chain) -- no kernel boundary, no host, nothing but the chain's few scalars
 // in global memory.  Iteration k uses Philox call offset (*offset_dev + k): exactly the numbers the launch-per-iteration
 // path draws, so both paths give bit-identical chains.
-template <class R, class Model, int NTH, int PPT, bool FAST>
-__global__ void __launch_bounds__(NTH, 1024 / NTH) sgld_persistent_kernel(SgldArgs sa, KArgs a, int K) {
+template <class R, class Model, int NTH, int PPT, bool FAST, bool LAT = false>
+__global__ void __launch_bounds__(NTH, small_min_ctas(NTH, LAT)) sgld_persistent_kernel(SgldArgs sa, KArgs a, int K) {
     extern __shared__ __align__(16) unsigned char small_smem[];
     const int c = blockIdx.x;
     const uint64_t o0 = *sa.offset_dev;
@@ -283,11 +294,11 @@ __global__ void __launch_bounds__(NTH, 1024 / NTH) sgld_persistent_kernel(SgldAr
     }
 }
 
-template <class R, class Model, int NTH, int PPT, bool FAST>
+template <class R, class Model, int NTH, int PPT, bool FAST, bool LAT = false>
 bool launch_persistent_shape(const SgldArgs& sa, const KArgs& a, int K, cudaStream_t stream) {
     const size_t bytes = small_smem_bytes<R>(NTH * PPT, Model::NX, Model::NP);
     if (bytes > 227 * 1024) return false;
-    auto kern = sgld_persistent_kernel<R, Model, NTH, PPT, FAST>;
+    auto kern = sgld_persistent_kernel<R, Model, NTH, PPT, FAST, LAT>;
     if (bytes > 48 * 1024) {
         static thread_local size_t granted = 0;
         if (granted < bytes) {
@@ -301,11 +312,13 @@ bool launch_persistent_shape(const SgldArgs& sa, const KArgs& a, int K, cudaStre
 template <class R, class Model>
 bool launch_persistent(const SgldArgs& sa, const KArgs& a, int K, cudaStream_t stream) {
     if (small_fast_config(a)) {
-        if (a.N <= 256) return launch_persistent_shape<R, Model, 256, 1, true>(sa, a, K, stream);
+        const bool lat = a.B <= sm_count();
+        if (a.N <= 256) return lat ? launch_persistent_shape<R, Model, 256, 1, true, true>(sa, a, K, stream) : launch_persistent_shape<R, Model, 256, 1, true>(sa, a, K, stream);
 #if SGM_SMALL_LATENCY_ITEMS > 0
         if (a.N <= 1024 && a.B <= SGM_SMALL_LATENCY_ITEMS) return launch_persistent_shape<R, Model, 1024, 1, true>(sa, a, K, stream);
 #endif
-        if (a.N <= 1024) return launch_persistent_shape<R, Model, SGM_SMALL_MID_NTH, SGM_SMALL_MID_PPT, true>(sa, a, K, stream);
+        if (a.N <= 1024) return lat ? launch_persistent_shape<R, Model, SGM_SMALL_MID_NTH, SGM_SMALL_MID_PPT, true, true>(sa, a, K, stream)
+                                    : launch_persistent_shape<R, Model, SGM_SMALL_MID_NTH, SGM_SMALL_MID_PPT, true>(sa, a, K, stream);
         return launch_persistent_shape<R, Model, 1024, 2, true>(sa, a, K, stream);
     }
     if (a.N <= 1024) return launch_persistent_shape<R, Model, 1024, 1, false>(sa, a, K, stream);
