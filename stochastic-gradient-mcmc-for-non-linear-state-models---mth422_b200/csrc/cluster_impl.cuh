@@ -21,7 +21,9 @@ struct ClusterPlan { int C, nl; };
 // 1024 < N <= 2048; from N = 4096 on the cooperative single-launch form of the tile kernels (coop_kernels.cuh) is faster
 // (N = 4096, one item: 0.41 ms against 0.48 ms).  `forced` (SGM_PATH_CLUSTER) takes any plan.
 inline bool cluster_plan(int N, int B, ClusterPlan& p, bool forced = true) {
-    if (N <= 256 || (!forced && (N <= 1024 || N > 2048))) return false;
+    // path = auto no longer selects this kernel: after the sampled-CDF search of the shared-memory kernel one CTA (1024 threads x 2
+    // particles) runs N = 2048 in 0.190 ms against 0.215 ms for the cluster of 8 x 256 (1-8 items; profiles/probe_r03k_latency.json)
+    if (N <= 256 || !forced) return false;
     static const int NLS[4] = {256, 512, 1024, 2048};
     for (int k = 0; k < (forced ? 4 : 1); ++k) {
         int C = 2;

@@ -16,8 +16,11 @@ namespace sgm {
 
 constexpr int COOP_MAX_Q = NT;            // tiles per item (N <= 65536: one tile per header thread, as in pf_header_kernel<..., 256>)
 
+#ifndef SGM_COOP_MIN_CTAS
+#define SGM_COOP_MIN_CTAS 2
+#endif
 template <class R, class Model, bool SORTED, int FM, bool RAGGED>
-__global__ void __launch_bounds__(NT, 2) pf_coop_kernel(KArgs a) {
+__global__ void __launch_bounds__(NT, SGM_COOP_MIN_CTAS) pf_coop_kernel(KArgs a) {
     namespace cgr = cooperative_groups;
     cgr::grid_group grid = cgr::this_grid();
     __shared__ __align__(32) R s_cdf_all[NWARP][SORTED ? WIN_BYTES / sizeof(R) : WT];

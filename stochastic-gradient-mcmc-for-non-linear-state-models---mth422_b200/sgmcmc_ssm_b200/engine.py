@@ -117,8 +117,9 @@ def _state(device):
 
 def cluster_plan(N, B, forced=False):
     """Mirror of cluster_plan() in csrc/cluster_impl.cuh: (cluster size, particles per CTA) when a batch of B items with N
-    particles runs the thread-block-cluster kernel (path='auto': 1024 < N <= 2048 only; forced: path='cluster'), else None."""
-    if N <= 256 or (not forced and not 1024 < N <= 2048):
+    particles runs the thread-block-cluster kernel (only when forced with path='cluster': path='auto' prefers the
+    shared-memory kernel up to N = 2048 and the cooperative tile kernel above), else None."""
+    if N <= 256 or not forced:
         return None
     for nl in ((256, 512, 1024, 2048) if forced else (256,)):
         C = 2

@@ -98,7 +98,7 @@ def test_graph_replay_equals_plain_enqueue_and_draws_fresh_randoms():
 
 
 @pytest.mark.parametrize("model,N,path", [("lgssm", 1000, "auto"), ("svm", 200, "auto"), ("garch", 2048, "auto"), ("lgssm", 1000, "cluster"),
-                                          ("svm", 8192, "cluster")])   # auto: one CTA per chain up to N = 1024, a cluster of 8 x 256 at 2048
+                                          ("svm", 8192, "cluster")])   # auto: one CTA per chain up to N = 2048; path='cluster': a cluster of CTAs per chain
 def test_persistent_kernel_equals_one_launch_sequence_per_iteration(model, N, path):
     """One work item per chain and N <= 2048: all iterations run inside ONE persistent kernel.  Iteration k uses the
     Philox call offset (base + k) either way, so the chains must be bit-identical to the launch-per-iteration path."""
@@ -112,7 +112,7 @@ def test_persistent_kernel_equals_one_launch_sequence_per_iteration(model, N, pa
     for persistent in (True, False):
         sg.set_seed(77)
         ch = DeviceChains([Sampler(n=1, m=1, observations=obs, parameters=make()) for _ in range(5)], persistent=persistent, **kw)
-        assert ch.persistent == persistent and ch.cluster == (persistent and (N > 1024 or path == "cluster"))
+        assert ch.persistent == persistent and ch.cluster == (persistent and path == "cluster")
         ch.run(7); ch.run(5)
         ch.pull_parameters()
         assert ch.launches == (2 if persistent else (3 if N <= 16384 else 124) * 5)
