@@ -67,7 +67,9 @@ bool launch_small(const KArgs& a, cudaStream_t stream) {
                                     : launch_small_shape<R, Model, SGM_SMALL_MID_NTH, SGM_SMALL_MID_PPT, true>(a, stream);
         return launch_small_shape<R, Model, 1024, 2, true>(a, stream);
     }
-    // every other configuration (injected randoms, Nemeth shrinkage, filter, traces, ...): two shapes, flags read at run time
+    // every other configuration (injected randoms, Nemeth shrinkage, filter, traces, ...): flags read at run time; at most one
+    // item per SM and N <= 1024: 512 threads x 2 particles without the 64-register cap of a 1024-thread CTA
+    if (a.N <= 1024 && a.B <= sm_count()) return launch_small_shape<R, Model, 512, 2, false, true>(a, stream);
     if (a.N <= 1024) return launch_small_shape<R, Model, 1024, 1, false>(a, stream);
     return launch_small_shape<R, Model, 1024, 2, false>(a, stream);
 }
@@ -321,6 +323,7 @@ bool launch_persistent(const SgldArgs& sa, const KArgs& a, int K, cudaStream_t s
                                     : launch_persistent_shape<R, Model, SGM_SMALL_MID_NTH, SGM_SMALL_MID_PPT, true>(sa, a, K, stream);
         return launch_persistent_shape<R, Model, 1024, 2, true>(sa, a, K, stream);
     }
+    if (a.N <= 1024 && a.B <= sm_count()) return launch_persistent_shape<R, Model, 512, 2, false, true>(sa, a, K, stream);
     if (a.N <= 1024) return launch_persistent_shape<R, Model, 1024, 1, false>(sa, a, K, stream);
     return launch_persistent_shape<R, Model, 1024, 2, false>(sa, a, K, stream);
 }
