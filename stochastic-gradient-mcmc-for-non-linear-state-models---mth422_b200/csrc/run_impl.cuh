@@ -65,6 +65,7 @@ bool launch_small(const KArgs& a, cudaStream_t stream) {
 #endif
         if (a.N <= 1024) return lat ? launch_small_shape<R, Model, SGM_SMALL_MID_NTH, SGM_SMALL_MID_PPT, true, true>(a, stream)
                                     : launch_small_shape<R, Model, SGM_SMALL_MID_NTH, SGM_SMALL_MID_PPT, true>(a, stream);
+        // (1024 < N <= 2048 at 512 threads x 4 particles without the register cap: SVM +2 %, LGSSM -3 % -- not worth a shape)
         return launch_small_shape<R, Model, 1024, 2, true>(a, stream);
     }
     // every other configuration (injected randoms, Nemeth shrinkage, filter, traces, ...): flags read at run time; at most one
