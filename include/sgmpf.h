@@ -83,8 +83,8 @@ enum { SGM_VARIATES_NATIVE = 0, SGM_VARIATES_F32 = 1 };
  *   SMALL   one CTA per item, particle system resident in shared memory, whole time loop in one launch (N <= 2048)
  *   CLUSTER one thread-block cluster (2..8 CTAs) per item, particle system in distributed shared memory, whole time loop
  *           in one launch (256 < N <= 16384 and few enough items that all clusters are resident: items x CTAs <= 148)
- *   AUTO    CLUSTER for 1024 < N <= 2048 with items x CTAs <= 148 (256 particles per CTA: where it wins), else
- *           SMALL while the batch is small (N <= 512 or items x N <= 1.2e6), else TILES */
+ *   AUTO    SMALL while N <= 2048 and the batch is small (N <= 512 or items x N <= 1.2e6), else TILES.  (CLUSTER is never
+ *           chosen automatically: measured slower than SMALL up to N = 2048 and than the cooperative TILES launch above.) */
 enum { SGM_PATH_AUTO = 0, SGM_PATH_TILES = 1, SGM_PATH_SMALL = 2, SGM_PATH_CLUSTER = 3 };
 
 /* error codes */
