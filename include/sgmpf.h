@@ -79,13 +79,16 @@ enum { SGM_VARIATES_NATIVE = 0, SGM_VARIATES_F32 = 1 };
 
 /* Kernel family of the O(N) smoothers.
  *   TILES   warp-tile kernels streaming the particle arrays through HBM / L2 (any N; the throughput path): one header + one step
- *           launch per time step, or ONE cooperative launch (grid barrier per step) when all CTAs of the batch are resident
+ *           launch per time step, or -- same device functions, bit-identical results -- ONE launch for the whole time loop when
+ *           the batch is small: an item's CTAs as a thread-block cluster with the cluster barrier between the steps
+ *           (N <= 16384, at most 592 CTAs), else a cooperative launch with a grid barrier (all CTAs resident: <= 148)
+ *   STEPS   TILES restricted to one header + one step launch per time step (what the single launches are checked against)
  *   SMALL   one CTA per item, particle system resident in shared memory, whole time loop in one launch (N <= 2048)
  *   CLUSTER one thread-block cluster (2..8 CTAs) per item, particle system in distributed shared memory, whole time loop
  *           in one launch (256 < N <= 16384 and few enough items that all clusters are resident: items x CTAs <= 148)
  *   AUTO    SMALL while N <= 2048 and the batch is small (N <= 512 or items x N <= 1.2e6), else TILES.  (CLUSTER is never
  *           chosen automatically: measured slower than SMALL up to N = 2048 and than the cooperative TILES launch above.) */
-enum { SGM_PATH_AUTO = 0, SGM_PATH_TILES = 1, SGM_PATH_SMALL = 2, SGM_PATH_CLUSTER = 3 };
+enum { SGM_PATH_AUTO = 0, SGM_PATH_TILES = 1, SGM_PATH_SMALL = 2, SGM_PATH_CLUSTER = 3, SGM_PATH_STEPS = 4 };
 
 /* error codes */
 enum { SGM_OK = 0, SGM_ERR_INVALID = -1, SGM_ERR_UNSUPPORTED = -2, SGM_ERR_WORKSPACE = -3,

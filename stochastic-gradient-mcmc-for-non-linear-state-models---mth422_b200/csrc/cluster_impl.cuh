@@ -22,7 +22,7 @@ struct ClusterPlan { int C, nl; };
 // (N = 4096, one item: 0.41 ms against 0.48 ms).  `forced` (SGM_PATH_CLUSTER) takes any plan.
 inline bool cluster_plan(int N, int B, ClusterPlan& p, bool forced = true) {
     // path = auto no longer selects this kernel: after the sampled-CDF search of the shared-memory kernel one CTA (1024 threads x 2
-    // particles) runs N = 2048 in 0.190 ms against 0.215 ms for the cluster of 8 x 256 (1-8 items; profiles/probe_r03k_latency.json)
+    // particles) runs N = 2048 in 0.190 ms against 0.215 ms for the cluster of 8 x 256 (1-8 items; profiles/probe_r03s_latency.json)
     if (N <= 256 || !forced) return false;
     static const int NLS[4] = {256, 512, 1024, 2048};
     for (int k = 0; k < (forced ? 4 : 1); ++k) {

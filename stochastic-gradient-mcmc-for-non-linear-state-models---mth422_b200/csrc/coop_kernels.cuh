@@ -19,10 +19,12 @@ constexpr int COOP_MAX_Q = NT;            // tiles per item (N <= 65536: one til
 #ifndef SGM_COOP_MIN_CTAS
 #define SGM_COOP_MIN_CTAS 2
 #endif
-template <class R, class Model, bool SORTED, int FM, bool RAGGED>
+// CL = true: the CTAs of ONE item form a thread-block cluster (G <= 8 CTAs, i.e. N <= 16384) and the barrier between two time
+// steps is the hardware cluster barrier (barrier.cluster arrive.release / wait.acquire) instead of the grid barrier's atomic +
+// polling round trips through L2.  Items are independent clusters: no cooperative launch, no limit on the batch size.
+template <class R, class Model, bool SORTED, int FM, bool RAGGED, bool CL = false>
 __global__ void __launch_bounds__(NT, SGM_COOP_MIN_CTAS) pf_coop_kernel(KArgs a) {
     namespace cgr = cooperative_groups;
-    cgr::grid_group grid = cgr::this_grid();
     __shared__ __align__(32) R s_cdf_all[NWARP][SORTED ? WIN_BYTES / sizeof(R) : WT];
     __shared__ double sh_d[NWARP];
     extern __shared__ double s_hdr[];                 // hdr_stride(Q) doubles
@@ -37,9 +39,17 @@ __global__ void __launch_bounds__(NT, SGM_COOP_MIN_CTAS) pf_coop_kernel(KArgs a)
     hc.Tb = a.T_buf[b]; hc.scanned = false; hc.gv[0] = hc.gv[1] = hc.grun = hc.gtot = 0.0; hc.acc = s_acc;
     const bool pre = a.Q >= 32 && (FM != FM_GENERIC || (SORTED && uses_spacings(a)));
     if (pre) header_gamma_scan<NT>(a, b, 0, sh_d, hc);
+    auto barrier_arrive = [&]() -> unsigned {
+        if constexpr (CL) { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); return 0u; }
+        else return cgr::this_grid().barrier_arrive();
+    };
+    auto barrier_wait = [&](unsigned token) {
+        if constexpr (CL) { (void)token; asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+        else cgr::this_grid().barrier_wait(std::move(token));
+    };
     // (drawing the warp tile's own variates of the next step there as well was tried and is slower: 0.47 -> 0.50 ms at N = 2^16 --
     // 16 more live registers across the header push the kernel to 128 registers with spills, and the wait is not idle enough)
-    grid.sync();
+    barrier_wait(barrier_arrive());
 #ifdef SGM_COOP_TIMING
     long long tc[5] = {0, 0, 0, 0, 0}, c0 = clock64(), c1;
 #define SGM_TICK(i) { c1 = clock64(); tc[i] += c1 - c0; c0 = c1; }
@@ -52,11 +62,11 @@ __global__ void __launch_bounds__(NT, SGM_COOP_MIN_CTAS) pf_coop_kernel(KArgs a)
         SGM_TICK(0)
         step_body<R, Model, SORTED, FM, RAGGED, WIN_BYTES>(a, b, t, g * NWARP + warp, lane, s_cdf_all[warp], s_hdr);
         SGM_TICK(1)
-        auto token = grid.barrier_arrive();
+        const unsigned token = barrier_arrive();
         SGM_TICK(2)
         if (pre && t + 1 < a.max_T) header_gamma_scan<NT>(a, b, t + 1, sh_d, hc);
         SGM_TICK(3)
-        grid.barrier_wait(std::move(token));
+        barrier_wait(token);
         SGM_TICK(4)
     }
 #ifdef SGM_COOP_TIMING

@@ -28,6 +28,9 @@ namespace sgmhost {
 #ifndef SGM_SMALL_LATENCY_ITEMS
 #define SGM_SMALL_LATENCY_ITEMS 0
 #endif
+#ifndef SGM_CLSYNC_MAX_CTAS          // batches up to this many CTAs take the cluster-synchronised single launch of the tile kernels
+#define SGM_CLSYNC_MAX_CTAS 592
+#endif
 #ifndef SGM_SMALL_MAX_PARTICLES
 #define SGM_SMALL_MAX_PARTICLES 1200000
 #endif
@@ -149,6 +152,44 @@ bool launch_coop_kernel(K kern, const KArgs& a, cudaStream_t stream) {
     if (cudaLaunchCooperativeKernel((const void*)kern, dim3(a.G, a.B), dim3(NT), params, dyn, stream) != cudaSuccess) { cudaGetLastError(); return false; }
     return true;
 }
+// the same kernel with one thread-block cluster per item (G <= 8 CTAs) and the cluster barrier between the steps
+template <class K>
+bool launch_clsync_kernel(K kern, const KArgs& a, cudaStream_t stream) {
+    const size_t dyn = hdr_stride(a.Q) * sizeof(double);
+    static thread_local bool attr_set = false;           // per instantiation
+    if (!attr_set) {
+        const size_t dyn_max = hdr_stride(COOP_MAX_Q) * sizeof(double);
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_max) != cudaSuccess) { cudaGetLastError(); return false; }
+        attr_set = true;
+    }
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(a.G, a.B); cfg.blockDim = dim3(NT); cfg.dynamicSmemBytes = dyn; cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = a.G; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    // every cluster of the batch must be resident at once: a cluster that has to wait for a free slot waits for a WHOLE time loop
+    // (measured: 64 items x 5 CTAs = 320 CTAs against 296 slots ran 0.40 ms instead of the per-step path's 0.32 ms)
+    static thread_local int max_clusters[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};      // per instantiation, by cluster size
+    if (max_clusters[a.G] == 0) {
+        int n = 0;
+        cudaLaunchConfig_t q = cfg;
+        q.gridDim = dim3(a.G, 4096); q.dynamicSmemBytes = hdr_stride(COOP_MAX_Q) * sizeof(double);
+        if (cudaOccupancyMaxActiveClusters(&n, kern, &q) != cudaSuccess) { cudaGetLastError(); n = 0; }
+        max_clusters[a.G] = n > 0 ? n : -1;
+    }
+    if (a.B > max_clusters[a.G]) return false;
+    if (cudaLaunchKernelEx(&cfg, kern, a) != cudaSuccess) { cudaGetLastError(); return false; }
+    return true;
+}
+template <class R, class Model>
+bool launch_clsync(const sgm_pf_desc* d, const KArgs& a, int fm, cudaStream_t stream) {
+    if (fm == FM_POY) return (a.N % WT == 0) ? launch_clsync_kernel(pf_coop_kernel<R, Model, true, FM_POY, false, true>, a, stream)
+                                             : launch_clsync_kernel(pf_coop_kernel<R, Model, true, FM_POY, true, true>, a, stream);
+    if (d->resample == SGM_RESAMPLE_MULTINOMIAL) return launch_clsync_kernel(pf_coop_kernel<R, Model, false, FM_GENERIC, false, true>, a, stream);
+    return launch_clsync_kernel(pf_coop_kernel<R, Model, true, FM_GENERIC, false, true>, a, stream);
+}
 template <class R, class Model>
 bool launch_coop(const sgm_pf_desc* d, const KArgs& a, int fm, cudaStream_t stream) {
     if (fm == FM_POY) return (a.N % WT == 0) ? launch_coop_kernel(pf_coop_kernel<R, Model, true, FM_POY, false>, a, stream)
@@ -164,7 +205,7 @@ int run_impl(const sgm_pf_desc* d, cudaStream_t stream) {
     const dim3 grid(a.G, a.B), block(NT);
     int64_t launches = 0;
     const bool pred = d->stat_kind == SGM_STAT_PRED;
-    const bool small_ok = a.N <= SGM_SMALL_MAX_N && !backward_pf(d->pf) && !pred && d->path != SGM_PATH_TILES &&
+    const bool small_ok = a.N <= SGM_SMALL_MAX_N && !backward_pf(d->pf) && !pred && d->path != SGM_PATH_TILES && d->path != SGM_PATH_STEPS &&
                           (a.N <= 512 || (int64_t)a.B * a.N <= SGM_SMALL_MAX_PARTICLES || d->path == SGM_PATH_SMALL);
     // few items (all clusters resident at once): a cluster of CTAs per item, particle system in distributed shared memory
     const bool cluster_ok = !backward_pf(d->pf) && !pred && (d->path == SGM_PATH_AUTO || d->path == SGM_PATH_CLUSTER) &&
@@ -228,12 +269,23 @@ int run_impl(const sgm_pf_desc* d, cudaStream_t stream) {
         };
         // few items (every CTA of the batch resident at once, at most one CTA per SM): the whole time loop in ONE
         // cooperative launch, grid barrier instead of the kernel boundary; same arithmetic, bit-identical results
-        static const bool no_coop = getenv("SGM_NO_COOP") != nullptr;            // A/B switch for the benches
+        static const bool no_coop_env = getenv("SGM_NO_COOP") != nullptr;        // A/B switch for the benches
+        const bool no_coop = no_coop_env || d->path == SGM_PATH_STEPS;
         // (Q <= 256: above that the per-step path builds its headers with 1024 threads, i.e. another summation order)
         const bool coop_ok = !no_coop && !piped && !backward_pf(d->pf) && !pred && a.Q <= NT && a.max_T > 0 &&
                              (int64_t)a.G * a.B <= 148;
         bool done_coop = false;
-        if (coop_ok) {
+        // N <= 16384 (an item = at most 8 CTAs = one portable cluster) and a batch of at most SGM_CLSYNC_MAX_CTAS CTAs: one launch
+        // with the cluster barrier between the steps (no co-residency requirement, so also for more CTAs than SMs)
+        static const bool no_clsync = getenv("SGM_NO_CLSYNC") != nullptr;         // A/B switch
+        const bool cl_ok = !no_coop && !no_clsync && !piped && !backward_pf(d->pf) && !pred && a.Q <= NT && a.max_T > 0 && a.G <= 8 &&
+                           (int64_t)a.G * a.B <= SGM_CLSYNC_MAX_CTAS;
+        if (cl_ok) {
+            if (d->ev_steps_begin) cudaEventRecord(reinterpret_cast<cudaEvent_t>(d->ev_steps_begin), stream);
+            done_coop = launch_clsync<R, Model>(d, a, fm == FM_POY ? FM_POY : FM_GENERIC, stream);
+            if (done_coop) { ++launches; if (d->ev_steps_end) cudaEventRecord(reinterpret_cast<cudaEvent_t>(d->ev_steps_end), stream); }
+        }
+        if (!done_coop && coop_ok) {
             if (d->ev_steps_begin) cudaEventRecord(reinterpret_cast<cudaEvent_t>(d->ev_steps_begin), stream);
             done_coop = launch_coop<R, Model>(d, a, fm == FM_POY ? FM_POY : FM_GENERIC, stream);
             if (done_coop) { ++launches; if (d->ev_steps_end) cudaEventRecord(reinterpret_cast<cudaEvent_t>(d->ev_steps_end), stream); }
@@ -338,7 +390,7 @@ int run_sgld_persistent(const sgm_pf_desc* d, const SgldArgs& sa, int K, cudaStr
     bool ok = false;
     // few chains: one cluster of CTAs per chain (N up to 8 x 2048); else one CTA per chain (N <= 2048)
     if (d->path == SGM_PATH_CLUSTER || (d->path == SGM_PATH_AUTO && a.N > 1024)) ok = run_sgld_cluster<R>(d, sa, a, K, s) == 1;
-    if (!ok && (d->n_particles > SGM_SMALL_MAX_N || d->path == SGM_PATH_TILES || d->path == SGM_PATH_CLUSTER)) return 0;
+    if (!ok && (d->n_particles > SGM_SMALL_MAX_N || d->path == SGM_PATH_TILES || d->path == SGM_PATH_STEPS || d->path == SGM_PATH_CLUSTER)) return 0;
     if (!ok) switch (d->model) {
         case SGM_MODEL_SVM: ok = launch_persistent<R, SvmPrior>(sa, a, K, s); break;
         case SGM_MODEL_LGSSM: ok = d->kernel == SGM_KERNEL_PRIOR ? launch_persistent<R, LgssmPrior>(sa, a, K, s) : launch_persistent<R, LgssmOptimal>(sa, a, K, s); break;

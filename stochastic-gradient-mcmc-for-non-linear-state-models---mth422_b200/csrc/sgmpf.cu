@@ -62,7 +62,7 @@ int validate(const sgm_pf_desc* d) {
     if (d->step_weights && !d->wts_off) return fail(SGM_ERR_INVALID, "step_weights given without wts_off");
     if (d->n2_mode < SGM_N2_AUTO || d->n2_mode > SGM_N2_TENSOR) return fail(SGM_ERR_INVALID, "unknown n2_mode");
     if (d->variates != SGM_VARIATES_NATIVE && d->variates != SGM_VARIATES_F32) return fail(SGM_ERR_INVALID, "unknown variates");
-    if (d->path < SGM_PATH_AUTO || d->path > SGM_PATH_CLUSTER || d->reserved1 != 0) return fail(SGM_ERR_INVALID, "unknown path");
+    if (d->path < SGM_PATH_AUTO || d->path > SGM_PATH_STEPS || d->reserved1 != 0) return fail(SGM_ERR_INVALID, "unknown path");
     if (d->path == SGM_PATH_CLUSTER && (d->n_particles <= 256 || d->n_particles > 16384 || d->pf == SGM_PF_POY_N2 || d->pf == SGM_PF_PARIS ||
                                         d->stat_kind == SGM_STAT_PRED || (int64_t)d->n_items * 2 > 148))
         return fail(SGM_ERR_UNSUPPORTED, "path = CLUSTER needs 256 < N <= 16384, an O(N) smoother and items x cluster size <= 148");

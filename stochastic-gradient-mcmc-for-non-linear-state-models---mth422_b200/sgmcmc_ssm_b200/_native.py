@@ -18,7 +18,7 @@ RESAMPLE = dict(multinomial=0, multinomial_sorted=1, sorted=1, systematic=2, str
 STAT = dict(score=0, suff=1, none=2, pred=3)
 N2_MODE = dict(auto=0, fp32_pipe=1, tensor=2)
 VARIATES = dict(native=0, f32=1)
-PATH = dict(auto=0, tiles=1, small=2, cluster=3)
+PATH = dict(auto=0, tiles=1, small=2, cluster=3, steps=4)
 STATUS_NAN_WEIGHT, STATUS_ZERO_WEIGHT, STATUS_AR_OVERFLOW = 1, 2, 4
 THETA_STRIDE = 12
 PRED_SLOTS, PRED_MAX_STEPS = 16, 14           # SGM_PRED_SLOTS, SGM_PRED_MAX_STEPS (include/sgmpf.h)

@@ -80,15 +80,18 @@ def test_shard_and_stream_invariance_bit_for_bit():
 @pytest.mark.parametrize("dtype,resample,N,per", [("f32", "multinomial_sorted", N16, 4), ("f32", "multinomial_sorted", 60000, 4),
                                                   ("f64", "multinomial", 8192, 30), ("f32", "multinomial_sorted", 10000, 25)])
 def test_cooperative_single_launch_equals_per_step_launches_bit_for_bit(dtype, resample, N, per):
-    """A batch whose CTAs are all resident at once (items x ceil(N / 2048) <= 148) runs the whole time loop in ONE cooperative
-    launch (csrc/coop_kernels.cuh: grid barrier instead of the kernel boundary, per-CTA header copies); bigger batches take
-    one header + one step launch per time step.  Same device functions, same counter-based randoms: bit-identical."""
+    """A small batch of the tile kernels runs the whole time loop in ONE launch (csrc/coop_kernels.cuh, per-CTA header copies):
+    N <= 16384 with the CTAs of an item as a thread-block cluster and the cluster barrier instead of the kernel boundary (the
+    8192 / 10000 cases), else cooperatively with a grid barrier when all CTAs are resident (the 60000 / 65536 cases);
+    path='steps' takes one header + one step launch per time step.  Same device functions, same counter-based randoms:
+    bit-identical."""
     import sgmcmc_ssm_b200 as sg
     it = _items(3 * per, seed=5)
-    kw = dict(dtype=dtype, rng="philox", resample=resample, seed=9, offset=2, path="tiles")
-    whole = sg.run_pf("svm", "prior", "poyiadjis_N", it, N, **kw)
+    kw = dict(dtype=dtype, rng="philox", resample=resample, seed=9, offset=2)
+    whole = sg.run_pf("svm", "prior", "poyiadjis_N", it, N, path="steps", **kw)
     pk = it.pack()
-    parts = [sg.run_pf("svm", "prior", "poyiadjis_N", pk.slice(i, i + per), N, item_id_base=i, **kw) for i in range(0, 3 * per, per)]
+    parts = [sg.run_pf("svm", "prior", "poyiadjis_N", pk.slice(i, i + per), N, item_id_base=i, path="tiles", **kw)
+             for i in range(0, 3 * per, per)]
     assert whole.launches > 100 and all(p.launches == 1 for p in parts), (whole.launches, [p.launches for p in parts])
     np.testing.assert_array_equal(whole.grad, np.concatenate([p.grad for p in parts]))
     np.testing.assert_array_equal(whole.loglik, np.concatenate([p.loglik for p in parts]))
