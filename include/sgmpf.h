@@ -81,7 +81,7 @@ enum { SGM_VARIATES_NATIVE = 0, SGM_VARIATES_F32 = 1 };
  *   TILES   warp-tile kernels streaming the particle arrays through HBM / L2 (any N; the throughput path): one header + one step
  *           launch per time step, or -- same device functions, bit-identical results -- ONE launch for the whole time loop when
  *           the batch is small: an item's CTAs as a thread-block cluster with the cluster barrier between the steps
- *           (N <= 16384, at most 592 CTAs), else a cooperative launch with a grid barrier (all CTAs resident: <= 148)
+ *           (N <= 32768, all clusters resident), else a cooperative launch with a grid barrier (all CTAs resident: <= 148)
  *   STEPS   TILES restricted to one header + one step launch per time step (what the single launches are checked against)
  *   SMALL   one CTA per item, particle system resident in shared memory, whole time loop in one launch (N <= 2048)
  *   CLUSTER one thread-block cluster (2..8 CTAs) per item, particle system in distributed shared memory, whole time loop

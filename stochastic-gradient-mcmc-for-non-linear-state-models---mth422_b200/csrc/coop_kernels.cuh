@@ -19,7 +19,7 @@ constexpr int COOP_MAX_Q = NT;            // tiles per item (N <= 65536: one til
 #ifndef SGM_COOP_MIN_CTAS
 #define SGM_COOP_MIN_CTAS 2
 #endif
-// CL = true: the CTAs of ONE item form a thread-block cluster (G <= 8 CTAs, i.e. N <= 16384) and the barrier between two time
+// CL = true: the CTAs of ONE item form a thread-block cluster (G <= 16 CTAs, i.e. N <= 32768) and the barrier between two time
 // steps is the hardware cluster barrier (barrier.cluster arrive.release / wait.acquire) instead of the grid barrier's atomic +
 // polling round trips through L2.  Items are independent clusters: no cooperative launch, no limit on the batch size.
 template <class R, class Model, bool SORTED, int FM, bool RAGGED, bool CL = false>

@@ -28,6 +28,9 @@ namespace sgmhost {
 #ifndef SGM_SMALL_LATENCY_ITEMS
 #define SGM_SMALL_LATENCY_ITEMS 0
 #endif
+#ifndef SGM_CLSYNC_MAX_CLUSTER       // largest cluster (CTAs of one item) of that launch: 8 is the portable limit, 16 the hardware's
+#define SGM_CLSYNC_MAX_CLUSTER 16
+#endif
 #ifndef SGM_CLSYNC_MAX_CTAS          // batches up to this many CTAs take the cluster-synchronised single launch of the tile kernels
 #define SGM_CLSYNC_MAX_CTAS 592
 #endif
@@ -160,6 +163,8 @@ bool launch_clsync_kernel(K kern, const KArgs& a, cudaStream_t stream) {
     if (!attr_set) {
         const size_t dyn_max = hdr_stride(COOP_MAX_Q) * sizeof(double);
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_max) != cudaSuccess) { cudaGetLastError(); return false; }
+        // clusters of 9-16 CTAs (16384 < N <= 32768) are a non-portable size: allowed on B200, the occupancy query below decides
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) cudaGetLastError();
         attr_set = true;
     }
     cudaLaunchConfig_t cfg;
@@ -171,7 +176,7 @@ bool launch_clsync_kernel(K kern, const KArgs& a, cudaStream_t stream) {
     cfg.attrs = attr; cfg.numAttrs = 1;
     // every cluster of the batch must be resident at once: a cluster that has to wait for a free slot waits for a WHOLE time loop
     // (measured: 64 items x 5 CTAs = 320 CTAs against 296 slots ran 0.40 ms instead of the per-step path's 0.32 ms)
-    static thread_local int max_clusters[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};      // per instantiation, by cluster size
+    static thread_local int max_clusters[17] = {0};                              // per instantiation, by cluster size
     if (max_clusters[a.G] == 0) {
         int n = 0;
         cudaLaunchConfig_t q = cfg;
@@ -275,10 +280,10 @@ int run_impl(const sgm_pf_desc* d, cudaStream_t stream) {
         const bool coop_ok = !no_coop && !piped && !backward_pf(d->pf) && !pred && a.Q <= NT && a.max_T > 0 &&
                              (int64_t)a.G * a.B <= 148;
         bool done_coop = false;
-        // N <= 16384 (an item = at most 8 CTAs = one portable cluster) and a batch of at most SGM_CLSYNC_MAX_CTAS CTAs: one launch
+        // N <= 32768 (an item = at most 16 CTAs = one cluster; 9-16 is a non-portable size) and a batch of at most SGM_CLSYNC_MAX_CTAS CTAs: one launch
         // with the cluster barrier between the steps (no co-residency requirement, so also for more CTAs than SMs)
         static const bool no_clsync = getenv("SGM_NO_CLSYNC") != nullptr;         // A/B switch
-        const bool cl_ok = !no_coop && !no_clsync && !piped && !backward_pf(d->pf) && !pred && a.Q <= NT && a.max_T > 0 && a.G <= 8 &&
+        const bool cl_ok = !no_coop && !no_clsync && !piped && !backward_pf(d->pf) && !pred && a.Q <= NT && a.max_T > 0 && a.G <= SGM_CLSYNC_MAX_CLUSTER &&
                            (int64_t)a.G * a.B <= SGM_CLSYNC_MAX_CTAS;
         if (cl_ok) {
             if (d->ev_steps_begin) cudaEventRecord(reinterpret_cast<cudaEvent_t>(d->ev_steps_begin), stream);

@@ -78,11 +78,12 @@ def test_shard_and_stream_invariance_bit_for_bit():
 
 
 @pytest.mark.parametrize("dtype,resample,N,per", [("f32", "multinomial_sorted", N16, 4), ("f32", "multinomial_sorted", 60000, 4),
-                                                  ("f64", "multinomial", 8192, 30), ("f32", "multinomial_sorted", 10000, 25)])
+                                                  ("f64", "multinomial", 8192, 30), ("f32", "multinomial_sorted", 10000, 25),
+                                                  ("f32", "multinomial_sorted", 32768, 3), ("f64", "multinomial_sorted", 20000, 2)])
 def test_cooperative_single_launch_equals_per_step_launches_bit_for_bit(dtype, resample, N, per):
     """A small batch of the tile kernels runs the whole time loop in ONE launch (csrc/coop_kernels.cuh, per-CTA header copies):
-    N <= 16384 with the CTAs of an item as a thread-block cluster and the cluster barrier instead of the kernel boundary (the
-    8192 / 10000 cases), else cooperatively with a grid barrier when all CTAs are resident (the 60000 / 65536 cases);
+    N <= 32768 with the CTAs of an item as a thread-block cluster and the cluster barrier instead of the kernel boundary (the
+    8192 / 10000 / 20000 / 32768 cases), else cooperatively with a grid barrier when all CTAs are resident (the 60000 / 65536 cases);
     path='steps' takes one header + one step launch per time step.  Same device functions, same counter-based randoms:
     bit-identical."""
     import sgmcmc_ssm_b200 as sg
